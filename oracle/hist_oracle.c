@@ -1,0 +1,812 @@
+/*
+ * hist_oracle.c -- CPU ORACLE for the histogram-tree training path.
+ *
+ * THIS FILE IS TEST INFRASTRUCTURE.  It is the checker the CUDA path is compared
+ * against (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl
+ * reference legs).  Nothing under xgboost_ray_b200/ may import, link or call it.
+ *
+ * PARITY UNPINNED: the arithmetic of this path lives in the third-party `xgboost`
+ * wheel (dmlc/xgboost, unpinned: reference setup.py:18 "xgboost>=0.90"), which is
+ * not vendored under /root/reference and not installable here.  The reference holds
+ * no golden vectors for it, only relational known-answer tests, which
+ * tests/test_oracle_*.py port.  This file restates the PUBLISHED algorithm of
+ * XGBoost 2.x CPU `tree_method="hist"`, anchored on the
+ * reference call sites:
+ *   xgb.DMatrix / QuantileDMatrix construction ... xgboost_ray/main.py:386,418,437
+ *   xgb.train(...)                              ... xgboost_ray/main.py:745-752
+ *   model.predict(...)                          ... xgboost_ray/main.py:804
+ *
+ * Sections (upstream file the restatement follows, from Appendix A):
+ *   A.2  cuts & bins      (src/common/quantile.{h,cc}: WQSummary::SetPrune, AddCutPoint)
+ *   A.4  gradients        (src/objective/regression_loss.h, multiclass_obj.cu)
+ *   A.5  histogram        (src/tree/hist/histogram.h) -- exact-integer (fixed point)
+ *                          or float64 accumulation
+ *   A.6  split enumeration(src/tree/hist/evaluate_splits.h, src/tree/param.h)
+ *   A.7  tree bookkeeping (src/tree/updater_quantile_hist.cc, driver.h)
+ *   A.8  row partition    (src/tree/common_row_partitioner.h)
+ *   A.9  prediction       (src/predictor/cpu_predictor.cc)
+ *   A.10 metrics          (src/metric/elementwise_metric.cu, multiclass_metric.cu)
+ *
+ * Deliberate, documented deviations (DESIGN.md "Oracle decisions"):
+ *   - sketch ranks are exact (int64) instead of fp32 GK summaries: the exact summary
+ *     is what XGBoost's sketch approximates and equals it for small inputs;
+ *   - a feature that has missing values is capped at 255 real bins (bin 255 is the
+ *     missing sentinel of the uint8 matrix);
+ *   - exp() in the objectives is a fixed IEEE-only sequence (or_expf) so that the
+ *     CUDA path can reproduce gradients bit-for-bit;
+ *   - histogram sums are exact integers of gradients quantised to `qbits` bits
+ *     (qbits==0 selects float64 accumulation, XGBoost's CPU behaviour).
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define OR_MISSING_BIN 255
+#define OR_RT_EPS 1e-6f
+#define OR_LEAF_BITS 40
+
+enum { OR_OBJ_SQUAREDERROR = 0, OR_OBJ_LOGISTIC = 1, OR_OBJ_SOFTPROB = 2 };
+
+typedef struct {
+  int32_t objective;
+  int32_t num_class;     /* 1 unless softprob */
+  int32_t max_depth;
+  int32_t max_bin;
+  float eta;
+  float gamma;
+  float min_child_weight;
+  float lambda;
+  float alpha;
+  float base_score;      /* probability space for logistic */
+  int32_t qbits;         /* 0 => float64 histogram */
+  int32_t nthread;       /* 0 => omp default */
+} OrParams;
+
+typedef struct {
+  int32_t n_features;
+  int32_t max_bin;
+  int32_t *cut_ptrs;    /* [F+1] */
+  float *cut_vals;      /* [cut_ptrs[F]] */
+  float *min_vals;      /* [F] */
+  uint8_t *has_missing; /* [F] */
+} OrCuts;
+
+typedef struct {
+  int32_t n_nodes, cap;
+  int32_t *left, *right, *parent;
+  int32_t *split_feature; /* -1 for leaf */
+  int32_t *split_bin;
+  float *split_cond;
+  uint8_t *default_left;
+  float *value;           /* leaf value (eta applied) for leaves, base_weight for internal */
+  float *base_weight;
+  float *loss_chg;
+  double *sum_hess;
+  double *sum_grad;
+} OrTree;
+
+typedef struct {
+  OrParams p;
+  int32_t n_features;
+  int32_t n_trees, cap_trees;
+  OrTree **trees;
+} OrModel;
+
+/* ------------------------------------------------------------------ util */
+static int is_missing(float x, float missing) {
+  return isnan(x) || (!isnan(missing) && x == missing);
+}
+
+/* Deterministic expf: only IEEE-754 binary32 add/mul (no fma contraction; the file is
+ * compiled with -ffp-contract=off) so CUDA can replay it bit-for-bit with __fmul_rn /
+ * __fadd_rn.  |rel err| <~ 2 ulp on [-88, 88]. */
+float or_expf(float x) {
+  if (x > 88.7f) x = 88.7f;
+  if (x < -103.0f) return 0.0f;
+  const float log2e = 1.44269504088896341f;
+  const float ln2_hi = 0.693359375f;          /* 0x3f318000 */
+  const float ln2_lo = -2.12194440e-4f;
+  float t = x * log2e;
+  float n = rintf(t);
+  float r = x - n * ln2_hi;
+  r = r - n * ln2_lo;
+  /* minimax-ish polynomial for exp(r), r in [-ln2/2, ln2/2] */
+  float p = 1.9875691500e-4f;
+  p = p * r + 1.3981999507e-3f;
+  p = p * r + 8.3334519073e-3f;
+  p = p * r + 4.1665795894e-2f;
+  p = p * r + 1.6666665459e-1f;
+  p = p * r + 5.0000001201e-1f;
+  float r2 = r * r;
+  float e = p * r2 + r;
+  e = e + 1.0f;
+  /* scale by 2^n in two steps to stay in range */
+  int ni = (int)n;
+  int n1 = ni / 2, n2 = ni - n1;
+  union { uint32_t u; float f; } s1, s2;
+  s1.u = (uint32_t)(n1 + 127) << 23;
+  s2.u = (uint32_t)(n2 + 127) << 23;
+  e = e * s1.f;
+  e = e * s2.f;
+  return e;
+}
+
+static float or_sigmoid(float x) {
+  /* regression_loss.h Sigmoid: 1/(1+exp(min(-x,88.7))+1e-16) */
+  float nx = -x;
+  if (nx > 88.7f) nx = 88.7f;
+  float denom = or_expf(nx) + 1.0f;
+  denom = denom + 1e-16f;
+  return 1.0f / denom;
+}
+
+/* ------------------------------------------------------------------ A.2 cuts */
+/* LSD radix sort of floats via order-preserving keys */
+static uint32_t f2key(float f) {
+  union { float f; uint32_t u; } v; v.f = f;
+  return (v.u & 0x80000000u) ? ~v.u : (v.u | 0x80000000u);
+}
+static float key2f(uint32_t k) {
+  union { float f; uint32_t u; } v;
+  v.u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return v.f;
+}
+static void radix_sort_keys(uint32_t *a, uint32_t *tmp, int64_t n) {
+  const int shifts[3] = {0, 11, 22};
+  const int bits[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    int nb = 1 << bits[pass];
+    int64_t *cnt = (int64_t *)calloc((size_t)nb + 1, sizeof(int64_t));
+    uint32_t mask = (uint32_t)nb - 1;
+    for (int64_t i = 0; i < n; ++i) cnt[((a[i] >> shifts[pass]) & mask) + 1]++;
+    for (int b = 0; b < nb; ++b) cnt[b + 1] += cnt[b];
+    for (int64_t i = 0; i < n; ++i) tmp[cnt[(a[i] >> shifts[pass]) & mask]++] = a[i];
+    memcpy(a, tmp, (size_t)n * sizeof(uint32_t));
+    free(cnt);
+  }
+}
+
+/* One feature: exact summary (distinct values, int64 rmin/rmax) -> SetPrune -> cuts.
+ * Returns number of cuts written to out_cuts (<= 256). */
+static int make_cuts_feature(const uint32_t *sorted_keys, int64_t cnt, int max_num_bins_cap,
+                             float *out_cuts, float *out_min) {
+  /* distinct summary */
+  int64_t m = 0;
+  for (int64_t i = 0; i < cnt; ++i)
+    if (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) ++m;
+  if (m == 0) {
+    float mval = 0.0f;
+    *out_min = mval - fabsf(mval) - 1e-5f;
+    float cpt = *out_min;
+    out_cuts[0] = cpt + (fabsf(cpt) + 1e-5f);
+    return 1;
+  }
+  float *val = (float *)malloc((size_t)m * sizeof(float));
+  int64_t *rmin = (int64_t *)malloc((size_t)m * sizeof(int64_t));
+  int64_t *rmax = (int64_t *)malloc((size_t)m * sizeof(int64_t));
+  int64_t u = -1;
+  for (int64_t i = 0; i < cnt; ++i) {
+    if (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) {
+      ++u; val[u] = key2f(sorted_keys[i]); rmin[u] = i; rmax[u] = i + 1;
+    } else rmax[u] = i + 1;
+  }
+  int64_t max_num_bins = m < max_num_bins_cap ? m : max_num_bins_cap;
+  int64_t maxsize = max_num_bins + 1;
+  /* WQSummary::SetPrune(src, maxsize) on the exact summary; wmin = rmax-rmin */
+  float *sel = (float *)malloc((size_t)(maxsize + 1) * sizeof(float));
+  int64_t size = 0;
+  if (m <= maxsize) {
+    for (int64_t i = 0; i < m; ++i) sel[size++] = val[i];
+  } else {
+    const double begin = (double)rmax[0];
+    const double range = (double)rmin[m - 1] - (double)rmax[0];
+    const int64_t n = maxsize - 1;
+    sel[size++] = val[0];
+    int64_t i = 1, lastidx = 0;
+    for (int64_t k = 1; k < n; ++k) {
+      double dx2 = 2.0 * (((double)k * range) / (double)n + begin);
+      while (i < m - 1 && dx2 >= (double)(rmax[i + 1] + rmin[i + 1])) ++i;
+      if (i == m - 1) break;
+      /* RMinNext(i) = rmin+wmin = rmax[i]; RMaxPrev(i+1) = rmax-wmin = rmin[i+1] */
+      if (dx2 < (double)(rmax[i] + rmin[i + 1])) {
+        if (i != lastidx) { sel[size++] = val[i]; lastidx = i; }
+      } else {
+        if (i + 1 != lastidx) { sel[size++] = val[i + 1]; lastidx = i + 1; }
+      }
+    }
+    if (lastidx != m - 1) sel[size++] = val[m - 1];
+  }
+  /* HistogramCuts: min_val, AddCutPoint(a, max_num_bins), last */
+  float mval = sel[0];
+  *out_min = mval - fabsf(mval) - 1e-5f;
+  int64_t required = size < max_num_bins ? size : max_num_bins;
+  int nc = 0;
+  for (int64_t i = 1; i < required; ++i) {
+    float cpt = sel[i];
+    if (i == 1 || cpt > out_cuts[nc - 1]) out_cuts[nc++] = cpt;
+  }
+  float cpt = sel[size - 1];
+  out_cuts[nc++] = cpt + (fabsf(cpt) + 1e-5f);
+  free(sel); free(val); free(rmin); free(rmax);
+  return nc;
+}
+
+OrCuts *or_cuts_create(const float *X, int64_t n, int32_t F, float missing, int32_t max_bin) {
+  if (max_bin < 2 || max_bin > 256) return NULL;
+  OrCuts *c = (OrCuts *)calloc(1, sizeof(OrCuts));
+  c->n_features = F; c->max_bin = max_bin;
+  c->cut_ptrs = (int32_t *)calloc((size_t)F + 1, sizeof(int32_t));
+  c->min_vals = (float *)calloc((size_t)F, sizeof(float));
+  c->has_missing = (uint8_t *)calloc((size_t)F, 1);
+  float *tmpc = (float *)malloc((size_t)F * 256 * sizeof(float));
+  int32_t *ncut = (int32_t *)calloc((size_t)F, sizeof(int32_t));
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int32_t f = 0; f < F; ++f) {
+    uint32_t *keys = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
+    uint32_t *tmp = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
+    int64_t cnt = 0; int miss = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      float x = X[i * F + f];
+      if (is_missing(x, missing)) { miss = 1; continue; }
+      if (x == 0.0f) x = 0.0f; /* -0 -> +0 */
+      keys[cnt++] = f2key(x);
+    }
+    radix_sort_keys(keys, tmp, cnt);
+    c->has_missing[f] = (uint8_t)miss;
+    int cap = max_bin;
+    if (miss && cap > 255) cap = 255;
+    ncut[f] = make_cuts_feature(keys, cnt, cap, tmpc + (size_t)f * 256, &c->min_vals[f]);
+    free(keys); free(tmp);
+  }
+  for (int32_t f = 0; f < F; ++f) c->cut_ptrs[f + 1] = c->cut_ptrs[f] + ncut[f];
+  c->cut_vals = (float *)malloc((size_t)(c->cut_ptrs[F] > 0 ? c->cut_ptrs[F] : 1) * sizeof(float));
+  for (int32_t f = 0; f < F; ++f)
+    memcpy(c->cut_vals + c->cut_ptrs[f], tmpc + (size_t)f * 256, (size_t)ncut[f] * sizeof(float));
+  free(tmpc); free(ncut);
+  return c;
+}
+
+/* build cuts from caller-supplied arrays (e.g. downloaded from the device path) */
+OrCuts *or_cuts_from_arrays(int32_t F, int32_t max_bin, const int32_t *ptrs, const float *vals,
+                            const float *mins, const uint8_t *has_missing) {
+  OrCuts *c = (OrCuts *)calloc(1, sizeof(OrCuts));
+  c->n_features = F; c->max_bin = max_bin;
+  c->cut_ptrs = (int32_t *)malloc(((size_t)F + 1) * sizeof(int32_t));
+  memcpy(c->cut_ptrs, ptrs, ((size_t)F + 1) * sizeof(int32_t));
+  c->cut_vals = (float *)malloc((size_t)ptrs[F] * sizeof(float));
+  memcpy(c->cut_vals, vals, (size_t)ptrs[F] * sizeof(float));
+  c->min_vals = (float *)malloc((size_t)F * sizeof(float));
+  memcpy(c->min_vals, mins, (size_t)F * sizeof(float));
+  c->has_missing = (uint8_t *)calloc((size_t)F, 1);
+  if (has_missing) memcpy(c->has_missing, has_missing, (size_t)F);
+  return c;
+}
+
+void or_cuts_free(OrCuts *c) {
+  if (!c) return;
+  free(c->cut_ptrs); free(c->cut_vals); free(c->min_vals); free(c->has_missing); free(c);
+}
+int32_t or_cuts_total(const OrCuts *c) { return c->cut_ptrs[c->n_features]; }
+void or_cuts_get(const OrCuts *c, int32_t *ptrs, float *vals, float *mins, uint8_t *has_missing) {
+  memcpy(ptrs, c->cut_ptrs, ((size_t)c->n_features + 1) * sizeof(int32_t));
+  memcpy(vals, c->cut_vals, (size_t)c->cut_ptrs[c->n_features] * sizeof(float));
+  memcpy(mins, c->min_vals, (size_t)c->n_features * sizeof(float));
+  memcpy(has_missing, c->has_missing, (size_t)c->n_features);
+}
+
+/* bin = upper_bound(cuts_f, x) clamped to the last bin; missing -> 255 (A.2) */
+void or_bin_matrix(const OrCuts *c, const float *X, int64_t n, float missing, uint8_t *bins) {
+  int32_t F = c->n_features;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    for (int32_t f = 0; f < F; ++f) {
+      float x = X[i * F + f];
+      if (is_missing(x, missing)) { bins[i * F + f] = OR_MISSING_BIN; continue; }
+      const float *cv = c->cut_vals + c->cut_ptrs[f];
+      int32_t nf = c->cut_ptrs[f + 1] - c->cut_ptrs[f];
+      int32_t lo = 0, hi = nf;
+      while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (cv[mid] > x) hi = mid; else lo = mid + 1; }
+      if (lo >= nf) lo = nf - 1;
+      bins[i * F + f] = (uint8_t)lo;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ A.4 gradients */
+/* margin [n*K] row-major, out g,h [n*K] */
+void or_gradients(int32_t objective, int32_t K, const float *margin, const float *label,
+                  const float *weight, int64_t n, float *g, float *h) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    float w = weight ? weight[i] : 1.0f;
+    if (objective == OR_OBJ_SQUAREDERROR) {
+      g[i] = (margin[i] - label[i]) * w;
+      h[i] = 1.0f * w;
+    } else if (objective == OR_OBJ_LOGISTIC) {
+      float p = or_sigmoid(margin[i]);
+      float hh = p * (1.0f - p);
+      if (hh < 1e-16f) hh = 1e-16f;
+      g[i] = (p - label[i]) * w;
+      h[i] = hh * w;
+    } else {
+      const float *m = margin + i * K;
+      float mx = m[0];
+      for (int k = 1; k < K; ++k) if (m[k] > mx) mx = m[k];
+      float s = 0.0f;
+      for (int k = 0; k < K; ++k) { float e = or_expf(m[k] - mx); s = s + e; }
+      int y = (int)label[i];
+      for (int k = 0; k < K; ++k) {
+        float p = or_expf(m[k] - mx) / s;
+        float hh = 2.0f * p * (1.0f - p);
+        if (hh < 1e-16f) hh = 1e-16f;
+        g[i * K + k] = (k == y ? p - 1.0f : p) * w;
+        h[i * K + k] = hh * w;
+      }
+    }
+  }
+}
+
+/* fixed-point quantisation: scale = 2^(qbits - e) with max|v| < 2^e  (exact products) */
+int32_t or_quant_exponent(float vmax) {
+  if (!(vmax > 0.0f)) return 0;
+  int e; frexpf(vmax, &e); /* vmax = m*2^e, m in [0.5,1) */
+  return e;
+}
+void or_quantize(const float *v, int64_t n, int64_t stride, int32_t qbits, int32_t *q, int32_t *out_exp) {
+  float vmax = 0.0f;
+  for (int64_t i = 0; i < n; ++i) { float a = fabsf(v[i * stride]); if (a > vmax) vmax = a; }
+  int32_t e = or_quant_exponent(vmax);
+  float scale = ldexpf(1.0f, qbits - e);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) q[i] = (int32_t)rintf(v[i * stride] * scale);
+  *out_exp = e;
+}
+
+/* ------------------------------------------------------------------ A.5 histogram */
+/* hist layout [F][256][2] int64 (g,h); rows given by ridx (or NULL = 0..n-1) */
+void or_hist_int(const uint8_t *bins, int32_t F, const int32_t *qg, const int32_t *qh,
+                 const int32_t *ridx, int64_t nrows, int64_t *hist) {
+  size_t hsz = (size_t)F * 256 * 2;
+  memset(hist, 0, hsz * sizeof(int64_t));
+#ifdef _OPENMP
+  int nt = omp_get_max_threads();
+#else
+  int nt = 1;
+#endif
+  if (nrows < 4096) nt = 1;
+  if (nt == 1) {
+    for (int64_t k = 0; k < nrows; ++k) {
+      int64_t r = ridx ? ridx[k] : k;
+      const uint8_t *b = bins + r * F;
+      int64_t g = qg[r], h = qh[r];
+      for (int32_t f = 0; f < F; ++f) {
+        int64_t *e = hist + ((size_t)f * 256 + b[f]) * 2;
+        e[0] += g; e[1] += h;
+      }
+    }
+    return;
+  }
+  int64_t *priv = (int64_t *)calloc(hsz * (size_t)nt, sizeof(int64_t));
+#pragma omp parallel num_threads(nt)
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    int64_t *ph = priv + hsz * (size_t)t;
+#pragma omp for schedule(static)
+    for (int64_t k = 0; k < nrows; ++k) {
+      int64_t r = ridx ? ridx[k] : k;
+      const uint8_t *b = bins + r * F;
+      int64_t g = qg[r], h = qh[r];
+      for (int32_t f = 0; f < F; ++f) {
+        int64_t *e = ph + ((size_t)f * 256 + b[f]) * 2;
+        e[0] += g; e[1] += h;
+      }
+    }
+#pragma omp for schedule(static)
+    for (int64_t j = 0; j < (int64_t)hsz; ++j) {
+      int64_t s = 0;
+      for (int t2 = 0; t2 < nt; ++t2) s += priv[hsz * (size_t)t2 + (size_t)j];
+      hist[j] = s;
+    }
+  }
+  free(priv);
+}
+
+static void hist_f64(const uint8_t *bins, int32_t F, const float *g, const float *h, int64_t gstride,
+                     const int32_t *ridx, int64_t nrows, double *hist) {
+  memset(hist, 0, (size_t)F * 256 * 2 * sizeof(double));
+  for (int64_t k = 0; k < nrows; ++k) {
+    int64_t r = ridx ? ridx[k] : k;
+    const uint8_t *b = bins + r * F;
+    double gg = g[r * gstride], hh = h[r * gstride];
+    for (int32_t f = 0; f < F; ++f) {
+      double *e = hist + ((size_t)f * 256 + b[f]) * 2;
+      e[0] += gg; e[1] += hh;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ A.6 split */
+static double thr_l1(double g, double a) {
+  if (g > a) return g - a;
+  if (g < -a) return g + a;
+  return 0.0;
+}
+static double calc_gain(const OrParams *p, double G, double H) {
+  if (H < (double)p->min_child_weight || H <= 0.0) return 0.0;
+  double t = p->alpha == 0.0f ? G : thr_l1(G, (double)p->alpha);
+  return (t * t) / (H + (double)p->lambda);
+}
+static float calc_weight(const OrParams *p, double G, double H) {
+  if (H < (double)p->min_child_weight || H <= 0.0) return 0.0f;
+  double t = p->alpha == 0.0f ? G : thr_l1(G, (double)p->alpha);
+  return (float)(-t / (H + (double)p->lambda));
+}
+
+typedef struct {
+  float loss_chg; int32_t feature; int32_t bin; float cond; int default_left;
+  double GL, HL, GR, HR; int valid;
+} SplitCand;
+
+/* SplitEntry::Update / NeedReplace (src/tree/param.h) */
+static int need_replace(const SplitCand *best, float new_chg, int32_t feat) {
+  if (isinf(new_chg)) return 0;
+  if (!best->valid) return new_chg > best->loss_chg; /* best->loss_chg initialised 0 */
+  if (best->feature <= feat) return new_chg > best->loss_chg;
+  return !(best->loss_chg > new_chg);
+}
+
+/* hist for this node as doubles [F][256][2]; total (G,H) */
+static void evaluate_node(const OrParams *p, const OrCuts *c, const double *hist, double G, double H,
+                          float root_gain, SplitCand *best) {
+  memset(best, 0, sizeof(*best));
+  best->loss_chg = 0.0f; best->feature = 0; best->valid = 0;
+  int32_t F = c->n_features;
+  for (int32_t f = 0; f < F; ++f) {
+    const double *hf = hist + (size_t)f * 512;
+    int32_t nf = c->cut_ptrs[f + 1] - c->cut_ptrs[f];
+    const float *cv = c->cut_vals + c->cut_ptrs[f];
+    /* forward: missing -> right */
+    double eg = 0.0, eh = 0.0;
+    for (int32_t i = 0; i < nf; ++i) {
+      eg += hf[i * 2]; eh += hf[i * 2 + 1];
+      if (eh >= (double)p->min_child_weight) {
+        double rg = G - eg, rh = H - eh;
+        if (rh >= (double)p->min_child_weight) {
+          float chg = (float)(calc_gain(p, eg, eh) + calc_gain(p, rg, rh) - (double)root_gain);
+          if (need_replace(best, chg, f)) {
+            best->loss_chg = chg; best->feature = f; best->bin = i; best->cond = cv[i];
+            best->default_left = 0; best->GL = eg; best->HL = eh; best->GR = rg; best->HR = rh;
+            best->valid = 1;
+          }
+        }
+      }
+    }
+    /* SplitContainsMissingValues: forward total != node total */
+    if (eg != G || eh != H) {
+      double bg = 0.0, bh = 0.0;
+      for (int32_t i = nf - 1; i >= 0; --i) {
+        bg += hf[i * 2]; bh += hf[i * 2 + 1];
+        if (bh >= (double)p->min_child_weight) {
+          double lg = G - bg, lh = H - bh;
+          if (lh >= (double)p->min_child_weight) {
+            float chg = (float)(calc_gain(p, lg, lh) + calc_gain(p, bg, bh) - (double)root_gain);
+            if (need_replace(best, chg, f)) {
+              best->loss_chg = chg; best->feature = f; best->bin = i - 1; /* rows with bin<=i-1 go left */
+              best->cond = (i == 0) ? c->min_vals[f] : cv[i - 1];
+              best->default_left = 1; best->GL = lg; best->HL = lh; best->GR = bg; best->HR = bh;
+              best->valid = 1;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ A.7 tree */
+static OrTree *tree_new(void) {
+  OrTree *t = (OrTree *)calloc(1, sizeof(OrTree));
+  t->cap = 64;
+#define ALLOC(field, type) t->field = (type *)calloc((size_t)t->cap, sizeof(type))
+  ALLOC(left, int32_t); ALLOC(right, int32_t); ALLOC(parent, int32_t); ALLOC(split_feature, int32_t);
+  ALLOC(split_bin, int32_t); ALLOC(split_cond, float); ALLOC(default_left, uint8_t); ALLOC(value, float);
+  ALLOC(base_weight, float); ALLOC(loss_chg, float); ALLOC(sum_hess, double); ALLOC(sum_grad, double);
+#undef ALLOC
+  return t;
+}
+static void tree_free(OrTree *t) {
+  free(t->left); free(t->right); free(t->parent); free(t->split_feature); free(t->split_bin);
+  free(t->split_cond); free(t->default_left); free(t->value); free(t->base_weight); free(t->loss_chg);
+  free(t->sum_hess); free(t->sum_grad); free(t);
+}
+static int32_t tree_add_node(OrTree *t, int32_t parent) {
+  if (t->n_nodes == t->cap) {
+    int32_t nc = t->cap * 2;
+#define GROW(field, type) t->field = (type *)realloc(t->field, (size_t)nc * sizeof(type))
+    GROW(left, int32_t); GROW(right, int32_t); GROW(parent, int32_t); GROW(split_feature, int32_t);
+    GROW(split_bin, int32_t); GROW(split_cond, float); GROW(default_left, uint8_t); GROW(value, float);
+    GROW(base_weight, float); GROW(loss_chg, float); GROW(sum_hess, double); GROW(sum_grad, double);
+#undef GROW
+    t->cap = nc;
+  }
+  int32_t id = t->n_nodes++;
+  t->left[id] = t->right[id] = -1; t->parent[id] = parent; t->split_feature[id] = -1; t->split_bin[id] = -1;
+  t->split_cond[id] = 0; t->default_left[id] = 0; t->value[id] = 0; t->base_weight[id] = 0;
+  t->loss_chg[id] = 0; t->sum_hess[id] = 0; t->sum_grad[id] = 0;
+  return id;
+}
+
+typedef struct {
+  int32_t nid, depth;
+  int64_t begin, count;   /* segment in ridx */
+  double G, H;
+  double *hist;           /* [F][256][2] doubles (decoded) */
+  int64_t *ihist;         /* exact integer hist when qbits>0 */
+  SplitCand split;
+} NodeWork;
+
+/* grow one tree on (bins, g, h); g/h may be strided (multi-class). Appends leaf values to margin
+ * cache: margin[r*mstride] += leaf. */
+static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins, int64_t n,
+                         const float *g, const float *h, int64_t gstride, float *margin, int64_t mstride) {
+  int32_t F = c->n_features;
+  size_t hsz = (size_t)F * 512;
+  OrTree *t = tree_new();
+  int32_t *ridx = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+  int32_t *rtmp = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+  for (int64_t i = 0; i < n; ++i) ridx[i] = (int32_t)i;
+  int32_t *qg = NULL, *qh = NULL; int32_t eg = 0, eh = 0; double inv_sg = 1.0, inv_sh = 1.0;
+  if (p->qbits > 0) {
+    qg = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    qh = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    or_quantize(g, n, gstride, p->qbits, qg, &eg);
+    or_quantize(h, n, gstride, p->qbits, qh, &eh);
+    inv_sg = ldexp(1.0, eg - p->qbits); inv_sh = ldexp(1.0, eh - p->qbits);
+  }
+  int32_t cap_level = 1; NodeWork *level = (NodeWork *)calloc(1, sizeof(NodeWork)); int32_t n_level = 1;
+  level[0].nid = tree_add_node(t, -1); level[0].depth = 0; level[0].begin = 0; level[0].count = n;
+  /* root histogram */
+  level[0].hist = (double *)malloc(hsz * sizeof(double));
+  if (p->qbits > 0) {
+    level[0].ihist = (int64_t *)malloc(hsz * sizeof(int64_t));
+    or_hist_int(bins, F, qg, qh, NULL, n, level[0].ihist);
+    for (size_t j = 0; j < hsz; j += 2) {
+      level[0].hist[j] = (double)level[0].ihist[j] * inv_sg;
+      level[0].hist[j + 1] = (double)level[0].ihist[j + 1] * inv_sh;
+    }
+  } else {
+    hist_f64(bins, F, g, h, gstride, NULL, n, level[0].hist);
+  }
+  { /* root sums = sum of feature-0 bins incl. the missing bin (every row lands in exactly one) */
+    double G = 0, H = 0;
+    if (p->qbits > 0) {
+      int64_t sg = 0, sh = 0;
+      for (int b = 0; b < 256; ++b) { sg += level[0].ihist[b * 2]; sh += level[0].ihist[b * 2 + 1]; }
+      G = (double)sg * inv_sg; H = (double)sh * inv_sh;
+    } else {
+      for (int64_t i = 0; i < n; ++i) { G += g[i * gstride]; H += h[i * gstride]; }
+    }
+    level[0].G = G; level[0].H = H;
+  }
+  t->sum_grad[0] = level[0].G; t->sum_hess[0] = level[0].H;
+  t->base_weight[0] = calc_weight(p, level[0].G, level[0].H);
+  (void)cap_level;
+  while (n_level > 0) {
+    /* evaluate */
+    NodeWork *next = (NodeWork *)calloc((size_t)n_level * 2, sizeof(NodeWork)); int32_t n_next = 0;
+    for (int32_t k = 0; k < n_level; ++k) {
+      NodeWork *w = &level[k];
+      float root_gain = (float)calc_gain(p, w->G, w->H);
+      int expand = 0;
+      if (w->depth < p->max_depth || p->max_depth == 0) {
+        evaluate_node(p, c, w->hist, w->G, w->H, root_gain, &w->split);
+        SplitCand *s = &w->split;
+        expand = s->valid && s->loss_chg > OR_RT_EPS && s->HL != 0.0 && s->HR != 0.0 &&
+                 !(s->loss_chg < p->gamma);
+      }
+      int32_t nid = w->nid;
+      if (!expand) {
+        if (p->qbits > 0) {
+          /* leaf refinement: leaf weight from 40-bit fixed-point sums of the fp32 gradients of the
+           * leaf's rows (exact int64, order independent), so leaf values do not depend on qbits */
+          int64_t sg = 0, sh = 0;
+          double kg = ldexp(1.0, OR_LEAF_BITS - eg), kh = ldexp(1.0, OR_LEAF_BITS - eh);
+          for (int64_t i = w->begin; i < w->begin + w->count; ++i) {
+            int64_t r = ridx[i];
+            sg += llrint((double)g[r * gstride] * kg); sh += llrint((double)h[r * gstride] * kh);
+          }
+          t->base_weight[nid] = calc_weight(p, (double)sg / kg, (double)sh / kh);
+        }
+        t->value[nid] = t->base_weight[nid] * p->eta;
+        for (int64_t i = w->begin; i < w->begin + w->count; ++i)
+          margin[(int64_t)ridx[i] * mstride] += t->value[nid];
+        continue;
+      }
+      SplitCand *s = &w->split;
+      int32_t l = tree_add_node(t, nid), r = tree_add_node(t, nid);
+      t->left[nid] = l; t->right[nid] = r; t->split_feature[nid] = s->feature; t->split_bin[nid] = s->bin;
+      t->split_cond[nid] = s->cond; t->default_left[nid] = (uint8_t)s->default_left;
+      t->loss_chg[nid] = s->loss_chg; t->value[nid] = t->base_weight[nid];
+      t->sum_grad[l] = s->GL; t->sum_hess[l] = s->HL; t->sum_grad[r] = s->GR; t->sum_hess[r] = s->HR;
+      t->base_weight[l] = calc_weight(p, s->GL, s->HL); t->base_weight[r] = calc_weight(p, s->GR, s->HR);
+      /* A.8 partition (stable): left iff non-missing && bin <= split_bin, missing -> default */
+      int64_t nl = 0, nr = 0;
+      for (int64_t i = w->begin; i < w->begin + w->count; ++i) {
+        int32_t row = ridx[i]; uint8_t b = bins[(int64_t)row * F + s->feature];
+        int go_left = (b == OR_MISSING_BIN && c->has_missing[s->feature]) ? s->default_left : ((int32_t)b <= s->bin);
+        if (go_left) ridx[w->begin + nl++] = row; else rtmp[nr++] = row;
+      }
+      memcpy(ridx + w->begin + nl, rtmp, (size_t)nr * sizeof(int32_t));
+      NodeWork *wl = &next[n_next++], *wr = &next[n_next++];
+      wl->nid = l; wl->depth = w->depth + 1; wl->begin = w->begin; wl->count = nl; wl->G = s->GL; wl->H = s->HL;
+      wr->nid = r; wr->depth = w->depth + 1; wr->begin = w->begin + nl; wr->count = nr; wr->G = s->GR; wr->H = s->HR;
+      int children_need_hist = (w->depth + 1 < p->max_depth) || p->max_depth == 0;
+      if (children_need_hist) {
+        /* A.5: build the smaller-hessian child from rows, sibling = parent - built */
+        NodeWork *bw = (s->HL < s->HR) ? wl : wr, *sw = (bw == wl) ? wr : wl;
+        bw->hist = (double *)malloc(hsz * sizeof(double)); sw->hist = (double *)malloc(hsz * sizeof(double));
+        if (p->qbits > 0) {
+          bw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t)); sw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t));
+          or_hist_int(bins, F, qg, qh, ridx + bw->begin, bw->count, bw->ihist);
+          for (size_t j = 0; j < hsz; ++j) sw->ihist[j] = w->ihist[j] - bw->ihist[j];
+          for (size_t j = 0; j < hsz; j += 2) {
+            bw->hist[j] = (double)bw->ihist[j] * inv_sg; bw->hist[j + 1] = (double)bw->ihist[j + 1] * inv_sh;
+            sw->hist[j] = (double)sw->ihist[j] * inv_sg; sw->hist[j + 1] = (double)sw->ihist[j + 1] * inv_sh;
+          }
+        } else {
+          hist_f64(bins, F, g, h, gstride, ridx + bw->begin, bw->count, bw->hist);
+          for (size_t j = 0; j < hsz; ++j) sw->hist[j] = w->hist[j] - bw->hist[j];
+        }
+      }
+    }
+    for (int32_t k = 0; k < n_level; ++k) { free(level[k].hist); free(level[k].ihist); }
+    free(level); level = next; n_level = n_next;
+  }
+  free(level); free(ridx); free(rtmp); free(qg); free(qh);
+  return t;
+}
+
+/* ------------------------------------------------------------------ model */
+OrModel *or_model_new(const OrParams *p, int32_t n_features) {
+  OrModel *m = (OrModel *)calloc(1, sizeof(OrModel));
+  m->p = *p; m->n_features = n_features; m->cap_trees = 16;
+  m->trees = (OrTree **)calloc((size_t)m->cap_trees, sizeof(OrTree *));
+  if (m->p.num_class < 1) m->p.num_class = 1;
+  return m;
+}
+void or_model_free(OrModel *m) {
+  if (!m) return;
+  for (int i = 0; i < m->n_trees; ++i) tree_free(m->trees[i]);
+  free(m->trees); free(m);
+}
+static void model_push(OrModel *m, OrTree *t) {
+  if (m->n_trees == m->cap_trees) {
+    m->cap_trees *= 2; m->trees = (OrTree **)realloc(m->trees, (size_t)m->cap_trees * sizeof(OrTree *));
+  }
+  m->trees[m->n_trees++] = t;
+}
+float or_base_margin(const OrParams *p) {
+  if (p->objective == OR_OBJ_LOGISTIC) return -logf(1.0f / p->base_score - 1.0f);
+  return p->base_score;
+}
+
+/* One boosting round.  margin [n*K] is the prediction cache (in/out).  custom_g/custom_h
+ * (may be NULL) replace the objective gradient (xgb.train(obj=...), test_xgboost_api.py:77-102). */
+int or_boost_one_round(OrModel *m, const OrCuts *c, const uint8_t *bins, int64_t n, const float *label,
+                       const float *weight, float *margin, const float *custom_g, const float *custom_h) {
+#ifdef _OPENMP
+  if (m->p.nthread > 0) omp_set_num_threads(m->p.nthread);
+#endif
+  int K = m->p.num_class;
+  float *g = NULL, *h = NULL;
+  const float *gg = custom_g, *hh = custom_h;
+  if (!custom_g) {
+    g = (float *)malloc((size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
+    h = (float *)malloc((size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
+    or_gradients(m->p.objective, K, margin, label, weight, n, g, h);
+    gg = g; hh = h;
+  }
+  for (int k = 0; k < K; ++k) {
+    OrTree *t = grow_tree(&m->p, c, bins, n, gg + k, hh + k, K, margin + k, K);
+    model_push(m, t);
+  }
+  free(g); free(h);
+  return 0;
+}
+
+int32_t or_num_trees(const OrModel *m) { return m->n_trees; }
+int32_t or_tree_num_nodes(const OrModel *m, int32_t t) { return m->trees[t]->n_nodes; }
+void or_tree_get(const OrModel *m, int32_t ti, int32_t *left, int32_t *right, int32_t *parent,
+                 int32_t *split_feature, int32_t *split_bin, float *split_cond, uint8_t *default_left,
+                 float *value, float *base_weight, float *loss_chg, double *sum_hess) {
+  const OrTree *t = m->trees[ti]; size_t n = (size_t)t->n_nodes;
+  memcpy(left, t->left, n * 4); memcpy(right, t->right, n * 4); memcpy(parent, t->parent, n * 4);
+  memcpy(split_feature, t->split_feature, n * 4); memcpy(split_bin, t->split_bin, n * 4);
+  memcpy(split_cond, t->split_cond, n * 4); memcpy(default_left, t->default_left, n);
+  memcpy(value, t->value, n * 4); memcpy(base_weight, t->base_weight, n * 4);
+  memcpy(loss_chg, t->loss_chg, n * 4); memcpy(sum_hess, t->sum_hess, n * 8);
+}
+
+/* A.9 prediction on raw floats: x < split_cond -> left; missing -> default */
+void or_predict_margin(const OrModel *m, const float *X, int64_t n, float missing, int32_t tree_begin,
+                       int32_t tree_end, const float *base_margin, float *out) {
+  int K = m->p.num_class; int32_t F = m->n_features;
+  float bm = or_base_margin(&m->p);
+  if (tree_end <= 0 || tree_end > m->n_trees) tree_end = m->n_trees;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    for (int k = 0; k < K; ++k) out[i * K + k] = base_margin ? base_margin[i * K + k] : bm;
+    for (int32_t ti = tree_begin; ti < tree_end; ++ti) {
+      const OrTree *t = m->trees[ti]; int32_t nid = 0;
+      while (t->split_feature[nid] >= 0) {
+        float x = X[i * F + t->split_feature[nid]];
+        if (is_missing(x, missing)) nid = t->default_left[nid] ? t->left[nid] : t->right[nid];
+        else nid = (x < t->split_cond[nid]) ? t->left[nid] : t->right[nid];
+      }
+      out[i * K + (ti % K)] += t->value[nid];
+    }
+  }
+}
+
+/* margin -> output transform (identity / sigmoid / softmax) in place */
+void or_transform(int32_t objective, int32_t K, float *m, int64_t n) {
+  if (objective == OR_OBJ_LOGISTIC) {
+    for (int64_t i = 0; i < n; ++i) m[i] = or_sigmoid(m[i]);
+  } else if (objective == OR_OBJ_SOFTPROB) {
+    for (int64_t i = 0; i < n; ++i) {
+      float *r = m + i * K; float mx = r[0];
+      for (int k = 1; k < K; ++k) if (r[k] > mx) mx = r[k];
+      float s = 0.0f;
+      for (int k = 0; k < K; ++k) { r[k] = or_expf(r[k] - mx); s = s + r[k]; }
+      for (int k = 0; k < K; ++k) r[k] = r[k] / s;
+    }
+  }
+}
+
+/* A.10 metrics on margins: returns (sum, wsum) so callers can combine shards.
+ * metric: 0 rmse, 1 logloss, 2 error, 3 mlogloss, 4 merror */
+void or_metric_sums(int32_t metric, int32_t K, const float *margin, const float *label, const float *weight,
+                    int64_t n, double *out_sum, double *out_wsum) {
+  double s = 0.0, ws = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    double w = weight ? weight[i] : 1.0; double v = 0.0;
+    if (metric == 0) { double d = (double)margin[i] - (double)label[i]; v = d * d; }
+    else if (metric == 1) {
+      float p = or_sigmoid(margin[i]); const float eps = 1e-16f; float y = label[i];
+      float pn = 1.0f - p;
+      float a = p < eps ? eps : p, b = pn < eps ? eps : pn;
+      v = -((double)y * log((double)a) + (1.0 - (double)y) * log((double)b));
+    } else if (metric == 2) { float p = or_sigmoid(margin[i]); v = (p > 0.5f) != (label[i] > 0.5f) ? 1.0 : 0.0; }
+    else {
+      const float *r = margin + i * K; int y = (int)label[i]; float mx = r[0]; int am = 0;
+      for (int k = 1; k < K; ++k) if (r[k] > mx) { mx = r[k]; am = k; }
+      if (metric == 4) v = (am != y) ? 1.0 : 0.0;
+      else {
+        float ssum = 0.0f; for (int k = 0; k < K; ++k) ssum = ssum + or_expf(r[k] - mx);
+        float p = or_expf(r[y] - mx) / ssum; if (p < 1e-16f) p = 1e-16f;
+        v = -log((double)p);
+      }
+    }
+    s += v * w; ws += w;
+  }
+  *out_sum = s; *out_wsum = ws;
+}
+
+int32_t or_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
