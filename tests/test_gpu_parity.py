@@ -1,0 +1,250 @@
+"""GPU parity tests: the sm_100a engine (through the C-ABI, via xgboost_ray_b200.engine) against the
+CPU oracle on the same seeded inputs.  Integer / index results are bit-exact; leaf values are
+compared with the tolerance BASELINE.json's north_star states (1e-5)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LEAF_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from xgboost_ray_b200 import engine
+    if engine.device_count() < 1:
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box")
+    return engine
+
+
+def make_data(n, f, seed, kind="uniform", nan_frac=0.0):
+    rng = np.random.RandomState(seed)
+    if kind == "uniform":
+        X = rng.uniform(0, 10, size=(n, f)).astype(np.float32)
+    elif kind == "lowcard":
+        X = rng.randint(0, 5, size=(n, f)).astype(np.float32)
+    elif kind == "mixed":
+        X = rng.normal(size=(n, f)).astype(np.float32)
+        X[:, ::3] = np.round(X[:, ::3] * 2)          # heavy ties
+        X[:, 1] = 3.0                                 # constant feature
+        if f > 2:
+            X[:, 2] = (X[:, 2] > 0).astype(np.float32)  # binary feature
+    if nan_frac > 0:
+        X[rng.uniform(size=X.shape) < nan_frac] = np.nan
+    return X
+
+
+# ------------------------------------------------------------------ histogram kernel (a10)
+@pytest.mark.parametrize("n,f", [(1, 1), (17, 3), (1000, 28), (5000, 100), (3000, 50), (2000, 200), (4097, 33)])
+def test_hist_kernel_bit_exact(eng, oracle, n, f):
+    rng = np.random.RandomState(n + f)
+    bins = rng.randint(0, 256, size=(n, f)).astype(np.uint8)
+    qg = rng.randint(-(1 << 18), 1 << 18, size=n).astype(np.int32)
+    qh = rng.randint(0, 1 << 18, size=n).astype(np.int32)
+    ref = oracle.hist_int(bins, qg, qh)
+    got, _ = eng.hist_build_raw(bins, qg, qh, window_rows=4096, chunk_rows=512)
+    assert np.array_equal(ref, got)
+
+
+def test_hist_kernel_adversarial_and_windows(eng, oracle):
+    n, f = 20000, 37
+    rng = np.random.RandomState(7)
+    bins = rng.randint(0, 256, size=(n, f)).astype(np.uint8)
+    bins[:, 0] = 9          # constant feature: every row hits the same cell
+    bins[:, 1] = bins[:, 1] & 1   # binary feature
+    bins[:, 2] = 255
+    qg = np.full(n, (1 << 18), np.int32)     # extreme values: a window of 8191 rows just fits int32
+    qg[::2] = -(1 << 18)
+    qh = np.full(n, (1 << 18), np.int32)
+    ref = oracle.hist_int(bins, qg, qh)
+    for window, chunk in ((8191, 512), (1024, 256), (8191, 8192)):
+        got, _ = eng.hist_build_raw(bins, qg, qh, window_rows=window, chunk_rows=chunk)
+        assert np.array_equal(ref, got), (window, chunk)
+
+
+def test_hist_kernel_gather(eng, oracle):
+    n, f = 30000, 100
+    rng = np.random.RandomState(11)
+    bins = rng.randint(0, 256, size=(n, f)).astype(np.uint8)
+    qg = rng.randint(-1000, 1000, size=n).astype(np.int32)
+    qh = rng.randint(0, 1000, size=n).astype(np.int32)
+    for nsel in (0, 1, 15, 16, 17, 4999, 30000):
+        ridx = rng.permutation(n)[:nsel].astype(np.int32)
+        ref = oracle.hist_int(bins, qg, qh, ridx) if nsel else np.zeros((f, 256, 2), np.int64)
+        got, _ = eng.hist_build_raw(bins, qg, qh, ridx=ridx, window_rows=4096, chunk_rows=1024)
+        assert np.array_equal(ref, got), nsel
+
+
+# ------------------------------------------------------------------ cuts and bins (a7, a8)
+@pytest.mark.parametrize("kind,nan_frac,n,f", [("uniform", 0.0, 5000, 7), ("lowcard", 0.0, 3000, 5),
+                                               ("mixed", 0.0, 4000, 9), ("mixed", 0.1, 4000, 9),
+                                               ("uniform", 0.3, 700, 33), ("uniform", 0.0, 200, 3)])
+def test_cuts_and_bins_bit_exact(eng, oracle, kind, nan_frac, n, f):
+    X = make_data(n, f, 3, kind, nan_frac)
+    if nan_frac > 0:
+        X[:, -1] = np.nan  # all-missing feature
+    oc = oracle.Cuts.from_data(X, 256)
+    dm = eng.DMatrix(X)
+    dm._ensure_quantized(256, keep_raw=True)
+    ptrs, vals, mins, hm = dm.get_cuts()
+    assert np.array_equal(ptrs, oc.ptrs)
+    assert np.array_equal(vals.view(np.uint32), oc.vals.view(np.uint32))
+    assert np.array_equal(mins.view(np.uint32), oc.mins.view(np.uint32))
+    assert np.array_equal(hm, oc.has_missing)
+    assert np.array_equal(dm.get_bins(), oc.bin(X))
+
+
+def test_cuts_small_max_bin(eng, oracle):
+    X = make_data(6000, 4, 5, "uniform")
+    for mb in (2, 16, 64):
+        oc = oracle.Cuts.from_data(X, mb)
+        dm = eng.DMatrix(X)
+        dm._ensure_quantized(mb)
+        ptrs, vals, mins, hm = dm.get_cuts()
+        assert np.array_equal(ptrs, oc.ptrs)
+        assert np.array_equal(vals.view(np.uint32), oc.vals.view(np.uint32))
+
+
+# ------------------------------------------------------------------ whole trees (a9-a14)
+def assert_same_model(eng_bst, or_bst, leaf_tol=LEAF_TOL):
+    trees = eng_bst.get_trees()
+    assert len(trees) == or_bst.num_trees
+    for i, t in enumerate(trees):
+        o = or_bst.tree(i)
+        assert len(t["left"]) == o.n_nodes, "tree %d node count" % i
+        assert np.array_equal(t["left"], o.left) and np.array_equal(t["right"], o.right), "tree %d topology" % i
+        assert np.array_equal(t["split_feature"], o.split_feature), "tree %d split features" % i
+        assert np.array_equal(t["split_bin"], o.split_bin), "tree %d split bins" % i
+        assert np.array_equal(t["default_left"], o.default_left), "tree %d default directions" % i
+        assert np.array_equal(t["split_cond"].view(np.uint32), o.split_cond.view(np.uint32)), "tree %d conds" % i
+        leaf = o.split_feature < 0
+        assert np.max(np.abs(t["value"][leaf] - o.value[leaf])) <= leaf_tol, "tree %d leaf values" % i
+        assert np.allclose(t["loss_chg"], o.loss_chg, rtol=0, atol=0), "tree %d loss_chg" % i
+
+
+def run_both(eng, oracle, params, X, y, rounds, weight=None, base_margin=None):
+    obst, _ = oracle.train(params, X, y, rounds, weight=weight, base_margin=base_margin)
+    dm = eng.DMatrix(X, label=y, weight=weight, base_margin=base_margin)
+    ebst = eng.train(params, dm, num_boost_round=rounds, verbose_eval=False)
+    return ebst, obst, dm
+
+
+@pytest.mark.parametrize("objective", ["reg:squarederror", "binary:logistic"])
+@pytest.mark.parametrize("n,f,depth", [(2000, 10, 4), (20000, 28, 6), (50000, 100, 8)])
+def test_trees_identical(eng, oracle, objective, n, f, depth):
+    X = make_data(n, f, 21, "uniform")
+    rng = np.random.RandomState(4)
+    lin = X[:, : min(f, 5)].sum(axis=1) + np.sin(X[:, 0]) + rng.normal(scale=0.5, size=n)
+    y = lin.astype(np.float32) if objective == "reg:squarederror" else (lin > np.median(lin)).astype(np.float32)
+    params = {"objective": objective, "max_depth": depth, "eta": 0.3, "base_score": 0.5, "hist_qbits": 18}
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 5)
+    assert_same_model(ebst, obst)
+    # margin cache == oracle margin cache
+    m = ebst.predict(dm, output_margin=True, training=True)
+    assert np.max(np.abs(m - obst.margin[:, 0])) <= 1e-5
+    # predict on raw floats == oracle predict
+    Xt = make_data(3000, f, 99, "uniform")
+    pe = ebst.predict(eng.DMatrix(Xt))
+    po = obst.predict(Xt)
+    assert np.max(np.abs(pe - po)) <= 1e-5
+
+
+def test_trees_identical_missing_and_weights(eng, oracle):
+    n, f = 8000, 12
+    X = make_data(n, f, 5, "mixed", nan_frac=0.15)
+    rng = np.random.RandomState(1)
+    y = (np.nan_to_num(X[:, 0]) + np.nan_to_num(X[:, 3]) > 0).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, size=n).astype(np.float32)
+    params = {"objective": "binary:logistic", "max_depth": 5, "base_score": 0.5, "min_child_weight": 2.0,
+              "lambda": 0.5, "gamma": 0.01}
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 6, weight=w)
+    assert_same_model(ebst, obst)
+    assert any((t["default_left"] == 1).any() for t in ebst.get_trees()), "test data should exercise default-left"
+    Xt = make_data(1000, f, 77, "mixed", nan_frac=0.2)
+    assert np.max(np.abs(ebst.predict(eng.DMatrix(Xt)) - obst.predict(Xt))) <= 1e-5
+
+
+def test_trees_identical_multiclass(eng, oracle):
+    n, f, K = 6000, 8, 4
+    X = make_data(n, f, 8, "uniform")
+    y = (np.floor(X[:, 0] / 2.5).astype(int) % K).astype(np.float32)
+    params = {"objective": "multi:softprob", "num_class": K, "max_depth": 4, "base_score": 0.5}
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 3)
+    assert ebst.num_trees() == 3 * K
+    assert_same_model(ebst, obst)
+    pe = ebst.predict(eng.DMatrix(X))
+    assert pe.shape == (n, K)
+    assert np.max(np.abs(pe - obst.predict(X))) <= 1e-5
+
+
+def test_toy_matrix_known_answers(eng, oracle):
+    """Ported relational known-answers of xgboost_ray/tests/test_end_to_end.py:72-139."""
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+    y = np.array([0, 1, 2, 3] * 8, np.float32)
+    params = {"max_depth": 2, "objective": "multi:softmax", "num_class": 4, "nthread": 1, "booster": "gbtree"}
+    bst = eng.train(params, eng.DMatrix(x, label=y), num_boost_round=2, verbose_eval=False)
+    assert list(bst.predict(eng.DMatrix(x))) == list(y)
+    test_x = eng.DMatrix(np.array([[0, 0, 1, 1], [0, 0, 1, 0]], np.float32))
+    b1 = eng.train(params, eng.DMatrix(x[::2], label=y[::2]), num_boost_round=2, verbose_eval=False)
+    assert list(b1.predict(test_x)) == [2, 2]
+    b2 = eng.train(params, eng.DMatrix(x[1::2], label=y[1::2]), num_boost_round=2, verbose_eval=False)
+    assert list(b2.predict(test_x)) == [3, 3]
+
+
+def test_metrics_match_oracle(eng, oracle):
+    n, f = 5000, 6
+    X = make_data(n, f, 2, "uniform")
+    y = (X[:, 0] > 5).astype(np.float32)
+    params = {"objective": "binary:logistic", "max_depth": 3, "base_score": 0.5, "eval_metric": ["logloss", "error"]}
+    dm = eng.DMatrix(X, label=y)
+    Xv = make_data(1000, f, 3, "uniform")
+    yv = (Xv[:, 0] > 5).astype(np.float32)
+    dv = eng.DMatrix(Xv, label=yv)
+    res = {}
+    ebst = eng.train(params, dm, num_boost_round=4, evals=[(dm, "train"), (dv, "valid")], evals_result=res,
+                     verbose_eval=False)
+    obst, _ = oracle.train(params, X, y, 4)
+    assert abs(res["train"]["logloss"][-1] - obst.metric("logloss", obst.margin, y)) < 1e-6
+    assert abs(res["train"]["error"][-1] - obst.metric("error", obst.margin, y)) < 1e-9
+    mv = obst.predict_margin(Xv)
+    assert abs(res["valid"]["logloss"][-1] - obst.metric("logloss", mv, yv)) < 1e-6
+    assert len(res["valid"]["logloss"]) == 4
+
+
+def test_custom_objective_and_continuation(eng, oracle):
+    n, f = 4000, 5
+    X = make_data(n, f, 12, "uniform")
+    y = (X[:, 1] * 0.5 + X[:, 2]).astype(np.float32)
+    params = {"objective": "reg:squarederror", "max_depth": 4, "base_score": 0.5}
+
+    def sq(pred, d):
+        return pred - d.get_label(), np.ones_like(pred)
+
+    a = eng.train(params, eng.DMatrix(X, label=y), num_boost_round=4, verbose_eval=False)
+    b = eng.train(params, eng.DMatrix(X, label=y), num_boost_round=4, obj=sq, verbose_eval=False)
+    ta, tb = a.get_trees(), b.get_trees()
+    for u, v in zip(ta, tb):
+        assert np.array_equal(u["split_feature"], v["split_feature"]) and np.array_equal(u["split_bin"], v["split_bin"])
+    # 2 + 2 continued == 4 uninterrupted (test_fault_tolerance.py:401-444 relational known-answer)
+    c = eng.train(params, eng.DMatrix(X, label=y), num_boost_round=2, verbose_eval=False)
+    d = eng.train(params, eng.DMatrix(X, label=y), num_boost_round=2, xgb_model=c, verbose_eval=False)
+    assert d.num_trees() == 4
+    for u, v in zip(ta, d.get_trees()):
+        assert np.array_equal(u["split_feature"], v["split_feature"]) and np.array_equal(u["split_bin"], v["split_bin"])
+        assert np.max(np.abs(u["value"] - v["value"])) <= 1e-6
+    # pickle round trip predicts identically (model object must be picklable, main.py:619)
+    import pickle
+    e = pickle.loads(pickle.dumps(a))
+    dmx = eng.DMatrix(X)
+    assert np.array_equal(a.predict(dmx), e.predict(dmx))
+    assert a.get_dump(dump_format="json") == e.get_dump(dump_format="json")
+
+
+def test_errors_surface(eng):
+    X = make_data(100, 3, 1)
+    with pytest.raises(eng.XGBoostError):
+        eng.train({"objective": "rank:pairwise"}, eng.DMatrix(X, label=X[:, 0]), 1, verbose_eval=False)
+    with pytest.raises(eng.XGBoostError):
+        eng.train({"objective": "reg:squarederror"}, eng.DMatrix(X), 1, verbose_eval=False)  # no labels
+    with pytest.raises(eng.XGBoostError):
+        eng.train({"max_bin": 1000}, eng.DMatrix(X, label=X[:, 0]), 1, verbose_eval=False)

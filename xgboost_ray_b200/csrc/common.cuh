@@ -1,0 +1,67 @@
+// common.cuh -- shared declarations for the sm_100a histogram-tree engine.
+//
+// Layouts (DESIGN.md "Data layout in HBM"):
+//   bins      uint8 [n_rows][row_stride]     row_stride = n_groups*32; group g owns bytes
+//                                            [g*32, g*32+gsize[g]) of a row, rest zero padding;
+//                                            bin 255 is the missing sentinel
+//   gpair     int2  [n_rows]                 (qg, qh) fixed-point gradient / hessian
+//   hist      int64 [node][group][2][256][32] plane 0 = sum qg, plane 1 = sum qh, slot = feature
+//                                            within group; 128 KiB per (node, group)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B2_GROUP_SLOTS 32
+#define B2_BINS 256
+#define B2_MISSING_BIN 255
+#define B2_PLANE_ELEMS (B2_BINS * B2_GROUP_SLOTS)          // 8192
+#define B2_GROUP_ELEMS (2 * B2_PLANE_ELEMS)                // 16384 int64 per (node, group)
+
+// one entry per node whose histogram is built from rows in this launch
+struct B2HistWork {
+  int32_t seg_begin;    // first position in ridx (or first row id when ridx == nullptr)
+  int32_t seg_count;    // rows of this node on this GPU
+  int32_t hist_index;   // node slot in the output level buffer
+  int32_t chunk_begin;  // exclusive prefix sum of ceil(seg_count / chunk_rows)
+};
+
+// per-split-node descriptor for the row partition kernel
+struct B2SplitWork {
+  int32_t seg_begin, seg_count;
+  int32_t feature_byte;   // byte offset of the split feature inside a row
+  int32_t split_bin;      // rows with bin <= split_bin go left
+  int32_t default_left;   // direction of the missing sentinel (only if feature has missing)
+  int32_t has_missing;
+  int32_t chunk_begin;    // prefix of ceil(seg_count / PART_CHUNK)
+  int32_t pad;
+};
+
+// candidate split written by the evaluation kernel, one per (node, group)
+struct B2SplitCand {
+  float loss_chg;
+  int32_t feature;       // global feature id, -1 = none
+  int32_t bin;           // split bin (rows with bin <= bin go left; -1 possible for backward)
+  int32_t default_left;
+  int64_t left_g, left_h; // fixed-point sums of the left child
+  uint32_t order;        // enumeration order key for tie-breaking
+  int32_t pad;
+};
+
+struct B2EvalNode {
+  int64_t sum_g, sum_h;  // node totals (fixed point)
+  int32_t hist_index;    // slot in level buffer
+  float root_gain;
+};
+
+struct B2TreeNodeDev {
+  int32_t left, right;
+  int32_t feature;       // -1 leaf
+  float cond;
+  float value;
+  int32_t default_left;
+};
+
+struct B2TrainParamDev {
+  double min_child_weight, lambda, alpha;
+  double inv_scale_g, inv_scale_h;
+};

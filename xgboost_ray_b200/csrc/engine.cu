@@ -1,0 +1,1227 @@
+// engine.cu -- host side of libb2hist.so: C-ABI (include/b2hist.h), device memory, level loop,
+// NCCL communicator.  One process drives one GPU (one Ray actor per GPU in the reference,
+// xgboost_ray/main.py:862-892); row-sharded data parallel, model replicated, per-level
+// histogram allreduce.
+//
+// Mirrors, for the hot path only, what `xgboost` does underneath xgboost_ray/main.py:745-752:
+//   gradient -> [per class tree] quantise -> root hist -> allreduce -> eval -> partition ->
+//   smaller-child hist -> allreduce -> sibling subtraction -> ... -> leaf sums -> margin update.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b2hist.h"
+#include "common.cuh"
+
+// ---------------------------------------------------------------- kernel launchers (other TUs)
+extern "C" {
+int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
+                   int, cudaStream_t);
+int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, cudaStream_t);
+int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
+                          const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, cudaStream_t);
+int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, cudaStream_t);
+int b2_part_chunk_rows();
+int b2_launch_partition(const uint8_t*, int, const int32_t*, int32_t*, const B2SplitWork*, int, int, int32_t*, int,
+                        cudaStream_t);
+int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const void*, int, int, const int32_t*, int,
+                        long long*, int, cudaStream_t);
+int b2_launch_pred_update(float*, int, int, const int32_t*, const int32_t*, const void*, int, int, const float*, int,
+                          cudaStream_t);
+int b2_launch_iota(int32_t*, int64_t, cudaStream_t);
+int b2_launch_gradient(int, int, const float*, const float*, const float*, int64_t, float2*, int, cudaStream_t);
+int b2_launch_pack_custom(const float*, const float*, int, int64_t, float2*, int, cudaStream_t);
+int b2_launch_absmax(const float2*, int64_t, uint32_t*, int, cudaStream_t);
+int b2_launch_quant_exponent(const uint32_t*, int32_t*, cudaStream_t);
+int b2_launch_quantize(const float2*, int64_t, const int32_t*, int, int2*, int, cudaStream_t);
+int b2_launch_metric(int, int, const float*, const float*, const float*, int64_t, double*, int, cudaStream_t);
+int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, const int32_t*, int, int, int, float*, int,
+                      cudaStream_t);
+int b2_launch_fill(float*, int64_t, float, int, cudaStream_t);
+int b2_launch_transform(int, int, float*, int64_t, int, cudaStream_t);
+int b2_launch_extract_keys(const float*, int64_t, int, int, float, uint32_t*, int64_t, unsigned long long*, int,
+                           cudaStream_t);
+size_t b2_sort_temp_bytes(int64_t);
+int b2_sketch_column(const uint32_t*, uint32_t*, int64_t, int64_t, void*, size_t, int32_t*, int32_t*, float*, long long*,
+                     int32_t*, int, float*, int32_t*, float*, int, cudaStream_t);
+int b2_launch_bin(const float*, int64_t, int, float, const int32_t*, const float*, const int32_t*, int, uint8_t*, int,
+                  cudaStream_t);
+}
+
+namespace {
+
+// ---------------------------------------------------------------- errors
+thread_local std::string g_last_error;
+struct B2Error { std::string msg; };
+[[noreturn]] void fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  throw B2Error{buf};
+}
+#define CUDA_CHECK(expr)                                                                       \
+  do {                                                                                         \
+    cudaError_t e_ = (expr);                                                                   \
+    if (e_ != cudaSuccess) fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+#define LAUNCH_CHECK(expr)                                                                     \
+  do {                                                                                         \
+    int e_ = (expr);                                                                           \
+    if (e_ != 0) fail("kernel launch failed (%s) at %s:%d", cudaGetErrorString((cudaError_t)e_), __FILE__, __LINE__); \
+  } while (0)
+#define API_BEGIN try {
+#define API_END                                            \
+  }                                                        \
+  catch (const B2Error& e) { g_last_error = e.msg; return -1; } \
+  catch (const std::exception& e) { g_last_error = e.what(); return -1; } \
+  return 0;
+
+// ---------------------------------------------------------------- device context
+struct Ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  int num_sms = 0;
+};
+std::mutex g_ctx_mu;
+std::map<int, Ctx*> g_ctx;
+Ctx* get_ctx(int device) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto it = g_ctx.find(device);
+  if (it != g_ctx.end()) { CUDA_CHECK(cudaSetDevice(device)); return it->second; }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) fail("no CUDA device available (%s): libb2hist has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) fail("invalid device %d (have %d)", device, n);
+  CUDA_CHECK(cudaSetDevice(device));
+  Ctx* c = new Ctx();
+  c->device = device;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) fail("device %d is sm_%d%d; this engine is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  c->num_sms = prop.multiProcessorCount;
+  g_ctx[device] = c;
+  return c;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = n;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e != cudaSuccess) { cap = 0; fail("cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e)); }
+    cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  ~DevBuf() { release(); }
+};
+
+// ---------------------------------------------------------------- NCCL (dlopen'ed)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { kNcclSum = 0, kNcclMax = 2 };
+enum { kNcclUint8 = 1, kNcclInt32 = 2, kNcclUint32 = 3, kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat32 = 7, kNcclFloat64 = 8 };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommAbort)(ncclComm_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl() {
+  static NcclApi api;
+  static std::once_flag once;
+  static std::string err;
+  std::call_once(once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // reuse torch's copy if loaded
+    for (int i = 0; !h && i < 3; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("cannot load libnccl: ") + dlerror(); return; }
+    api.lib = h;
+#define LOAD(field, sym) *(void**)(&api.field) = dlsym(h, sym); if (!api.field) err = std::string("missing symbol ") + sym;
+    LOAD(GetUniqueId, "ncclGetUniqueId") LOAD(CommInitRank, "ncclCommInitRank") LOAD(AllReduce, "ncclAllReduce")
+    LOAD(AllGather, "ncclAllGather") LOAD(CommAbort, "ncclCommAbort") LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+  });
+  if (!err.empty()) fail("%s", err.c_str());
+  return &api;
+}
+#define NCCL_CHECK(expr)                                                                              \
+  do {                                                                                                \
+    int r_ = (expr);                                                                                  \
+    if (r_ != 0) fail("NCCL error %d (%s) at %s:%d", r_, nccl()->GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+struct Comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+  std::atomic<bool> aborted{false};
+};
+
+void allreduce(Comm* c, void* buf, size_t count, int dtype, int op, cudaStream_t s) {
+  if (!c || c->world <= 1 || count == 0) return;
+  if (c->aborted.load()) fail("communicator aborted");
+  NCCL_CHECK(nccl()->AllReduce(buf, buf, count, dtype, op, c->comm, s));
+}
+
+// ---------------------------------------------------------------- handles
+enum HandleKind { kComm = 1, kMatrix = 2, kBooster = 3 };
+struct HandleBase { int kind; };
+template <typename T>
+T* from_handle(B2Handle h, int kind, const char* what) {
+  if (!h) fail("null %s handle", what);
+  HandleBase* b = reinterpret_cast<HandleBase*>(h);
+  if (b->kind != kind) fail("handle is not a %s", what);
+  return reinterpret_cast<T*>(h);
+}
+
+struct CommH : HandleBase { Comm c; };
+
+struct Matrix : HandleBase {
+  Ctx* ctx = nullptr;
+  int64_t n = 0;
+  int F = 0;
+  float missing = NAN;
+  DevBuf<float> raw;     // [n][F], optional
+  bool has_raw = false;
+  DevBuf<uint8_t> bins;  // [n][row_stride]
+  bool quantized = false;
+  int n_groups = 0, row_stride = 0, max_bin = 0;
+  std::vector<int32_t> group_first, group_size, feat_byte;
+  std::vector<int32_t> cut_ptrs;
+  std::vector<float> cut_vals, min_vals;
+  std::vector<uint8_t> has_missing;
+  std::vector<int32_t> nbins;
+  DevBuf<int32_t> d_group_first, d_group_size, d_feat_byte, d_cut_ptrs, d_nbins;
+  DevBuf<float> d_cut_vals;
+  DevBuf<uint8_t> d_has_missing;
+  DevBuf<float> label, weight, base_margin;
+  int64_t n_label = 0, n_weight = 0, n_base_margin = 0;
+};
+
+void setup_groups(Matrix* m) {
+  const int F = m->F;
+  m->n_groups = (F + B2_GROUP_SLOTS - 1) / B2_GROUP_SLOTS;
+  if (m->n_groups < 1) m->n_groups = 1;
+  m->row_stride = m->n_groups * B2_GROUP_SLOTS;
+  m->group_first.assign(m->n_groups, 0);
+  m->group_size.assign(m->n_groups, 0);
+  m->feat_byte.assign(F, 0);
+  const int base = F / m->n_groups, rem = F % m->n_groups;
+  int f = 0;
+  for (int g = 0; g < m->n_groups; ++g) {
+    const int sz = base + (g < rem ? 1 : 0);
+    m->group_first[g] = f; m->group_size[g] = sz;
+    for (int s = 0; s < sz; ++s) m->feat_byte[f + s] = g * B2_GROUP_SLOTS + s;
+    f += sz;
+  }
+}
+
+template <typename T>
+void upload(DevBuf<T>& d, const std::vector<T>& h, cudaStream_t s) {
+  d.ensure(h.size() ? h.size() : 1);
+  if (!h.empty()) CUDA_CHECK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+
+void upload_cuts(Matrix* m) {
+  cudaStream_t s = m->ctx->stream;
+  m->nbins.resize(m->F);
+  for (int f = 0; f < m->F; ++f) m->nbins[f] = m->cut_ptrs[f + 1] - m->cut_ptrs[f];
+  upload(m->d_group_first, m->group_first, s); upload(m->d_group_size, m->group_size, s);
+  upload(m->d_feat_byte, m->feat_byte, s); upload(m->d_cut_ptrs, m->cut_ptrs, s);
+  upload(m->d_cut_vals, m->cut_vals, s); upload(m->d_nbins, m->nbins, s);
+  upload(m->d_has_missing, m->has_missing, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+// GPU sketch: exact global summary per feature -> cuts (sketch.cu).  Multi-GPU: the column keys of
+// every rank are allgathered (padded to the largest shard) so all ranks compute identical cuts.
+void make_cuts(Matrix* m, Comm* comm, int max_bin) {
+  Ctx* ctx = m->ctx; cudaStream_t s = ctx->stream;
+  if (max_bin < 2 || max_bin > 256) fail("max_bin must be in [2, 256] (uint8 bin matrix), got %d", max_bin);
+  if (!m->has_raw) fail("matrix has no raw data to sketch");
+  const int world = comm ? comm->world : 1;
+  // largest shard
+  DevBuf<long long> d_cnt; d_cnt.ensure(2);
+  long long h_n = m->n, h_max = m->n;
+  if (world > 1) {
+    CUDA_CHECK(cudaMemcpyAsync(d_cnt.p, &h_n, sizeof(long long), cudaMemcpyHostToDevice, s));
+    allreduce(comm, d_cnt.p, 1, kNcclInt64, kNcclMax, s);
+    CUDA_CHECK(cudaMemcpyAsync(&h_max, d_cnt.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  const int64_t n_pad = h_max, n_total = n_pad * world;
+  DevBuf<uint32_t> keys_local, keys_all, keys_sorted;
+  DevBuf<int32_t> flags, idx, m_scratch; DevBuf<float> uval; DevBuf<long long> rmin;
+  DevBuf<unsigned long long> d_nmiss; DevBuf<float> d_cuts, d_mins; DevBuf<int32_t> d_ncuts;
+  DevBuf<uint8_t> temp;
+  const size_t nt = (size_t)std::max<int64_t>(n_total, 1);
+  keys_local.ensure((size_t)std::max<int64_t>(n_pad, 1)); keys_all.ensure(nt); keys_sorted.ensure(nt);
+  flags.ensure(nt); idx.ensure(nt); uval.ensure(nt); rmin.ensure(nt); m_scratch.ensure(1);
+  const size_t temp_bytes = b2_sort_temp_bytes(n_total > 0 ? n_total : 1);
+  temp.ensure(temp_bytes ? temp_bytes : 1);
+  const int F = m->F;
+  d_nmiss.ensure((size_t)F); d_cuts.ensure((size_t)F * 256); d_mins.ensure((size_t)F); d_ncuts.ensure((size_t)F);
+  CUDA_CHECK(cudaMemsetAsync(d_nmiss.p, 0, (size_t)F * sizeof(unsigned long long), s));
+  std::vector<unsigned long long> nmiss(F, 0);
+  long long n_global = m->n;
+  if (world > 1) {
+    CUDA_CHECK(cudaMemcpyAsync(d_cnt.p, &h_n, sizeof(long long), cudaMemcpyHostToDevice, s));
+    allreduce(comm, d_cnt.p, 1, kNcclInt64, kNcclSum, s);
+    CUDA_CHECK(cudaMemcpyAsync(&n_global, d_cnt.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  for (int f = 0; f < F; ++f) {
+    LAUNCH_CHECK(b2_launch_extract_keys(m->raw.p, m->n, F, f, m->missing, keys_local.p, n_pad, d_nmiss.p + f, ctx->num_sms, s));
+    const uint32_t* kin = keys_local.p;
+    if (world > 1) {
+      NCCL_CHECK(nccl()->AllGather(keys_local.p, keys_all.p, (size_t)n_pad, kNcclUint32, comm->comm, s));
+      allreduce(comm, d_nmiss.p + f, 1, kNcclUint64, kNcclSum, s);
+      kin = keys_all.p;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(&nmiss[f], d_nmiss.p + f, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    const int64_t n_valid = (int64_t)n_global - (int64_t)nmiss[f];
+    const int cap = (nmiss[f] > 0 && max_bin > 255) ? 255 : max_bin;
+    LAUNCH_CHECK(b2_sketch_column(kin, keys_sorted.p, n_total, n_valid, temp.p, temp_bytes, flags.p, idx.p, uval.p, rmin.p,
+                                  m_scratch.p, cap, d_cuts.p + (size_t)f * 256, d_ncuts.p + f, d_mins.p + f, ctx->num_sms, s));
+  }
+  std::vector<float> h_cuts((size_t)F * 256), h_mins(F);
+  std::vector<int32_t> h_nc(F);
+  CUDA_CHECK(cudaMemcpyAsync(h_cuts.data(), d_cuts.p, h_cuts.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(h_mins.data(), d_mins.p, (size_t)F * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(h_nc.data(), d_ncuts.p, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  m->cut_ptrs.assign(F + 1, 0);
+  m->cut_vals.clear(); m->min_vals = h_mins; m->has_missing.assign(F, 0);
+  for (int f = 0; f < F; ++f) {
+    m->cut_ptrs[f + 1] = m->cut_ptrs[f] + h_nc[f];
+    m->cut_vals.insert(m->cut_vals.end(), h_cuts.begin() + (size_t)f * 256, h_cuts.begin() + (size_t)f * 256 + h_nc[f]);
+    m->has_missing[f] = nmiss[f] > 0 ? 1 : 0;
+  }
+  m->max_bin = max_bin;
+}
+
+void bin_matrix(Matrix* m) {
+  Ctx* ctx = m->ctx; cudaStream_t s = ctx->stream;
+  setup_groups(m);
+  upload_cuts(m);
+  m->bins.ensure((size_t)std::max<int64_t>(m->n, 1) * m->row_stride);
+  CUDA_CHECK(cudaMemsetAsync(m->bins.p, 0, (size_t)std::max<int64_t>(m->n, 1) * m->row_stride, s));
+  LAUNCH_CHECK(b2_launch_bin(m->raw.p, m->n, m->F, m->missing, m->d_cut_ptrs.p, m->d_cut_vals.p, m->d_feat_byte.p,
+                             m->row_stride, m->bins.p, ctx->num_sms, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  m->quantized = true;
+}
+
+// ---------------------------------------------------------------- booster
+enum { kObjSquaredError = 0, kObjLogistic = 1, kObjSoftprob = 2 };
+struct Params {
+  int objective = kObjSquaredError;
+  std::string objective_name = "reg:squarederror";
+  int num_class = 1;
+  int max_depth = 6;
+  float eta = 0.3f, gamma = 0.0f, min_child_weight = 1.0f, lambda = 1.0f, alpha = 0.0f, base_score = 0.5f;
+  int qbits = 18;
+  int hist_chunk_rows = 0;  // 0 = auto
+  int profile = 1;
+  int num_feature = 0;
+  int device = 0;
+};
+
+struct TreeHost {
+  std::vector<int32_t> left, right, parent, feature, split_bin;
+  std::vector<float> cond, value, base_weight, loss_chg;
+  std::vector<double> sum_hess;
+  std::vector<uint8_t> default_left;
+  int add(int par) {
+    int id = (int)left.size();
+    left.push_back(-1); right.push_back(-1); parent.push_back(par); feature.push_back(-1); split_bin.push_back(-1);
+    cond.push_back(0.f); value.push_back(0.f); base_weight.push_back(0.f); loss_chg.push_back(0.f); sum_hess.push_back(0.0);
+    default_left.push_back(0);
+    return id;
+  }
+  int size() const { return (int)left.size(); }
+};
+
+struct SegWorkH { int32_t seg_begin, seg_count, id, chunk_begin, buf, pad0, pad1, pad2; };
+
+struct Timers {
+  double hist_ms = 0, round_ms = 0;
+  long long hist_launches = 0, hist_rows = 0, kernel_launches = 0, rounds = 0;
+  double hist_bytes = 0, allreduce_bytes = 0;
+  void reset() { *this = Timers(); }
+};
+
+struct EvalCache { DevBuf<float> margin; int n_trees_applied = 0; int64_t n = 0; };
+
+struct Booster : HandleBase {
+  Ctx* ctx = nullptr;
+  Params p;
+  Matrix* train = nullptr;
+  int n_features = 0;
+  Comm* comm = nullptr;
+  std::vector<TreeHost> trees;
+  std::atomic<bool> cancel{false};
+  // device model cache for prediction
+  DevBuf<B2TreeNodeDev> d_nodes; DevBuf<int32_t> d_tree_offset; int d_trees_synced = 0;
+  std::vector<B2TreeNodeDev> h_nodes; std::vector<int32_t> h_tree_offset;
+  // training state
+  bool margin_ready = false;
+  DevBuf<float> margin;          // [n][K]
+  DevBuf<float2> gh;             // [K][n]
+  DevBuf<int2> q;                // [n]
+  DevBuf<int32_t> ridx[2];
+  DevBuf<long long> hist[2];
+  size_t node_elems = 0;
+  DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
+  DevBuf<B2HistWork> d_hist_work; DevBuf<B2SplitWork> d_split_work; DevBuf<SegWorkH> d_seg_work;
+  DevBuf<B2EvalNode> d_eval_nodes; DevBuf<B2SplitCand> d_cands; DevBuf<int32_t> d_counters, d_triples;
+  DevBuf<long long> d_leaf_sums; DevBuf<float> d_leaf_values; DevBuf<double> d_metric;
+  DevBuf<float> d_custom_g, d_custom_h;
+  std::map<Matrix*, EvalCache*> eval_cache;
+  // profiling
+  Timers t;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hist_events;
+  cudaEvent_t round_start = nullptr, round_stop = nullptr;
+  ~Booster() {
+    for (auto e : ev_pool) cudaEventDestroy(e);
+    if (round_start) cudaEventDestroy(round_start);
+    if (round_stop) cudaEventDestroy(round_stop);
+    for (auto& kv : eval_cache) delete kv.second;
+  }
+};
+
+cudaEvent_t get_event(Booster* b) {
+  if (b->ev_used == b->ev_pool.size()) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); b->ev_pool.push_back(e); }
+  return b->ev_pool[b->ev_used++];
+}
+void resolve_events(Booster* b) {
+  for (auto& pr : b->hist_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) b->t.hist_ms += ms;
+  }
+  b->hist_events.clear();
+  b->ev_used = 0;
+}
+
+void parse_params(const char* text, Params* p, int* max_bin_out) {
+  std::string s(text ? text : "");
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t nl = s.find('\n', pos);
+    if (nl == std::string::npos) nl = s.size();
+    std::string line = s.substr(pos, nl - pos);
+    pos = nl + 1;
+    size_t eq = line.find('=');
+    if (eq == std::string::npos) continue;
+    std::string k = line.substr(0, eq), v = line.substr(eq + 1);
+    auto f = [&]() { return (float)atof(v.c_str()); };
+    auto i = [&]() { return atoi(v.c_str()); };
+    if (k == "objective") {
+      p->objective_name = v;
+      if (v == "reg:squarederror" || v == "reg:linear") p->objective = kObjSquaredError;
+      else if (v == "binary:logistic") p->objective = kObjLogistic;
+      else if (v == "multi:softprob" || v == "multi:softmax") p->objective = kObjSoftprob;
+      else fail("unsupported objective '%s' (supported: reg:squarederror, binary:logistic, multi:softprob, multi:softmax)", v.c_str());
+    } else if (k == "num_class") p->num_class = i();
+    else if (k == "max_depth") p->max_depth = i();
+    else if (k == "eta" || k == "learning_rate") p->eta = f();
+    else if (k == "gamma" || k == "min_split_loss") p->gamma = f();
+    else if (k == "min_child_weight") p->min_child_weight = f();
+    else if (k == "lambda" || k == "reg_lambda") p->lambda = f();
+    else if (k == "alpha" || k == "reg_alpha") p->alpha = f();
+    else if (k == "base_score") p->base_score = f();
+    else if (k == "hist_qbits") p->qbits = i();
+    else if (k == "hist_chunk_rows") p->hist_chunk_rows = i();
+    else if (k == "profile") p->profile = i();
+    else if (k == "num_feature") p->num_feature = i();
+    else if (k == "device") p->device = i();
+    else if (k == "max_bin") { if (max_bin_out) *max_bin_out = i(); }
+    // unknown keys (nthread, tree_method, verbosity, ...) are accepted and ignored, like xgboost
+  }
+  if (p->objective != kObjSoftprob) p->num_class = 1;
+  if (p->objective == kObjSoftprob && p->num_class < 2) fail("multi:softprob needs num_class >= 2");
+  if (p->max_depth < 1 || p->max_depth > 14) fail("max_depth must be in [1, 14], got %d", p->max_depth);
+  if (p->qbits < 8 || p->qbits > 24) fail("hist_qbits must be in [8, 24], got %d", p->qbits);
+}
+
+float base_margin_value(const Params& p) {
+  if (p.objective == kObjLogistic) return -logf(1.0f / p.base_score - 1.0f);
+  return p.base_score;
+}
+
+// -- host replicas of the gain / weight formulas (A.6, A.7); same IEEE sequence as the kernels
+double h_thr_l1(double g, double a) { if (g > a) return g - a; if (g < -a) return g + a; return 0.0; }
+double h_calc_gain(const Params& p, double G, double H) {
+  if (H < (double)p.min_child_weight || H <= 0.0) return 0.0;
+  double t = p.alpha == 0.0f ? G : h_thr_l1(G, (double)p.alpha);
+  return (t * t) / (H + (double)p.lambda);
+}
+float h_calc_weight(const Params& p, double G, double H) {
+  if (H < (double)p.min_child_weight || H <= 0.0) return 0.0f;
+  double t = p.alpha == 0.0f ? G : h_thr_l1(G, (double)p.alpha);
+  return (float)(-t / (H + (double)p.lambda));
+}
+
+struct NodeState {
+  int nid, depth, buf;
+  int64_t begin, count;
+  long long sg, sh;
+  int hist_slot;
+  float root_gain;
+};
+
+int window_rows_for(int qbits) {
+  // |q| <= 2^qbits, int32 cell: rows * 2^qbits <= 2^31 - 1
+  long long w = ((1LL << 31) - 1) >> qbits;
+  return (int)std::min<long long>(w, 1LL << 30);
+}
+
+void launch_hist(Booster* b, const int32_t* ridx, const std::vector<B2HistWork>& work, int total_chunks, int chunk_rows,
+                 long long* level_hist, int64_t rows) {
+  Matrix* m = b->train; cudaStream_t s = b->ctx->stream;
+  if (work.empty() || total_chunks == 0) return;
+  b->d_hist_work.ensure(work.size());
+  CUDA_CHECK(cudaMemcpyAsync(b->d_hist_work.p, work.data(), work.size() * sizeof(B2HistWork), cudaMemcpyHostToDevice, s));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (b->p.profile) { e0 = get_event(b); e1 = get_event(b); CUDA_CHECK(cudaEventRecord(e0, s)); }
+  LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, ridx, b->d_hist_work.p, (int)work.size(), total_chunks,
+                              chunk_rows, window_rows_for(b->p.qbits), m->n_groups, level_hist, b->ctx->num_sms, s));
+  if (b->p.profile) { CUDA_CHECK(cudaEventRecord(e1, s)); b->hist_events.push_back({e0, e1}); }
+  b->t.hist_launches++; b->t.kernel_launches++; b->t.hist_rows += rows;
+  b->t.hist_bytes += (double)rows * (m->F + 8 + (ridx ? 4 : 0)) + (double)work.size() * m->F * 256.0 * 16.0;
+}
+
+int pick_chunk_rows(Booster* b, int64_t rows) {
+  if (b->p.hist_chunk_rows > 0) return b->p.hist_chunk_rows;
+  const int n_streams = std::max(1, b->ctx->num_sms * 3 / b->train->n_groups);
+  int64_t target = rows / ((int64_t)n_streams * 4);
+  int c = 512;
+  while (c < target && c < 8192) c <<= 1;
+  return c;
+}
+
+// Grow one tree for class k from gh[k] (already on device); updates margin[:, k].
+void grow_tree(Booster* b, int k) {
+  Matrix* m = b->train; Ctx* ctx = b->ctx; cudaStream_t s = ctx->stream; const Params& p = b->p;
+  const int64_t n = m->n; const int K = p.num_class; const int G = m->n_groups;
+  const float2* gh = b->gh.p + (size_t)k * n;
+  // ---- fixed-point quantisation (global scale via allreduce max)
+  b->d_absmax.ensure(2); b->d_qexp.ensure(2);
+  CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * sizeof(uint32_t), s));
+  LAUNCH_CHECK(b2_launch_absmax(gh, n, b->d_absmax.p, ctx->num_sms, s));
+  allreduce(b->comm, b->d_absmax.p, 2, kNcclUint32, kNcclMax, s);
+  LAUNCH_CHECK(b2_launch_quant_exponent(b->d_absmax.p, b->d_qexp.p, s));
+  b->q.ensure((size_t)std::max<int64_t>(n, 1));
+  LAUNCH_CHECK(b2_launch_quantize(gh, n, b->d_qexp.p, p.qbits, b->q.p, ctx->num_sms, s));
+  b->t.kernel_launches += 3;
+  int32_t h_qexp[2];
+  CUDA_CHECK(cudaMemcpyAsync(h_qexp, b->d_qexp.p, sizeof(h_qexp), cudaMemcpyDeviceToHost, s));
+
+  B2TrainParamDev dp;
+  dp.min_child_weight = (double)p.min_child_weight; dp.lambda = (double)p.lambda; dp.alpha = (double)p.alpha;
+  dp.inv_scale_g = dp.inv_scale_h = 1.0;
+
+  b->node_elems = (size_t)G * B2_GROUP_ELEMS;
+  const size_t max_level_nodes = (size_t)1 << (p.max_depth - 1);
+  b->hist[0].ensure(max_level_nodes * b->node_elems);
+  b->hist[1].ensure(max_level_nodes * b->node_elems);
+  b->ridx[0].ensure((size_t)std::max<int64_t>(n, 1)); b->ridx[1].ensure((size_t)std::max<int64_t>(n, 1));
+  LAUNCH_CHECK(b2_launch_iota(b->ridx[0].p, n, s));
+  b->d_eval_nodes.ensure(max_level_nodes); b->d_cands.ensure(max_level_nodes * G);
+  b->d_counters.ensure(2 * max_level_nodes); b->d_triples.ensure(3 * max_level_nodes);
+  b->d_split_work.ensure(max_level_nodes);
+
+  TreeHost tree;
+  std::vector<NodeState> level(1);
+  level[0] = NodeState{tree.add(-1), 0, 0, 0, n, 0, 0, 0, 0.f};
+  // ---- root histogram (no gather)
+  CUDA_CHECK(cudaMemsetAsync(b->hist[0].p, 0, b->node_elems * sizeof(long long), s));
+  {
+    std::vector<B2HistWork> work;
+    const int chunk_rows = pick_chunk_rows(b, n);
+    const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
+    if (n > 0) work.push_back(B2HistWork{0, (int32_t)n, 0, 0});
+    launch_hist(b, nullptr, work, chunks, chunk_rows, b->hist[0].p, n);
+  }
+  allreduce(b->comm, b->hist[0].p, b->node_elems, kNcclInt64, kNcclSum, s);
+  b->t.allreduce_bytes += (double)b->node_elems * 8;
+  {
+    B2EvalNode rn{0, 0, 0, 0.f};
+    CUDA_CHECK(cudaMemcpyAsync(b->d_eval_nodes.p, &rn, sizeof(rn), cudaMemcpyHostToDevice, s));
+    LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_eval_nodes.p, b->d_qexp.p, p.qbits, dp, s));
+    b->t.kernel_launches++;
+  }
+  struct Leaf { int nid, buf; int64_t begin, count; };
+  std::vector<Leaf> leaves;
+  std::vector<B2SplitCand> h_cands;
+  std::vector<B2EvalNode> h_eval;
+  double inv_sg = 1.0, inv_sh = 1.0;
+  bool have_scales = false;
+  int cur_buf = 0;   // hist buffer of the current level
+  for (int depth = 0; !level.empty(); ++depth) {
+    const int nl = (int)level.size();
+    const bool can_split = depth < p.max_depth;
+    if (can_split) {
+      if (depth > 0) {
+        h_eval.resize(nl);
+        for (int i = 0; i < nl; ++i) h_eval[i] = B2EvalNode{level[i].sg, level[i].sh, level[i].hist_slot, level[i].root_gain};
+        CUDA_CHECK(cudaMemcpyAsync(b->d_eval_nodes.p, h_eval.data(), nl * sizeof(B2EvalNode), cudaMemcpyHostToDevice, s));
+      }
+      LAUNCH_CHECK(b2_launch_eval_splits(b->hist[cur_buf].p, G, b->d_eval_nodes.p, nl, m->d_group_first.p, m->d_group_size.p,
+                                         m->d_nbins.p, m->d_has_missing.p, b->d_qexp.p, p.qbits, dp, b->d_cands.p, s));
+      b->t.kernel_launches++;
+      h_cands.resize((size_t)nl * G);
+      CUDA_CHECK(cudaMemcpyAsync(h_cands.data(), b->d_cands.p, h_cands.size() * sizeof(B2SplitCand), cudaMemcpyDeviceToHost, s));
+      B2EvalNode root_node;
+      if (depth == 0) CUDA_CHECK(cudaMemcpyAsync(&root_node, b->d_eval_nodes.p, sizeof(root_node), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (b->cancel.load()) fail("training cancelled");
+      if (!have_scales) {
+        inv_sg = ldexp(1.0, h_qexp[0] - p.qbits); inv_sh = ldexp(1.0, h_qexp[1] - p.qbits); have_scales = true;
+      }
+      if (depth == 0) {
+        level[0].sg = root_node.sum_g; level[0].sh = root_node.sum_h; level[0].root_gain = root_node.root_gain;
+        const double Gr = (double)root_node.sum_g * inv_sg, Hr = (double)root_node.sum_h * inv_sh;
+        tree.sum_hess[0] = Hr; tree.base_weight[0] = h_calc_weight(p, Gr, Hr);
+      }
+    } else if (!have_scales) {
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      inv_sg = ldexp(1.0, h_qexp[0] - p.qbits); inv_sh = ldexp(1.0, h_qexp[1] - p.qbits); have_scales = true;
+    }
+    // ---- decide
+    std::vector<NodeState> next;
+    std::vector<B2SplitWork> swork;
+    std::vector<int> split_parent;  // index into level
+    int pchunks = 0; const int pchunk = b2_part_chunk_rows();
+    for (int i = 0; i < nl; ++i) {
+      NodeState& nd = level[i];
+      bool expand = false; B2SplitCand best{}; best.feature = -1;
+      if (can_split) {
+        for (int g = 0; g < G; ++g) {
+          const B2SplitCand& c = h_cands[(size_t)i * G + g];
+          if (c.feature < 0) continue;
+          if (best.feature < 0 || c.loss_chg > best.loss_chg || (c.loss_chg == best.loss_chg && c.order < best.order)) best = c;
+        }
+        if (best.feature >= 0) {
+          const double HL = (double)best.left_h * inv_sh, HR = (double)(nd.sh - best.left_h) * inv_sh;
+          expand = best.loss_chg > 1e-6f && HL != 0.0 && HR != 0.0 && !(best.loss_chg < p.gamma);
+        }
+      }
+      if (!expand) { leaves.push_back(Leaf{nd.nid, nd.buf, nd.begin, nd.count}); continue; }
+      const int l = tree.add(nd.nid), r = tree.add(nd.nid);
+      const int f = best.feature;
+      tree.left[nd.nid] = l; tree.right[nd.nid] = r; tree.feature[nd.nid] = f; tree.split_bin[nd.nid] = best.bin;
+      tree.default_left[nd.nid] = (uint8_t)best.default_left; tree.loss_chg[nd.nid] = best.loss_chg;
+      tree.value[nd.nid] = tree.base_weight[nd.nid];
+      tree.cond[nd.nid] = best.bin < 0 ? m->min_vals[f] : m->cut_vals[m->cut_ptrs[f] + best.bin];
+      const long long lg = best.left_g, lh = best.left_h, rg = nd.sg - lg, rh = nd.sh - lh;
+      const double GL = (double)lg * inv_sg, HL = (double)lh * inv_sh, GR = (double)rg * inv_sg, HR = (double)rh * inv_sh;
+      tree.sum_hess[l] = HL; tree.sum_hess[r] = HR;
+      tree.base_weight[l] = h_calc_weight(p, GL, HL); tree.base_weight[r] = h_calc_weight(p, GR, HR);
+      B2SplitWork sw{};
+      sw.seg_begin = (int32_t)nd.begin; sw.seg_count = (int32_t)nd.count; sw.feature_byte = m->feat_byte[f];
+      sw.split_bin = best.bin; sw.default_left = best.default_left; sw.has_missing = m->has_missing[f];
+      sw.chunk_begin = pchunks; pchunks += (int)((nd.count + pchunk - 1) / pchunk);
+      swork.push_back(sw); split_parent.push_back(i);
+      NodeState ls{l, depth + 1, nd.buf ^ 1, nd.begin, 0, lg, lh, -1, (float)h_calc_gain(p, GL, HL)};
+      NodeState rs{r, depth + 1, nd.buf ^ 1, 0, 0, rg, rh, -1, (float)h_calc_gain(p, GR, HR)};
+      next.push_back(ls); next.push_back(rs);
+    }
+    if (swork.empty()) break;
+    // ---- partition rows of split nodes into the other index buffer
+    const int ns = (int)swork.size();
+    const int in_buf = level[split_parent[0]].buf;  // all nodes of a level share the buffer parity
+    CUDA_CHECK(cudaMemsetAsync(b->d_counters.p, 0, 2 * ns * sizeof(int32_t), s));
+    CUDA_CHECK(cudaMemcpyAsync(b->d_split_work.p, swork.data(), ns * sizeof(B2SplitWork), cudaMemcpyHostToDevice, s));
+    LAUNCH_CHECK(b2_launch_partition(m->bins.p, m->row_stride, b->ridx[in_buf].p, b->ridx[in_buf ^ 1].p, b->d_split_work.p, ns,
+                                     pchunks, b->d_counters.p, ctx->num_sms, s));
+    b->t.kernel_launches++;
+    std::vector<int32_t> h_counters(2 * ns);
+    CUDA_CHECK(cudaMemcpyAsync(h_counters.data(), b->d_counters.p, 2 * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int j = 0; j < ns; ++j) {
+      const NodeState& par = level[split_parent[j]];
+      NodeState& ls = next[2 * j]; NodeState& rs = next[2 * j + 1];
+      ls.begin = par.begin; ls.count = h_counters[2 * j];
+      rs.begin = par.begin + ls.count; rs.count = par.count - ls.count;
+    }
+    // ---- histograms of the next level: build the smaller-hessian child, subtract for the sibling
+    if (depth + 1 < p.max_depth) {
+      const int nb = ns;
+      std::vector<B2HistWork> work; std::vector<int32_t> triples(3 * nb);
+      int64_t rows = 0, max_rows_level = 0;
+      for (int j = 0; j < nb; ++j) max_rows_level += std::min(next[2 * j].count, next[2 * j + 1].count) + 0;
+      // build set: smaller hessian (global decision, identical on every rank)
+      std::vector<int> built(nb);
+      int64_t build_rows = 0;
+      for (int j = 0; j < nb; ++j) {
+        const NodeState& ls = next[2 * j]; const NodeState& rs = next[2 * j + 1];
+        const double HL = (double)ls.sh * inv_sh, HR = (double)rs.sh * inv_sh;
+        built[j] = (HL < HR) ? 0 : 1;
+        build_rows += next[2 * j + built[j]].count;
+      }
+      const int chunk_rows = pick_chunk_rows(b, build_rows);
+      int chunks = 0;
+      for (int j = 0; j < nb; ++j) {
+        NodeState& bn = next[2 * j + built[j]]; NodeState& sn = next[2 * j + (built[j] ^ 1)];
+        bn.hist_slot = j; sn.hist_slot = nb + j;
+        triples[3 * j] = level[split_parent[j]].hist_slot; triples[3 * j + 1] = j; triples[3 * j + 2] = nb + j;
+        if (bn.count > 0) {
+          work.push_back(B2HistWork{(int32_t)bn.begin, (int32_t)bn.count, j, chunks});
+          chunks += (int)((bn.count + chunk_rows - 1) / chunk_rows);
+          rows += bn.count;
+        }
+      }
+      const int nbuf = cur_buf ^ 1;
+      CUDA_CHECK(cudaMemsetAsync(b->hist[nbuf].p, 0, (size_t)nb * b->node_elems * sizeof(long long), s));
+      launch_hist(b, b->ridx[in_buf ^ 1].p, work, chunks, chunk_rows, b->hist[nbuf].p, rows);
+      allreduce(b->comm, b->hist[nbuf].p, (size_t)nb * b->node_elems, kNcclInt64, kNcclSum, s);
+      b->t.allreduce_bytes += (double)nb * b->node_elems * 8;
+      CUDA_CHECK(cudaMemcpyAsync(b->d_triples.p, triples.data(), triples.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+      LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[cur_buf].p, b->hist[nbuf].p, b->d_triples.p, nb, (int64_t)b->node_elems, s));
+      b->t.kernel_launches++;
+      cur_buf = nbuf;
+      (void)max_rows_level;
+    }
+    level.swap(next);
+  }
+  // ---- leaves: 40-bit fixed-point leaf sums -> allreduce -> weights -> margin update
+  const int nleaf = (int)leaves.size();
+  std::vector<SegWorkH> lwork; int lchunks = 0; const int pchunk = b2_part_chunk_rows();
+  for (int i = 0; i < nleaf; ++i) {
+    if (leaves[i].count <= 0) continue;
+    lwork.push_back(SegWorkH{(int32_t)leaves[i].begin, (int32_t)leaves[i].count, i, lchunks, leaves[i].buf, 0, 0, 0});
+    lchunks += (int)((leaves[i].count + pchunk - 1) / pchunk);
+  }
+  b->d_leaf_sums.ensure((size_t)2 * nleaf); b->d_leaf_values.ensure((size_t)nleaf);
+  CUDA_CHECK(cudaMemsetAsync(b->d_leaf_sums.p, 0, (size_t)2 * nleaf * sizeof(long long), s));
+  if (!lwork.empty()) {
+    b->d_seg_work.ensure(lwork.size());
+    CUDA_CHECK(cudaMemcpyAsync(b->d_seg_work.p, lwork.data(), lwork.size() * sizeof(SegWorkH), cudaMemcpyHostToDevice, s));
+    LAUNCH_CHECK(b2_launch_leaf_sums(gh, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, (int)lwork.size(), lchunks, b->d_qexp.p,
+                                     40, b->d_leaf_sums.p, ctx->num_sms, s));
+    b->t.kernel_launches++;
+  }
+  allreduce(b->comm, b->d_leaf_sums.p, (size_t)2 * nleaf, kNcclInt64, kNcclSum, s);
+  std::vector<long long> h_sums((size_t)2 * nleaf);
+  CUDA_CHECK(cudaMemcpyAsync(h_sums.data(), b->d_leaf_sums.p, h_sums.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (!have_scales) { inv_sg = ldexp(1.0, h_qexp[0] - p.qbits); inv_sh = ldexp(1.0, h_qexp[1] - p.qbits); }
+  const double kg = ldexp(1.0, 40 - h_qexp[0]), kh = ldexp(1.0, 40 - h_qexp[1]);
+  std::vector<float> h_leaf(nleaf);
+  for (int i = 0; i < nleaf; ++i) {
+    const int nid = leaves[i].nid;
+    tree.base_weight[nid] = h_calc_weight(p, (double)h_sums[2 * i] / kg, (double)h_sums[2 * i + 1] / kh);
+    tree.value[nid] = tree.base_weight[nid] * p.eta;
+    h_leaf[i] = tree.value[nid];
+  }
+  if (!lwork.empty()) {
+    CUDA_CHECK(cudaMemcpyAsync(b->d_leaf_values.p, h_leaf.data(), nleaf * sizeof(float), cudaMemcpyHostToDevice, s));
+    LAUNCH_CHECK(b2_launch_pred_update(b->margin.p, K, k, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, (int)lwork.size(),
+                                       lchunks, b->d_leaf_values.p, ctx->num_sms, s));
+    b->t.kernel_launches++;
+    CUDA_CHECK(cudaStreamSynchronize(s));  // h_leaf / lwork go out of scope
+  }
+  b->trees.push_back(std::move(tree));
+}
+
+void sync_device_trees(Booster* b) {
+  if (b->d_trees_synced == (int)b->trees.size()) return;
+  b->h_nodes.clear(); b->h_tree_offset.clear();
+  for (auto& t : b->trees) {
+    b->h_tree_offset.push_back((int32_t)b->h_nodes.size());
+    for (int i = 0; i < t.size(); ++i)
+      b->h_nodes.push_back(B2TreeNodeDev{t.left[i], t.right[i], t.feature[i], t.cond[i], t.value[i], (int32_t)t.default_left[i]});
+  }
+  cudaStream_t s = b->ctx->stream;
+  upload(b->d_nodes, b->h_nodes, s); upload(b->d_tree_offset, b->h_tree_offset, s);
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  b->d_trees_synced = (int)b->trees.size();
+}
+
+void init_margin(Booster* b, float* margin, Matrix* m) {
+  const int K = b->p.num_class; cudaStream_t s = b->ctx->stream;
+  if (m->n_base_margin > 0) {
+    if (m->n_base_margin != m->n * K) fail("base_margin has %lld values, expected %lld", (long long)m->n_base_margin, (long long)(m->n * K));
+    CUDA_CHECK(cudaMemcpyAsync(margin, m->base_margin.p, (size_t)m->n * K * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    LAUNCH_CHECK(b2_launch_fill(margin, m->n * K, base_margin_value(b->p), b->ctx->num_sms, s));
+  }
+}
+
+void ensure_train_margin(Booster* b) {
+  if (b->margin_ready) return;
+  Matrix* m = b->train;
+  b->margin.ensure((size_t)std::max<int64_t>(m->n * b->p.num_class, 1));
+  init_margin(b, b->margin.p, m);
+  if (!b->trees.empty()) {
+    if (!m->has_raw) fail("continuing training from existing trees needs the raw data of the train matrix (B2_MatrixEnsureRaw)");
+    sync_device_trees(b);
+    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, 0, (int)b->trees.size(),
+                                   b->p.num_class, b->margin.p, b->ctx->num_sms, b->ctx->stream));
+  }
+  b->margin_ready = true;
+}
+
+void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64_t len) {
+  if (!b->train) fail("this booster has no train matrix (prediction-only)");
+  Matrix* m = b->train; cudaStream_t s = b->ctx->stream; const int K = b->p.num_class; const int64_t n = m->n;
+  CUDA_CHECK(cudaSetDevice(b->ctx->device));
+  if (b->cancel.load()) fail("training cancelled");
+  if (!b->round_start) { CUDA_CHECK(cudaEventCreate(&b->round_start)); CUDA_CHECK(cudaEventCreate(&b->round_stop)); }
+  if (b->p.profile) CUDA_CHECK(cudaEventRecord(b->round_start, s));
+  ensure_train_margin(b);
+  b->gh.ensure((size_t)std::max<int64_t>(n * K, 1));
+  if (custom_g) {
+    if (len != n * K) fail("custom gradient has %lld values, expected %lld", (long long)len, (long long)(n * K));
+    b->d_custom_g.ensure((size_t)std::max<int64_t>(len, 1)); b->d_custom_h.ensure((size_t)std::max<int64_t>(len, 1));
+    CUDA_CHECK(cudaMemcpyAsync(b->d_custom_g.p, custom_g, len * sizeof(float), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(b->d_custom_h.p, custom_h, len * sizeof(float), cudaMemcpyHostToDevice, s));
+    LAUNCH_CHECK(b2_launch_pack_custom(b->d_custom_g.p, b->d_custom_h.p, K, n, b->gh.p, b->ctx->num_sms, s));
+  } else {
+    if (m->n_label != n) fail("train matrix has %lld labels for %lld rows", (long long)m->n_label, (long long)n);
+    LAUNCH_CHECK(b2_launch_gradient(b->p.objective, K, b->margin.p, m->label.p, m->n_weight ? m->weight.p : nullptr, n, b->gh.p,
+                                    b->ctx->num_sms, s));
+  }
+  b->t.kernel_launches++;
+  for (int k = 0; k < K; ++k) grow_tree(b, k);
+  if (b->p.profile) {
+    CUDA_CHECK(cudaEventRecord(b->round_stop, s));
+    CUDA_CHECK(cudaEventSynchronize(b->round_stop));
+    float ms = 0.f; CUDA_CHECK(cudaEventElapsedTime(&ms, b->round_start, b->round_stop));
+    b->t.round_ms += ms;
+    resolve_events(b);
+  } else {
+    CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  b->t.rounds++;
+}
+
+int metric_id(const char* name) {
+  std::string s(name ? name : "");
+  if (s == "rmse") return 0;
+  if (s == "logloss") return 1;
+  if (s == "error") return 2;
+  if (s == "mlogloss") return 3;
+  if (s == "merror") return 4;
+  fail("unsupported eval metric '%s' (supported: rmse, logloss, error, mlogloss, merror)", s.c_str());
+}
+
+// margin of matrix m under the current model (cached per matrix, only new trees are applied)
+float* eval_margin(Booster* b, Matrix* m) {
+  if (b->train && m == b->train) { ensure_train_margin(b); return b->margin.p; }
+  if (!m->has_raw) fail("evaluation / prediction matrix has no raw data on the device");
+  if (m->F != b->n_features) fail("feature count mismatch: matrix has %d, model has %d", m->F, b->n_features);
+  EvalCache*& c = b->eval_cache[m];
+  const int K = b->p.num_class;
+  if (!c || c->n != m->n) {
+    delete c; c = new EvalCache(); c->n = m->n;
+    c->margin.ensure((size_t)std::max<int64_t>(m->n * K, 1));
+    init_margin(b, c->margin.p, m);
+    c->n_trees_applied = 0;
+  }
+  const int nt = (int)b->trees.size();
+  if (c->n_trees_applied < nt) {
+    sync_device_trees(b);
+    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, c->n_trees_applied, nt, K,
+                                   c->margin.p, b->ctx->num_sms, b->ctx->stream));
+    c->n_trees_applied = nt;
+  }
+  return c->margin.p;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* B2_GetLastError(void) { return g_last_error.c_str(); }
+int B2_GetVersion(void) { return 100; }
+int B2_DeviceCount(int* out) {
+  API_BEGIN
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { n = 0; cudaGetLastError(); }
+  *out = n;
+  API_END
+}
+
+int B2_GetUniqueId(uint8_t out[128]) {
+  API_BEGIN
+  ncclUniqueId id;
+  NCCL_CHECK(nccl()->GetUniqueId(&id));
+  memcpy(out, id.internal, 128);
+  API_END
+}
+int B2_CommCreate(const uint8_t uid[128], int rank, int world, int device, B2Handle* out) {
+  API_BEGIN
+  if (world < 1 || rank < 0 || rank >= world) fail("invalid rank %d / world %d", rank, world);
+  get_ctx(device);
+  CommH* h = new CommH(); h->kind = kComm;
+  h->c.rank = rank; h->c.world = world; h->c.device = device;
+  if (world > 1) {
+    ncclUniqueId id; memcpy(id.internal, uid, 128);
+    int r = nccl()->CommInitRank(&h->c.comm, world, id, rank);
+    if (r != 0) { delete h; fail("ncclCommInitRank failed: %s", nccl()->GetErrorString(r)); }
+  }
+  *out = (B2Handle)h;
+  API_END
+}
+int B2_CommRank(B2Handle comm, int* rank, int* world) {
+  API_BEGIN
+  CommH* h = from_handle<CommH>(comm, kComm, "communicator");
+  *rank = h->c.rank; *world = h->c.world;
+  API_END
+}
+int B2_CommAbort(B2Handle comm) {
+  API_BEGIN
+  CommH* h = from_handle<CommH>(comm, kComm, "communicator");
+  if (h->c.comm && !h->c.aborted.exchange(true)) nccl()->CommAbort(h->c.comm);
+  API_END
+}
+int B2_CommFree(B2Handle comm) {
+  API_BEGIN
+  CommH* h = from_handle<CommH>(comm, kComm, "communicator");
+  if (h->c.comm && !h->c.aborted.load()) nccl()->CommDestroy(h->c.comm);
+  delete h;
+  API_END
+}
+
+int B2_MatrixCreateFromDense(const float* data, int64_t n_rows, int32_t n_cols, float missing, int device, B2Handle* out) {
+  API_BEGIN
+  if (n_rows < 0 || n_cols <= 0) fail("invalid matrix shape %lld x %d", (long long)n_rows, n_cols);
+  if (n_rows >= (1LL << 31)) fail("at most 2^31-1 rows per GPU shard (row ids are int32), got %lld", (long long)n_rows);
+  Ctx* ctx = get_ctx(device);
+  Matrix* m = new Matrix(); m->kind = kMatrix; m->ctx = ctx; m->n = n_rows; m->F = n_cols; m->missing = missing;
+  try {
+    m->raw.ensure((size_t)std::max<int64_t>(n_rows * n_cols, 1));
+    if (n_rows > 0) CUDA_CHECK(cudaMemcpyAsync(m->raw.p, data, (size_t)n_rows * n_cols * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  } catch (...) { delete m; throw; }
+  m->has_raw = true;
+  *out = (B2Handle)m;
+  API_END
+}
+int B2_MatrixSetFloatInfo(B2Handle mh, const char* field, const float* values, int64_t len) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(m->ctx->device));
+  std::string f(field ? field : "");
+  DevBuf<float>* dst = nullptr; int64_t* cnt = nullptr;
+  if (f == "label") { dst = &m->label; cnt = &m->n_label; if (len != m->n) fail("label length %lld != rows %lld", (long long)len, (long long)m->n); }
+  else if (f == "weight") { dst = &m->weight; cnt = &m->n_weight; if (len != m->n && len != 0) fail("weight length %lld != rows %lld", (long long)len, (long long)m->n); }
+  else if (f == "base_margin") { dst = &m->base_margin; cnt = &m->n_base_margin; if (len != 0 && (m->n == 0 || len % m->n != 0)) fail("base_margin length %lld is not a multiple of rows %lld", (long long)len, (long long)m->n); }
+  else fail("unknown float info field '%s'", f.c_str());
+  dst->ensure((size_t)std::max<int64_t>(len, 1));
+  if (len > 0) CUDA_CHECK(cudaMemcpyAsync(dst->p, values, len * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(m->ctx->stream));
+  *cnt = len;
+  API_END
+}
+int B2_MatrixNumRow(B2Handle mh, int64_t* out) { API_BEGIN *out = from_handle<Matrix>(mh, kMatrix, "matrix")->n; API_END }
+int B2_MatrixNumCol(B2Handle mh, int32_t* out) { API_BEGIN *out = from_handle<Matrix>(mh, kMatrix, "matrix")->F; API_END }
+
+int B2_MatrixQuantize(B2Handle mh, B2Handle commh, int32_t max_bin, B2Handle refh, int32_t keep_raw) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(m->ctx->device));
+  Comm* comm = commh ? &from_handle<CommH>(commh, kComm, "communicator")->c : nullptr;
+  if (!m->has_raw) fail("matrix has no raw data on the device (already quantised without keep_raw?)");
+  if (refh) {
+    Matrix* r = from_handle<Matrix>(refh, kMatrix, "matrix");
+    if (!r->quantized) fail("reference matrix is not quantised");
+    if (r->F != m->F) fail("reference matrix has %d features, this one %d", r->F, m->F);
+    m->cut_ptrs = r->cut_ptrs; m->cut_vals = r->cut_vals; m->min_vals = r->min_vals; m->has_missing = r->has_missing; m->max_bin = r->max_bin;
+  } else {
+    make_cuts(m, comm, max_bin);
+  }
+  bin_matrix(m);
+  if (!keep_raw) { m->raw.release(); m->has_raw = false; }
+  API_END
+}
+int B2_MatrixEnsureRaw(B2Handle mh, const float* data) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(m->ctx->device));
+  if (m->has_raw) return 0;
+  m->raw.ensure((size_t)std::max<int64_t>(m->n * m->F, 1));
+  if (m->n > 0) CUDA_CHECK(cudaMemcpyAsync(m->raw.p, data, (size_t)m->n * m->F * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(m->ctx->stream));
+  m->has_raw = true;
+  API_END
+}
+int B2_MatrixCutsSize(B2Handle mh, int32_t* total) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  if (!m->quantized) fail("matrix is not quantised");
+  *total = m->cut_ptrs[m->F];
+  API_END
+}
+int B2_MatrixGetCuts(B2Handle mh, int32_t* ptrs, float* vals, float* mins, uint8_t* has_missing) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  if (!m->quantized) fail("matrix is not quantised");
+  memcpy(ptrs, m->cut_ptrs.data(), (m->F + 1) * sizeof(int32_t));
+  memcpy(vals, m->cut_vals.data(), m->cut_vals.size() * sizeof(float));
+  memcpy(mins, m->min_vals.data(), m->F * sizeof(float));
+  memcpy(has_missing, m->has_missing.data(), m->F);
+  API_END
+}
+int B2_MatrixGetBins(B2Handle mh, uint8_t* out) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(m->ctx->device));
+  if (!m->quantized) fail("matrix is not quantised");
+  std::vector<uint8_t> h((size_t)m->n * m->row_stride);
+  if (m->n > 0) CUDA_CHECK(cudaMemcpy(h.data(), m->bins.p, h.size(), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < m->n; ++i)
+    for (int f = 0; f < m->F; ++f) out[i * m->F + f] = h[(size_t)i * m->row_stride + m->feat_byte[f]];
+  API_END
+}
+int B2_MatrixFree(B2Handle mh) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  cudaSetDevice(m->ctx->device);
+  delete m;
+  API_END
+}
+
+int B2_BoosterCreate(const char* params, B2Handle trainh, B2Handle commh, B2Handle* out) {
+  API_BEGIN
+  Matrix* m = trainh ? from_handle<Matrix>(trainh, kMatrix, "matrix") : nullptr;
+  if (m && !m->quantized) fail("train matrix must be quantised (B2_MatrixQuantize) before B2_BoosterCreate");
+  Booster* b = new Booster(); b->kind = kBooster; b->train = m;
+  b->comm = commh ? &from_handle<CommH>(commh, kComm, "communicator")->c : nullptr;
+  try {
+    parse_params(params, &b->p, nullptr);
+    if (m) { b->ctx = m->ctx; b->n_features = m->F; CUDA_CHECK(cudaSetDevice(m->ctx->device)); }
+    else {  // prediction-only booster (model loaded with B2_BoosterAddTree)
+      if (b->p.num_feature <= 0) fail("a booster without a train matrix needs num_feature=<n> in params");
+      b->ctx = get_ctx(b->p.device); b->n_features = b->p.num_feature;
+    }
+  } catch (...) { delete b; throw; }
+  *out = (B2Handle)b;
+  API_END
+}
+int B2_BoosterUpdateOneIter(B2Handle bh, int32_t iter) {
+  API_BEGIN
+  (void)iter;
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  boost_round(b, nullptr, nullptr, 0);
+  API_END
+}
+int B2_BoosterBoostOneIter(B2Handle bh, const float* grad, const float* hess, int64_t len) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  if (!grad || !hess) fail("grad/hess must not be NULL");
+  boost_round(b, grad, hess, len);
+  API_END
+}
+int B2_BoosterEvalSet(B2Handle bh, B2Handle mh, const char* metric, double* out) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(b->ctx->device));
+  cudaStream_t s = b->ctx->stream;
+  const int mid = metric_id(metric);
+  if (m->n_label != m->n) fail("evaluation matrix has no labels");
+  float* margin = eval_margin(b, m);
+  b->d_metric.ensure(2);
+  CUDA_CHECK(cudaMemsetAsync(b->d_metric.p, 0, 2 * sizeof(double), s));
+  LAUNCH_CHECK(b2_launch_metric(mid, b->p.num_class, margin, m->label.p, m->n_weight ? m->weight.p : nullptr, m->n, b->d_metric.p,
+                                b->ctx->num_sms, s));
+  allreduce(b->comm, b->d_metric.p, 2, kNcclFloat64, kNcclSum, s);
+  double h[2];
+  CUDA_CHECK(cudaMemcpyAsync(h, b->d_metric.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  double v = h[1] > 0 ? h[0] / h[1] : 0.0;
+  *out = mid == 0 ? sqrt(v) : v;
+  API_END
+}
+int B2_BoosterPredict(B2Handle bh, B2Handle mh, int32_t output_margin, int32_t tree_begin, int32_t tree_end, float* out,
+                      int64_t out_len) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(b->ctx->device));
+  cudaStream_t s = b->ctx->stream; const int K = b->p.num_class;
+  if (out_len != m->n * K) fail("output buffer has %lld values, expected %lld", (long long)out_len, (long long)(m->n * K));
+  if (!m->has_raw) fail("prediction matrix has no raw data on the device (B2_MatrixEnsureRaw)");
+  if (m->F != b->n_features) fail("feature count mismatch: matrix has %d, model has %d", m->F, b->n_features);
+  const int nt = (int)b->trees.size();
+  if (tree_end <= 0 || tree_end > nt) tree_end = nt;
+  if (tree_begin < 0 || tree_begin > tree_end) fail("invalid tree range [%d, %d)", tree_begin, tree_end);
+  DevBuf<float> tmp; tmp.ensure((size_t)std::max<int64_t>(out_len, 1));
+  init_margin(b, tmp.p, m);
+  sync_device_trees(b);
+  LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, tree_begin, tree_end, K, tmp.p,
+                                 b->ctx->num_sms, s));
+  if (!output_margin) LAUNCH_CHECK(b2_launch_transform(b->p.objective, K, tmp.p, m->n, b->ctx->num_sms, s));
+  if (out_len > 0) CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, out_len * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  API_END
+}
+int B2_BoosterGetTrainMargin(B2Handle bh, float* out, int64_t out_len) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  CUDA_CHECK(cudaSetDevice(b->ctx->device));
+  if (!b->train) fail("this booster has no train matrix (prediction-only)");
+  const int64_t want = b->train->n * b->p.num_class;
+  if (out_len != want) fail("output buffer has %lld values, expected %lld", (long long)out_len, (long long)want);
+  ensure_train_margin(b);
+  if (want > 0) CUDA_CHECK(cudaMemcpyAsync(out, b->margin.p, want * sizeof(float), cudaMemcpyDeviceToHost, b->ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(b->ctx->stream));
+  API_END
+}
+int B2_BoosterResetTrainMargin(B2Handle bh) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  CUDA_CHECK(cudaSetDevice(b->ctx->device));
+  if (!b->train) fail("this booster has no train matrix (prediction-only)");
+  b->margin_ready = false;
+  ensure_train_margin(b);
+  CUDA_CHECK(cudaStreamSynchronize(b->ctx->stream));
+  API_END
+}
+int B2_BoosterNumTrees(B2Handle bh, int32_t* out) { API_BEGIN *out = (int32_t)from_handle<Booster>(bh, kBooster, "booster")->trees.size(); API_END }
+int B2_BoosterTreeNumNodes(B2Handle bh, int32_t tree, int32_t* out) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  if (tree < 0 || tree >= (int)b->trees.size()) fail("tree index %d out of range", tree);
+  *out = b->trees[tree].size();
+  API_END
+}
+int B2_BoosterGetTree(B2Handle bh, int32_t tree, int32_t* left, int32_t* right, int32_t* parent, int32_t* split_feature,
+                      int32_t* split_bin, float* split_cond, uint8_t* default_left, float* value, float* base_weight,
+                      float* loss_chg, double* sum_hess) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  if (tree < 0 || tree >= (int)b->trees.size()) fail("tree index %d out of range", tree);
+  const TreeHost& t = b->trees[tree]; const size_t n = t.size();
+  memcpy(left, t.left.data(), n * 4); memcpy(right, t.right.data(), n * 4); memcpy(parent, t.parent.data(), n * 4);
+  memcpy(split_feature, t.feature.data(), n * 4); memcpy(split_bin, t.split_bin.data(), n * 4);
+  memcpy(split_cond, t.cond.data(), n * 4); memcpy(default_left, t.default_left.data(), n);
+  memcpy(value, t.value.data(), n * 4); memcpy(base_weight, t.base_weight.data(), n * 4);
+  memcpy(loss_chg, t.loss_chg.data(), n * 4); memcpy(sum_hess, t.sum_hess.data(), n * 8);
+  API_END
+}
+int B2_BoosterAddTree(B2Handle bh, int32_t n_nodes, const int32_t* left, const int32_t* right, const int32_t* parent,
+                      const int32_t* split_feature, const int32_t* split_bin, const float* split_cond,
+                      const uint8_t* default_left, const float* value, const float* base_weight, const float* loss_chg,
+                      const double* sum_hess) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  if (n_nodes < 1) fail("a tree needs at least one node");
+  TreeHost t;
+  for (int i = 0; i < n_nodes; ++i) {
+    t.add(parent[i]);
+    if (left[i] >= n_nodes || right[i] >= n_nodes) fail("child index out of range in tree");
+    if (split_feature[i] >= b->n_features) fail("split feature %d out of range", split_feature[i]);
+    t.left[i] = left[i]; t.right[i] = right[i]; t.feature[i] = split_feature[i]; t.split_bin[i] = split_bin ? split_bin[i] : -1;
+    t.cond[i] = split_cond[i]; t.default_left[i] = default_left[i]; t.value[i] = value[i];
+    t.base_weight[i] = base_weight ? base_weight[i] : 0.f; t.loss_chg[i] = loss_chg ? loss_chg[i] : 0.f;
+    t.sum_hess[i] = sum_hess ? sum_hess[i] : 0.0;
+  }
+  b->trees.push_back(std::move(t));
+  b->margin_ready = false;
+  API_END
+}
+int B2_BoosterGetTimers(B2Handle bh, int32_t reset, char* out, int64_t out_cap) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  const Timers& t = b->t;
+  snprintf(out, (size_t)out_cap,
+           "{\"hist_ms\": %.6f, \"hist_launches\": %lld, \"hist_rows\": %lld, \"hist_bytes\": %.1f, \"kernel_launches\": %lld, "
+           "\"round_ms\": %.6f, \"rounds\": %lld, \"allreduce_bytes\": %.1f, \"num_sms\": %d, \"n_groups\": %d, \"row_stride\": %d}",
+           t.hist_ms, t.hist_launches, t.hist_rows, t.hist_bytes, t.kernel_launches, t.round_ms, t.rounds, t.allreduce_bytes,
+           b->ctx->num_sms, b->train ? b->train->n_groups : 0, b->train ? b->train->row_stride : 0);
+  if (reset) b->t.reset();
+  API_END
+}
+int B2_BoosterCancel(B2Handle bh) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  b->cancel.store(true);
+  API_END
+}
+int B2_BoosterFree(B2Handle bh) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  cudaSetDevice(b->ctx->device);
+  delete b;
+  API_END
+}
+
+int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const int32_t* qg, const int32_t* qh,
+                    const int32_t* ridx, int64_t n_sel, int32_t window_rows, int32_t chunk_rows, int device, int64_t* out,
+                    float* kernel_ms) {
+  API_BEGIN
+  Ctx* ctx = get_ctx(device); cudaStream_t s = ctx->stream;
+  Matrix m; m.kind = kMatrix; m.ctx = ctx; m.n = n_rows; m.F = n_cols;
+  setup_groups(&m);
+  std::vector<uint8_t> padded((size_t)std::max<int64_t>(n_rows, 1) * m.row_stride, 0);
+  for (int64_t i = 0; i < n_rows; ++i)
+    for (int f = 0; f < n_cols; ++f) padded[(size_t)i * m.row_stride + m.feat_byte[f]] = bins[i * n_cols + f];
+  std::vector<int2> gp((size_t)std::max<int64_t>(n_rows, 1));
+  for (int64_t i = 0; i < n_rows; ++i) gp[i] = make_int2(qg[i], qh[i]);
+  DevBuf<uint8_t> d_bins; DevBuf<int2> d_gp; DevBuf<int32_t> d_ridx; DevBuf<long long> d_hist; DevBuf<B2HistWork> d_work;
+  d_bins.ensure(padded.size()); d_gp.ensure(gp.size());
+  CUDA_CHECK(cudaMemcpyAsync(d_bins.p, padded.data(), padded.size(), cudaMemcpyHostToDevice, s));
+  CUDA_CHECK(cudaMemcpyAsync(d_gp.p, gp.data(), gp.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+  if (ridx) {
+    d_ridx.ensure((size_t)std::max<int64_t>(n_sel, 1));
+    if (n_sel > 0) CUDA_CHECK(cudaMemcpyAsync(d_ridx.p, ridx, n_sel * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  }
+  const size_t node_elems = (size_t)m.n_groups * B2_GROUP_ELEMS;
+  d_hist.ensure(node_elems);
+  CUDA_CHECK(cudaMemsetAsync(d_hist.p, 0, node_elems * sizeof(long long), s));
+  if (chunk_rows <= 0) chunk_rows = 2048;
+  if (window_rows <= 0) window_rows = 8192;
+  B2HistWork w{0, (int32_t)n_sel, 0, 0};
+  d_work.ensure(1);
+  CUDA_CHECK(cudaMemcpyAsync(d_work.p, &w, sizeof(w), cudaMemcpyHostToDevice, s));
+  const int chunks = (int)((n_sel + chunk_rows - 1) / chunk_rows);
+  cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, s));
+  if (n_sel > 0)
+    LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
+                                window_rows, m.n_groups, d_hist.p, ctx->num_sms, s));
+  CUDA_CHECK(cudaEventRecord(e1, s));
+  std::vector<long long> h(node_elems);
+  CUDA_CHECK(cudaMemcpyAsync(h.data(), d_hist.p, node_elems * sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (kernel_ms) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); *kernel_ms = ms; }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  for (int f = 0; f < n_cols; ++f) {
+    const int g = m.feat_byte[f] / B2_GROUP_SLOTS, sl = m.feat_byte[f] % B2_GROUP_SLOTS;
+    for (int bb = 0; bb < 256; ++bb) {
+      out[((size_t)f * 256 + bb) * 2] = h[(size_t)g * B2_GROUP_ELEMS + bb * 32 + sl];
+      out[((size_t)f * 256 + bb) * 2 + 1] = h[(size_t)g * B2_GROUP_ELEMS + B2_PLANE_ELEMS + bb * 32 + sl];
+    }
+  }
+  API_END
+}
+
+}  // extern "C"

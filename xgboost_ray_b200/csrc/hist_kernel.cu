@@ -1,0 +1,206 @@
+// hist_kernel.cu -- feature x bin gradient/hessian histogram build for sm_100a.
+//
+// Replaces the BuildHist stage that the reference reaches through xgb.train()
+// (xgboost_ray/main.py:745-752).  Bandwidth-bound scatter-reduce:
+// no tensor cores.  Design (DESIGN.md "Histogram kernel"):
+//
+//  * A CTA owns ONE feature group (<= 32 features -> 32 "slots") of ONE node at a time and keeps
+//    its histogram in shared memory as two int32 planes [256 bins][32 slots] (g and h): 64 KiB, so
+//    three CTAs are resident per SM.  Because a bin row is exactly 32 words, the bank of an update
+//    is its SLOT and does not depend on the bin value.
+//  * A lane loads 16 bin bytes of one row (LDG.128 straight to registers; staging rows through
+//    shared memory would spend the shared-memory bandwidth that the atomics are bound by).  Two
+//    lanes cover the 32-byte group slice of a row, 16 rows per warp.  Lane l pre-rotates its bytes
+//    by (l>>1) so that at step j the 32 lanes of a warp touch 32 DIFFERENT slots: every ATOMS.ADD
+//    is bank-conflict free for any data, one wavefront per instruction.
+//  * Sums are exact integers (fixed-point gradients), so the result is independent of the order
+//    of rows, CTAs and GPUs.  A CTA flushes its planes to the global int64 histogram when it moves
+//    to another node or before `window_rows` rows could overflow an int32 cell.
+//  * Rows of a node are addressed through the row-index segment list (gather) except at the root.
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kHistThreads = 256;
+constexpr int kRowsPerWarpIter = 16;
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, int v) {
+  asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+// result byte i = source byte (i + rot) & 15
+__device__ __forceinline__ uint4 rotate_bytes(uint4 v, int rot) {
+  uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+  if (rot & 4) { uint32_t t = w0; w0 = w1; w1 = w2; w2 = w3; w3 = t; }
+  if (rot & 8) { uint32_t t0 = w0, t1 = w1; w0 = w2; w1 = w3; w2 = t0; w3 = t1; }
+  int bs = (rot & 3) * 8;
+  uint4 r;
+  r.x = __funnelshift_r(w0, w1, bs);
+  r.y = __funnelshift_r(w1, w2, bs);
+  r.z = __funnelshift_r(w2, w3, bs);
+  r.w = __funnelshift_r(w3, w0, bs);
+  return r;
+}
+
+struct RowData {
+  uint4 bins;
+  int2 gp;
+};
+
+template <bool kGather>
+__device__ __forceinline__ RowData load_row(const uint8_t* __restrict__ bins, const int2* __restrict__ gpair,
+                                            const int32_t* __restrict__ ridx, int64_t pos, bool valid,
+                                            int row_stride, int lane_byte_off) {
+  RowData d;
+  d.bins = make_uint4(0, 0, 0, 0);
+  d.gp = make_int2(0, 0);
+  if (valid) {
+    int64_t rid = kGather ? (int64_t)__ldg(ridx + pos) : pos;
+    d.bins = ldg_nc_v4(bins + rid * row_stride + lane_byte_off);
+    d.gp = __ldg(gpair + rid);
+  }
+  return d;
+}
+
+// 16 steps: one byte (= one feature slot) per step, two conflict-free shared atomics per step
+__device__ __forceinline__ void accumulate_row(const RowData& d, uint32_t smem_g, int rot, int half) {
+  uint4 b = rotate_bytes(d.bins, rot);
+  const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+  const uint32_t base = smem_g + half * 64;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint32_t bin = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+    uint32_t slot_off = ((uint32_t)(j + rot) & 15u) * 4u;
+    uint32_t a = base + bin * (B2_GROUP_SLOTS * 4) + slot_off;
+    red_shared_add(a, d.gp.x);
+    red_shared_add(a + B2_PLANE_ELEMS * 4, d.gp.y);
+  }
+}
+
+__device__ __forceinline__ void flush_planes(int32_t* s_hist, unsigned long long* out_g) {
+  // out layout for this (node, group): [2][256][32] int64 == same index space as the smem planes
+  for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) {
+    int v = s_hist[e];
+    if (v != 0) {
+      atomicAdd(out_g + e, (unsigned long long)(long long)v);
+      s_hist[e] = 0;
+    }
+  }
+}
+
+template <bool kGather>
+__global__ void __launch_bounds__(kHistThreads, 3)
+hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                  const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
+                  int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist) {
+  extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][32]
+  __shared__ int s_cur_work;
+  const int group = blockIdx.x % n_groups;
+  const int stream = blockIdx.x / n_groups;
+  const int n_streams = gridDim.x / n_groups;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int rot = lane >> 1, half = lane & 1;
+  const int lane_byte_off = group * 32 + half * 16;
+  const uint32_t smem_g = (uint32_t)__cvta_generic_to_shared(s_hist);
+
+  for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) s_hist[e] = 0;
+  __syncthreads();
+
+  int cur = -1;          // work index whose partial sums are in shared memory
+  int rows_in_window = 0;
+  for (int chunk = stream; chunk < total_chunks; chunk += n_streams) {
+    // locate the node of this chunk (uniform across the CTA): last w with chunk_begin <= chunk
+    int lo = 0, hi = n_work - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const int w = lo;
+    const int seg_begin = __ldg(&work[w].seg_begin), seg_count = __ldg(&work[w].seg_count);
+    const int row0 = (chunk - __ldg(&work[w].chunk_begin)) * chunk_rows;
+    const int nrows = min(chunk_rows, seg_count - row0);
+    if (cur >= 0 && (w != cur || rows_in_window + nrows > window_rows)) {
+      __syncthreads();
+      flush_planes(s_hist, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
+      __syncthreads();
+      rows_in_window = 0;
+    }
+    cur = w;
+    rows_in_window += nrows;
+    const int64_t pos0 = (int64_t)seg_begin + row0;
+    const int iter_rows = n_warps * kRowsPerWarpIter;
+    int r = warp * kRowsPerWarpIter + rot;
+    RowData d = load_row<kGather>(bins, gpair, ridx, pos0 + r, r < nrows, row_stride, lane_byte_off);
+    for (; r - rot < nrows; r += iter_rows) {   // warp-uniform trip count
+      const int rn = r + iter_rows;
+      RowData nx = load_row<kGather>(bins, gpair, ridx, pos0 + rn, rn < nrows, row_stride, lane_byte_off);
+      accumulate_row(d, smem_g, rot, half);
+      d = nx;
+    }
+  }
+  if (cur >= 0) {
+    __syncthreads();
+    flush_planes(s_hist, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
+  }
+  (void)s_cur_work;
+}
+
+// ---------------------------------------------------------------- sibling = parent - built
+__global__ void hist_subtract_kernel(const long long* __restrict__ parent_level, long long* __restrict__ level,
+                                     const int32_t* __restrict__ triples, int n_pairs, int64_t node_elems) {
+  // triples[3*p] = parent slot (prev level), built slot, sibling slot (this level)
+  const int p = blockIdx.y;
+  if (p >= n_pairs) return;
+  const long long* par = parent_level + (size_t)triples[3 * p] * node_elems;
+  const long long* built = level + (size_t)triples[3 * p + 1] * node_elems;
+  long long* sib = level + (size_t)triples[3 * p + 2] * node_elems;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < node_elems; i += (int64_t)gridDim.x * blockDim.x)
+    sib[i] = par[i] - built[i];
+}
+
+}  // namespace b2
+
+extern "C" {
+
+// Launch on `stream`.  grid = n_groups * n_streams persistent CTAs; returns the cudaError.
+int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const int32_t* ridx,
+                   const B2HistWork* work, int n_work, int total_chunks, int chunk_rows, int window_rows,
+                   int n_groups, long long* hist, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  const int smem = B2_GROUP_ELEMS * (int)sizeof(int32_t);  // 64 KiB
+  if (!attr_set) {
+    cudaFuncSetAttribute(b2::hist_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(b2::hist_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  if (total_chunks <= 0 || n_work <= 0) return 0;
+  int n_streams = (num_sms * 3) / n_groups;
+  if (n_streams < 1) n_streams = 1;
+  if (n_streams > total_chunks) n_streams = total_chunks;
+  dim3 grid(n_groups * n_streams), block(b2::kHistThreads);
+  if (ridx)
+    b2::hist_build_kernel<true><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
+                                                              chunk_rows, window_rows, n_groups, hist);
+  else
+    b2::hist_build_kernel<false><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
+                                                               chunk_rows, window_rows, n_groups, hist);
+  return (int)cudaGetLastError();
+}
+
+int b2_launch_hist_subtract(const long long* parent_level, long long* level, const int32_t* triples, int n_pairs,
+                            int64_t node_elems, cudaStream_t stream) {
+  if (n_pairs <= 0) return 0;
+  int bx = (int)((node_elems + 256 * 8 - 1) / (256 * 8));
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n_pairs);
+  b2::hist_subtract_kernel<<<grid, 256, 0, stream>>>(parent_level, level, triples, n_pairs, node_elems);
+  return (int)cudaGetLastError();
+}
+}

@@ -1,0 +1,250 @@
+// objective_kernel.cu -- objective gradients, fixed-point quantisation, metrics, tree traversal.
+//
+// Replaces the objective / metric / predictor stages that the reference reaches through
+// xgb.train() and Booster.predict() (xgboost_ray/main.py:745-752, 804; SURVEY.md 8a rows a9, a14;
+// Appendix A.4, A.9, A.10).  Compiled with --fmad=false: b2_expf below is a fixed sequence of
+// IEEE-754 binary32 mul/add, replayed identically by the CPU oracle, so gradients are bit-equal.
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ float b2_expf(float x) {
+  if (x > 88.7f) x = 88.7f;
+  if (x < -103.0f) return 0.0f;
+  const float log2e = 1.44269504088896341f;
+  const float ln2_hi = 0.693359375f;
+  const float ln2_lo = -2.12194440e-4f;
+  float t = __fmul_rn(x, log2e);
+  float n = rintf(t);
+  float r = __fadd_rn(x, -__fmul_rn(n, ln2_hi));
+  r = __fadd_rn(r, -__fmul_rn(n, ln2_lo));
+  float p = 1.9875691500e-4f;
+  p = __fadd_rn(__fmul_rn(p, r), 1.3981999507e-3f);
+  p = __fadd_rn(__fmul_rn(p, r), 8.3334519073e-3f);
+  p = __fadd_rn(__fmul_rn(p, r), 4.1665795894e-2f);
+  p = __fadd_rn(__fmul_rn(p, r), 1.6666665459e-1f);
+  p = __fadd_rn(__fmul_rn(p, r), 5.0000001201e-1f);
+  float r2 = __fmul_rn(r, r);
+  float e = __fadd_rn(__fmul_rn(p, r2), r);
+  e = __fadd_rn(e, 1.0f);
+  int ni = (int)n;
+  int n1 = ni / 2, n2 = ni - n1;
+  e = __fmul_rn(e, __uint_as_float((uint32_t)(n1 + 127) << 23));
+  e = __fmul_rn(e, __uint_as_float((uint32_t)(n2 + 127) << 23));
+  return e;
+}
+__device__ __forceinline__ float b2_sigmoid(float x) {
+  float nx = -x;
+  if (nx > 88.7f) nx = 88.7f;
+  float denom = __fadd_rn(b2_expf(nx), 1.0f);
+  denom = __fadd_rn(denom, 1e-16f);
+  return __fdiv_rn(1.0f, denom);
+}
+
+// gh layout: class-major [K][n] float2 so that each class tree reads a contiguous slice
+__global__ void gradient_kernel(int objective, int K, const float* __restrict__ margin, const float* __restrict__ label,
+                                const float* __restrict__ weight, int64_t n, float2* __restrict__ gh) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float w = weight ? weight[i] : 1.0f;
+    if (objective == 0) {
+      gh[i] = make_float2(__fmul_rn(__fadd_rn(margin[i], -label[i]), w), w);
+    } else if (objective == 1) {
+      const float p = b2_sigmoid(margin[i]);
+      float hh = __fmul_rn(p, __fadd_rn(1.0f, -p));
+      if (hh < 1e-16f) hh = 1e-16f;
+      gh[i] = make_float2(__fmul_rn(__fadd_rn(p, -label[i]), w), __fmul_rn(hh, w));
+    } else {
+      const float* m = margin + i * K;
+      float mx = m[0];
+      for (int k = 1; k < K; ++k) if (m[k] > mx) mx = m[k];
+      float s = 0.0f;
+      for (int k = 0; k < K; ++k) s = __fadd_rn(s, b2_expf(__fadd_rn(m[k], -mx)));
+      const int y = (int)label[i];
+      for (int k = 0; k < K; ++k) {
+        const float p = __fdiv_rn(b2_expf(__fadd_rn(m[k], -mx)), s);
+        float hh = __fmul_rn(__fmul_rn(2.0f, p), __fadd_rn(1.0f, -p));
+        if (hh < 1e-16f) hh = 1e-16f;
+        const float g = (k == y) ? __fadd_rn(p, -1.0f) : p;
+        gh[(int64_t)k * n + i] = make_float2(__fmul_rn(g, w), __fmul_rn(hh, w));
+      }
+    }
+  }
+}
+
+// interleave user-supplied gradients (custom objective): g,h row-major [n][K] -> gh [K][n]
+__global__ void pack_custom_kernel(const float* __restrict__ g, const float* __restrict__ h, int K, int64_t n,
+                                   float2* __restrict__ gh) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * K; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / K; const int k = (int)(i % K);
+    gh[(int64_t)k * n + row] = make_float2(g[i], h[i]);
+  }
+}
+
+// absmax[0] = max|g|, absmax[1] = max|h| as float bit patterns (non-negative floats order as uints)
+__global__ void absmax_kernel(const float2* __restrict__ gh, int64_t n, uint32_t* __restrict__ absmax) {
+  float mg = 0.0f, mh = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = gh[i];
+    mg = fmaxf(mg, fabsf(v.x)); mh = fmaxf(mh, fabsf(v.y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+    mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&absmax[0], __float_as_uint(mg));
+    atomicMax(&absmax[1], __float_as_uint(mh));
+  }
+}
+
+// exponent e with vmax < 2^e (frexp convention), q = rint(v * 2^(qbits - e))
+__device__ __forceinline__ int frexp_exponent(uint32_t bits) {
+  if (bits == 0) return 0;
+  return (int)((bits >> 23) & 0xffu) - 126;
+}
+__global__ void quant_exponent_kernel(const uint32_t* __restrict__ absmax, int32_t* __restrict__ qexp) {
+  if (threadIdx.x < 2) qexp[threadIdx.x] = frexp_exponent(absmax[threadIdx.x]);
+}
+__global__ void quantize_kernel(const float2* __restrict__ gh, int64_t n, const int32_t* __restrict__ qexp, int qbits,
+                                int2* __restrict__ q) {
+  const float sg = ldexpf(1.0f, qbits - qexp[0]), sh = ldexpf(1.0f, qbits - qexp[1]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = gh[i];
+    q[i] = make_int2((int)rintf(__fmul_rn(v.x, sg)), (int)rintf(__fmul_rn(v.y, sh)));
+  }
+}
+
+// metric sums (sum loss*w, sum w) -> out[2] doubles; metric: 0 rmse 1 logloss 2 error 3 mlogloss 4 merror
+__global__ void metric_kernel(int metric, int K, const float* __restrict__ margin, const float* __restrict__ label,
+                              const float* __restrict__ weight, int64_t n, double* __restrict__ out) {
+  double s = 0.0, ws = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double w = weight ? (double)weight[i] : 1.0;
+    double v = 0.0;
+    if (metric == 0) { const double d = (double)margin[i] - (double)label[i]; v = d * d; }
+    else if (metric == 1) {
+      const float p = b2_sigmoid(margin[i]); const float eps = 1e-16f; const float y = label[i];
+      const float pn = 1.0f - p; const float a = p < eps ? eps : p, b = pn < eps ? eps : pn;
+      v = -((double)y * log((double)a) + (1.0 - (double)y) * log((double)b));
+    } else if (metric == 2) { const float p = b2_sigmoid(margin[i]); v = ((p > 0.5f) != (label[i] > 0.5f)) ? 1.0 : 0.0; }
+    else {
+      const float* r = margin + i * K; const int y = (int)label[i]; float mx = r[0]; int am = 0;
+      for (int k = 1; k < K; ++k) if (r[k] > mx) { mx = r[k]; am = k; }
+      if (metric == 4) v = (am != y) ? 1.0 : 0.0;
+      else {
+        float ssum = 0.0f;
+        for (int k = 0; k < K; ++k) ssum = __fadd_rn(ssum, b2_expf(__fadd_rn(r[k], -mx)));
+        float p = __fdiv_rn(b2_expf(__fadd_rn(r[y], -mx)), ssum);
+        if (p < 1e-16f) p = 1e-16f;
+        v = -log((double)p);
+      }
+    }
+    s += v * w; ws += w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ws += __shfl_xor_sync(0xffffffffu, ws, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], ws); }
+}
+
+// A.9 traversal on raw floats: x < cond -> left, missing -> default.  nodes of all trees are
+// concatenated; tree_offset[t] is the first node of tree t; tree t adds to class t % K.
+__global__ void predict_kernel(const float* __restrict__ X, int64_t n, int F, float missing, int missing_is_nan,
+                               const B2TreeNodeDev* __restrict__ nodes, const int32_t* __restrict__ tree_offset,
+                               int tree_begin, int tree_end, int K, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* x = X + i * F;
+    for (int t = tree_begin; t < tree_end; ++t) {
+      const B2TreeNodeDev* tn = nodes + tree_offset[t];
+      int nid = 0;
+      B2TreeNodeDev nd = tn[0];
+      while (nd.feature >= 0) {
+        const float v = x[nd.feature];
+        const bool miss = isnan(v) || (!missing_is_nan && v == missing);
+        nid = miss ? (nd.default_left ? nd.left : nd.right) : (v < nd.cond ? nd.left : nd.right);
+        nd = tn[nid];
+      }
+      out[i * K + (t % K)] += nd.value;
+    }
+  }
+}
+
+__global__ void fill_kernel(float* out, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
+}
+
+// margin -> prediction transform in place (sigmoid / softmax)
+__global__ void transform_kernel(int objective, int K, float* __restrict__ m, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (objective == 1) m[i] = b2_sigmoid(m[i]);
+    else if (objective == 2) {
+      float* r = m + i * K; float mx = r[0];
+      for (int k = 1; k < K; ++k) if (r[k] > mx) mx = r[k];
+      float s = 0.0f;
+      for (int k = 0; k < K; ++k) { r[k] = b2_expf(__fadd_rn(r[k], -mx)); s = __fadd_rn(s, r[k]); }
+      for (int k = 0; k < K; ++k) r[k] = __fdiv_rn(r[k], s);
+    }
+  }
+}
+
+}  // namespace b2
+
+static inline int grid_for(int64_t n, int num_sms) {
+  int64_t g = (n + 255) / 256;
+  int64_t cap = (int64_t)num_sms * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" {
+int b2_launch_gradient(int objective, int K, const float* margin, const float* label, const float* weight, int64_t n,
+                       float2* gh, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::gradient_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, K, margin, label, weight, n, gh);
+  return (int)cudaGetLastError();
+}
+int b2_launch_pack_custom(const float* g, const float* h, int K, int64_t n, float2* gh, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::pack_custom_kernel<<<grid_for(n * K, num_sms), 256, 0, s>>>(g, h, K, n, gh);
+  return (int)cudaGetLastError();
+}
+int b2_launch_absmax(const float2* gh, int64_t n, uint32_t* absmax, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::absmax_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(gh, n, absmax);
+  return (int)cudaGetLastError();
+}
+int b2_launch_quant_exponent(const uint32_t* absmax, int32_t* qexp, cudaStream_t s) {
+  b2::quant_exponent_kernel<<<1, 32, 0, s>>>(absmax, qexp);
+  return (int)cudaGetLastError();
+}
+int b2_launch_quantize(const float2* gh, int64_t n, const int32_t* qexp, int qbits, int2* q, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::quantize_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(gh, n, qexp, qbits, q);
+  return (int)cudaGetLastError();
+}
+int b2_launch_metric(int metric, int K, const float* margin, const float* label, const float* weight, int64_t n,
+                     double* out, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::metric_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(metric, K, margin, label, weight, n, out);
+  return (int)cudaGetLastError();
+}
+int b2_launch_predict(const float* X, int64_t n, int F, float missing, const B2TreeNodeDev* nodes,
+                      const int32_t* tree_offset, int tree_begin, int tree_end, int K, float* out, int num_sms,
+                      cudaStream_t s) {
+  if (n <= 0 || tree_end <= tree_begin) return 0;
+  b2::predict_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(X, n, F, missing, missing != missing ? 1 : 0, nodes, tree_offset,
+                                                         tree_begin, tree_end, K, out);
+  return (int)cudaGetLastError();
+}
+int b2_launch_fill(float* out, int64_t n, float v, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::fill_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(out, n, v);
+  return (int)cudaGetLastError();
+}
+int b2_launch_transform(int objective, int K, float* m, int64_t n, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::transform_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, K, m, n);
+  return (int)cudaGetLastError();
+}
+}

@@ -1,0 +1,180 @@
+// partition_kernel.cu -- row partition (UpdatePosition), leaf sums and prediction-cache update.
+//
+// Replaces XGBoost's ApplySplit/UpdatePosition and UpdatePredictionCache stages reached through
+// xgb.train() (xgboost_ray/main.py:745-752; Appendix A.8/A.9).
+// Rows of a node live in a contiguous segment of a row-index list; a split rewrites the segment
+// as [left rows | right rows] into the other (ping-pong) list.  Histogram sums are exact integers,
+// so the order of rows inside a child segment is irrelevant to the model.
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kPartThreads = 256;
+constexpr int kPartChunk = 2048;  // rows per CTA work item
+
+struct SegWork {  // generic (segment, id) descriptor, chunked
+  int32_t seg_begin, seg_count, id, chunk_begin;
+  int32_t buf, pad0, pad1, pad2;
+};
+
+__global__ void __launch_bounds__(kPartThreads)
+partition_kernel(const uint8_t* __restrict__ bins, int row_stride, const int32_t* __restrict__ ridx_in,
+                 int32_t* __restrict__ ridx_out, const B2SplitWork* __restrict__ work, int n_work, int total_chunks,
+                 int32_t* __restrict__ counters /* [2*n_work]: left, right */) {
+  __shared__ int s_warp_left[kPartThreads / 32][kPartChunk / kPartThreads];
+  __shared__ int s_base_left, s_base_right;
+  __shared__ int s_pref[kPartThreads / 32][kPartChunk / kPartThreads];
+  constexpr int kIters = kPartChunk / kPartThreads;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = n_work - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const B2SplitWork w = work[lo];
+    const int row0 = (chunk - w.chunk_begin) * kPartChunk;
+    const int nrows = min(kPartChunk, w.seg_count - row0);
+    int rid[kIters]; bool left[kIters]; unsigned bal[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int r = it * kPartThreads + threadIdx.x;
+      const bool valid = r < nrows;
+      rid[it] = valid ? __ldg(ridx_in + w.seg_begin + row0 + r) : 0;
+      int b = valid ? (int)bins[(int64_t)rid[it] * row_stride + w.feature_byte] : 0;
+      bool l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : (b <= w.split_bin);
+      left[it] = valid && l;
+      bal[it] = __ballot_sync(0xffffffffu, left[it]);
+      if (lane == 0) s_warp_left[warp][it] = __popc(bal[it]);
+    }
+    __syncthreads();
+    // exclusive prefix over (it, warp) in row order: index = it*8 + warp
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int it = 0; it < kIters; ++it)
+        for (int wp = 0; wp < kPartThreads / 32; ++wp) { s_pref[wp][it] = acc; acc += s_warp_left[wp][it]; }
+      s_base_left = atomicAdd(&counters[2 * lo], acc);
+      s_base_right = atomicAdd(&counters[2 * lo + 1], nrows - acc);
+    }
+    __syncthreads();
+    const int base_l = s_base_left, base_r = s_base_right;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int r = it * kPartThreads + threadIdx.x;
+      if (r < nrows) {
+        const int lrank = s_pref[warp][it] + __popc(bal[it] & ((1u << lane) - 1u));
+        if (left[it]) ridx_out[w.seg_begin + base_l + lrank] = rid[it];
+        else {
+          const int rrank = r - lrank;  // rights before this row inside the chunk
+          ridx_out[w.seg_begin + w.seg_count - 1 - (base_r + rrank)] = rid[it];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- leaf refinement: 40-bit fixed-point sums of the fp32 gradients per leaf (exact int64)
+__global__ void __launch_bounds__(256)
+leaf_sums_kernel(const float2* __restrict__ gh, const int32_t* __restrict__ ridx0, const int32_t* __restrict__ ridx1,
+                 const SegWork* __restrict__ work, int n_work, int total_chunks, const int32_t* __restrict__ qexp,
+                 int leaf_bits, long long* __restrict__ sums /* [n_leaves][2] */) {
+  __shared__ long long sg[8], sh[8];
+  const double kg = ldexp(1.0, leaf_bits - qexp[0]), kh = ldexp(1.0, leaf_bits - qexp[1]);
+  for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = n_work - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const SegWork w = work[lo];
+    const int32_t* ridx = w.buf ? ridx1 : ridx0;
+    const int row0 = (chunk - w.chunk_begin) * kPartChunk;
+    const int nrows = min(kPartChunk, w.seg_count - row0);
+    long long ag = 0, ah = 0;
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+      const int row = ridx ? __ldg(ridx + w.seg_begin + row0 + r) : (w.seg_begin + row0 + r);
+      const float2 v = __ldg(gh + row);
+      ag += __double2ll_rn(__dmul_rn((double)v.x, kg));
+      ah += __double2ll_rn(__dmul_rn((double)v.y, kh));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ag += __shfl_xor_sync(0xffffffffu, ag, o); ah += __shfl_xor_sync(0xffffffffu, ah, o); }
+    if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = ag; sh[threadIdx.x >> 5] = ah; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long tg = 0, th = 0;
+      for (int i = 0; i < 8; ++i) { tg += sg[i]; th += sh[i]; }
+      atomicAdd((unsigned long long*)&sums[2 * w.id], (unsigned long long)tg);
+      atomicAdd((unsigned long long*)&sums[2 * w.id + 1], (unsigned long long)th);
+    }
+    __syncthreads();
+  }
+}
+
+// margin[row*K + k] += leaf_value[leaf]
+__global__ void __launch_bounds__(256)
+pred_update_kernel(float* __restrict__ margin, int K, int k, const int32_t* __restrict__ ridx0,
+                   const int32_t* __restrict__ ridx1, const SegWork* __restrict__ work, int n_work, int total_chunks,
+                   const float* __restrict__ leaf_value) {
+  for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = n_work - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const SegWork w = work[lo];
+    const int32_t* ridx = w.buf ? ridx1 : ridx0;
+    const int row0 = (chunk - w.chunk_begin) * kPartChunk;
+    const int nrows = min(kPartChunk, w.seg_count - row0);
+    const float v = __ldg(leaf_value + w.id);
+    for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+      const int64_t row = ridx ? __ldg(ridx + w.seg_begin + row0 + r) : (w.seg_begin + row0 + r);
+      margin[row * K + k] += v;
+    }
+  }
+}
+
+__global__ void iota_kernel(int32_t* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (int32_t)i;
+}
+
+}  // namespace b2
+
+extern "C" {
+int b2_part_chunk_rows() { return b2::kPartChunk; }
+
+int b2_launch_partition(const uint8_t* bins, int row_stride, const int32_t* ridx_in, int32_t* ridx_out,
+                        const B2SplitWork* work, int n_work, int total_chunks, int32_t* counters, int num_sms,
+                        cudaStream_t stream) {
+  if (total_chunks <= 0) return 0;
+  int grid = total_chunks < num_sms * 8 ? total_chunks : num_sms * 8;
+  b2::partition_kernel<<<grid, b2::kPartThreads, 0, stream>>>(bins, row_stride, ridx_in, ridx_out, work, n_work,
+                                                             total_chunks, counters);
+  return (int)cudaGetLastError();
+}
+int b2_launch_leaf_sums(const float2* gh, const int32_t* ridx0, const int32_t* ridx1, const void* work, int n_work,
+                        int total_chunks, const int32_t* qexp, int leaf_bits, long long* sums, int num_sms,
+                        cudaStream_t stream) {
+  if (total_chunks <= 0) return 0;
+  int grid = total_chunks < num_sms * 8 ? total_chunks : num_sms * 8;
+  b2::leaf_sums_kernel<<<grid, 256, 0, stream>>>(gh, ridx0, ridx1, (const b2::SegWork*)work, n_work, total_chunks, qexp,
+                                                leaf_bits, sums);
+  return (int)cudaGetLastError();
+}
+int b2_launch_pred_update(float* margin, int K, int k, const int32_t* ridx0, const int32_t* ridx1, const void* work,
+                          int n_work, int total_chunks, const float* leaf_value, int num_sms, cudaStream_t stream) {
+  if (total_chunks <= 0) return 0;
+  int grid = total_chunks < num_sms * 8 ? total_chunks : num_sms * 8;
+  b2::pred_update_kernel<<<grid, 256, 0, stream>>>(margin, K, k, ridx0, ridx1, (const b2::SegWork*)work, n_work,
+                                                  total_chunks, leaf_value);
+  return (int)cudaGetLastError();
+}
+int b2_launch_iota(int32_t* out, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  int grid = (int)((n + 1023) / 1024);
+  if (grid > 4096) grid = 4096;
+  b2::iota_kernel<<<grid, 256, 0, stream>>>(out, n);
+  return (int)cudaGetLastError();
+}
+}

@@ -1,0 +1,205 @@
+// sketch.cu -- GPU quantile cuts and binning of an actor's RayDMatrix shard.
+//
+// Replaces the DMatrix quantisation the reference triggers at xgboost_ray/main.py:386/418/437
+// (Appendix A.2).  Per feature: order-preserving uint32 keys of the
+// (global) column are radix sorted (cub::DeviceRadixSort -- library sort, one-time preprocessing),
+// the exact distinct-value summary (value, rmin, rmax as int64 ranks) is built, XGBoost's
+// WQSummary::SetPrune selection rule is evaluated with one thread per target rank, and the cut
+// values are emitted.  Binning is bin = upper_bound(cuts_f, x) into the padded group-major row
+// layout used by the histogram kernel.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ bool is_missing(float x, float missing, int missing_is_nan) {
+  return isnan(x) || (!missing_is_nan && x == missing);
+}
+
+__global__ void extract_keys_kernel(const float* __restrict__ X, int64_t n, int F, int f, float missing,
+                                    int missing_is_nan, uint32_t* __restrict__ keys, int64_t n_padded,
+                                    unsigned long long* __restrict__ n_missing) {
+  unsigned long long cnt = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t k = 0xffffffffu;
+    if (i < n) {
+      float x = X[i * F + f];
+      if (is_missing(x, missing, missing_is_nan)) cnt++;
+      else { if (x == 0.0f) x = 0.0f; k = f2key(x); }
+    }
+    keys[i] = k;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_missing, cnt);
+}
+
+__global__ void head_flags_kernel(const uint32_t* __restrict__ keys, int64_t n_valid, int32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_valid; i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+__global__ void scatter_unique_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ flags,
+                                      const int32_t* __restrict__ idx, int64_t n_valid, float* __restrict__ uval,
+                                      long long* __restrict__ rmin, int32_t* __restrict__ m_out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_valid; i += (int64_t)gridDim.x * blockDim.x) {
+    if (flags[i]) { uval[idx[i]] = key2f(keys[i]); rmin[idx[i]] = i; }
+    if (i == n_valid - 1) *m_out = idx[i] + flags[i];
+  }
+}
+
+// One block.  WQSummary::SetPrune + HistogramCuts::AddCutPoint on the exact summary (A.2).
+__global__ void __launch_bounds__(256)
+prune_cuts_kernel(const float* __restrict__ uval, const long long* __restrict__ rmin, const int32_t* __restrict__ m_ptr,
+                  long long n_valid, int max_bin_cap, float* __restrict__ cut_out /*[256]*/, int32_t* __restrict__ n_cut_out,
+                  float* __restrict__ min_out) {
+  __shared__ int sel[260];
+  __shared__ int choice[260];
+  const int m = n_valid > 0 ? *m_ptr : 0;
+  if (m == 0) {
+    if (threadIdx.x == 0) {
+      float mval = 0.0f;
+      float mn = __fadd_rn(__fadd_rn(mval, -fabsf(mval)), -1e-5f);
+      *min_out = mn;
+      cut_out[0] = __fadd_rn(mn, __fadd_rn(fabsf(mn), 1e-5f));
+      *n_cut_out = 1;
+    }
+    return;
+  }
+  const int max_num_bins = m < max_bin_cap ? m : max_bin_cap;
+  const int maxsize = max_num_bins + 1;
+  int size = 0;
+  auto RMAX = [&](int u) -> long long { return (u + 1 < m) ? rmin[u + 1] : n_valid; };
+  if (m > maxsize) {
+    const double begin = (double)RMAX(0);
+    const double range = __dadd_rn((double)rmin[m - 1], -begin);
+    const int n = maxsize - 1;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      int c = -1;
+      if (k >= 1) {
+        const double dx2 = 2.0 * __dadd_rn(__ddiv_rn(__dmul_rn((double)k, range), (double)n), begin);
+        // i = 1 + #{ j in [2, m-1] : rmin[j]+rmax[j] <= dx2 }
+        int lo = 2, hi = m;  // first j in [2,m) with S(j) > dx2
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          double S = (double)(rmin[mid] + RMAX(mid));
+          if (dx2 >= S) lo = mid + 1; else hi = mid;
+        }
+        const int i = lo - 1;
+        if (i < m - 1) c = (dx2 < (double)(RMAX(i) + rmin[i + 1])) ? i : i + 1;
+      }
+      choice[k] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      sel[size++] = 0;
+      int lastidx = 0;
+      for (int k = 1; k < n; ++k) {
+        int c = choice[k];
+        if (c < 0) break;
+        if (c != lastidx) { sel[size++] = c; lastidx = c; }
+      }
+      if (lastidx != m - 1) sel[size++] = m - 1;
+    }
+  } else if (threadIdx.x == 0) {
+    for (int i = 0; i < m; ++i) sel[size++] = i;
+  }
+  if (threadIdx.x == 0) {
+    const float mval = uval[sel[0]];
+    *min_out = __fadd_rn(__fadd_rn(mval, -fabsf(mval)), -1e-5f);
+    const int required = size < max_num_bins ? size : max_num_bins;
+    int nc = 0;
+    for (int i = 1; i < required; ++i) {
+      const float cpt = uval[sel[i]];
+      if (i == 1 || cpt > cut_out[nc - 1]) cut_out[nc++] = cpt;
+    }
+    const float cpt = uval[sel[size - 1]];
+    cut_out[nc++] = __fadd_rn(cpt, __fadd_rn(fabsf(cpt), 1e-5f));
+    *n_cut_out = nc;
+  }
+}
+
+// bin = upper_bound(cuts_f, x) clamped; missing -> 255.  One thread per matrix element.
+__global__ void bin_kernel(const float* __restrict__ X, int64_t n, int F, float missing, int missing_is_nan,
+                           const int32_t* __restrict__ cut_ptrs, const float* __restrict__ cut_vals,
+                           const int32_t* __restrict__ feat_byte, int row_stride, uint8_t* __restrict__ bins) {
+  const int64_t total = n * F;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / F; const int f = (int)(e - row * F);
+    const float x = X[e];
+    int b;
+    if (is_missing(x, missing, missing_is_nan)) b = B2_MISSING_BIN;
+    else {
+      const int p0 = cut_ptrs[f], nf = cut_ptrs[f + 1] - p0;
+      const float* cv = cut_vals + p0;
+      int lo = 0, hi = nf;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(cv + mid) > x) hi = mid; else lo = mid + 1; }
+      b = lo >= nf ? nf - 1 : lo;
+    }
+    bins[row * row_stride + feat_byte[f]] = (uint8_t)b;
+  }
+}
+
+}  // namespace b2
+
+static inline int sk_grid(int64_t n, int num_sms) {
+  int64_t g = (n + 255) / 256, cap = (int64_t)num_sms * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" {
+
+int b2_launch_extract_keys(const float* X, int64_t n, int F, int f, float missing, uint32_t* keys, int64_t n_padded,
+                           unsigned long long* n_missing, int num_sms, cudaStream_t s) {
+  if (n_padded <= 0) return 0;
+  b2::extract_keys_kernel<<<sk_grid(n_padded, num_sms), 256, 0, s>>>(X, n, F, f, missing, missing != missing ? 1 : 0, keys,
+                                                                    n_padded, n_missing);
+  return (int)cudaGetLastError();
+}
+
+size_t b2_sort_temp_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, n);
+  return bytes > scan_bytes ? bytes : scan_bytes;
+}
+
+// keys_in [n_total] (any order, 0xffffffff = missing/padding) -> cuts of one feature.
+// Scratch: keys_sorted [n_total], flags/idx int32 [n_total], uval float [n_total], rmin int64 [n_total].
+int b2_sketch_column(const uint32_t* keys_in, uint32_t* keys_sorted, int64_t n_total, int64_t n_valid, void* temp,
+                     size_t temp_bytes, int32_t* flags, int32_t* idx, float* uval, long long* rmin, int32_t* m_scratch,
+                     int max_bin_cap, float* cut_out, int32_t* n_cut_out, float* min_out, int num_sms, cudaStream_t s) {
+  cudaError_t e;
+  if (n_total > 0) {
+    e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_in, keys_sorted, n_total, 0, 32, s);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (n_valid > 0) {
+    b2::head_flags_kernel<<<sk_grid(n_valid, num_sms), 256, 0, s>>>(keys_sorted, n_valid, flags);
+    e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, flags, idx, n_valid, s);
+    if (e != cudaSuccess) return (int)e;
+    b2::scatter_unique_kernel<<<sk_grid(n_valid, num_sms), 256, 0, s>>>(keys_sorted, flags, idx, n_valid, uval, rmin, m_scratch);
+  }
+  b2::prune_cuts_kernel<<<1, 256, 0, s>>>(uval, rmin, m_scratch, n_valid, max_bin_cap, cut_out, n_cut_out, min_out);
+  return (int)cudaGetLastError();
+}
+
+int b2_launch_bin(const float* X, int64_t n, int F, float missing, const int32_t* cut_ptrs, const float* cut_vals,
+                  const int32_t* feat_byte, int row_stride, uint8_t* bins, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::bin_kernel<<<sk_grid(n * F, num_sms), 256, 0, s>>>(X, n, F, missing, missing != missing ? 1 : 0, cut_ptrs, cut_vals,
+                                                        feat_byte, row_stride, bins);
+  return (int)cudaGetLastError();
+}
+}
