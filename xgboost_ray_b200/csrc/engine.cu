@@ -519,6 +519,8 @@ int pick_chunk_rows(Booster* b, int64_t rows) {
   int64_t target = rows / ((int64_t)n_streams * 4);
   int c = 512;
   while (c < target && c < 8192) c <<= 1;
+  const int w = window_rows_for(b->p.qbits);
+  while (c > w && c > 1) c >>= 1;
   return c;
 }
 
@@ -1197,8 +1199,9 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
   const size_t node_elems = (size_t)m.n_groups * B2_GROUP_ELEMS;
   d_hist.ensure(node_elems);
   CUDA_CHECK(cudaMemsetAsync(d_hist.p, 0, node_elems * sizeof(long long), s));
-  if (chunk_rows <= 0) chunk_rows = 2048;
   if (window_rows <= 0) window_rows = 8192;
+  if (chunk_rows <= 0) chunk_rows = 2048;
+  if (chunk_rows > window_rows) chunk_rows = window_rows;
   B2HistWork w{0, (int32_t)n_sel, 0, 0};
   d_work.ensure(1);
   CUDA_CHECK(cudaMemcpyAsync(d_work.p, &w, sizeof(w), cudaMemcpyHostToDevice, s));

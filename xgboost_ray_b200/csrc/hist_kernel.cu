@@ -181,6 +181,7 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
     attr_set = true;
   }
   if (total_chunks <= 0 || n_work <= 0) return 0;
+  if (chunk_rows > window_rows) return (int)cudaErrorInvalidValue;  // a chunk must fit one int32 window
   int n_streams = (num_sms * 3) / n_groups;
   if (n_streams < 1) n_streams = 1;
   if (n_streams > total_chunks) n_streams = total_chunks;

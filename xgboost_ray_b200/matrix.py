@@ -1,0 +1,244 @@
+"""RayDMatrix: lazily loaded, row-sharded training / prediction data.
+
+Host-side mirror of xgboost_ray/matrix.py for the hot path:
+  RayShardingMode            matrix.py:105-124
+  _get_sharding_indices      matrix.py:1088-1110  (here: slices / strided views, not Python int lists)
+  combine_data               matrix.py:1113-1157
+  RayDMatrix                 matrix.py:696-968    (central loading; FIXED file sharding for file lists)
+  RayQuantileDMatrix / RayDeviceQuantileDMatrix   matrix.py:971-1033
+
+One shard maps to one GPU actor.  A shard is a dict of float32 numpy blocks (data, label, weight,
+base_margin, ...), which is what the device upload consumes; the Ray object store of the reference
+is replaced by plain process-local references handed to the actor processes.
+"""
+import uuid
+from enum import Enum
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from xgboost_ray_b200.data_sources import LoadedFrame, RayFileType, resolve_data_source  # noqa: F401
+
+
+class RayShardingMode(Enum):
+    INTERLEAVED = 1
+    BATCH = 2
+    FIXED = 3
+
+
+def _get_sharding_indices(sharding: RayShardingMode, rank: int, num_actors: int, n: int):
+    """Rows of `rank`: a slice (zero-copy selection) -- same row sets as matrix.py:1088-1110."""
+    if sharding == RayShardingMode.BATCH:
+        n_per_actor, extras = divmod(n, num_actors)
+        start = rank * n_per_actor + min(rank, extras)
+        stop = start + n_per_actor + (1 if rank < extras else 0)
+        return slice(start, stop)
+    if sharding == RayShardingMode.INTERLEAVED:
+        return slice(rank, n, num_actors)
+    raise ValueError(
+        f"Invalid value for `sharding` parameter: {sharding}"
+        f"\nFIX THIS by passing any item of the `RayShardingMode` enum, for instance `RayShardingMode.BATCH`.")
+
+
+def combine_data(sharding: RayShardingMode, data: Iterable) -> np.ndarray:
+    """Reassemble per-actor prediction arrays in original row order (matrix.py:1113-1157)."""
+    if sharding not in (RayShardingMode.BATCH, RayShardingMode.INTERLEAVED):
+        raise ValueError(
+            f"Invalid value for `sharding` parameter: {sharding}"
+            f"\nFIX THIS by passing any item of the `RayShardingMode` enum, for instance `RayShardingMode.BATCH`.")
+    data = [np.asarray(d) for d in data if len(d)]
+    if not data:
+        return np.zeros(0, np.float32)
+    if sharding == RayShardingMode.BATCH:
+        return np.concatenate(data) if data[0].ndim == 1 else np.vstack(data)
+    n = sum(len(d) for d in data)
+    out = np.empty((n,) + data[0].shape[1:], dtype=data[0].dtype)
+    for r, d in enumerate(data):
+        out[r::len(data)] = d
+    return out
+
+
+def _column_or_array(frame: LoadedFrame, spec, exclude: set):
+    """`spec` is None, a column name of the loaded frame, or an array-like of row values."""
+    if spec is None:
+        return None
+    if isinstance(spec, str):
+        exclude.add(spec)
+        return np.ascontiguousarray(frame.column(spec), dtype=np.float32)
+    if hasattr(spec, "values") and not isinstance(spec, np.ndarray):
+        spec = spec.values
+    return np.ascontiguousarray(np.asarray(spec), dtype=np.float32)
+
+
+class RayDMatrix:
+    """See xgboost_ray/matrix.py:696-786 for the argument contract."""
+
+    def __init__(self, data, label=None, weight=None, feature_weights=None, base_margin=None, missing=None,
+                 label_lower_bound=None, label_upper_bound=None, feature_names=None, feature_types=None, qid=None,
+                 enable_categorical=None, num_actors: Optional[int] = None, filetype: Optional[RayFileType] = None,
+                 ignore: Optional[List[str]] = None, distributed: Optional[bool] = None,
+                 sharding: RayShardingMode = RayShardingMode.INTERLEAVED, lazy: bool = False, **kwargs):
+        if kwargs.get("group", None) is not None:
+            raise ValueError("`group` parameter is not supported. If you are using XGBoost-Ray, use `qid` parameter instead.")
+        if qid is not None and weight is not None:
+            raise NotImplementedError("per-group weight is not implemented.")
+        if qid is not None:
+            raise NotImplementedError("ranking (qid) is not supported by the B200 engine")
+        self._uid = uuid.uuid4().int
+        self.data, self.label, self.weight, self.base_margin = data, label, weight, base_margin
+        self.feature_weights = feature_weights
+        self.label_lower_bound, self.label_upper_bound = label_lower_bound, label_upper_bound
+        self.feature_names, self.feature_types = feature_names, feature_types
+        self.qid = qid
+        self.enable_categorical = enable_categorical
+        self.missing = missing
+        self.num_actors = num_actors
+        self.sharding = sharding
+        self.filetype = filetype
+        self.ignore = ignore
+        self.kwargs = kwargs
+        self.data_source = resolve_data_source(data, filetype)
+        if distributed is None:
+            distributed = _detect_distributed(self.data_source, data)
+        elif distributed and not self.data_source.supports_distributed_loading:
+            raise ValueError(f"Distributed data loading is not supported for input data of type {type(data)}. "
+                             f"\nFIX THIS by passing file names or setting `distributed=False`.")
+        self.distributed = bool(distributed)
+        if self.distributed:
+            self.sharding = RayShardingMode.FIXED if sharding == RayShardingMode.FIXED else sharding
+        self.refs: Dict[int, Dict[str, Optional[np.ndarray]]] = {}
+        self.n = None
+        self.loaded = False
+        self._columns = None
+        if num_actors is not None and not lazy:
+            self.load_data(num_actors)
+
+    # -- reference API
+    @property
+    def has_label(self):
+        return self.label is not None
+
+    def assert_enough_shards_for_actors(self, num_actors: int):
+        n = self.data_source.get_n(self.data)
+        if self.distributed and num_actors > n:
+            raise RuntimeError(f"Trying to shard data for {num_actors} actors, but the maximum number of shards "
+                               f"(i.e. the number of data files) is {n}. Consider using fewer actors.")
+
+    def assign_shards_to_actors(self, actors: Sequence) -> bool:
+        return False  # locality-aware assignment only exists for distributed frames (out of scope)
+
+    def _split(self, frame: LoadedFrame):
+        exclude = set()
+        y = _column_or_array(frame, self.label, exclude)
+        w = _column_or_array(frame, self.weight, exclude)
+        b = _column_or_array(frame, self.base_margin, exclude)
+        ll = _column_or_array(frame, self.label_lower_bound, exclude)
+        lu = _column_or_array(frame, self.label_upper_bound, exclude)
+        fw = None if self.feature_weights is None else np.asarray(self.feature_weights, np.float32)
+        x = frame.drop(exclude) if exclude else frame
+        return x, y, w, fw, b, ll, lu
+
+    def load_data(self, num_actors: Optional[int] = None, rank: Optional[int] = None):
+        """Central loading (matrix.py:431-487): read once, shard per rank.  Distributed (file lists,
+        matrix.py:614-693): rank r reads files r, r+W, ... itself."""
+        if self.loaded and rank is None:
+            return
+        if num_actors is not None:
+            if self.num_actors is not None and num_actors != self.num_actors:
+                raise ValueError(f"The `RayDMatrix` was initialized or `load_data()`has been called with a different "
+                                 f"numbers of `actors`. Existing value: {self.num_actors}. Current value: {num_actors}."
+                                 f"\nFIX THIS by not instantiating the matrix with `num_actors` and making sure "
+                                 f"calls to `load_data()` or `get_data()` use the same numbers.")
+            self.num_actors = num_actors
+        if self.num_actors is None:
+            raise ValueError("Trying to load data for `RayDMatrix` object, but `num_actors` is not set."
+                             "\nFIX THIS by passing `num_actors` on instantiation or when calling `load_data()`.")
+        W = self.num_actors
+        if self.distributed:
+            self.assert_enough_shards_for_actors(W)
+            ranks = [rank] if rank is not None else list(range(W))
+            n_files = self.data_source.get_n(self.data)
+            total = 0
+            for r in ranks:
+                idx = list(range(n_files))[_get_sharding_indices(
+                    RayShardingMode.INTERLEAVED if self.sharding != RayShardingMode.BATCH else RayShardingMode.BATCH,
+                    r, W, n_files)]
+                frame = self.data_source.load_data(self.data, ignore=self.ignore, indices=idx, **self.kwargs)
+                x, y, w, fw, b, ll, lu = self._split(frame)
+                self._columns = x.columns
+                self.refs[r] = {"data": x.values, "label": y, "weight": w, "feature_weights": fw, "base_margin": b,
+                                "label_lower_bound": ll, "label_upper_bound": lu, "qid": None}
+                total += len(x)
+            self.n = total if rank is None else self.n
+            self.sharding = RayShardingMode.FIXED
+        else:
+            n_src = self.data_source.get_n(self.data)
+            if W > n_src and self.data_source.needs_partitions:
+                raise RuntimeError(f"Trying to shard data for {W} actors, but the maximum number of shards "
+                                   f"(i.e. the number of data rows) is {n_src}. Consider using fewer actors.")
+            frame = self.data_source.load_data(self.data, ignore=self.ignore, indices=None, **self.kwargs)
+            x, y, w, fw, b, ll, lu = self._split(frame)
+            n = len(x)
+            for v, name in ((y, "label"), (w, "weight"), (ll, "label_lower_bound"), (lu, "label_upper_bound")):
+                if v is not None and len(v) != n:
+                    raise ValueError(f"`{name}` has {len(v)} rows but the data has {n}")
+            self._columns = x.columns
+            for r in range(W):
+                sl = _get_sharding_indices(self.sharding, r, W, n)
+                sel = lambda a: None if a is None else np.ascontiguousarray(a[sl])  # noqa: E731
+                self.refs[r] = {"data": sel(x.values), "label": sel(y), "weight": sel(w), "feature_weights": fw,
+                                "base_margin": sel(b), "label_lower_bound": sel(ll), "label_upper_bound": sel(lu),
+                                "qid": None}
+            self.n = n
+        self.loaded = True
+
+    def get_data(self, rank: int, num_actors: Optional[int] = None) -> Dict[str, Optional[np.ndarray]]:
+        self.load_data(num_actors=num_actors, rank=rank if (self.distributed and rank not in self.refs) else None)
+        if rank not in self.refs:
+            self.load_data(num_actors=num_actors, rank=rank)
+        return dict(self.refs[rank])
+
+    def unload_data(self):
+        self.refs = {}
+        self.loaded = False
+
+    def update_matrix_properties(self, matrix):
+        """numpy sources reset names to f0..fN (data_sources/numpy.py:21-23); frames keep theirs."""
+        names = self.feature_names if self.feature_names is not None else self._columns
+        try:
+            matrix.feature_names = list(names) if names is not None else None
+        except Exception:
+            pass
+
+    def __hash__(self):
+        return self._uid
+
+    def __eq__(self, other):
+        return isinstance(other, RayDMatrix) and self.__hash__() == other.__hash__()
+
+
+class RayQuantileDMatrix(RayDMatrix):
+    """Quantised on the device at construction time on the actor (main.py:380-386)."""
+
+
+class RayDeviceQuantileDMatrix(RayDMatrix):
+    """Kept for API compatibility (matrix.py:977-1033); every matrix of this engine is a device
+    quantile matrix, so no cupy iterator is involved."""
+
+    def __init__(self, *args, max_bin: int = 256, **kwargs):
+        if kwargs.get("qid") is not None:
+            raise ValueError("RayDeviceQuantileDMatrix does not support ranking (qid)")
+        self.max_bin = max_bin
+        super().__init__(*args, **kwargs)
+
+
+def _detect_distributed(source, data) -> bool:
+    """File lists with more than one file are loaded per actor (matrix.py:1063-1085)."""
+    if not source.supports_distributed_loading:
+        return False
+    return isinstance(data, (list, tuple)) and len(data) > 1
+
+
+def concat_dataframes(dfs: List[Optional[np.ndarray]]):
+    filtered = [d for d in dfs if d is not None]
+    return np.concatenate(filtered) if filtered else None
