@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- boosting rounds/sec on synthetic 10M x 100 (BASELINE.json metric, config C3).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one boosting round (gradient -> all tree levels -> prediction-cache update, including
+the per-level histogram allreduce) over the fixed synthetic matrix; the 10M rows are row-sharded
+INTERLEAVED over the N ranks (strong scaling, one process per GPU).  `value` is timed with the
+quantised matrix resident in HBM; `e2e` goes through the xgb.train() replacement with HOST buffers
+(upload + GPU sketch/binning + K rounds + a per-round metric read-back, all inside the timed region).
+`--impl reference` times the CPU path (the oracle port of XGBoost hist; `xgboost` itself is not
+installable here) on the host cores for the same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PARAMS = {"objective": "reg:squarederror", "max_depth": 8, "eta": 0.3, "lambda": 1.0, "gamma": 0.0,
+          "min_child_weight": 1.0, "max_bin": 256, "base_score": 0.5, "tree_method": "hist"}
+
+
+def synth_block(block, rows, cols, seed=1234):
+    """Deterministic block of the C3 dataset: x~U[0,10), y = sum_{j<10} a_j x_j + sin(x_10) + N(0,0.1)."""
+    rng = np.random.default_rng([seed, block])
+    X = rng.random((rows, cols), dtype=np.float32) * np.float32(10.0)
+    a = np.random.default_rng(seed).normal(size=10).astype(np.float32)
+    k = min(10, cols)
+    y = X[:, :k] @ a[:k]
+    if cols > 10:
+        y = y + np.sin(X[:, 10])
+    y = y + rng.normal(scale=0.1, size=rows).astype(np.float32)
+    return X, y.astype(np.float32)
+
+
+def synth_shard(n_rows, cols, rank, world, block_rows=1_000_000):
+    """Rows rank, rank+world, ... of the global matrix (INTERLEAVED sharding, matrix.py:1100)."""
+    xs, ys = [], []
+    for b, start in enumerate(range(0, n_rows, block_rows)):
+        rows = min(block_rows, n_rows - start)
+        X, y = synth_block(b, rows, cols)
+        first = (rank - start) % world
+        xs.append(X[first::world])
+        ys.append(y[first::world])
+    return np.ascontiguousarray(np.concatenate(xs)), np.ascontiguousarray(np.concatenate(ys))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for name, i in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(s[i].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def hist_traffic_per_launch():
+    """dram bytes per launch of the histogram kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "hist_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port (kind "port") with all host threads, full config."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = O.lib().or_num_threads()
+    X, y = synth_shard(args.rows, args.cols, 0, 1)
+    params = dict(PARAMS, max_depth=args.depth, hist_qbits=0)   # qbits=0: float64 histograms = XGBoost CPU hist
+    t0 = time.time()
+    cuts = O.Cuts.from_data(X, 256)
+    bins = cuts.bin(X)
+    t_quant = time.time() - t0
+    bst = O.Booster(params, cuts)
+    bst.init_margin(X.shape[0])
+    for _ in range(args.warmup):
+        bst.boost(bins, y)
+    t0 = time.time()
+    for _ in range(args.steps):
+        bst.boost(bins, y)
+    dt = time.time() - t0
+    v = args.steps / dt
+    line = {"impl": "reference", "metric": "boosting rounds/sec", "value": v, "unit": "rounds/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 synthetic %dx%d reg:squarederror depth %d 256 bins" % (args.rows, args.cols, args.depth),
+                       "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256},
+            "cpu_baseline": {"value": v, "unit": "rounds/s", "cores": cores, "kind": "port",
+                             "sample": "full workload, %d timed rounds; CPU quantisation %.1fs not in the timed region" % (args.steps, t_quant)},
+            "e2e": {"value": v, "unit": "rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--cols", type=int, default=100)
+    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--qbits", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from xgboost_ray_b200 import engine as E
+
+    torch.cuda.set_device(local_rank)
+    os.environ["B2_DEVICE"] = str(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    params = dict(PARAMS, max_depth=args.depth)
+    if args.qbits is not None:
+        params["hist_qbits"] = args.qbits
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- communicator: rank 0's NCCL id broadcast through torch.distributed (plumbing only)
+    comm_args = {"b2_world": world, "b2_rank": rank, "b2_device": local_rank}
+    if world > 1:
+        uid = [E.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm_args["b2_uid"] = uid[0]
+
+    X, y = synth_shard(args.rows, args.cols, rank, world)
+    sampler = ClockSampler(local_rank)
+    with E.CommunicatorContext(**comm_args):
+        # ================= device-resident arm: matrix quantised and resident before timing
+        dm = E.DMatrix(X, label=y)
+        t0 = time.time()
+        dm._ensure_quantized(256)
+        t_quant = time.time() - t0
+        bst = E.Booster(params, cache=[dm])
+        for r in range(args.warmup):
+            bst.update(dm, r)
+        bst.get_timers(reset=True)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        t0 = time.perf_counter()
+        for r in range(args.steps):
+            bst.update(dm, args.warmup + r)
+        barrier()
+        wall = time.perf_counter() - t0
+        sampler.stop_flag.set()
+        timers = bst.get_timers(reset=True)
+        wall = max_over_ranks(wall)
+        dev_ms = max_over_ranks(timers["round_ms"])
+        hist_ms = max_over_ranks(timers["hist_ms"])
+        ms_per_step = 1e3 * wall / args.steps
+        value = args.steps / wall
+        final_rmse = float(bst.eval_set([(dm, "train")], 0).split(":")[-1])
+        del bst
+
+        # ================= e2e arm: host buffers -> xgb.train replacement, copies inside the timed region
+        e2e = None
+        if not args.no_e2e:
+            barrier()
+            t0 = time.perf_counter()
+            d2 = E.DMatrix(X, label=y)
+            res = {}
+            b2 = E.train(params, d2, num_boost_round=args.steps, evals=[(d2, "train")], evals_result=res, verbose_eval=False)
+            barrier()
+            e2e_wall = max_over_ranks(time.perf_counter() - t0)
+            e2e = {"value": args.steps / e2e_wall, "unit": "rounds/s",
+                   "h2d_bytes_per_step": int((X.nbytes + y.nbytes) / args.steps),
+                   "d2h_bytes_per_step": 8, "seconds_total": e2e_wall,
+                   "api": "xgboost_ray_b200.engine.train (the xgb.train replacement an actor calls, host numpy in)",
+                   "final_train_rmse": res["train"]["rmse"][-1]}
+            del b2, d2
+
+        # ================= CPU baseline (rank 0, N=1): oracle port on the host cores, bounded sample
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            O.build()
+            ptrs, vals, mins, hm = dm.get_cuts()
+            cuts = O.Cuts.from_arrays(ptrs, vals, mins, hm, 256)
+            bins = dm.get_bins()
+            ob = O.Booster(dict(params, hist_qbits=0), cuts)
+            ob.init_margin(X.shape[0])
+            ob.boost(bins, y)  # warm-up round
+            n_cpu, t0 = 0, time.time()
+            while n_cpu < 3 or (time.time() - t0 < 10 and n_cpu < 20):
+                ob.boost(bins, y)
+                n_cpu += 1
+            dt = time.time() - t0
+            cpu = {"value": n_cpu / dt, "unit": "rounds/s", "cores": int(O.lib().or_num_threads()), "kind": "port",
+                   "sample": "%d full-size rounds (%dx%d, depth %d) of the oracle port, float64 histograms, %.1fs" % (
+                       n_cpu, args.rows, args.cols, args.depth, dt)}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = measured_peak()
+    hist_bytes_per_launch = timers["hist_bytes"] / max(1, timers["hist_launches"])
+    hist_ms_per_launch = hist_ms / max(1, timers["hist_launches"])
+    achieved = hist_bytes_per_launch / (hist_ms_per_launch * 1e-3) / 1e9 if hist_ms_per_launch > 0 else 0.0
+    line = {
+        "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int64 fixed-point histograms (int32 shared-memory cells), f64 gain", "data": "synthetic",
+        "config": {"workload": "C3 synthetic %dx%d reg:squarederror depth %d 256 bins, rows INTERLEAVED over %d rank(s)" % (
+                       args.rows, args.cols, args.depth, world),
+                   "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256, "parallelism": "dp%d" % world,
+                   "hist_qbits": params.get("hist_qbits", 18), "l2": "inputs_larger_than_l2",
+                   "device_ms_per_step": dev_ms / args.steps, "quantise_seconds": t_quant, "final_train_rmse": final_rmse},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_kind, "kernel": "b2::hist_build_kernel",
+                     "algorithmic_bytes_per_launch": hist_bytes_per_launch, "ms_per_launch": hist_ms_per_launch,
+                     "launches": timers["hist_launches"], "share_of_step": hist_ms / max(dev_ms, 1e-9),
+                     "traffic": hist_traffic_per_launch()},
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timers["kernel_launches"]),
+        "clocks": sampler.summary(),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

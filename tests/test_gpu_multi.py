@@ -1,0 +1,61 @@
+"""Multi-GPU parity (needs >= 2 GPUs; run with `gpurun --gpus 2`): the public train()/predict() with
+one actor process per GPU and the NCCL histogram allreduce produce the SAME model as one GPU and as
+the oracle (integer histograms make the model independent of the world size)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    from xgboost_ray_b200 import engine
+    return engine.device_count()
+
+
+def _dump(bst):
+    return bst.get_dump(dump_format="json", with_stats=True)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("sharding", ["INTERLEAVED", "BATCH"])
+def test_two_gpu_model_identical_to_one_gpu_and_oracle(oracle, sharding):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from xgboost_ray_b200 import RayDMatrix, RayParams, RayShardingMode, predict, train
+    rng = np.random.RandomState(5)
+    n, f = 30001, 20   # odd row count: shards of different size
+    x = rng.uniform(0, 10, size=(n, f)).astype(np.float32)
+    x[rng.uniform(size=x.shape) < 0.05] = np.nan
+    y = (np.nan_to_num(x[:, 0]) + np.nan_to_num(x[:, 1]) * 0.5 + rng.normal(size=n) > 7).astype(np.float32)
+    params = {"objective": "binary:logistic", "max_depth": 6, "eta": 0.3, "base_score": 0.5, "eval_metric": ["logloss", "error"]}
+    mode = getattr(RayShardingMode, sharding)
+    res1, res2 = {}, {}
+    d1 = RayDMatrix(x, y, sharding=mode)
+    b1 = train(params, d1, num_boost_round=6, evals=[(d1, "train")], evals_result=res1, ray_params=RayParams(num_actors=1))
+    d2 = RayDMatrix(x, y, sharding=mode)
+    b2 = train(params, d2, num_boost_round=6, evals=[(d2, "train")], evals_result=res2, ray_params=RayParams(num_actors=2))
+    assert _dump(b1) == _dump(b2)                                   # byte-identical trees
+    assert np.allclose(res1["train"]["logloss"], res2["train"]["logloss"], rtol=0, atol=1e-9)
+    ob, _ = oracle.train(params, x, y, 6)
+    for i, t in enumerate(b2.get_trees()):
+        o = ob.tree(i)
+        assert np.array_equal(t["split_feature"], o.split_feature) and np.array_equal(t["split_bin"], o.split_bin)
+        assert np.array_equal(t["default_left"], o.default_left)
+        leaf = o.split_feature < 0
+        assert np.max(np.abs(t["value"][leaf] - o.value[leaf])) <= 1e-5
+    p2 = predict(b2, RayDMatrix(x, sharding=mode), ray_params=RayParams(num_actors=2))
+    assert np.max(np.abs(p2 - ob.predict(x))) <= 1e-5               # recombined in original row order
+
+
+@pytest.mark.timeout(900)
+def test_two_gpu_toy_matrix(oracle):
+    """test_end_to_end.py:162-211 on real GPUs: halves over-fit alone, two actors are exact."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from xgboost_ray_b200 import RayDMatrix, RayParams, predict, train
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+    y = np.array([0, 1, 2, 3] * 8, np.float32)
+    params = {"max_depth": 2, "objective": "multi:softmax", "num_class": 4}
+    bst = train(params, RayDMatrix(x, y), num_boost_round=2, ray_params=RayParams(num_actors=2))
+    assert list(predict(bst, RayDMatrix(x), ray_params=RayParams(num_actors=2))) == list(y)
+    assert bst.num_trees() == 8

@@ -1,0 +1,95 @@
+"""Host-layer tests on CPU: spawned actors (one process each), world_size 2 over `gloo` through the
+test-only stand-in engine (tests/cpu_engine.py).  Ports the hot-path subset of
+xgboost_ray/tests/test_end_to_end.py, test_xgboost_api.py and test_fault_tolerance.py."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(autouse=True)
+def use_cpu_engine(monkeypatch):
+    monkeypatch.setenv("XGBOOST_RAY_B200_ENGINE", "tests.cpu_engine")
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    import importlib
+    import xgboost_ray_b200.xgb as seam
+    importlib.reload(seam)
+    yield
+    monkeypatch.delenv("XGBOOST_RAY_B200_ENGINE")
+    importlib.reload(seam)
+
+
+X_TOY = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+Y_TOY = np.array([0, 1, 2, 3] * 8, np.float32)
+TOY_PARAMS = {"booster": "gbtree", "nthread": 1, "max_depth": 2, "objective": "multi:softmax", "num_class": 4}
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("sharding", ["INTERLEAVED", "BATCH"])
+def test_two_actor_training_learns_full_matrix(sharding):
+    """test_end_to_end.py:162-211: each half alone over-fits, 2 actors with the exchange step are exact."""
+    from xgboost_ray_b200 import RayDMatrix, RayParams, RayShardingMode, predict, train
+    mode = getattr(RayShardingMode, sharding)
+    evals_result, extra = {}, {}
+    dtrain = RayDMatrix(X_TOY, Y_TOY, sharding=mode)
+    bst = train(TOY_PARAMS, dtrain, num_boost_round=2, evals=[(dtrain, "train")], evals_result=evals_result,
+                additional_results=extra, ray_params=RayParams(num_actors=2, checkpoint_frequency=1))
+    assert extra["total_n"] == 32 and extra["training_time_s"] > 0
+    assert len(evals_result["train"]["mlogloss"]) == 2
+    pred = predict(bst, RayDMatrix(X_TOY, sharding=mode), ray_params=RayParams(num_actors=2))
+    assert list(pred) == list(Y_TOY)                  # recombined in original row order
+    bst2 = pickle.loads(pickle.dumps(bst))
+    assert bst2.get_dump() == bst.get_dump()
+
+
+@pytest.mark.timeout(300)
+def test_callbacks_see_ranks_and_queue_returns():
+    from tests.fault_injection import RankRecorder
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    extra = {}
+    train(TOY_PARAMS, RayDMatrix(X_TOY, Y_TOY), num_boost_round=2, additional_results=extra,
+          ray_params=RayParams(num_actors=2), callbacks=[RankRecorder()])
+    got = sorted(item[1] for per_rank in extra["callback_returns"] for item in per_rank)
+    assert got == [0, 1]                               # test_xgboost_api.py:154-178
+
+
+@pytest.mark.timeout(600)
+def test_restart_from_checkpoint_gives_same_model(tmp_path):
+    """test_fault_tolerance.py:401-444: failure at round 6, restart from checkpoint 5 == uninterrupted."""
+    from tests.fault_injection import DieOnceCallback
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    rng = np.random.RandomState(0)
+    x = rng.uniform(0, 10, size=(400, 4)).astype(np.float32)
+    y = (x[:, 0] + x[:, 1] > 10).astype(np.float32)
+    params = {"objective": "binary:logistic", "max_depth": 3, "nthread": 1}
+    ref = train(params, RayDMatrix(x, y), num_boost_round=10, ray_params=RayParams(num_actors=2, checkpoint_frequency=1))
+    extra = {}
+    bst = train(params, RayDMatrix(x, y), num_boost_round=10, additional_results=extra,
+                ray_params=RayParams(num_actors=2, max_actor_restarts=1, checkpoint_frequency=5),
+                callbacks=[DieOnceCallback(str(tmp_path / "lock"), rank=1, at=6)])
+    assert os.path.exists(str(tmp_path / "lock"))
+    assert bst.num_boosted_rounds() == 10
+    assert bst.get_dump() == ref.get_dump()
+    with pytest.raises(RuntimeError, match="maximum number of retries"):
+        train(params, RayDMatrix(x, y), num_boost_round=10, ray_params=RayParams(num_actors=2, max_actor_restarts=0),
+              callbacks=[DieOnceCallback(str(tmp_path / "lock2"), rank=0, at=2)])
+
+
+@pytest.mark.timeout(300)
+def test_validation_errors():
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    d = RayDMatrix(X_TOY, Y_TOY)
+    with pytest.raises(ValueError, match="num_actors"):
+        train(TOY_PARAMS, d, ray_params=RayParams())
+    with pytest.raises(ValueError, match="RayDMatrix"):
+        train(TOY_PARAMS, X_TOY, ray_params=RayParams(num_actors=1))
+    with pytest.raises(ValueError, match="exact"):
+        train(dict(TOY_PARAMS, tree_method="exact"), d, ray_params=RayParams(num_actors=1))
+    with pytest.raises(TypeError, match="invalid keyword"):
+        train(TOY_PARAMS, d, ray_params=RayParams(num_actors=1), totally_invalid_kwarg=1)
+    with pytest.raises(ValueError, match="no label"):
+        train(TOY_PARAMS, RayDMatrix(X_TOY), ray_params=RayParams(num_actors=1))
+    # engine error propagates as a training failure (main.py:770-785)
+    with pytest.raises(RuntimeError):
+        train(dict(TOY_PARAMS, objective="rank:pairwise"), RayDMatrix(X_TOY, Y_TOY), ray_params=RayParams(num_actors=1))

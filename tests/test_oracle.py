@@ -1,0 +1,145 @@
+"""CPU tests of the oracle: golden fixtures + the reference's relational known-answers."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.golden.make_golden import CASES, run_case
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_golden(oracle, name):
+    want = json.load(open(os.path.join(GOLD, name + ".json")))
+    got = run_case(name)
+    for k in ("cut_ptrs", "cut_vals_bits", "min_vals_bits", "has_missing", "bins_sum_per_feature"):
+        assert got[k] == want[k], k
+    assert len(got["trees"]) == len(want["trees"])
+    for a, b in zip(got["trees"], want["trees"]):
+        for k in ("left", "right", "split_feature", "split_bin", "default_left"):
+            assert a[k] == b[k], k
+        assert np.allclose(a["value"], b["value"], rtol=0, atol=1e-7)
+    assert np.allclose(got["pred_head"], want["pred_head"], rtol=0, atol=1e-6)
+
+
+def test_cut_semantics_binary_feature(oracle):
+    """A.2: 0/1 feature -> cuts [1, 2.00001], bins 0/1, min_val -1e-5 (pinned by the toy tests)."""
+    x = np.array([[0.0], [1.0], [1.0], [0.0]], np.float32)
+    c = oracle.Cuts.from_data(x)
+    assert list(c.ptrs) == [0, 2]
+    assert c.vals[0] == np.float32(1.0) and abs(c.vals[1] - 2.00001) < 1e-6
+    assert abs(c.mins[0] + 1e-5) < 1e-9
+    assert list(c.bin(x)[:, 0]) == [0, 1, 1, 0]
+
+
+def test_cuts_cap_and_missing(oracle):
+    rng = np.random.RandomState(0)
+    x = rng.normal(size=(5000, 3)).astype(np.float32)
+    x[::7, 1] = np.nan
+    x[:, 2] = 5.0
+    c = oracle.Cuts.from_data(x, 256)
+    n = np.diff(c.ptrs)
+    assert n[0] == 256 and n[1] == 255 and n[2] == 1      # missing caps a feature at 255 real bins
+    assert list(c.has_missing) == [0, 1, 0]
+    b = c.bin(x)
+    assert (b[::7, 1] == 255).all() and b[:, 0].max() == 255 and (b[:, 2] == 0).all()
+    # every cut value is strictly increasing and the last one exceeds the column maximum
+    for f in range(3):
+        v = c.vals[c.ptrs[f]:c.ptrs[f + 1]]
+        assert (np.diff(v) > 0).all() and v[-1] > np.nanmax(x[:, f])
+    # quantile bins are balanced
+    counts = np.bincount(b[:, 0], minlength=256)
+    assert counts.max() <= 3 * counts.mean()
+
+
+def test_bin_upper_bound_rule(oracle):
+    x = np.arange(100, dtype=np.float32).reshape(-1, 1)
+    c = oracle.Cuts.from_data(x, 256)
+    b = c.bin(np.array([[-5.0], [0.0], [0.5], [1.0], [98.5], [99.0], [1e6]], np.float32))
+    assert list(b[:, 0]) == [0, 0, 0, 1, 98, 99, 99]       # bin = #cuts <= x, clamped to the last bin
+
+
+def test_toy_matrix_known_answers(oracle):
+    """xgboost_ray/tests/test_end_to_end.py:72-139."""
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+    y = np.array([0, 1, 2, 3] * 8, np.float32)
+    p = {"max_depth": 2, "objective": "multi:softmax", "num_class": 4}
+    bst, _ = oracle.train(p, x, y, 2)
+    assert list(bst.predict(x)) == list(y)
+    t = np.array([[0, 0, 1, 1], [0, 0, 1, 0]], np.float32)
+    assert list(oracle.train(p, x[::2], y[::2], 2)[0].predict(t)) == [2, 2]
+    assert list(oracle.train(p, x[1::2], y[1::2], 2)[0].predict(t)) == [3, 3]
+    # 38 rounds x 4 classes = 152 trees (test_end_to_end.py:238)
+    assert oracle.train(p, x, y, 38)[0].num_trees == 152
+
+
+def test_row_order_independence_is_the_allreduce_property(oracle):
+    """Fixed-point histograms make the model independent of row order / sharding: training on any
+    permutation (= any INTERLEAVED / BATCH shard concatenation) yields the identical model."""
+    rng = np.random.RandomState(3)
+    x = rng.uniform(0, 10, size=(4000, 6)).astype(np.float32)
+    y = (x[:, 0] * x[:, 1] + rng.normal(size=4000)).astype(np.float32)
+    p = {"objective": "reg:squarederror", "max_depth": 5}
+    a, _ = oracle.train(p, x, y, 4)
+    perm = np.concatenate([np.arange(0, 4000, 2), np.arange(1, 4000, 2)])
+    b, _ = oracle.train(p, x[perm], y[perm], 4)
+    for i in range(4):
+        ta, tb = a.tree(i), b.tree(i)
+        assert np.array_equal(ta.split_feature, tb.split_feature) and np.array_equal(ta.split_bin, tb.split_bin)
+        assert np.array_equal(ta.value, tb.value)
+
+
+def test_boost_from_prediction(oracle):
+    """4 rounds + 4 rounds from base_margin == 8 rounds (tests/test_sklearn.py:1155-1197)."""
+    from sklearn.datasets import load_breast_cancer
+    X, y = load_breast_cancer(return_X_y=True)
+    X = X.astype(np.float32)
+    p = {"objective": "binary:logistic", "max_depth": 6, "eta": 0.3, "base_score": 0.5}
+    full, _ = oracle.train(p, X, y, 8)
+    first, _ = oracle.train(p, X, y, 4)
+    margin = first.predict(X, output_margin=True)
+    second, _ = oracle.train(p, X, y, 4, base_margin=margin)
+    pred = second.predict(X, base_margin=margin)
+    assert np.allclose(pred, full.predict(X), rtol=0, atol=1e-6)
+
+
+def test_fixed_point_agrees_with_float64(oracle):
+    from sklearn.datasets import load_breast_cancer
+    X, y = load_breast_cancer(return_X_y=True)
+    X = X.astype(np.float32)
+    for qb in (14, 18, 22):
+        a, _ = oracle.train({"objective": "binary:logistic", "hist_qbits": qb}, X, y, 8)
+        b, _ = oracle.train({"objective": "binary:logistic", "hist_qbits": 0}, X, y, 8)
+        for i in range(8):
+            ta, tb = a.tree(i), b.tree(i)
+            assert np.array_equal(ta.split_feature, tb.split_feature) and np.array_equal(ta.split_bin, tb.split_bin)
+            leaf = ta.split_feature < 0
+            assert np.max(np.abs(ta.value[leaf] - tb.value[leaf])) <= 1e-5   # north_star leaf tolerance
+
+
+def test_accuracy_ballpark_vs_sklearn(oracle):
+    """Independent sanity (not parity): same ballpark as sklearn's HistGradientBoosting on digits 0/1."""
+    from sklearn.datasets import load_digits
+    from sklearn.ensemble import HistGradientBoostingClassifier
+    d = load_digits(n_class=2)
+    X, y = d.data.astype(np.float32), d.target.astype(np.float32)
+    bst, _ = oracle.train({"objective": "binary:logistic", "max_depth": 4}, X[::2], y[::2], 10)
+    err = np.mean((bst.predict(X[1::2]) > 0.5) != y[1::2])
+    sk = HistGradientBoostingClassifier(max_iter=10, max_depth=4).fit(X[::2], y[::2])
+    assert err < 0.1 and err <= (1 - sk.score(X[1::2], y[1::2])) + 0.05   # test_sklearn.py:115-141 bar
+
+
+def test_deterministic_exp(oracle):
+    xs = np.linspace(-80, 80, 4001).astype(np.float32)
+    got = np.array([oracle.lib().or_expf(float(v)) for v in xs], np.float64)
+    ref = np.exp(xs.astype(np.float64))
+    assert np.max(np.abs(got - ref) / ref) < 4e-7
+
+
+def test_empty_and_tiny_inputs(oracle):
+    x = np.zeros((1, 2), np.float32)
+    bst, _ = oracle.train({"objective": "reg:squarederror", "max_depth": 3, "base_score": 0.5}, x, np.ones(1, np.float32), 2)
+    assert bst.num_trees == 2 and all(t.n_nodes == 1 for t in bst.trees())
+    assert abs(bst.predict(x)[0] - (0.5 + 0.075 + 0.06375)) < 1e-6    # -G/(H+lambda)*eta twice

@@ -125,6 +125,7 @@ def _paths(data, indices=None) -> List[str]:
 
 class CSV(DataSource):
     supports_distributed_loading = True
+    needs_partitions = False
 
     @staticmethod
     def is_data_type(data, filetype=None):
@@ -147,6 +148,7 @@ class CSV(DataSource):
 
 class Parquet(DataSource):
     supports_distributed_loading = True
+    needs_partitions = False
 
     @staticmethod
     def is_data_type(data, filetype=None):

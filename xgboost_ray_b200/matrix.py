@@ -141,8 +141,6 @@ class RayDMatrix:
     def load_data(self, num_actors: Optional[int] = None, rank: Optional[int] = None):
         """Central loading (matrix.py:431-487): read once, shard per rank.  Distributed (file lists,
         matrix.py:614-693): rank r reads files r, r+W, ... itself."""
-        if self.loaded and rank is None:
-            return
         if num_actors is not None:
             if self.num_actors is not None and num_actors != self.num_actors:
                 raise ValueError(f"The `RayDMatrix` was initialized or `load_data()`has been called with a different "
@@ -150,6 +148,8 @@ class RayDMatrix:
                                  f"\nFIX THIS by not instantiating the matrix with `num_actors` and making sure "
                                  f"calls to `load_data()` or `get_data()` use the same numbers.")
             self.num_actors = num_actors
+        if self.loaded and rank is None:
+            return
         if self.num_actors is None:
             raise ValueError("Trying to load data for `RayDMatrix` object, but `num_actors` is not set."
                              "\nFIX THIS by passing `num_actors` on instantiation or when calling `load_data()`.")
