@@ -376,11 +376,11 @@ void or_hist_int(const uint8_t *bins, int32_t F, const int32_t *qg, const int32_
   size_t hsz = (size_t)F * 256 * 2;
   memset(hist, 0, hsz * sizeof(int64_t));
 #ifdef _OPENMP
-  int nt = omp_get_max_threads();
+  int nt = omp_in_parallel() ? 1 : omp_get_max_threads();
 #else
   int nt = 1;
 #endif
-  if (nrows < 4096) nt = 1;
+  if (nrows < 65536) nt = 1;
   if (nt == 1) {
     for (int64_t k = 0; k < nrows; ++k) {
       int64_t r = ridx ? ridx[k] : k;
@@ -422,10 +422,9 @@ void or_hist_int(const uint8_t *bins, int32_t F, const int32_t *qg, const int32_
   free(priv);
 }
 
-static void hist_f64(const uint8_t *bins, int32_t F, const float *g, const float *h, int64_t gstride,
-                     const int32_t *ridx, int64_t nrows, double *hist) {
-  memset(hist, 0, (size_t)F * 256 * 2 * sizeof(double));
-  for (int64_t k = 0; k < nrows; ++k) {
+static void hist_f64_serial(const uint8_t *bins, int32_t F, const float *g, const float *h, int64_t gstride,
+                            const int32_t *ridx, int64_t k0, int64_t k1, double *hist) {
+  for (int64_t k = k0; k < k1; ++k) {
     int64_t r = ridx ? ridx[k] : k;
     const uint8_t *b = bins + r * F;
     double gg = g[r * gstride], hh = h[r * gstride];
@@ -434,6 +433,39 @@ static void hist_f64(const uint8_t *bins, int32_t F, const float *g, const float
       e[0] += gg; e[1] += hh;
     }
   }
+}
+/* float64 accumulation (XGBoost CPU hist arithmetic).  Row-parallel with per-thread private
+ * histograms when called outside a parallel region on a large node, serial otherwise. */
+static void hist_f64(const uint8_t *bins, int32_t F, const float *g, const float *h, int64_t gstride,
+                     const int32_t *ridx, int64_t nrows, double *hist) {
+  size_t hsz = (size_t)F * 512;
+  memset(hist, 0, hsz * sizeof(double));
+#ifdef _OPENMP
+  int nt = omp_in_parallel() ? 1 : omp_get_max_threads();
+#else
+  int nt = 1;
+#endif
+  if (nrows < 65536) nt = 1;
+  if (nt == 1) { hist_f64_serial(bins, F, g, h, gstride, ridx, 0, nrows, hist); return; }
+  double *priv = (double *)calloc(hsz * (size_t)nt, sizeof(double));
+#pragma omp parallel num_threads(nt)
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    int64_t k0 = nrows * t / nt, k1 = nrows * (t + 1) / nt;
+    hist_f64_serial(bins, F, g, h, gstride, ridx, k0, k1, priv + hsz * (size_t)t);
+#pragma omp barrier
+#pragma omp for schedule(static)
+    for (int64_t j = 0; j < (int64_t)hsz; ++j) {
+      double sacc = 0;
+      for (int t2 = 0; t2 < nt; ++t2) sacc += priv[hsz * (size_t)t2 + (size_t)j];
+      hist[j] = sacc;
+    }
+  }
+  free(priv);
 }
 
 /* ------------------------------------------------------------------ A.6 split */
@@ -556,6 +588,58 @@ typedef struct {
   SplitCand split;
 } NodeWork;
 
+/* A.8 stable partition of ridx[begin, begin+count) into [left | right]; returns #left.
+ * Block-parallel (count, prefix, scatter) for large segments. */
+static int64_t partition_segment(int32_t *ridx, int32_t *rtmp, int64_t begin, int64_t count, const uint8_t *bins,
+                                 int32_t F, int32_t feature, int32_t split_bin, int has_missing, int default_left) {
+#define GO_LEFT(row) ((bins[(int64_t)(row) * F + feature] == OR_MISSING_BIN && has_missing) \
+                          ? default_left : ((int32_t)bins[(int64_t)(row) * F + feature] <= split_bin))
+#ifdef _OPENMP
+  int nt = omp_in_parallel() ? 1 : omp_get_max_threads();
+#else
+  int nt = 1;
+#endif
+  if (count < 65536) nt = 1;
+  if (nt == 1) {
+    int64_t nl = 0, nr = 0;
+    for (int64_t i = begin; i < begin + count; ++i) {
+      int32_t row = ridx[i];
+      if (GO_LEFT(row)) ridx[begin + nl++] = row; else rtmp[begin + nr++] = row;
+    }
+    memcpy(ridx + begin + nl, rtmp + begin, (size_t)nr * sizeof(int32_t));
+    return nl;
+  }
+  int64_t *cl = (int64_t *)calloc((size_t)nt + 1, sizeof(int64_t));
+  int64_t nl_total = 0;
+#pragma omp parallel num_threads(nt)
+  {
+#ifdef _OPENMP
+    int t = omp_get_thread_num();
+#else
+    int t = 0;
+#endif
+    int64_t k0 = begin + count * t / nt, k1 = begin + count * (t + 1) / nt, c0 = 0;
+    for (int64_t i = k0; i < k1; ++i) c0 += GO_LEFT(ridx[i]) ? 1 : 0;
+    cl[t + 1] = c0;
+#pragma omp barrier
+#pragma omp single
+    {
+      for (int i = 0; i < nt; ++i) cl[i + 1] += cl[i];
+      nl_total = cl[nt];
+    }
+    int64_t lpos = begin + cl[t], rpos = begin + nl_total + ((k0 - begin) - cl[t]);
+    for (int64_t i = k0; i < k1; ++i) {
+      int32_t row = ridx[i];
+      if (GO_LEFT(row)) rtmp[lpos++] = row; else rtmp[rpos++] = row;
+    }
+#pragma omp barrier
+    memcpy(ridx + k0, rtmp + k0, (size_t)(k1 - k0) * sizeof(int32_t));
+  }
+  free(cl);
+  return nl_total;
+#undef GO_LEFT
+}
+
 /* grow one tree on (bins, g, h); g/h may be strided (multi-class). Appends leaf values to margin
  * cache: margin[r*mstride] += leaf. */
 static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins, int64_t n,
@@ -603,25 +687,33 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
   t->base_weight[0] = calc_weight(p, level[0].G, level[0].H);
   (void)cap_level;
   while (n_level > 0) {
-    /* evaluate */
     NodeWork *next = (NodeWork *)calloc((size_t)n_level * 2, sizeof(NodeWork)); int32_t n_next = 0;
+    /* phase A: evaluate all nodes of the level (node-parallel) */
+    int8_t *expand_flag = (int8_t *)calloc((size_t)n_level, 1);
+#pragma omp parallel for schedule(dynamic, 1)
     for (int32_t k = 0; k < n_level; ++k) {
       NodeWork *w = &level[k];
-      float root_gain = (float)calc_gain(p, w->G, w->H);
-      int expand = 0;
       if (w->depth < p->max_depth || p->max_depth == 0) {
+        float root_gain = (float)calc_gain(p, w->G, w->H);
         evaluate_node(p, c, w->hist, w->G, w->H, root_gain, &w->split);
-        SplitCand *s = &w->split;
-        expand = s->valid && s->loss_chg > OR_RT_EPS && s->HL != 0.0 && s->HR != 0.0 &&
-                 !(s->loss_chg < p->gamma);
+        SplitCand *sc = &w->split;
+        expand_flag[k] = sc->valid && sc->loss_chg > OR_RT_EPS && sc->HL != 0.0 && sc->HR != 0.0 &&
+                         !(sc->loss_chg < p->gamma);
       }
+    }
+    /* phase B: apply in node order (ids are allocated consecutively, A.7) */
+    int32_t n_pairs = 0;
+    int32_t *pair_parent = (int32_t *)malloc((size_t)n_level * sizeof(int32_t));
+    for (int32_t k = 0; k < n_level; ++k) {
+      NodeWork *w = &level[k];
       int32_t nid = w->nid;
-      if (!expand) {
+      if (!expand_flag[k]) {
         if (p->qbits > 0) {
           /* leaf refinement: leaf weight from 40-bit fixed-point sums of the fp32 gradients of the
            * leaf's rows (exact int64, order independent), so leaf values do not depend on qbits */
           int64_t sg = 0, sh = 0;
           double kg = ldexp(1.0, OR_LEAF_BITS - eg), kh = ldexp(1.0, OR_LEAF_BITS - eh);
+#pragma omp parallel for reduction(+ : sg, sh) schedule(static) if (w->count > 65536)
           for (int64_t i = w->begin; i < w->begin + w->count; ++i) {
             int64_t r = ridx[i];
             sg += llrint((double)g[r * gstride] * kg); sh += llrint((double)h[r * gstride] * kh);
@@ -629,8 +721,10 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
           t->base_weight[nid] = calc_weight(p, (double)sg / kg, (double)sh / kh);
         }
         t->value[nid] = t->base_weight[nid] * p->eta;
+        const float lv = t->value[nid];
+#pragma omp parallel for schedule(static) if (w->count > 65536)
         for (int64_t i = w->begin; i < w->begin + w->count; ++i)
-          margin[(int64_t)ridx[i] * mstride] += t->value[nid];
+          margin[(int64_t)ridx[i] * mstride] += lv;
         continue;
       }
       SplitCand *s = &w->split;
@@ -641,35 +735,43 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
       t->sum_grad[l] = s->GL; t->sum_hess[l] = s->HL; t->sum_grad[r] = s->GR; t->sum_hess[r] = s->HR;
       t->base_weight[l] = calc_weight(p, s->GL, s->HL); t->base_weight[r] = calc_weight(p, s->GR, s->HR);
       /* A.8 partition (stable): left iff non-missing && bin <= split_bin, missing -> default */
-      int64_t nl = 0, nr = 0;
-      for (int64_t i = w->begin; i < w->begin + w->count; ++i) {
-        int32_t row = ridx[i]; uint8_t b = bins[(int64_t)row * F + s->feature];
-        int go_left = (b == OR_MISSING_BIN && c->has_missing[s->feature]) ? s->default_left : ((int32_t)b <= s->bin);
-        if (go_left) ridx[w->begin + nl++] = row; else rtmp[nr++] = row;
-      }
-      memcpy(ridx + w->begin + nl, rtmp, (size_t)nr * sizeof(int32_t));
+      int64_t nl = partition_segment(ridx, rtmp, w->begin, w->count, bins, F, s->feature, s->bin,
+                                     c->has_missing[s->feature], s->default_left);
+      int64_t nr = w->count - nl;
       NodeWork *wl = &next[n_next++], *wr = &next[n_next++];
       wl->nid = l; wl->depth = w->depth + 1; wl->begin = w->begin; wl->count = nl; wl->G = s->GL; wl->H = s->HL;
       wr->nid = r; wr->depth = w->depth + 1; wr->begin = w->begin + nl; wr->count = nr; wr->G = s->GR; wr->H = s->HR;
-      int children_need_hist = (w->depth + 1 < p->max_depth) || p->max_depth == 0;
-      if (children_need_hist) {
-        /* A.5: build the smaller-hessian child from rows, sibling = parent - built */
-        NodeWork *bw = (s->HL < s->HR) ? wl : wr, *sw = (bw == wl) ? wr : wl;
+      pair_parent[n_pairs++] = k;
+    }
+    /* phase C: histograms of the children (A.5): build the smaller-hessian child from rows,
+     * sibling = parent - built.  Node-parallel when there are many nodes, row-parallel otherwise. */
+    if (n_pairs > 0 && ((level[pair_parent[0]].depth + 1 < p->max_depth) || p->max_depth == 0)) {
+#ifdef _OPENMP
+      int node_parallel = n_pairs >= omp_get_max_threads();
+#else
+      int node_parallel = 0;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) if (node_parallel)
+      for (int32_t j = 0; j < n_pairs; ++j) {
+        NodeWork *w = &level[pair_parent[j]];
+        NodeWork *wl = &next[2 * j], *wr = &next[2 * j + 1];
+        NodeWork *bw = (wl->H < wr->H) ? wl : wr, *sw = (bw == wl) ? wr : wl;
         bw->hist = (double *)malloc(hsz * sizeof(double)); sw->hist = (double *)malloc(hsz * sizeof(double));
         if (p->qbits > 0) {
           bw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t)); sw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t));
           or_hist_int(bins, F, qg, qh, ridx + bw->begin, bw->count, bw->ihist);
-          for (size_t j = 0; j < hsz; ++j) sw->ihist[j] = w->ihist[j] - bw->ihist[j];
-          for (size_t j = 0; j < hsz; j += 2) {
-            bw->hist[j] = (double)bw->ihist[j] * inv_sg; bw->hist[j + 1] = (double)bw->ihist[j + 1] * inv_sh;
-            sw->hist[j] = (double)sw->ihist[j] * inv_sg; sw->hist[j + 1] = (double)sw->ihist[j + 1] * inv_sh;
+          for (size_t jj = 0; jj < hsz; ++jj) sw->ihist[jj] = w->ihist[jj] - bw->ihist[jj];
+          for (size_t jj = 0; jj < hsz; jj += 2) {
+            bw->hist[jj] = (double)bw->ihist[jj] * inv_sg; bw->hist[jj + 1] = (double)bw->ihist[jj + 1] * inv_sh;
+            sw->hist[jj] = (double)sw->ihist[jj] * inv_sg; sw->hist[jj + 1] = (double)sw->ihist[jj + 1] * inv_sh;
           }
         } else {
           hist_f64(bins, F, g, h, gstride, ridx + bw->begin, bw->count, bw->hist);
-          for (size_t j = 0; j < hsz; ++j) sw->hist[j] = w->hist[j] - bw->hist[j];
+          for (size_t jj = 0; jj < hsz; ++jj) sw->hist[jj] = w->hist[jj] - bw->hist[jj];
         }
       }
     }
+    free(expand_flag); free(pair_parent);
     for (int32_t k = 0; k < n_level; ++k) { free(level[k].hist); free(level[k].ihist); }
     free(level); level = next; n_level = n_next;
   }

@@ -4,6 +4,8 @@
 //   bins      uint8 [n_rows][row_stride]     row_stride = n_groups*32; group g owns bytes
 //                                            [g*32, g*32+gsize[g]) of a row, rest zero padding;
 //                                            bin 255 is the missing sentinel
+//   bins_col  uint8 [n_features][col_stride] feature-major copy, read by the row partition (1 byte/row
+//                                            from a 128-byte row would cost a whole DRAM burst per row)
 //   gpair     int2  [n_rows]                 (qg, qh) fixed-point gradient / hessian
 //   hist      int64 [node][group][2][256][32] plane 0 = sum qg, plane 1 = sum qh, slot = feature
 //                                            within group; 128 KiB per (node, group)
@@ -28,7 +30,7 @@ struct B2HistWork {
 // per-split-node descriptor for the row partition kernel
 struct B2SplitWork {
   int32_t seg_begin, seg_count;
-  int32_t feature_byte;   // byte offset of the split feature inside a row
+  int32_t feature;        // split feature id: column of the feature-major bin copy
   int32_t split_bin;      // rows with bin <= split_bin go left
   int32_t default_left;   // direction of the missing sentinel (only if feature has missing)
   int32_t has_missing;

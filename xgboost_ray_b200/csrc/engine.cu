@@ -33,7 +33,7 @@ int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const i
                           const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, cudaStream_t);
 int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, cudaStream_t);
 int b2_part_chunk_rows();
-int b2_launch_partition(const uint8_t*, int, const int32_t*, int32_t*, const B2SplitWork*, int, int, int32_t*, int,
+int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, int, int, int32_t*, int,
                         cudaStream_t);
 int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const void*, int, int, const int32_t*, int,
                         long long*, int, cudaStream_t);
@@ -55,8 +55,8 @@ int b2_launch_extract_keys(const float*, int64_t, int, int, float, uint32_t*, in
 size_t b2_sort_temp_bytes(int64_t);
 int b2_sketch_column(const uint32_t*, uint32_t*, int64_t, int64_t, void*, size_t, int32_t*, int32_t*, float*, long long*,
                      int32_t*, int, float*, int32_t*, float*, int, cudaStream_t);
-int b2_launch_bin(const float*, int64_t, int, float, const int32_t*, const float*, const int32_t*, int, uint8_t*, int,
-                  cudaStream_t);
+int b2_launch_bin(const float*, int64_t, int, float, const int32_t*, const float*, const int32_t*, int, uint8_t*, uint8_t*,
+                  int64_t, int, cudaStream_t);
 }
 
 namespace {
@@ -204,6 +204,8 @@ struct Matrix : HandleBase {
   DevBuf<float> raw;     // [n][F], optional
   bool has_raw = false;
   DevBuf<uint8_t> bins;  // [n][row_stride]
+  DevBuf<uint8_t> bins_col;  // [F][col_stride] feature-major copy for the row partition
+  int64_t col_stride = 0;
   bool quantized = false;
   int n_groups = 0, row_stride = 0, max_bin = 0;
   std::vector<int32_t> group_first, group_size, feat_byte;
@@ -327,8 +329,10 @@ void bin_matrix(Matrix* m) {
   upload_cuts(m);
   m->bins.ensure((size_t)std::max<int64_t>(m->n, 1) * m->row_stride);
   CUDA_CHECK(cudaMemsetAsync(m->bins.p, 0, (size_t)std::max<int64_t>(m->n, 1) * m->row_stride, s));
+  m->col_stride = (std::max<int64_t>(m->n, 1) + 127) & ~(int64_t)127;
+  m->bins_col.ensure((size_t)m->col_stride * m->F);
   LAUNCH_CHECK(b2_launch_bin(m->raw.p, m->n, m->F, m->missing, m->d_cut_ptrs.p, m->d_cut_vals.p, m->d_feat_byte.p,
-                             m->row_stride, m->bins.p, ctx->num_sms, s));
+                             m->row_stride, m->bins.p, m->bins_col.p, m->col_stride, ctx->num_sms, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   m->quantized = true;
 }
@@ -643,7 +647,7 @@ void grow_tree(Booster* b, int k) {
       tree.sum_hess[l] = HL; tree.sum_hess[r] = HR;
       tree.base_weight[l] = h_calc_weight(p, GL, HL); tree.base_weight[r] = h_calc_weight(p, GR, HR);
       B2SplitWork sw{};
-      sw.seg_begin = (int32_t)nd.begin; sw.seg_count = (int32_t)nd.count; sw.feature_byte = m->feat_byte[f];
+      sw.seg_begin = (int32_t)nd.begin; sw.seg_count = (int32_t)nd.count; sw.feature = f;
       sw.split_bin = best.bin; sw.default_left = best.default_left; sw.has_missing = m->has_missing[f];
       sw.chunk_begin = pchunks; pchunks += (int)((nd.count + pchunk - 1) / pchunk);
       swork.push_back(sw); split_parent.push_back(i);
@@ -657,7 +661,7 @@ void grow_tree(Booster* b, int k) {
     const int in_buf = level[split_parent[0]].buf;  // all nodes of a level share the buffer parity
     CUDA_CHECK(cudaMemsetAsync(b->d_counters.p, 0, 2 * ns * sizeof(int32_t), s));
     CUDA_CHECK(cudaMemcpyAsync(b->d_split_work.p, swork.data(), ns * sizeof(B2SplitWork), cudaMemcpyHostToDevice, s));
-    LAUNCH_CHECK(b2_launch_partition(m->bins.p, m->row_stride, b->ridx[in_buf].p, b->ridx[in_buf ^ 1].p, b->d_split_work.p, ns,
+    LAUNCH_CHECK(b2_launch_partition(m->bins_col.p, m->col_stride, b->ridx[in_buf].p, b->ridx[in_buf ^ 1].p, b->d_split_work.p, ns,
                                      pchunks, b->d_counters.p, ctx->num_sms, s));
     b->t.kernel_launches++;
     std::vector<int32_t> h_counters(2 * ns);

@@ -69,6 +69,24 @@ __device__ __forceinline__ RowData load_row(const uint8_t* __restrict__ bins, co
   return d;
 }
 
+// row id of chunk-row r (or -1 past the end of the chunk); root level: identity
+template <bool kGather>
+__device__ __forceinline__ int64_t fetch_rid(const int32_t* __restrict__ ridx, int64_t pos0, int r, int nrows) {
+  if (r >= nrows) return -1;
+  return kGather ? (int64_t)__ldg(ridx + pos0 + r) : pos0 + r;
+}
+__device__ __forceinline__ RowData load_row_id(const uint8_t* __restrict__ bins, const int2* __restrict__ gpair,
+                                               int64_t rid, int row_stride, int lane_byte_off) {
+  RowData d;
+  d.bins = make_uint4(0, 0, 0, 0);
+  d.gp = make_int2(0, 0);
+  if (rid >= 0) {
+    d.bins = ldg_nc_v4(bins + rid * row_stride + lane_byte_off);
+    d.gp = __ldg(gpair + rid);
+  }
+  return d;
+}
+
 // 16 steps: one byte (= one feature slot) per step, two conflict-free shared atomics per step
 __device__ __forceinline__ void accumulate_row(const RowData& d, uint32_t smem_g, int rot, int half) {
   uint4 b = rotate_bytes(d.bins, rot);
@@ -136,13 +154,29 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
     rows_in_window += nrows;
     const int64_t pos0 = (int64_t)seg_begin + row0;
     const int iter_rows = n_warps * kRowsPerWarpIter;
-    int r = warp * kRowsPerWarpIter + rot;
-    RowData d = load_row<kGather>(bins, gpair, ridx, pos0 + r, r < nrows, row_stride, lane_byte_off);
-    for (; r - rot < nrows; r += iter_rows) {   // warp-uniform trip count
-      const int rn = r + iter_rows;
-      RowData nx = load_row<kGather>(bins, gpair, ridx, pos0 + rn, rn < nrows, row_stride, lane_byte_off);
-      accumulate_row(d, smem_g, rot, half);
-      d = nx;
+    // 3-stage register pipeline: while stage k is accumulated, the loads of the next two
+    // iterations are in flight, and (gather) the row ids of three more iterations behind them,
+    // so no load waits on the ridx -> bins dependency.
+    const int r0 = warp * kRowsPerWarpIter + rot;
+    int64_t id0 = fetch_rid<kGather>(ridx, pos0, r0, nrows);
+    int64_t id1 = fetch_rid<kGather>(ridx, pos0, r0 + iter_rows, nrows);
+    int64_t id2 = fetch_rid<kGather>(ridx, pos0, r0 + 2 * iter_rows, nrows);
+    RowData s0 = load_row_id(bins, gpair, id0, row_stride, lane_byte_off);
+    id0 = fetch_rid<kGather>(ridx, pos0, r0 + 3 * iter_rows, nrows);
+    RowData s1 = load_row_id(bins, gpair, id1, row_stride, lane_byte_off);
+    id1 = fetch_rid<kGather>(ridx, pos0, r0 + 4 * iter_rows, nrows);
+    RowData s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
+    id2 = fetch_rid<kGather>(ridx, pos0, r0 + 5 * iter_rows, nrows);
+    for (int r = r0 - rot; r < nrows; r += 3 * iter_rows) {   // warp-uniform trip count
+      accumulate_row(s0, smem_g, rot, half);
+      s0 = load_row_id(bins, gpair, id0, row_stride, lane_byte_off);
+      id0 = fetch_rid<kGather>(ridx, pos0, r + rot + 6 * iter_rows, nrows);
+      if (r + iter_rows < nrows) accumulate_row(s1, smem_g, rot, half);
+      s1 = load_row_id(bins, gpair, id1, row_stride, lane_byte_off);
+      id1 = fetch_rid<kGather>(ridx, pos0, r + rot + 7 * iter_rows, nrows);
+      if (r + 2 * iter_rows < nrows) accumulate_row(s2, smem_g, rot, half);
+      s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
+      id2 = fetch_rid<kGather>(ridx, pos0, r + rot + 8 * iter_rows, nrows);
     }
   }
   if (cur >= 0) {

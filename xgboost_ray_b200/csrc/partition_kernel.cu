@@ -18,7 +18,7 @@ struct SegWork {  // generic (segment, id) descriptor, chunked
 };
 
 __global__ void __launch_bounds__(kPartThreads)
-partition_kernel(const uint8_t* __restrict__ bins, int row_stride, const int32_t* __restrict__ ridx_in,
+partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const int32_t* __restrict__ ridx_in,
                  int32_t* __restrict__ ridx_out, const B2SplitWork* __restrict__ work, int n_work, int total_chunks,
                  int32_t* __restrict__ counters /* [2*n_work]: left, right */) {
   __shared__ int s_warp_left[kPartThreads / 32][kPartChunk / kPartThreads];
@@ -41,7 +41,7 @@ partition_kernel(const uint8_t* __restrict__ bins, int row_stride, const int32_t
       const int r = it * kPartThreads + threadIdx.x;
       const bool valid = r < nrows;
       rid[it] = valid ? __ldg(ridx_in + w.seg_begin + row0 + r) : 0;
-      int b = valid ? (int)bins[(int64_t)rid[it] * row_stride + w.feature_byte] : 0;
+      int b = valid ? (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid[it]) : 0;
       bool l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : (b <= w.split_bin);
       left[it] = valid && l;
       bal[it] = __ballot_sync(0xffffffffu, left[it]);
@@ -144,12 +144,12 @@ __global__ void iota_kernel(int32_t* out, int64_t n) {
 extern "C" {
 int b2_part_chunk_rows() { return b2::kPartChunk; }
 
-int b2_launch_partition(const uint8_t* bins, int row_stride, const int32_t* ridx_in, int32_t* ridx_out,
+int b2_launch_partition(const uint8_t* bins_col, int64_t col_stride, const int32_t* ridx_in, int32_t* ridx_out,
                         const B2SplitWork* work, int n_work, int total_chunks, int32_t* counters, int num_sms,
                         cudaStream_t stream) {
   if (total_chunks <= 0) return 0;
   int grid = total_chunks < num_sms * 8 ? total_chunks : num_sms * 8;
-  b2::partition_kernel<<<grid, b2::kPartThreads, 0, stream>>>(bins, row_stride, ridx_in, ridx_out, work, n_work,
+  b2::partition_kernel<<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, n_work,
                                                              total_chunks, counters);
   return (int)cudaGetLastError();
 }

@@ -130,7 +130,8 @@ prune_cuts_kernel(const float* __restrict__ uval, const long long* __restrict__ 
 // bin = upper_bound(cuts_f, x) clamped; missing -> 255.  One thread per matrix element.
 __global__ void bin_kernel(const float* __restrict__ X, int64_t n, int F, float missing, int missing_is_nan,
                            const int32_t* __restrict__ cut_ptrs, const float* __restrict__ cut_vals,
-                           const int32_t* __restrict__ feat_byte, int row_stride, uint8_t* __restrict__ bins) {
+                           const int32_t* __restrict__ feat_byte, int row_stride, uint8_t* __restrict__ bins,
+                           uint8_t* __restrict__ bins_col, int64_t col_stride) {
   const int64_t total = n * F;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = e / F; const int f = (int)(e - row * F);
@@ -145,6 +146,7 @@ __global__ void bin_kernel(const float* __restrict__ X, int64_t n, int F, float 
       b = lo >= nf ? nf - 1 : lo;
     }
     bins[row * row_stride + feat_byte[f]] = (uint8_t)b;
+    bins_col[(int64_t)f * col_stride + row] = (uint8_t)b;
   }
 }
 
@@ -196,10 +198,11 @@ int b2_sketch_column(const uint32_t* keys_in, uint32_t* keys_sorted, int64_t n_t
 }
 
 int b2_launch_bin(const float* X, int64_t n, int F, float missing, const int32_t* cut_ptrs, const float* cut_vals,
-                  const int32_t* feat_byte, int row_stride, uint8_t* bins, int num_sms, cudaStream_t s) {
+                  const int32_t* feat_byte, int row_stride, uint8_t* bins, uint8_t* bins_col, int64_t col_stride, int num_sms,
+                  cudaStream_t s) {
   if (n <= 0) return 0;
   b2::bin_kernel<<<sk_grid(n * F, num_sms), 256, 0, s>>>(X, n, F, missing, missing != missing ? 1 : 0, cut_ptrs, cut_vals,
-                                                        feat_byte, row_stride, bins);
+                                                        feat_byte, row_stride, bins, bins_col, col_stride);
   return (int)cudaGetLastError();
 }
 }
