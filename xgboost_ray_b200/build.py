@@ -21,6 +21,7 @@ SOURCES = {
     "hist_kernel.cu": [],
     "split_kernel.cu": ["--fmad=false"],
     "partition_kernel.cu": ["--fmad=false"],
+    "control_kernel.cu": ["--fmad=false"],
     "objective_kernel.cu": ["--fmad=false"],   # bit-exact gradients vs the oracle
     "sketch.cu": ["--fmad=false"],
     "engine.cu": [],

@@ -63,6 +63,32 @@ struct B2TreeNodeDev {
   int32_t default_left;
 };
 
+// ---- device-resident control tables of the sync-free level loop (control_kernel.cu)
+struct B2LevelCtl {
+  int32_t n_nodes;            // nodes of this level (to evaluate / decide)
+  int32_t n_split;            // nodes that expand (filled by decide)
+  int32_t part_chunks;        // partition work items of this level
+  int32_t hist_n_work;        // histogram build list of THIS level (filled by the previous finalize)
+  int32_t hist_total_chunks;
+  int32_t hist_chunk_rows;
+  int32_t n_pairs;            // (parent, built, sibling) triples of this level
+  int32_t pad;
+};
+struct B2NodeSeg { int32_t nid, begin, count, buf; };
+struct B2LeafDev { int32_t nid, buf, begin, count; };
+struct B2SegWork {  // generic chunked (segment, id) descriptor
+  int32_t seg_begin, seg_count, id, chunk_begin;
+  int32_t buf, pad0, pad1, pad2;
+};
+struct B2TreeDev {            // arrays of capacity max_nodes
+  int32_t *left, *right, *parent, *feature, *split_bin, *default_left;
+  float* loss_chg;
+  long long *sum_g, *sum_h;   // fixed-point node totals
+  float *leaf_weight, *leaf_value;
+  int32_t* n_nodes;
+};
+struct B2CtlParams { double mcw, lambda, alpha; float gamma, eta; };
+
 struct B2TrainParamDev {
   double min_child_weight, lambda, alpha;
   double inv_scale_g, inv_scale_h;

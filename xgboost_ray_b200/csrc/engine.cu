@@ -27,18 +27,28 @@
 // ---------------------------------------------------------------- kernel launchers (other TUs)
 extern "C" {
 int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
-                   int, cudaStream_t);
-int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, cudaStream_t);
+                   const B2LevelCtl*, int, cudaStream_t);
+int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, const B2LevelCtl*, cudaStream_t);
 int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
-                          const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, cudaStream_t);
+                          const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, const B2LevelCtl*, cudaStream_t);
 int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, cudaStream_t);
 int b2_part_chunk_rows();
-int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, int, int, int32_t*, int,
-                        cudaStream_t);
-int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const void*, int, int, const int32_t*, int,
+int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, const B2LevelCtl*, int, int32_t*,
+                        int, cudaStream_t);
+int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const int32_t*, int,
                         long long*, int, cudaStream_t);
-int b2_launch_pred_update(float*, int, int, const int32_t*, const int32_t*, const void*, int, int, const float*, int,
+int b2_launch_pred_update(float*, int, int, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const float*, int,
                           cudaStream_t);
+int b2_launch_decide(B2LevelCtl*, B2LevelCtl*, const B2NodeSeg*, B2NodeSeg*, const B2EvalNode*, B2EvalNode*, const B2SplitCand*,
+                     int, int, B2TreeDev, B2SplitWork*, int32_t*, B2LeafDev*, int32_t*, const uint8_t*, const int32_t*, int,
+                     B2CtlParams, cudaStream_t);
+int b2_launch_finalize_level(const B2LevelCtl*, B2LevelCtl*, B2NodeSeg*, B2EvalNode*, const B2SplitWork*, const int32_t*,
+                             const int32_t*, B2HistWork*, int32_t*, int, int, int, int, int, long long*, cudaStream_t);
+int b2_launch_leaf_plan(const B2LeafDev*, const int32_t*, B2SegWork*, B2LevelCtl*, cudaStream_t);
+int b2_launch_leaf_values(const B2LeafDev*, const int32_t*, const long long*, const int32_t*, int, B2CtlParams, float*, B2TreeDev,
+                          cudaStream_t);
+int b2_launch_tree_init(B2TreeDev, B2LevelCtl*, B2NodeSeg*, B2EvalNode*, int32_t*, int, cudaStream_t);
+int b2_launch_root_record(B2TreeDev, const B2EvalNode*, cudaStream_t);
 int b2_launch_iota(int32_t*, int64_t, cudaStream_t);
 int b2_launch_gradient(int, int, const float*, const float*, const float*, int64_t, float2*, int, cudaStream_t);
 int b2_launch_pack_custom(const float*, const float*, int, int64_t, float2*, int, cudaStream_t);
@@ -367,7 +377,6 @@ struct TreeHost {
   int size() const { return (int)left.size(); }
 };
 
-struct SegWorkH { int32_t seg_begin, seg_count, id, chunk_begin, buf, pad0, pad1, pad2; };
 
 struct Timers {
   double hist_ms = 0, round_ms = 0;
@@ -398,9 +407,19 @@ struct Booster : HandleBase {
   DevBuf<long long> hist[2];
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
-  DevBuf<B2HistWork> d_hist_work; DevBuf<B2SplitWork> d_split_work; DevBuf<SegWorkH> d_seg_work;
-  DevBuf<B2EvalNode> d_eval_nodes; DevBuf<B2SplitCand> d_cands; DevBuf<int32_t> d_counters, d_triples;
+  // device-resident control tables of the sync-free level loop (control_kernel.cu)
+  int ctl_depth = 0;                       // max_depth the tables are sized for
+  DevBuf<int32_t> t_i32;                   // 6 int32 arrays [max_nodes] + n_nodes + n_leaves
+  DevBuf<float> t_f32;                     // loss_chg, leaf_weight, leaf_value [max_nodes]
+  DevBuf<long long> t_i64;                 // sum_g, sum_h [max_nodes] + level_rows [max_depth+1]
+  DevBuf<B2LevelCtl> d_ctl;                // [0],[1] level ping-pong, [2] leaf pass
+  DevBuf<B2NodeSeg> d_seg[2]; DevBuf<B2EvalNode> d_ev[2];
+  DevBuf<B2HistWork> d_hist_work; DevBuf<B2SplitWork> d_split_work; DevBuf<B2SegWork> d_seg_work;
+  DevBuf<B2SplitCand> d_cands; DevBuf<int32_t> d_counters, d_triples, d_pair_parent;
+  DevBuf<B2LeafDev> d_leaves;
   DevBuf<long long> d_leaf_sums; DevBuf<float> d_leaf_values; DevBuf<double> d_metric;
+  std::vector<void*> staging;              // pinned host copies of finished trees, one per class tree of a round
+  size_t staging_bytes = 0;
   DevBuf<float> d_custom_g, d_custom_h;
   std::map<Matrix*, EvalCache*> eval_cache;
   // profiling
@@ -413,6 +432,7 @@ struct Booster : HandleBase {
     if (round_start) cudaEventDestroy(round_start);
     if (round_stop) cudaEventDestroy(round_stop);
     for (auto& kv : eval_cache) delete kv.second;
+    for (void* h : staging) cudaFreeHost(h);
   }
 };
 
@@ -488,33 +508,10 @@ float h_calc_weight(const Params& p, double G, double H) {
   return (float)(-t / (H + (double)p.lambda));
 }
 
-struct NodeState {
-  int nid, depth, buf;
-  int64_t begin, count;
-  long long sg, sh;
-  int hist_slot;
-  float root_gain;
-};
-
 int window_rows_for(int qbits) {
   // |q| <= 2^qbits, int32 cell: rows * 2^qbits <= 2^31 - 1
   long long w = ((1LL << 31) - 1) >> qbits;
   return (int)std::min<long long>(w, 1LL << 30);
-}
-
-void launch_hist(Booster* b, const int32_t* ridx, const std::vector<B2HistWork>& work, int total_chunks, int chunk_rows,
-                 long long* level_hist, int64_t rows) {
-  Matrix* m = b->train; cudaStream_t s = b->ctx->stream;
-  if (work.empty() || total_chunks == 0) return;
-  b->d_hist_work.ensure(work.size());
-  CUDA_CHECK(cudaMemcpyAsync(b->d_hist_work.p, work.data(), work.size() * sizeof(B2HistWork), cudaMemcpyHostToDevice, s));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (b->p.profile) { e0 = get_event(b); e1 = get_event(b); CUDA_CHECK(cudaEventRecord(e0, s)); }
-  LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, ridx, b->d_hist_work.p, (int)work.size(), total_chunks,
-                              chunk_rows, window_rows_for(b->p.qbits), m->n_groups, level_hist, b->ctx->num_sms, s));
-  if (b->p.profile) { CUDA_CHECK(cudaEventRecord(e1, s)); b->hist_events.push_back({e0, e1}); }
-  b->t.hist_launches++; b->t.kernel_launches++; b->t.hist_rows += rows;
-  b->t.hist_bytes += (double)rows * (m->F + 8 + (ridx ? 4 : 0)) + (double)work.size() * m->F * 256.0 * 16.0;
 }
 
 int pick_chunk_rows(Booster* b, int64_t rows) {
@@ -528,11 +525,67 @@ int pick_chunk_rows(Booster* b, int64_t rows) {
   return c;
 }
 
-// Grow one tree for class k from gh[k] (already on device); updates margin[:, k].
-void grow_tree(Booster* b, int k) {
+// layout of the per-tree read-back block (device t_* buffers are copied verbatim into one pinned block)
+struct TreeLayout {
+  size_t max_nodes, i32_count, f32_count, i64_count, bytes;
+  size_t off_f32, off_i64, off_qexp;
+};
+TreeLayout tree_layout(int max_depth) {
+  TreeLayout L;
+  L.max_nodes = ((size_t)1 << (max_depth + 1));
+  L.i32_count = 6 * L.max_nodes + 2;
+  L.f32_count = 3 * L.max_nodes;
+  L.i64_count = 2 * L.max_nodes + (size_t)max_depth + 2;
+  L.off_f32 = L.i32_count * 4;
+  L.off_i64 = (L.off_f32 + L.f32_count * 4 + 7) & ~(size_t)7;
+  L.off_qexp = L.off_i64 + L.i64_count * 8;
+  L.bytes = L.off_qexp + 16;
+  return L;
+}
+B2TreeDev tree_dev(Booster* b) {
+  const TreeLayout L = tree_layout(b->ctl_depth);
+  B2TreeDev t;
+  int32_t* i = b->t_i32.p; const size_t m = L.max_nodes;
+  t.left = i; t.right = i + m; t.parent = i + 2 * m; t.feature = i + 3 * m; t.split_bin = i + 4 * m; t.default_left = i + 5 * m;
+  t.n_nodes = i + 6 * m;
+  t.loss_chg = b->t_f32.p; t.leaf_weight = b->t_f32.p + m; t.leaf_value = b->t_f32.p + 2 * m;
+  t.sum_g = b->t_i64.p; t.sum_h = b->t_i64.p + m;
+  return t;
+}
+
+void ensure_ctl_tables(Booster* b) {
+  const int D = b->p.max_depth; const int G = b->train->n_groups;
+  if (b->ctl_depth == D) return;
+  b->ctl_depth = D;
+  const TreeLayout L = tree_layout(D);
+  const size_t lcap = (size_t)1 << D, half = (size_t)1 << (D > 0 ? D - 1 : 0);
+  b->t_i32.ensure(L.i32_count); b->t_f32.ensure(L.f32_count); b->t_i64.ensure(L.i64_count);
+  b->d_ctl.ensure(3);
+  for (int k = 0; k < 2; ++k) { b->d_seg[k].ensure(lcap); b->d_ev[k].ensure(lcap); }
+  b->d_hist_work.ensure(half); b->d_split_work.ensure(half); b->d_cands.ensure(half * G);
+  b->d_counters.ensure(2 * half); b->d_triples.ensure(3 * half); b->d_pair_parent.ensure(half);
+  b->d_leaves.ensure(L.max_nodes); b->d_seg_work.ensure(L.max_nodes);
+  b->d_leaf_sums.ensure(2 * lcap); b->d_leaf_values.ensure(lcap);
+  b->node_elems = (size_t)G * B2_GROUP_ELEMS;
+  b->hist[0].ensure(half * b->node_elems); b->hist[1].ensure(half * b->node_elems);
+  CUDA_CHECK(cudaMemsetAsync(b->t_i64.p, 0, L.i64_count * 8, b->ctx->stream));
+}
+
+void record_hist_launch(Booster* b, cudaEvent_t& e0, cudaEvent_t& e1, bool begin) {
+  if (!b->p.profile) return;
+  if (begin) { e0 = get_event(b); e1 = get_event(b); CUDA_CHECK(cudaEventRecord(e0, b->ctx->stream)); }
+  else { CUDA_CHECK(cudaEventRecord(e1, b->ctx->stream)); b->hist_events.push_back({e0, e1}); }
+}
+
+// Grow one tree for class k from gh[k] (already on device); updates margin[:, k].  No host
+// synchronisation: every data-dependent decision is taken by the control kernels, the host
+// enqueues a fixed sequence and the finished tree is copied into pinned block `slot`.
+void grow_tree(Booster* b, int k, int slot) {
   Matrix* m = b->train; Ctx* ctx = b->ctx; cudaStream_t s = ctx->stream; const Params& p = b->p;
-  const int64_t n = m->n; const int K = p.num_class; const int G = m->n_groups;
+  const int64_t n = m->n; const int K = p.num_class; const int G = m->n_groups; const int D = p.max_depth;
   const float2* gh = b->gh.p + (size_t)k * n;
+  ensure_ctl_tables(b);
+  const TreeLayout L = tree_layout(D);
   // ---- fixed-point quantisation (global scale via allreduce max)
   b->d_absmax.ensure(2); b->d_qexp.ensure(2);
   CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * sizeof(uint32_t), s));
@@ -541,216 +594,150 @@ void grow_tree(Booster* b, int k) {
   LAUNCH_CHECK(b2_launch_quant_exponent(b->d_absmax.p, b->d_qexp.p, s));
   b->q.ensure((size_t)std::max<int64_t>(n, 1));
   LAUNCH_CHECK(b2_launch_quantize(gh, n, b->d_qexp.p, p.qbits, b->q.p, ctx->num_sms, s));
-  b->t.kernel_launches += 3;
-  int32_t h_qexp[2];
-  CUDA_CHECK(cudaMemcpyAsync(h_qexp, b->d_qexp.p, sizeof(h_qexp), cudaMemcpyDeviceToHost, s));
+  b->ridx[0].ensure((size_t)std::max<int64_t>(n, 1)); b->ridx[1].ensure((size_t)std::max<int64_t>(n, 1));
+  LAUNCH_CHECK(b2_launch_iota(b->ridx[0].p, n, s));
+  b->t.kernel_launches += 4;
 
   B2TrainParamDev dp;
   dp.min_child_weight = (double)p.min_child_weight; dp.lambda = (double)p.lambda; dp.alpha = (double)p.alpha;
   dp.inv_scale_g = dp.inv_scale_h = 1.0;
+  B2CtlParams cp; cp.mcw = dp.min_child_weight; cp.lambda = dp.lambda; cp.alpha = dp.alpha; cp.gamma = p.gamma; cp.eta = p.eta;
+  const B2TreeDev tree = tree_dev(b);
+  int32_t* d_n_leaves = tree.n_nodes + 1;
+  long long* d_level_rows = b->t_i64.p + 2 * L.max_nodes;
+  B2LevelCtl* ctl = b->d_ctl.p;
+  const int window = window_rows_for(p.qbits);
+  const int n_streams = std::max(1, ctx->num_sms * 3 / G);
+  const int pchunk = b2_part_chunk_rows();
+  const int max_part_chunks_total = (int)((n + pchunk - 1) / pchunk);
 
-  b->node_elems = (size_t)G * B2_GROUP_ELEMS;
-  const size_t max_level_nodes = (size_t)1 << (p.max_depth - 1);
-  b->hist[0].ensure(max_level_nodes * b->node_elems);
-  b->hist[1].ensure(max_level_nodes * b->node_elems);
-  b->ridx[0].ensure((size_t)std::max<int64_t>(n, 1)); b->ridx[1].ensure((size_t)std::max<int64_t>(n, 1));
-  LAUNCH_CHECK(b2_launch_iota(b->ridx[0].p, n, s));
-  b->d_eval_nodes.ensure(max_level_nodes); b->d_cands.ensure(max_level_nodes * G);
-  b->d_counters.ensure(2 * max_level_nodes); b->d_triples.ensure(3 * max_level_nodes);
-  b->d_split_work.ensure(max_level_nodes);
-
-  TreeHost tree;
-  std::vector<NodeState> level(1);
-  level[0] = NodeState{tree.add(-1), 0, 0, 0, n, 0, 0, 0, 0.f};
-  // ---- root histogram (no gather)
+  LAUNCH_CHECK(b2_launch_tree_init(tree, ctl, b->d_seg[0].p, b->d_ev[0].p, d_n_leaves, (int)n, s));
+  // ---- root histogram (no gather; row count known on the host)
   CUDA_CHECK(cudaMemsetAsync(b->hist[0].p, 0, b->node_elems * sizeof(long long), s));
   {
-    std::vector<B2HistWork> work;
     const int chunk_rows = pick_chunk_rows(b, n);
     const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
-    if (n > 0) work.push_back(B2HistWork{0, (int32_t)n, 0, 0});
-    launch_hist(b, nullptr, work, chunks, chunk_rows, b->hist[0].p, n);
+    if (n > 0) {
+      B2HistWork w{0, (int32_t)n, 0, 0};
+      CUDA_CHECK(cudaMemcpyAsync(b->d_hist_work.p, &w, sizeof(w), cudaMemcpyHostToDevice, s));
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      record_hist_launch(b, e0, e1, true);
+      LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
+                                  b->hist[0].p, nullptr, ctx->num_sms, s));
+      record_hist_launch(b, e0, e1, false);
+      b->t.hist_launches++; b->t.kernel_launches++;
+    }
   }
   allreduce(b->comm, b->hist[0].p, b->node_elems, kNcclInt64, kNcclSum, s);
   b->t.allreduce_bytes += (double)b->node_elems * 8;
-  {
-    B2EvalNode rn{0, 0, 0, 0.f};
-    CUDA_CHECK(cudaMemcpyAsync(b->d_eval_nodes.p, &rn, sizeof(rn), cudaMemcpyHostToDevice, s));
-    LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_eval_nodes.p, b->d_qexp.p, p.qbits, dp, s));
-    b->t.kernel_launches++;
-  }
-  struct Leaf { int nid, buf; int64_t begin, count; };
-  std::vector<Leaf> leaves;
-  std::vector<B2SplitCand> h_cands;
-  std::vector<B2EvalNode> h_eval;
-  double inv_sg = 1.0, inv_sh = 1.0;
-  bool have_scales = false;
-  int cur_buf = 0;   // hist buffer of the current level
-  for (int depth = 0; !level.empty(); ++depth) {
-    const int nl = (int)level.size();
-    const bool can_split = depth < p.max_depth;
+  LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_ev[0].p, b->d_qexp.p, p.qbits, dp, s));
+  LAUNCH_CHECK(b2_launch_root_record(tree, b->d_ev[0].p, s));
+  b->t.kernel_launches += 3;
+  int hb = 0;  // hist buffer holding the current level
+  for (int d = 0; d <= D; ++d) {
+    const int cur = d & 1, nxt = cur ^ 1;
+    const int max_nodes_level = 1 << d;
+    const bool can_split = d < D;
     if (can_split) {
-      if (depth > 0) {
-        h_eval.resize(nl);
-        for (int i = 0; i < nl; ++i) h_eval[i] = B2EvalNode{level[i].sg, level[i].sh, level[i].hist_slot, level[i].root_gain};
-        CUDA_CHECK(cudaMemcpyAsync(b->d_eval_nodes.p, h_eval.data(), nl * sizeof(B2EvalNode), cudaMemcpyHostToDevice, s));
-      }
-      LAUNCH_CHECK(b2_launch_eval_splits(b->hist[cur_buf].p, G, b->d_eval_nodes.p, nl, m->d_group_first.p, m->d_group_size.p,
-                                         m->d_nbins.p, m->d_has_missing.p, b->d_qexp.p, p.qbits, dp, b->d_cands.p, s));
+      LAUNCH_CHECK(b2_launch_eval_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_group_first.p, m->d_group_size.p,
+                                         m->d_nbins.p, m->d_has_missing.p, b->d_qexp.p, p.qbits, dp, b->d_cands.p, ctl + cur, s));
       b->t.kernel_launches++;
-      h_cands.resize((size_t)nl * G);
-      CUDA_CHECK(cudaMemcpyAsync(h_cands.data(), b->d_cands.p, h_cands.size() * sizeof(B2SplitCand), cudaMemcpyDeviceToHost, s));
-      B2EvalNode root_node;
-      if (depth == 0) CUDA_CHECK(cudaMemcpyAsync(&root_node, b->d_eval_nodes.p, sizeof(root_node), cudaMemcpyDeviceToHost, s));
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      if (b->cancel.load()) fail("training cancelled");
-      if (!have_scales) {
-        inv_sg = ldexp(1.0, h_qexp[0] - p.qbits); inv_sh = ldexp(1.0, h_qexp[1] - p.qbits); have_scales = true;
-      }
-      if (depth == 0) {
-        level[0].sg = root_node.sum_g; level[0].sh = root_node.sum_h; level[0].root_gain = root_node.root_gain;
-        const double Gr = (double)root_node.sum_g * inv_sg, Hr = (double)root_node.sum_h * inv_sh;
-        tree.sum_hess[0] = Hr; tree.base_weight[0] = h_calc_weight(p, Gr, Hr);
-      }
-    } else if (!have_scales) {
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      inv_sg = ldexp(1.0, h_qexp[0] - p.qbits); inv_sh = ldexp(1.0, h_qexp[1] - p.qbits); have_scales = true;
     }
-    // ---- decide
-    std::vector<NodeState> next;
-    std::vector<B2SplitWork> swork;
-    std::vector<int> split_parent;  // index into level
-    int pchunks = 0; const int pchunk = b2_part_chunk_rows();
-    for (int i = 0; i < nl; ++i) {
-      NodeState& nd = level[i];
-      bool expand = false; B2SplitCand best{}; best.feature = -1;
-      if (can_split) {
-        for (int g = 0; g < G; ++g) {
-          const B2SplitCand& c = h_cands[(size_t)i * G + g];
-          if (c.feature < 0) continue;
-          if (best.feature < 0 || c.loss_chg > best.loss_chg || (c.loss_chg == best.loss_chg && c.order < best.order)) best = c;
-        }
-        if (best.feature >= 0) {
-          const double HL = (double)best.left_h * inv_sh, HR = (double)(nd.sh - best.left_h) * inv_sh;
-          expand = best.loss_chg > 1e-6f && HL != 0.0 && HR != 0.0 && !(best.loss_chg < p.gamma);
-        }
-      }
-      if (!expand) { leaves.push_back(Leaf{nd.nid, nd.buf, nd.begin, nd.count}); continue; }
-      const int l = tree.add(nd.nid), r = tree.add(nd.nid);
-      const int f = best.feature;
-      tree.left[nd.nid] = l; tree.right[nd.nid] = r; tree.feature[nd.nid] = f; tree.split_bin[nd.nid] = best.bin;
-      tree.default_left[nd.nid] = (uint8_t)best.default_left; tree.loss_chg[nd.nid] = best.loss_chg;
-      tree.value[nd.nid] = tree.base_weight[nd.nid];
-      tree.cond[nd.nid] = best.bin < 0 ? m->min_vals[f] : m->cut_vals[m->cut_ptrs[f] + best.bin];
-      const long long lg = best.left_g, lh = best.left_h, rg = nd.sg - lg, rh = nd.sh - lh;
-      const double GL = (double)lg * inv_sg, HL = (double)lh * inv_sh, GR = (double)rg * inv_sg, HR = (double)rh * inv_sh;
-      tree.sum_hess[l] = HL; tree.sum_hess[r] = HR;
-      tree.base_weight[l] = h_calc_weight(p, GL, HL); tree.base_weight[r] = h_calc_weight(p, GR, HR);
-      B2SplitWork sw{};
-      sw.seg_begin = (int32_t)nd.begin; sw.seg_count = (int32_t)nd.count; sw.feature = f;
-      sw.split_bin = best.bin; sw.default_left = best.default_left; sw.has_missing = m->has_missing[f];
-      sw.chunk_begin = pchunks; pchunks += (int)((nd.count + pchunk - 1) / pchunk);
-      swork.push_back(sw); split_parent.push_back(i);
-      NodeState ls{l, depth + 1, nd.buf ^ 1, nd.begin, 0, lg, lh, -1, (float)h_calc_gain(p, GL, HL)};
-      NodeState rs{r, depth + 1, nd.buf ^ 1, 0, 0, rg, rh, -1, (float)h_calc_gain(p, GR, HR)};
-      next.push_back(ls); next.push_back(rs);
-    }
-    if (swork.empty()) break;
-    // ---- partition rows of split nodes into the other index buffer
-    const int ns = (int)swork.size();
-    const int in_buf = level[split_parent[0]].buf;  // all nodes of a level share the buffer parity
-    CUDA_CHECK(cudaMemsetAsync(b->d_counters.p, 0, 2 * ns * sizeof(int32_t), s));
-    CUDA_CHECK(cudaMemcpyAsync(b->d_split_work.p, swork.data(), ns * sizeof(B2SplitWork), cudaMemcpyHostToDevice, s));
-    LAUNCH_CHECK(b2_launch_partition(m->bins_col.p, m->col_stride, b->ridx[in_buf].p, b->ridx[in_buf ^ 1].p, b->d_split_work.p, ns,
-                                     pchunks, b->d_counters.p, ctx->num_sms, s));
+    LAUNCH_CHECK(b2_launch_decide(ctl + cur, ctl + nxt, b->d_seg[cur].p, b->d_seg[nxt].p, b->d_ev[cur].p, b->d_ev[nxt].p,
+                                  b->d_cands.p, G, can_split ? 1 : 0, tree, b->d_split_work.p, b->d_pair_parent.p, b->d_leaves.p,
+                                  d_n_leaves, m->d_has_missing.p, b->d_qexp.p, p.qbits, cp, s));
     b->t.kernel_launches++;
-    std::vector<int32_t> h_counters(2 * ns);
-    CUDA_CHECK(cudaMemcpyAsync(h_counters.data(), b->d_counters.p, 2 * ns * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    for (int j = 0; j < ns; ++j) {
-      const NodeState& par = level[split_parent[j]];
-      NodeState& ls = next[2 * j]; NodeState& rs = next[2 * j + 1];
-      ls.begin = par.begin; ls.count = h_counters[2 * j];
-      rs.begin = par.begin + ls.count; rs.count = par.count - ls.count;
+    if (!can_split) break;
+    // ---- partition rows of the expanding nodes into the other index list
+    CUDA_CHECK(cudaMemsetAsync(b->d_counters.p, 0, 2 * (size_t)max_nodes_level * sizeof(int32_t), s));
+    LAUNCH_CHECK(b2_launch_partition(m->bins_col.p, m->col_stride, b->ridx[cur].p, b->ridx[nxt].p, b->d_split_work.p, ctl + cur,
+                                     max_part_chunks_total + max_nodes_level, b->d_counters.p, ctx->num_sms, s));
+    const bool need_hist = d + 1 < D;
+    LAUNCH_CHECK(b2_launch_finalize_level(ctl + cur, ctl + nxt, b->d_seg[nxt].p, b->d_ev[nxt].p, b->d_split_work.p, b->d_counters.p,
+                                          b->d_pair_parent.p, b->d_hist_work.p, b->d_triples.p, max_nodes_level, need_hist ? 1 : 0,
+                                          n_streams, window, p.hist_chunk_rows, d_level_rows + d + 1, s));
+    b->t.kernel_launches += 2;
+    if (need_hist) {
+      // ---- histograms of level d+1: built children in slots [0, 2^d), siblings in [2^d, 2^(d+1))
+      const int nh = hb ^ 1;
+      CUDA_CHECK(cudaMemsetAsync(b->hist[nh].p, 0, (size_t)max_nodes_level * b->node_elems * sizeof(long long), s));
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      record_hist_launch(b, e0, e1, true);
+      LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G,
+                                  b->hist[nh].p, ctl + nxt, ctx->num_sms, s));
+      record_hist_launch(b, e0, e1, false);
+      allreduce(b->comm, b->hist[nh].p, (size_t)max_nodes_level * b->node_elems, kNcclInt64, kNcclSum, s);
+      b->t.allreduce_bytes += (double)max_nodes_level * b->node_elems * 8;
+      LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[hb].p, b->hist[nh].p, b->d_triples.p, max_nodes_level, (int64_t)b->node_elems,
+                                           ctl + nxt, s));
+      b->t.hist_launches++; b->t.kernel_launches += 2;
+      hb = nh;
     }
-    // ---- histograms of the next level: build the smaller-hessian child, subtract for the sibling
-    if (depth + 1 < p.max_depth) {
-      const int nb = ns;
-      std::vector<B2HistWork> work; std::vector<int32_t> triples(3 * nb);
-      int64_t rows = 0, max_rows_level = 0;
-      for (int j = 0; j < nb; ++j) max_rows_level += std::min(next[2 * j].count, next[2 * j + 1].count) + 0;
-      // build set: smaller hessian (global decision, identical on every rank)
-      std::vector<int> built(nb);
-      int64_t build_rows = 0;
-      for (int j = 0; j < nb; ++j) {
-        const NodeState& ls = next[2 * j]; const NodeState& rs = next[2 * j + 1];
-        const double HL = (double)ls.sh * inv_sh, HR = (double)rs.sh * inv_sh;
-        built[j] = (HL < HR) ? 0 : 1;
-        build_rows += next[2 * j + built[j]].count;
-      }
-      const int chunk_rows = pick_chunk_rows(b, build_rows);
-      int chunks = 0;
-      for (int j = 0; j < nb; ++j) {
-        NodeState& bn = next[2 * j + built[j]]; NodeState& sn = next[2 * j + (built[j] ^ 1)];
-        bn.hist_slot = j; sn.hist_slot = nb + j;
-        triples[3 * j] = level[split_parent[j]].hist_slot; triples[3 * j + 1] = j; triples[3 * j + 2] = nb + j;
-        if (bn.count > 0) {
-          work.push_back(B2HistWork{(int32_t)bn.begin, (int32_t)bn.count, j, chunks});
-          chunks += (int)((bn.count + chunk_rows - 1) / chunk_rows);
-          rows += bn.count;
-        }
-      }
-      const int nbuf = cur_buf ^ 1;
-      CUDA_CHECK(cudaMemsetAsync(b->hist[nbuf].p, 0, (size_t)nb * b->node_elems * sizeof(long long), s));
-      launch_hist(b, b->ridx[in_buf ^ 1].p, work, chunks, chunk_rows, b->hist[nbuf].p, rows);
-      allreduce(b->comm, b->hist[nbuf].p, (size_t)nb * b->node_elems, kNcclInt64, kNcclSum, s);
-      b->t.allreduce_bytes += (double)nb * b->node_elems * 8;
-      CUDA_CHECK(cudaMemcpyAsync(b->d_triples.p, triples.data(), triples.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-      LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[cur_buf].p, b->hist[nbuf].p, b->d_triples.p, nb, (int64_t)b->node_elems, s));
-      b->t.kernel_launches++;
-      cur_buf = nbuf;
-      (void)max_rows_level;
-    }
-    level.swap(next);
   }
   // ---- leaves: 40-bit fixed-point leaf sums -> allreduce -> weights -> margin update
-  const int nleaf = (int)leaves.size();
-  std::vector<SegWorkH> lwork; int lchunks = 0; const int pchunk = b2_part_chunk_rows();
-  for (int i = 0; i < nleaf; ++i) {
-    if (leaves[i].count <= 0) continue;
-    lwork.push_back(SegWorkH{(int32_t)leaves[i].begin, (int32_t)leaves[i].count, i, lchunks, leaves[i].buf, 0, 0, 0});
-    lchunks += (int)((leaves[i].count + pchunk - 1) / pchunk);
+  const size_t lcap = (size_t)1 << D;
+  const int max_leaf_chunks = max_part_chunks_total + (int)lcap;
+  LAUNCH_CHECK(b2_launch_leaf_plan(b->d_leaves.p, d_n_leaves, b->d_seg_work.p, ctl + 2, s));
+  CUDA_CHECK(cudaMemsetAsync(b->d_leaf_sums.p, 0, 2 * lcap * sizeof(long long), s));
+  LAUNCH_CHECK(b2_launch_leaf_sums(gh, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks, b->d_qexp.p, 40,
+                                   b->d_leaf_sums.p, ctx->num_sms, s));
+  allreduce(b->comm, b->d_leaf_sums.p, 2 * lcap, kNcclInt64, kNcclSum, s);
+  LAUNCH_CHECK(b2_launch_leaf_values(b->d_leaves.p, d_n_leaves, b->d_leaf_sums.p, b->d_qexp.p, 40, cp, b->d_leaf_values.p, tree, s));
+  LAUNCH_CHECK(b2_launch_pred_update(b->margin.p, K, k, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks,
+                                     b->d_leaf_values.p, ctx->num_sms, s));
+  b->t.kernel_launches += 4;
+  // ---- read the finished tree back (pinned, asynchronous; resolved at the end of the round)
+  if (b->staging_bytes != L.bytes) {
+    for (void* h : b->staging) cudaFreeHost(h);
+    b->staging.clear(); b->staging_bytes = L.bytes;
   }
-  b->d_leaf_sums.ensure((size_t)2 * nleaf); b->d_leaf_values.ensure((size_t)nleaf);
-  CUDA_CHECK(cudaMemsetAsync(b->d_leaf_sums.p, 0, (size_t)2 * nleaf * sizeof(long long), s));
-  if (!lwork.empty()) {
-    b->d_seg_work.ensure(lwork.size());
-    CUDA_CHECK(cudaMemcpyAsync(b->d_seg_work.p, lwork.data(), lwork.size() * sizeof(SegWorkH), cudaMemcpyHostToDevice, s));
-    LAUNCH_CHECK(b2_launch_leaf_sums(gh, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, (int)lwork.size(), lchunks, b->d_qexp.p,
-                                     40, b->d_leaf_sums.p, ctx->num_sms, s));
-    b->t.kernel_launches++;
+  while ((int)b->staging.size() <= slot) { void* h = nullptr; CUDA_CHECK(cudaMallocHost(&h, L.bytes)); b->staging.push_back(h); }
+  char* st = (char*)b->staging[slot];
+  CUDA_CHECK(cudaMemcpyAsync(st, b->t_i32.p, L.i32_count * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(st + L.off_f32, b->t_f32.p, L.f32_count * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(st + L.off_i64, b->t_i64.p, L.i64_count * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(st + L.off_qexp, b->d_qexp.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+}
+
+// after the stream is synchronised: turn read-back block `slot` into a host tree (A.7 bookkeeping)
+void materialize_tree(Booster* b, int slot) {
+  Matrix* m = b->train; const Params& p = b->p;
+  const TreeLayout L = tree_layout(p.max_depth);
+  const char* st = (const char*)b->staging[slot];
+  const int32_t* i32 = (const int32_t*)st; const size_t mx = L.max_nodes;
+  const float* f32 = (const float*)(st + L.off_f32);
+  const long long* i64 = (const long long*)(st + L.off_i64);
+  const int32_t* qexp = (const int32_t*)(st + L.off_qexp);
+  const int nn = i32[6 * mx];
+  if (nn < 1 || (size_t)nn > mx) fail("corrupt tree read-back (n_nodes=%d)", nn);
+  const double inv_sg = ldexp(1.0, qexp[0] - p.qbits), inv_sh = ldexp(1.0, qexp[1] - p.qbits);
+  TreeHost t;
+  for (int i = 0; i < nn; ++i) {
+    t.add(i32[2 * mx + i]);
+    t.left[i] = i32[i]; t.right[i] = i32[mx + i]; t.feature[i] = i32[3 * mx + i];
+    const double G = (double)i64[i] * inv_sg, H = (double)i64[mx + i] * inv_sh;
+    t.sum_hess[i] = H;
+    if (t.feature[i] >= 0) {
+      const int f = t.feature[i], bin = i32[4 * mx + i];
+      t.split_bin[i] = bin; t.default_left[i] = (uint8_t)i32[5 * mx + i]; t.loss_chg[i] = f32[i];
+      t.cond[i] = bin < 0 ? m->min_vals[f] : m->cut_vals[m->cut_ptrs[f] + bin];
+      t.base_weight[i] = h_calc_weight(p, G, H);
+      t.value[i] = t.base_weight[i];
+    } else {
+      t.base_weight[i] = f32[mx + i];
+      t.value[i] = f32[2 * mx + i];
+    }
   }
-  allreduce(b->comm, b->d_leaf_sums.p, (size_t)2 * nleaf, kNcclInt64, kNcclSum, s);
-  std::vector<long long> h_sums((size_t)2 * nleaf);
-  CUDA_CHECK(cudaMemcpyAsync(h_sums.data(), b->d_leaf_sums.p, h_sums.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaStreamSynchronize(s));
-  if (!have_scales) { inv_sg = ldexp(1.0, h_qexp[0] - p.qbits); inv_sh = ldexp(1.0, h_qexp[1] - p.qbits); }
-  const double kg = ldexp(1.0, 40 - h_qexp[0]), kh = ldexp(1.0, 40 - h_qexp[1]);
-  std::vector<float> h_leaf(nleaf);
-  for (int i = 0; i < nleaf; ++i) {
-    const int nid = leaves[i].nid;
-    tree.base_weight[nid] = h_calc_weight(p, (double)h_sums[2 * i] / kg, (double)h_sums[2 * i + 1] / kh);
-    tree.value[nid] = tree.base_weight[nid] * p.eta;
-    h_leaf[i] = tree.value[nid];
-  }
-  if (!lwork.empty()) {
-    CUDA_CHECK(cudaMemcpyAsync(b->d_leaf_values.p, h_leaf.data(), nleaf * sizeof(float), cudaMemcpyHostToDevice, s));
-    LAUNCH_CHECK(b2_launch_pred_update(b->margin.p, K, k, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, (int)lwork.size(),
-                                       lchunks, b->d_leaf_values.p, ctx->num_sms, s));
-    b->t.kernel_launches++;
-    CUDA_CHECK(cudaStreamSynchronize(s));  // h_leaf / lwork go out of scope
-  }
-  b->trees.push_back(std::move(tree));
+  // histogram rows of this tree for the roofline accounting: root + built children per level
+  const long long* level_rows = i64 + 2 * mx;
+  long long rows = m->n; int launches_nonempty = m->n > 0 ? 1 : 0;
+  for (int d = 1; d < p.max_depth; ++d) { rows += level_rows[d]; if (level_rows[d] > 0) launches_nonempty++; }
+  long long gathered = rows - m->n;
+  int built_nodes = 0;
+  for (int i = 0; i < nn; ++i) if (t.feature[i] >= 0) built_nodes++;   // one built child per split (+ root)
+  b->t.hist_rows += rows;
+  b->t.hist_bytes += (double)rows * (m->F + 8) + (double)gathered * 4 + (double)(built_nodes + 1) * m->F * 256.0 * 16.0;
+  b->trees.push_back(std::move(t));
 }
 
 void sync_device_trees(Booster* b) {
@@ -812,7 +799,7 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
                                     b->ctx->num_sms, s));
   }
   b->t.kernel_launches++;
-  for (int k = 0; k < K; ++k) grow_tree(b, k);
+  for (int k = 0; k < K; ++k) grow_tree(b, k, k);
   if (b->p.profile) {
     CUDA_CHECK(cudaEventRecord(b->round_stop, s));
     CUDA_CHECK(cudaEventSynchronize(b->round_stop));
@@ -822,6 +809,7 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
   } else {
     CUDA_CHECK(cudaStreamSynchronize(s));
   }
+  for (int k = 0; k < K; ++k) materialize_tree(b, k);
   b->t.rounds++;
 }
 
@@ -1214,7 +1202,7 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
   CUDA_CHECK(cudaEventRecord(e0, s));
   if (n_sel > 0)
     LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
-                                window_rows, m.n_groups, d_hist.p, ctx->num_sms, s));
+                                window_rows, m.n_groups, d_hist.p, nullptr, ctx->num_sms, s));
   CUDA_CHECK(cudaEventRecord(e1, s));
   std::vector<long long> h(node_elems);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), d_hist.p, node_elems * sizeof(long long), cudaMemcpyDeviceToHost, s));

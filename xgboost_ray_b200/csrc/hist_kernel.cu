@@ -117,12 +117,15 @@ template <bool kGather>
 __global__ void __launch_bounds__(kHistThreads, 3)
 hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                   const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
-                  int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist) {
+                  int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
+                  const B2LevelCtl* __restrict__ ctl) {
+  if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
   extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][32]
   __shared__ int s_cur_work;
   const int group = blockIdx.x % n_groups;
   const int stream = blockIdx.x / n_groups;
   const int n_streams = gridDim.x / n_groups;
+  if (stream >= total_chunks) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int rot = lane >> 1, half = lane & 1;
   const int lane_byte_off = group * 32 + half * 16;
@@ -188,7 +191,9 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
 
 // ---------------------------------------------------------------- sibling = parent - built
 __global__ void hist_subtract_kernel(const long long* __restrict__ parent_level, long long* __restrict__ level,
-                                     const int32_t* __restrict__ triples, int n_pairs, int64_t node_elems) {
+                                     const int32_t* __restrict__ triples, int n_pairs, int64_t node_elems,
+                                     const B2LevelCtl* __restrict__ ctl) {
+  if (ctl) n_pairs = ctl->n_pairs;
   // triples[3*p] = parent slot (prev level), built slot, sibling slot (this level)
   const int p = blockIdx.y;
   if (p >= n_pairs) return;
@@ -206,7 +211,7 @@ extern "C" {
 // Launch on `stream`.  grid = n_groups * n_streams persistent CTAs; returns the cudaError.
 int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const int32_t* ridx,
                    const B2HistWork* work, int n_work, int total_chunks, int chunk_rows, int window_rows,
-                   int n_groups, long long* hist, int num_sms, cudaStream_t stream) {
+                   int n_groups, long long* hist, const B2LevelCtl* ctl, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   const int smem = B2_GROUP_ELEMS * (int)sizeof(int32_t);  // 64 KiB
   if (!attr_set) {
@@ -214,28 +219,30 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
     cudaFuncSetAttribute(b2::hist_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
-  if (total_chunks <= 0 || n_work <= 0) return 0;
-  if (chunk_rows > window_rows) return (int)cudaErrorInvalidValue;  // a chunk must fit one int32 window
+  // with ctl the work list / chunk counts live in device memory (sync-free level loop) and the grid is the
+  // full persistent grid; without it they are host values
+  if (!ctl && (total_chunks <= 0 || n_work <= 0)) return 0;
+  if (!ctl && chunk_rows > window_rows) return (int)cudaErrorInvalidValue;  // a chunk must fit one int32 window
   int n_streams = (num_sms * 3) / n_groups;
   if (n_streams < 1) n_streams = 1;
-  if (n_streams > total_chunks) n_streams = total_chunks;
+  if (!ctl && n_streams > total_chunks) n_streams = total_chunks;
   dim3 grid(n_groups * n_streams), block(b2::kHistThreads);
   if (ridx)
     b2::hist_build_kernel<true><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                              chunk_rows, window_rows, n_groups, hist);
+                                                              chunk_rows, window_rows, n_groups, hist, ctl);
   else
     b2::hist_build_kernel<false><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                               chunk_rows, window_rows, n_groups, hist);
+                                                               chunk_rows, window_rows, n_groups, hist, ctl);
   return (int)cudaGetLastError();
 }
 
 int b2_launch_hist_subtract(const long long* parent_level, long long* level, const int32_t* triples, int n_pairs,
-                            int64_t node_elems, cudaStream_t stream) {
-  if (n_pairs <= 0) return 0;
+                            int64_t node_elems, const B2LevelCtl* ctl, cudaStream_t stream) {
+  if (n_pairs <= 0) return 0;   // with ctl: n_pairs is the upper bound, the real count is read on the device
   int bx = (int)((node_elems + 256 * 8 - 1) / (256 * 8));
   if (bx < 1) bx = 1;
   dim3 grid(bx, n_pairs);
-  b2::hist_subtract_kernel<<<grid, 256, 0, stream>>>(parent_level, level, triples, n_pairs, node_elems);
+  b2::hist_subtract_kernel<<<grid, 256, 0, stream>>>(parent_level, level, triples, n_pairs, node_elems, ctl);
   return (int)cudaGetLastError();
 }
 }

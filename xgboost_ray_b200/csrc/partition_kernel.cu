@@ -12,15 +12,13 @@ namespace b2 {
 constexpr int kPartThreads = 256;
 constexpr int kPartChunk = 2048;  // rows per CTA work item
 
-struct SegWork {  // generic (segment, id) descriptor, chunked
-  int32_t seg_begin, seg_count, id, chunk_begin;
-  int32_t buf, pad0, pad1, pad2;
-};
+typedef B2SegWork SegWork;
 
 __global__ void __launch_bounds__(kPartThreads)
 partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const int32_t* __restrict__ ridx_in,
-                 int32_t* __restrict__ ridx_out, const B2SplitWork* __restrict__ work, int n_work, int total_chunks,
+                 int32_t* __restrict__ ridx_out, const B2SplitWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl,
                  int32_t* __restrict__ counters /* [2*n_work]: left, right */) {
+  const int n_work = ctl->n_split, total_chunks = ctl->part_chunks;
   __shared__ int s_warp_left[kPartThreads / 32][kPartChunk / kPartThreads];
   __shared__ int s_base_left, s_base_right;
   __shared__ int s_pref[kPartThreads / 32][kPartChunk / kPartThreads];
@@ -77,8 +75,9 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
 // ---- leaf refinement: 40-bit fixed-point sums of the fp32 gradients per leaf (exact int64)
 __global__ void __launch_bounds__(256)
 leaf_sums_kernel(const float2* __restrict__ gh, const int32_t* __restrict__ ridx0, const int32_t* __restrict__ ridx1,
-                 const SegWork* __restrict__ work, int n_work, int total_chunks, const int32_t* __restrict__ qexp,
+                 const SegWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl, const int32_t* __restrict__ qexp,
                  int leaf_bits, long long* __restrict__ sums /* [n_leaves][2] */) {
+  const int n_work = ctl->hist_n_work, total_chunks = ctl->hist_total_chunks;
   __shared__ long long sg[8], sh[8];
   const double kg = ldexp(1.0, leaf_bits - qexp[0]), kh = ldexp(1.0, leaf_bits - qexp[1]);
   for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
@@ -115,8 +114,9 @@ leaf_sums_kernel(const float2* __restrict__ gh, const int32_t* __restrict__ ridx
 // margin[row*K + k] += leaf_value[leaf]
 __global__ void __launch_bounds__(256)
 pred_update_kernel(float* __restrict__ margin, int K, int k, const int32_t* __restrict__ ridx0,
-                   const int32_t* __restrict__ ridx1, const SegWork* __restrict__ work, int n_work, int total_chunks,
+                   const int32_t* __restrict__ ridx1, const SegWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl,
                    const float* __restrict__ leaf_value) {
+  const int n_work = ctl->hist_n_work, total_chunks = ctl->hist_total_chunks;
   for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int lo = 0, hi = n_work - 1;
     while (lo < hi) {
@@ -145,29 +145,25 @@ extern "C" {
 int b2_part_chunk_rows() { return b2::kPartChunk; }
 
 int b2_launch_partition(const uint8_t* bins_col, int64_t col_stride, const int32_t* ridx_in, int32_t* ridx_out,
-                        const B2SplitWork* work, int n_work, int total_chunks, int32_t* counters, int num_sms,
+                        const B2SplitWork* work, const B2LevelCtl* ctl, int max_chunks, int32_t* counters, int num_sms,
                         cudaStream_t stream) {
-  if (total_chunks <= 0) return 0;
-  int grid = total_chunks < num_sms * 8 ? total_chunks : num_sms * 8;
-  b2::partition_kernel<<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, n_work,
-                                                             total_chunks, counters);
+  if (max_chunks <= 0) return 0;
+  int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
+  b2::partition_kernel<<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
   return (int)cudaGetLastError();
 }
-int b2_launch_leaf_sums(const float2* gh, const int32_t* ridx0, const int32_t* ridx1, const void* work, int n_work,
-                        int total_chunks, const int32_t* qexp, int leaf_bits, long long* sums, int num_sms,
-                        cudaStream_t stream) {
-  if (total_chunks <= 0) return 0;
-  int grid = total_chunks < num_sms * 8 ? total_chunks : num_sms * 8;
-  b2::leaf_sums_kernel<<<grid, 256, 0, stream>>>(gh, ridx0, ridx1, (const b2::SegWork*)work, n_work, total_chunks, qexp,
-                                                leaf_bits, sums);
+int b2_launch_leaf_sums(const float2* gh, const int32_t* ridx0, const int32_t* ridx1, const void* work, const B2LevelCtl* ctl,
+                        int max_chunks, const int32_t* qexp, int leaf_bits, long long* sums, int num_sms, cudaStream_t stream) {
+  if (max_chunks <= 0) return 0;
+  int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
+  b2::leaf_sums_kernel<<<grid, 256, 0, stream>>>(gh, ridx0, ridx1, (const b2::SegWork*)work, ctl, qexp, leaf_bits, sums);
   return (int)cudaGetLastError();
 }
 int b2_launch_pred_update(float* margin, int K, int k, const int32_t* ridx0, const int32_t* ridx1, const void* work,
-                          int n_work, int total_chunks, const float* leaf_value, int num_sms, cudaStream_t stream) {
-  if (total_chunks <= 0) return 0;
-  int grid = total_chunks < num_sms * 8 ? total_chunks : num_sms * 8;
-  b2::pred_update_kernel<<<grid, 256, 0, stream>>>(margin, K, k, ridx0, ridx1, (const b2::SegWork*)work, n_work,
-                                                  total_chunks, leaf_value);
+                          const B2LevelCtl* ctl, int max_chunks, const float* leaf_value, int num_sms, cudaStream_t stream) {
+  if (max_chunks <= 0) return 0;
+  int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
+  b2::pred_update_kernel<<<grid, 256, 0, stream>>>(margin, K, k, ridx0, ridx1, (const b2::SegWork*)work, ctl, leaf_value);
   return (int)cudaGetLastError();
 }
 int b2_launch_iota(int32_t* out, int64_t n, cudaStream_t stream) {

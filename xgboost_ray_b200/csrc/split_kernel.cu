@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(256)
 eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const B2EvalNode* __restrict__ nodes,
                    const int32_t* __restrict__ group_first, const int32_t* __restrict__ group_size,
                    const int32_t* __restrict__ nbins, const uint8_t* __restrict__ has_missing,
-                   const int32_t* __restrict__ qexp, int qbits, B2TrainParamDev p, B2SplitCand* __restrict__ cands) {
+                   const int32_t* __restrict__ qexp, int qbits, B2TrainParamDev p, B2SplitCand* __restrict__ cands,
+                   const B2LevelCtl* __restrict__ ctl) {
   const int node = blockIdx.x / n_groups, group = blockIdx.x % n_groups;
+  if (ctl && node >= ctl->n_nodes) return;
   const int s = threadIdx.x & 31, q = threadIdx.x >> 5;
   __shared__ long long cs_g[8][32], cs_h[8][32];
   __shared__ unsigned long long wkey[8];
@@ -162,10 +164,10 @@ extern "C" {
 int b2_launch_eval_splits(const long long* level_hist, int n_groups, const B2EvalNode* nodes, int n_nodes,
                           const int32_t* group_first, const int32_t* group_size, const int32_t* nbins,
                           const uint8_t* has_missing, const int32_t* qexp, int qbits, B2TrainParamDev p,
-                          B2SplitCand* cands, cudaStream_t stream) {
-  if (n_nodes <= 0) return 0;
+                          B2SplitCand* cands, const B2LevelCtl* ctl, cudaStream_t stream) {
+  if (n_nodes <= 0) return 0;   // with ctl: n_nodes is the upper bound of the level
   b2::eval_splits_kernel<<<n_nodes * n_groups, 256, 0, stream>>>(level_hist, n_groups, nodes, group_first, group_size,
-                                                               nbins, has_missing, qexp, qbits, p, cands);
+                                                               nbins, has_missing, qexp, qbits, p, cands, ctl);
   return (int)cudaGetLastError();
 }
 int b2_launch_root_totals(const long long* level_hist, int n_groups, B2EvalNode* nodes, const int32_t* qexp, int qbits,
