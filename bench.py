@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--qbits", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", type=int, default=1, help="2 = per-phase CUDA-event timers (adds event records)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -174,7 +175,7 @@ def main():
     os.environ["B2_DEVICE"] = str(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    params = dict(PARAMS, max_depth=args.depth)
+    params = dict(PARAMS, max_depth=args.depth, profile=args.profile)
     if args.qbits is not None:
         params["hist_qbits"] = args.qbits
 
@@ -280,7 +281,7 @@ def main():
                        args.rows, args.cols, args.depth, world),
                    "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256, "parallelism": "dp%d" % world,
                    "hist_qbits": params.get("hist_qbits", 18), "l2": "inputs_larger_than_l2",
-                   "device_ms_per_step": dev_ms / args.steps, "quantise_seconds": t_quant, "final_train_rmse": final_rmse},
+                   "device_ms_per_step": dev_ms / args.steps, "phase_ms_per_step": {k: v / args.steps for k, v in timers.get("phase_ms", {}).items()}, "quantise_seconds": t_quant, "final_train_rmse": final_rmse},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_kind, "kernel": "b2::hist_build_kernel",
                      "algorithmic_bytes_per_launch": hist_bytes_per_launch, "ms_per_launch": hist_ms_per_launch,

@@ -166,7 +166,7 @@ finalize_level_kernel(const B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __rest
         c = 512;
         while (c < target && c < 8192) c <<= 1;
       }
-      while (c > window_rows && c > 1) c >>= 1;
+      if (c > window_rows) c = window_rows;   // one chunk = one int32 window
       s_chunk_rows = c;
       if (stat_rows) *stat_rows = s_rows;
     }

@@ -27,7 +27,8 @@
 // ---------------------------------------------------------------- kernel launchers (other TUs)
 extern "C" {
 int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
-                   const B2LevelCtl*, int, cudaStream_t);
+                   const B2LevelCtl*, long long*, int, cudaStream_t);
+size_t b2_hist_scratch_elems(int, int);
 int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, const B2LevelCtl*, cudaStream_t);
 int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
                           const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, const B2LevelCtl*, cudaStream_t);
@@ -380,6 +381,7 @@ struct TreeHost {
 
 struct Timers {
   double hist_ms = 0, round_ms = 0;
+  double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // profile=2: quant, hist, allreduce, subtract, eval+decide, partition+finalize, leaf, other
   long long hist_launches = 0, hist_rows = 0, kernel_launches = 0, rounds = 0;
   double hist_bytes = 0, allreduce_bytes = 0;
   void reset() { *this = Timers(); }
@@ -405,6 +407,7 @@ struct Booster : HandleBase {
   DevBuf<int2> q;                // [n]
   DevBuf<int32_t> ridx[2];
   DevBuf<long long> hist[2];
+  DevBuf<long long> hist_scratch;   // CTA-private int64 window accumulators (kept all-zero between launches)
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
   // device-resident control tables of the sync-free level loop (control_kernel.cu)
@@ -426,6 +429,7 @@ struct Booster : HandleBase {
   Timers t;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hist_events;
+  std::vector<std::pair<int, cudaEvent_t>> phase_marks;   // (phase that ENDS at this event)
   cudaEvent_t round_start = nullptr, round_stop = nullptr;
   ~Booster() {
     for (auto e : ev_pool) cudaEventDestroy(e);
@@ -440,7 +444,19 @@ cudaEvent_t get_event(Booster* b) {
   if (b->ev_used == b->ev_pool.size()) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); b->ev_pool.push_back(e); }
   return b->ev_pool[b->ev_used++];
 }
+void mark_phase(Booster* b, int phase) {
+  if (b->p.profile < 2) return;
+  cudaEvent_t e = get_event(b);
+  CUDA_CHECK(cudaEventRecord(e, b->ctx->stream));
+  b->phase_marks.push_back({phase, e});
+}
 void resolve_events(Booster* b) {
+  for (size_t i = 1; i < b->phase_marks.size(); ++i) {
+    float ms = 0.f;
+    if (b->phase_marks[i].first >= 0 && cudaEventElapsedTime(&ms, b->phase_marks[i - 1].second, b->phase_marks[i].second) == cudaSuccess)
+      b->t.phase_ms[b->phase_marks[i].first] += ms;
+  }
+  b->phase_marks.clear();
   for (auto& pr : b->hist_events) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) b->t.hist_ms += ms;
@@ -521,7 +537,7 @@ int pick_chunk_rows(Booster* b, int64_t rows) {
   int c = 512;
   while (c < target && c < 8192) c <<= 1;
   const int w = window_rows_for(b->p.qbits);
-  while (c > w && c > 1) c >>= 1;
+  if (c > w) c = w;   // one chunk = one int32 window
   return c;
 }
 
@@ -568,6 +584,9 @@ void ensure_ctl_tables(Booster* b) {
   b->d_leaf_sums.ensure(2 * lcap); b->d_leaf_values.ensure(lcap);
   b->node_elems = (size_t)G * B2_GROUP_ELEMS;
   b->hist[0].ensure(half * b->node_elems); b->hist[1].ensure(half * b->node_elems);
+  const size_t se = b2_hist_scratch_elems(G, b->ctx->num_sms);
+  b->hist_scratch.ensure(se);
+  CUDA_CHECK(cudaMemsetAsync(b->hist_scratch.p, 0, se * sizeof(long long), b->ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(b->t_i64.p, 0, L.i64_count * 8, b->ctx->stream));
 }
 
@@ -586,6 +605,7 @@ void grow_tree(Booster* b, int k, int slot) {
   const float2* gh = b->gh.p + (size_t)k * n;
   ensure_ctl_tables(b);
   const TreeLayout L = tree_layout(D);
+  mark_phase(b, -1);
   // ---- fixed-point quantisation (global scale via allreduce max)
   b->d_absmax.ensure(2); b->d_qexp.ensure(2);
   CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * sizeof(uint32_t), s));
@@ -612,6 +632,7 @@ void grow_tree(Booster* b, int k, int slot) {
   const int max_part_chunks_total = (int)((n + pchunk - 1) / pchunk);
 
   LAUNCH_CHECK(b2_launch_tree_init(tree, ctl, b->d_seg[0].p, b->d_ev[0].p, d_n_leaves, (int)n, s));
+  mark_phase(b, 0);
   // ---- root histogram (no gather; row count known on the host)
   CUDA_CHECK(cudaMemsetAsync(b->hist[0].p, 0, b->node_elems * sizeof(long long), s));
   {
@@ -623,12 +644,14 @@ void grow_tree(Booster* b, int k, int slot) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
       LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
-                                  b->hist[0].p, nullptr, ctx->num_sms, s));
+                                  b->hist[0].p, nullptr, b->hist_scratch.p, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       b->t.hist_launches++; b->t.kernel_launches++;
     }
   }
+  mark_phase(b, 1);
   allreduce(b->comm, b->hist[0].p, b->node_elems, kNcclInt64, kNcclSum, s);
+  mark_phase(b, 2);
   b->t.allreduce_bytes += (double)b->node_elems * 8;
   LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_ev[0].p, b->d_qexp.p, p.qbits, dp, s));
   LAUNCH_CHECK(b2_launch_root_record(tree, b->d_ev[0].p, s));
@@ -647,6 +670,7 @@ void grow_tree(Booster* b, int k, int slot) {
                                   b->d_cands.p, G, can_split ? 1 : 0, tree, b->d_split_work.p, b->d_pair_parent.p, b->d_leaves.p,
                                   d_n_leaves, m->d_has_missing.p, b->d_qexp.p, p.qbits, cp, s));
     b->t.kernel_launches++;
+    mark_phase(b, 4);
     if (!can_split) break;
     // ---- partition rows of the expanding nodes into the other index list
     CUDA_CHECK(cudaMemsetAsync(b->d_counters.p, 0, 2 * (size_t)max_nodes_level * sizeof(int32_t), s));
@@ -657,6 +681,7 @@ void grow_tree(Booster* b, int k, int slot) {
                                           b->d_pair_parent.p, b->d_hist_work.p, b->d_triples.p, max_nodes_level, need_hist ? 1 : 0,
                                           n_streams, window, p.hist_chunk_rows, d_level_rows + d + 1, s));
     b->t.kernel_launches += 2;
+    mark_phase(b, 5);
     if (need_hist) {
       // ---- histograms of level d+1: built children in slots [0, 2^d), siblings in [2^d, 2^(d+1))
       const int nh = hb ^ 1;
@@ -664,13 +689,16 @@ void grow_tree(Booster* b, int k, int slot) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
       LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G,
-                                  b->hist[nh].p, ctl + nxt, ctx->num_sms, s));
+                                  b->hist[nh].p, ctl + nxt, b->hist_scratch.p, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
+      mark_phase(b, 1);
       allreduce(b->comm, b->hist[nh].p, (size_t)max_nodes_level * b->node_elems, kNcclInt64, kNcclSum, s);
+      mark_phase(b, 2);
       b->t.allreduce_bytes += (double)max_nodes_level * b->node_elems * 8;
       LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[hb].p, b->hist[nh].p, b->d_triples.p, max_nodes_level, (int64_t)b->node_elems,
                                            ctl + nxt, s));
       b->t.hist_launches++; b->t.kernel_launches += 2;
+      mark_phase(b, 3);
       hb = nh;
     }
   }
@@ -686,6 +714,7 @@ void grow_tree(Booster* b, int k, int slot) {
   LAUNCH_CHECK(b2_launch_pred_update(b->margin.p, K, k, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks,
                                      b->d_leaf_values.p, ctx->num_sms, s));
   b->t.kernel_launches += 4;
+  mark_phase(b, 6);
   // ---- read the finished tree back (pinned, asynchronous; resolved at the end of the round)
   if (b->staging_bytes != L.bytes) {
     for (void* h : b->staging) cudaFreeHost(h);
@@ -1148,9 +1177,12 @@ int B2_BoosterGetTimers(B2Handle bh, int32_t reset, char* out, int64_t out_cap) 
   const Timers& t = b->t;
   snprintf(out, (size_t)out_cap,
            "{\"hist_ms\": %.6f, \"hist_launches\": %lld, \"hist_rows\": %lld, \"hist_bytes\": %.1f, \"kernel_launches\": %lld, "
-           "\"round_ms\": %.6f, \"rounds\": %lld, \"allreduce_bytes\": %.1f, \"num_sms\": %d, \"n_groups\": %d, \"row_stride\": %d}",
+           "\"round_ms\": %.6f, \"rounds\": %lld, \"allreduce_bytes\": %.1f, \"num_sms\": %d, \"n_groups\": %d, \"row_stride\": %d, "
+           "\"phase_ms\": {\"quant\": %.4f, \"hist\": %.4f, \"allreduce\": %.4f, \"subtract\": %.4f, \"eval_decide\": %.4f, "
+           "\"partition_finalize\": %.4f, \"leaf\": %.4f}}",
            t.hist_ms, t.hist_launches, t.hist_rows, t.hist_bytes, t.kernel_launches, t.round_ms, t.rounds, t.allreduce_bytes,
-           b->ctx->num_sms, b->train ? b->train->n_groups : 0, b->train ? b->train->row_stride : 0);
+           b->ctx->num_sms, b->train ? b->train->n_groups : 0, b->train ? b->train->row_stride : 0, t.phase_ms[0], t.phase_ms[1],
+           t.phase_ms[2], t.phase_ms[3], t.phase_ms[4], t.phase_ms[5], t.phase_ms[6]);
   if (reset) b->t.reset();
   API_END
 }
@@ -1180,7 +1212,10 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
     for (int f = 0; f < n_cols; ++f) padded[(size_t)i * m.row_stride + m.feat_byte[f]] = bins[i * n_cols + f];
   std::vector<int2> gp((size_t)std::max<int64_t>(n_rows, 1));
   for (int64_t i = 0; i < n_rows; ++i) gp[i] = make_int2(qg[i], qh[i]);
-  DevBuf<uint8_t> d_bins; DevBuf<int2> d_gp; DevBuf<int32_t> d_ridx; DevBuf<long long> d_hist; DevBuf<B2HistWork> d_work;
+  DevBuf<uint8_t> d_bins; DevBuf<int2> d_gp; DevBuf<int32_t> d_ridx; DevBuf<long long> d_hist, d_scratch; DevBuf<B2HistWork> d_work;
+  const size_t se = b2_hist_scratch_elems(m.n_groups, ctx->num_sms);
+  d_scratch.ensure(se);
+  CUDA_CHECK(cudaMemsetAsync(d_scratch.p, 0, se * sizeof(long long), s));
   d_bins.ensure(padded.size()); d_gp.ensure(gp.size());
   CUDA_CHECK(cudaMemcpyAsync(d_bins.p, padded.data(), padded.size(), cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_gp.p, gp.data(), gp.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
@@ -1202,7 +1237,7 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
   CUDA_CHECK(cudaEventRecord(e0, s));
   if (n_sel > 0)
     LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
-                                window_rows, m.n_groups, d_hist.p, nullptr, ctx->num_sms, s));
+                                window_rows, m.n_groups, d_hist.p, nullptr, d_scratch.p, ctx->num_sms, s));
   CUDA_CHECK(cudaEventRecord(e1, s));
   std::vector<long long> h(node_elems);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), d_hist.p, node_elems * sizeof(long long), cudaMemcpyDeviceToHost, s));

@@ -17,6 +17,8 @@
 //    of rows, CTAs and GPUs.  A CTA flushes its planes to the global int64 histogram when it moves
 //    to another node or before `window_rows` rows could overflow an int32 cell.
 //  * Rows of a node are addressed through the row-index segment list (gather) except at the root.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -86,30 +88,60 @@ __device__ __forceinline__ RowData load_row_id(const uint8_t* __restrict__ bins,
   }
   return d;
 }
+// diagnostic (debug_mode 2): synthesise the row instead of loading it
+__device__ __forceinline__ RowData fake_row(int64_t rid) {
+  RowData d;
+  uint32_t x = (uint32_t)rid * 2654435761u + 12345u;
+  d.bins = make_uint4(x, x * 1664525u + 1013904223u, x ^ (x >> 13), x * 22695477u + 1u);
+  d.gp = make_int2(rid >= 0 ? 3 : 0, rid >= 0 ? 1 : 0);
+  return d;
+}
 
-// 16 steps: one byte (= one feature slot) per step, two conflict-free shared atomics per step
-__device__ __forceinline__ void accumulate_row(const RowData& d, uint32_t smem_g, int rot, int half) {
+// 16 steps: one byte (= one feature slot) per step, two conflict-free shared atomics per step.
+// Shared layout: int32 [256 bins][2 planes (g,h)][32 slots] = 256 B per bin, so bin*256 is the byte
+// placed at byte position 1 by ONE prmt; the cell address is that plus a per-lane, per-step offset.
+__device__ __forceinline__ void accumulate_row(const RowData& d, uint32_t smem_g, int rot, int half, int debug_mode = 0,
+                                               unsigned* sink = nullptr) {
+  if (debug_mode == 1) {  // diagnostic: consume the loads without touching shared memory
+    *sink += d.bins.x ^ d.bins.y ^ d.bins.z ^ d.bins.w ^ (unsigned)d.gp.x ^ (unsigned)d.gp.y;
+    return;
+  }
   uint4 b = rotate_bytes(d.bins, rot);
   const uint32_t w[4] = {b.x, b.y, b.z, b.w};
   const uint32_t base = smem_g + half * 64;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    uint32_t bin = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-    uint32_t slot_off = ((uint32_t)(j + rot) & 15u) * 4u;
-    uint32_t a = base + bin * (B2_GROUP_SLOTS * 4) + slot_off;
+    const uint32_t bin256 = __byte_perm(w[j >> 2], 0u, 0x4404u | ((uint32_t)(j & 3) << 4));
+    const uint32_t slot_off = ((uint32_t)(j + rot) & 15u) * 4u;
+    const uint32_t a = base + bin256 + slot_off;
     red_shared_add(a, d.gp.x);
-    red_shared_add(a + B2_PLANE_ELEMS * 4, d.gp.y);
+    red_shared_add(a + B2_GROUP_SLOTS * 4, d.gp.y);
   }
 }
 
-__device__ __forceinline__ void flush_planes(int32_t* s_hist, unsigned long long* out_g) {
-  // out layout for this (node, group): [2][256][32] int64 == same index space as the smem planes
-  for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) {
-    int v = s_hist[e];
-    if (v != 0) {
-      atomicAdd(out_g + e, (unsigned long long)(long long)v);
-      s_hist[e] = 0;
+// shared cell e = bin*64 + plane*32 + slot  ->  global cell plane*8192 + bin*32 + slot
+__device__ __forceinline__ int global_cell(int e) { return ((e >> 5) & 1) * B2_PLANE_ELEMS + (e >> 6) * B2_GROUP_SLOTS + (e & 31); }
+
+// window flush: move the int32 partial sums into this CTA's PRIVATE int64 scratch (plain coalesced
+// read-modify-write in L2, no atomics: only this CTA touches its scratch block)
+__device__ __forceinline__ void flush_to_scratch(int32_t* s_hist, long long* scratch) {
+  for (int e = threadIdx.x * 4; e < B2_GROUP_ELEMS; e += blockDim.x * 4) {
+    int4 v = *reinterpret_cast<int4*>(s_hist + e);
+    if ((v.x | v.y | v.z | v.w) != 0) {
+      longlong2 a = *reinterpret_cast<longlong2*>(scratch + e), b = *reinterpret_cast<longlong2*>(scratch + e + 2);
+      a.x += v.x; a.y += v.y; b.x += v.z; b.y += v.w;
+      *reinterpret_cast<longlong2*>(scratch + e) = a; *reinterpret_cast<longlong2*>(scratch + e + 2) = b;
+      *reinterpret_cast<int4*>(s_hist + e) = make_int4(0, 0, 0, 0);
     }
+  }
+}
+// node flush: shared (+ scratch if it was used) -> global int64 histogram with atomics
+__device__ __forceinline__ void flush_planes(int32_t* s_hist, long long* scratch, bool scratch_dirty, unsigned long long* out) {
+  for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) {
+    long long v = s_hist[e];
+    if (scratch_dirty) { v += scratch[e]; scratch[e] = 0; }
+    if (v != 0) atomicAdd(out + global_cell(e), (unsigned long long)v);
+    s_hist[e] = 0;
   }
 }
 
@@ -118,7 +150,7 @@ __global__ void __launch_bounds__(kHistThreads, 3)
 hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                   const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
                   int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
-                  const B2LevelCtl* __restrict__ ctl) {
+                  const B2LevelCtl* __restrict__ ctl, long long* __restrict__ scratch_all, int debug_mode) {
   if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
   extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][32]
   __shared__ int s_cur_work;
@@ -136,6 +168,8 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
 
   int cur = -1;          // work index whose partial sums are in shared memory
   int rows_in_window = 0;
+  bool scratch_dirty = false;
+  long long* scratch = scratch_all + (size_t)blockIdx.x * B2_GROUP_ELEMS;
   for (int chunk = stream; chunk < total_chunks; chunk += n_streams) {
     // locate the node of this chunk (uniform across the CTA): last w with chunk_begin <= chunk
     int lo = 0, hi = n_work - 1;
@@ -148,8 +182,11 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
     const int row0 = (chunk - __ldg(&work[w].chunk_begin)) * chunk_rows;
     const int nrows = min(chunk_rows, seg_count - row0);
     if (cur >= 0 && (w != cur || rows_in_window + nrows > window_rows)) {
+      // node change or int32 window full: add the partial sums to the global int64 histogram.
+      // (A CTA-private int64 scratch with plain read-modify-write was measured 30 % SLOWER: 256 KB of
+      // L2 traffic per window per CTA evicts the streamed rows; RED.64 moves half the bytes.)
       __syncthreads();
-      flush_planes(s_hist, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
+      flush_planes(s_hist, scratch, false, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
       __syncthreads();
       rows_in_window = 0;
     }
@@ -164,27 +201,31 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
     int64_t id0 = fetch_rid<kGather>(ridx, pos0, r0, nrows);
     int64_t id1 = fetch_rid<kGather>(ridx, pos0, r0 + iter_rows, nrows);
     int64_t id2 = fetch_rid<kGather>(ridx, pos0, r0 + 2 * iter_rows, nrows);
-    RowData s0 = load_row_id(bins, gpair, id0, row_stride, lane_byte_off);
+    unsigned sink = 0;
+#define B2_LOAD(id) (debug_mode == 2 ? fake_row(id) : load_row_id(bins, gpair, id, row_stride, lane_byte_off))
+    RowData s0 = B2_LOAD(id0);
     id0 = fetch_rid<kGather>(ridx, pos0, r0 + 3 * iter_rows, nrows);
-    RowData s1 = load_row_id(bins, gpair, id1, row_stride, lane_byte_off);
+    RowData s1 = B2_LOAD(id1);
     id1 = fetch_rid<kGather>(ridx, pos0, r0 + 4 * iter_rows, nrows);
-    RowData s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
+    RowData s2 = B2_LOAD(id2);
     id2 = fetch_rid<kGather>(ridx, pos0, r0 + 5 * iter_rows, nrows);
     for (int r = r0 - rot; r < nrows; r += 3 * iter_rows) {   // warp-uniform trip count
-      accumulate_row(s0, smem_g, rot, half);
-      s0 = load_row_id(bins, gpair, id0, row_stride, lane_byte_off);
+      accumulate_row(s0, smem_g, rot, half, debug_mode, &sink);
+      s0 = B2_LOAD(id0);
       id0 = fetch_rid<kGather>(ridx, pos0, r + rot + 6 * iter_rows, nrows);
-      if (r + iter_rows < nrows) accumulate_row(s1, smem_g, rot, half);
-      s1 = load_row_id(bins, gpair, id1, row_stride, lane_byte_off);
+      if (r + iter_rows < nrows) accumulate_row(s1, smem_g, rot, half, debug_mode, &sink);
+      s1 = B2_LOAD(id1);
       id1 = fetch_rid<kGather>(ridx, pos0, r + rot + 7 * iter_rows, nrows);
-      if (r + 2 * iter_rows < nrows) accumulate_row(s2, smem_g, rot, half);
-      s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
+      if (r + 2 * iter_rows < nrows) accumulate_row(s2, smem_g, rot, half, debug_mode, &sink);
+      s2 = B2_LOAD(id2);
       id2 = fetch_rid<kGather>(ridx, pos0, r + rot + 8 * iter_rows, nrows);
     }
+#undef B2_LOAD
+    if (sink == 0x9e3779b9u) s_hist[threadIdx.x] = (int)sink;
   }
   if (cur >= 0) {
     __syncthreads();
-    flush_planes(s_hist, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
+    flush_planes(s_hist, scratch, scratch_dirty, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
   }
   (void)s_cur_work;
 }
@@ -209,10 +250,19 @@ __global__ void hist_subtract_kernel(const long long* __restrict__ parent_level,
 extern "C" {
 
 // Launch on `stream`.  grid = n_groups * n_streams persistent CTAs; returns the cudaError.
+// scratch: zero-initialised int64 [b2_hist_scratch_elems(n_groups, num_sms)], kept all-zero between launches
+size_t b2_hist_scratch_elems(int n_groups, int num_sms) {
+  int n_streams = (num_sms * 3) / n_groups;
+  if (n_streams < 1) n_streams = 1;
+  return (size_t)n_groups * n_streams * B2_GROUP_ELEMS;
+}
+
 int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const int32_t* ridx,
                    const B2HistWork* work, int n_work, int total_chunks, int chunk_rows, int window_rows,
-                   int n_groups, long long* hist, const B2LevelCtl* ctl, int num_sms, cudaStream_t stream) {
+                   int n_groups, long long* hist, const B2LevelCtl* ctl, long long* scratch, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
+  static int debug_mode = -1;
+  if (debug_mode < 0) { const char* e = getenv("B2_HIST_DEBUG_MODE"); debug_mode = e ? atoi(e) : 0; }
   const int smem = B2_GROUP_ELEMS * (int)sizeof(int32_t);  // 64 KiB
   if (!attr_set) {
     cudaFuncSetAttribute(b2::hist_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -229,10 +279,10 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
   dim3 grid(n_groups * n_streams), block(b2::kHistThreads);
   if (ridx)
     b2::hist_build_kernel<true><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                              chunk_rows, window_rows, n_groups, hist, ctl);
+                                                              chunk_rows, window_rows, n_groups, hist, ctl, scratch, debug_mode);
   else
     b2::hist_build_kernel<false><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                               chunk_rows, window_rows, n_groups, hist, ctl);
+                                                               chunk_rows, window_rows, n_groups, hist, ctl, scratch, debug_mode);
   return (int)cudaGetLastError();
 }
 
