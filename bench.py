@@ -234,14 +234,17 @@ def main():
         if not args.no_e2e:
             barrier()
             t0 = time.perf_counter()
-            d2 = E.DMatrix(X, label=y)
+            d2 = E.DMatrix(X, label=y)                      # host -> device upload
+            t_up = time.perf_counter() - t0
+            d2._ensure_quantized(256)                       # GPU sketch + binning (train() would do it itself)
+            t_q = time.perf_counter() - t0 - t_up
             res = {}
             b2 = E.train(params, d2, num_boost_round=args.steps, evals=[(d2, "train")], evals_result=res, verbose_eval=False)
             barrier()
             e2e_wall = max_over_ranks(time.perf_counter() - t0)
             e2e = {"value": args.steps / e2e_wall, "unit": "rounds/s",
                    "h2d_bytes_per_step": int((X.nbytes + y.nbytes) / args.steps),
-                   "d2h_bytes_per_step": 8, "seconds_total": e2e_wall,
+                   "d2h_bytes_per_step": 8, "seconds_total": e2e_wall, "seconds_upload": t_up, "seconds_quantise": t_q,
                    "api": "xgboost_ray_b200.engine.train (the xgb.train replacement an actor calls, host numpy in)",
                    "final_train_rmse": res["train"]["rmse"][-1]}
             del b2, d2

@@ -162,7 +162,10 @@ finalize_level_kernel(const B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __rest
     if (threadIdx.x == 0) {
       int c = chunk_rows_override;
       if (c <= 0) {
-        const long long target = s_rows / ((long long)n_streams * 4);
+        // large levels: ~4 chunks per CTA stream for balance; small levels: ~1, because every extra
+        // (CTA, node) pair costs a full 16K-cell flush
+        const long long per_stream = s_rows / n_streams;
+        const long long target = per_stream >= 16384 ? per_stream / 4 : per_stream;
         c = 512;
         while (c < target && c < 8192) c <<= 1;
       }

@@ -533,7 +533,8 @@ int window_rows_for(int qbits) {
 int pick_chunk_rows(Booster* b, int64_t rows) {
   if (b->p.hist_chunk_rows > 0) return b->p.hist_chunk_rows;
   const int n_streams = std::max(1, b->ctx->num_sms * 3 / b->train->n_groups);
-  int64_t target = rows / ((int64_t)n_streams * 4);
+  const int64_t per_stream = rows / n_streams;
+  int64_t target = per_stream >= 16384 ? per_stream / 4 : per_stream;
   int c = 512;
   while (c < target && c < 8192) c <<= 1;
   const int w = window_rows_for(b->p.qbits);

@@ -2,7 +2,8 @@
 //
 // Replaces XGBoost's EvaluateSplits stage reached through xgb.train()
 // (xgboost_ray/main.py:745-752).  One CTA per
-// (node, feature group): 256 threads = 32 slots (features) x 8 bin chunks of 32 bins.
+// (node, feature group): 1024 threads = 32 slots (features) x 32 bin chunks of 8 bins (the scan is
+// latency bound, so short per-thread load chains matter more than thread count).
 // Prefix sums are exact int64, gains are IEEE fp64 with explicit round-to-nearest ops (no fma
 // contraction), so every rank and the CPU oracle compute identical candidates.
 #include "common.cuh"
@@ -33,7 +34,10 @@ __device__ __forceinline__ void consider(Best& b, float chg, uint32_t order, int
 }
 
 // feat_meta: per group: first feature id, size; per feature: nbins, has_missing
-__global__ void __launch_bounds__(256)
+constexpr int kEvalChunks = 32;                 // bin chunks per feature
+constexpr int kEvalBinsPerChunk = 256 / kEvalChunks;
+
+__global__ void __launch_bounds__(32 * kEvalChunks)
 eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const B2EvalNode* __restrict__ nodes,
                    const int32_t* __restrict__ group_first, const int32_t* __restrict__ group_size,
                    const int32_t* __restrict__ nbins, const uint8_t* __restrict__ has_missing,
@@ -42,8 +46,8 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
   const int node = blockIdx.x / n_groups, group = blockIdx.x % n_groups;
   if (ctl && node >= ctl->n_nodes) return;
   const int s = threadIdx.x & 31, q = threadIdx.x >> 5;
-  __shared__ long long cs_g[8][32], cs_h[8][32];
-  __shared__ unsigned long long wkey[8];
+  __shared__ long long cs_g[kEvalChunks][32], cs_h[kEvalChunks][32];
+  __shared__ unsigned long long wkey[kEvalChunks];
   const B2EvalNode nd = nodes[node];
   // inverse scales: 2^(e - qbits)
   p.inv_scale_g = ldexp(1.0, qexp[0] - qbits);
@@ -57,17 +61,17 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
 
   long long sg = 0, sh = 0;
   if (active) {
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      int b = q * 32 + i;
+#pragma unroll
+    for (int i = 0; i < kEvalBinsPerChunk; ++i) {
+      int b = q * kEvalBinsPerChunk + i;
       if (b < nf) { sg += hg[b * 32 + s]; sh += hh[b * 32 + s]; }
     }
   }
   cs_g[q][s] = sg; cs_h[q][s] = sh;
   __syncthreads();
   long long pg = 0, ph = 0, real_g = 0, real_h = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
+#pragma unroll 8
+  for (int k = 0; k < kEvalChunks; ++k) {
     long long a = cs_g[k][s], b = cs_h[k][s];
     if (k < q) { pg += a; ph += b; }
     real_g += a; real_h += b;
@@ -78,8 +82,9 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
   const bool node_has_missing = fmiss && (real_g != tot_g || real_h != tot_h);
   Best best; best.key = 0; best.bin = 0; best.default_left = 0; best.lg = 0; best.lh = 0;
   if (active) {
-    for (int i = 0; i < 32; ++i) {
-      const int b = q * 32 + i;
+#pragma unroll 2
+    for (int i = 0; i < kEvalBinsPerChunk; ++i) {
+      const int b = q * kEvalBinsPerChunk + i;
       if (b >= nf) break;
       const long long eg_excl = pg, eh_excl = ph;
       pg += hg[b * 32 + s]; ph += hh[b * 32 + s];
@@ -121,8 +126,8 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
   if (s == 0) wkey[q] = k;
   __syncthreads();
   unsigned long long kmax = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) kmax = wkey[i] > kmax ? wkey[i] : kmax;
+#pragma unroll 8
+  for (int i = 0; i < kEvalChunks; ++i) kmax = wkey[i] > kmax ? wkey[i] : kmax;
   B2SplitCand* out = cands + (size_t)node * n_groups + group;
   if (kmax == 0) {
     if (threadIdx.x == 0) {
@@ -166,7 +171,7 @@ int b2_launch_eval_splits(const long long* level_hist, int n_groups, const B2Eva
                           const uint8_t* has_missing, const int32_t* qexp, int qbits, B2TrainParamDev p,
                           B2SplitCand* cands, const B2LevelCtl* ctl, cudaStream_t stream) {
   if (n_nodes <= 0) return 0;   // with ctl: n_nodes is the upper bound of the level
-  b2::eval_splits_kernel<<<n_nodes * n_groups, 256, 0, stream>>>(level_hist, n_groups, nodes, group_first, group_size,
+  b2::eval_splits_kernel<<<n_nodes * n_groups, 32 * b2::kEvalChunks, 0, stream>>>(level_hist, n_groups, nodes, group_first, group_size,
                                                                nbins, has_missing, qexp, qbits, p, cands, ctl);
   return (int)cudaGetLastError();
 }
