@@ -116,7 +116,7 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     O.build()
-    cores = O.lib().or_num_threads()
+    cores = O.use_all_cores()
     X, y = synth_shard(args.rows, args.cols, 0, 1)
     params = dict(PARAMS, max_depth=args.depth, hist_qbits=0)   # qbits=0: float64 histograms = XGBoost CPU hist
     t0 = time.time()
@@ -254,6 +254,7 @@ def main():
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
             O.build()
+            O.use_all_cores()
             ptrs, vals, mins, hm = dm.get_cuts()
             cuts = O.Cuts.from_arrays(ptrs, vals, mins, hm, 256)
             bins = dm.get_bins()

@@ -905,6 +905,14 @@ void or_metric_sums(int32_t metric, int32_t K, const float *margin, const float 
   *out_sum = s; *out_wsum = ws;
 }
 
+void or_set_num_threads(int32_t n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int32_t or_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

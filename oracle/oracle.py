@@ -77,8 +77,16 @@ def lib():
         L.or_expf.restype = C.c_float
         L.or_expf.argtypes = [C.c_float]
         L.or_num_threads.restype = C.c_int32
+        L.or_set_num_threads.argtypes = [C.c_int32]
         _lib = L
     return _lib
+
+
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use every host core it can."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().or_set_num_threads(n)
+    return lib().or_num_threads()
 
 
 def _fp(a):
