@@ -369,31 +369,48 @@ void or_quantize(const float *v, int64_t n, int64_t stride, int32_t qbits, int32
   *out_exp = e;
 }
 
+/* persistent per-thread scratch for row-parallel histograms (a fresh calloc per node is a page-fault
+ * storm with many threads) */
+static void *g_pool = NULL;
+static size_t g_pool_bytes = 0;
+static void *pool_get(size_t bytes) {
+  if (bytes > g_pool_bytes) { free(g_pool); g_pool = malloc(bytes); g_pool_bytes = g_pool ? bytes : 0; }
+  return g_pool;
+}
+#define OR_ROWS_PER_THREAD 32768
+static int hist_threads(int64_t nrows) {
+#ifdef _OPENMP
+  if (omp_in_parallel()) return 1;
+  int64_t nt = nrows / OR_ROWS_PER_THREAD;
+  int mx = omp_get_max_threads();
+  if (nt > mx) nt = mx;
+  return nt < 1 ? 1 : (int)nt;
+#else
+  (void)nrows; return 1;
+#endif
+}
+
 /* ------------------------------------------------------------------ A.5 histogram */
 /* hist layout [F][256][2] int64 (g,h); rows given by ridx (or NULL = 0..n-1) */
+static void hist_int_serial(const uint8_t *bins, int32_t F, const int32_t *qg, const int32_t *qh, const int32_t *ridx,
+                            int64_t k0, int64_t k1, int64_t *hist) {
+  for (int64_t k = k0; k < k1; ++k) {
+    int64_t r = ridx ? ridx[k] : k;
+    const uint8_t *b = bins + r * F;
+    int64_t g = qg[r], h = qh[r];
+    for (int32_t f = 0; f < F; ++f) {
+      int64_t *e = hist + ((size_t)f * 256 + b[f]) * 2;
+      e[0] += g; e[1] += h;
+    }
+  }
+}
 void or_hist_int(const uint8_t *bins, int32_t F, const int32_t *qg, const int32_t *qh,
                  const int32_t *ridx, int64_t nrows, int64_t *hist) {
   size_t hsz = (size_t)F * 256 * 2;
   memset(hist, 0, hsz * sizeof(int64_t));
-#ifdef _OPENMP
-  int nt = omp_in_parallel() ? 1 : omp_get_max_threads();
-#else
-  int nt = 1;
-#endif
-  if (nrows < 65536) nt = 1;
-  if (nt == 1) {
-    for (int64_t k = 0; k < nrows; ++k) {
-      int64_t r = ridx ? ridx[k] : k;
-      const uint8_t *b = bins + r * F;
-      int64_t g = qg[r], h = qh[r];
-      for (int32_t f = 0; f < F; ++f) {
-        int64_t *e = hist + ((size_t)f * 256 + b[f]) * 2;
-        e[0] += g; e[1] += h;
-      }
-    }
-    return;
-  }
-  int64_t *priv = (int64_t *)calloc(hsz * (size_t)nt, sizeof(int64_t));
+  int nt = hist_threads(nrows);
+  if (nt == 1) { hist_int_serial(bins, F, qg, qh, ridx, 0, nrows, hist); return; }
+  int64_t *priv = (int64_t *)pool_get(hsz * (size_t)nt * sizeof(int64_t));
 #pragma omp parallel num_threads(nt)
   {
 #ifdef _OPENMP
@@ -402,24 +419,16 @@ void or_hist_int(const uint8_t *bins, int32_t F, const int32_t *qg, const int32_
     int t = 0;
 #endif
     int64_t *ph = priv + hsz * (size_t)t;
+    memset(ph, 0, hsz * sizeof(int64_t));
+    hist_int_serial(bins, F, qg, qh, ridx, nrows * t / nt, nrows * (t + 1) / nt, ph);
+#pragma omp barrier
 #pragma omp for schedule(static)
-    for (int64_t k = 0; k < nrows; ++k) {
-      int64_t r = ridx ? ridx[k] : k;
-      const uint8_t *b = bins + r * F;
-      int64_t g = qg[r], h = qh[r];
-      for (int32_t f = 0; f < F; ++f) {
-        int64_t *e = ph + ((size_t)f * 256 + b[f]) * 2;
-        e[0] += g; e[1] += h;
-      }
-    }
-#pragma omp for schedule(static)
-    for (int64_t j = 0; j < (int64_t)hsz; ++j) {
-      int64_t s = 0;
-      for (int t2 = 0; t2 < nt; ++t2) s += priv[hsz * (size_t)t2 + (size_t)j];
-      hist[j] = s;
+    for (int64_t jj = 0; jj < (int64_t)hsz; ++jj) {
+      int64_t sacc = 0;
+      for (int t2 = 0; t2 < nt; ++t2) sacc += priv[hsz * (size_t)t2 + (size_t)jj];
+      hist[jj] = sacc;
     }
   }
-  free(priv);
 }
 
 static void hist_f64_serial(const uint8_t *bins, int32_t F, const float *g, const float *h, int64_t gstride,
@@ -440,14 +449,9 @@ static void hist_f64(const uint8_t *bins, int32_t F, const float *g, const float
                      const int32_t *ridx, int64_t nrows, double *hist) {
   size_t hsz = (size_t)F * 512;
   memset(hist, 0, hsz * sizeof(double));
-#ifdef _OPENMP
-  int nt = omp_in_parallel() ? 1 : omp_get_max_threads();
-#else
-  int nt = 1;
-#endif
-  if (nrows < 65536) nt = 1;
+  int nt = hist_threads(nrows);
   if (nt == 1) { hist_f64_serial(bins, F, g, h, gstride, ridx, 0, nrows, hist); return; }
-  double *priv = (double *)calloc(hsz * (size_t)nt, sizeof(double));
+  double *priv = (double *)pool_get(hsz * (size_t)nt * sizeof(double));
 #pragma omp parallel num_threads(nt)
   {
 #ifdef _OPENMP
@@ -455,17 +459,16 @@ static void hist_f64(const uint8_t *bins, int32_t F, const float *g, const float
 #else
     int t = 0;
 #endif
-    int64_t k0 = nrows * t / nt, k1 = nrows * (t + 1) / nt;
-    hist_f64_serial(bins, F, g, h, gstride, ridx, k0, k1, priv + hsz * (size_t)t);
+    memset(priv + hsz * (size_t)t, 0, hsz * sizeof(double));
+    hist_f64_serial(bins, F, g, h, gstride, ridx, nrows * t / nt, nrows * (t + 1) / nt, priv + hsz * (size_t)t);
 #pragma omp barrier
 #pragma omp for schedule(static)
-    for (int64_t j = 0; j < (int64_t)hsz; ++j) {
+    for (int64_t j2 = 0; j2 < (int64_t)hsz; ++j2) {
       double sacc = 0;
-      for (int t2 = 0; t2 < nt; ++t2) sacc += priv[hsz * (size_t)t2 + (size_t)j];
-      hist[j] = sacc;
+      for (int t2 = 0; t2 < nt; ++t2) sacc += priv[hsz * (size_t)t2 + (size_t)j2];
+      hist[j2] = sacc;
     }
   }
-  free(priv);
 }
 
 /* ------------------------------------------------------------------ A.6 split */
@@ -746,28 +749,29 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
     /* phase C: histograms of the children (A.5): build the smaller-hessian child from rows,
      * sibling = parent - built.  Node-parallel when there are many nodes, row-parallel otherwise. */
     if (n_pairs > 0 && ((level[pair_parent[0]].depth + 1 < p->max_depth) || p->max_depth == 0)) {
-#ifdef _OPENMP
-      int node_parallel = n_pairs >= omp_get_max_threads();
-#else
-      int node_parallel = 0;
-#endif
-#pragma omp parallel for schedule(dynamic, 1) if (node_parallel)
-      for (int32_t j = 0; j < n_pairs; ++j) {
-        NodeWork *w = &level[pair_parent[j]];
-        NodeWork *wl = &next[2 * j], *wr = &next[2 * j + 1];
-        NodeWork *bw = (wl->H < wr->H) ? wl : wr, *sw = (bw == wl) ? wr : wl;
-        bw->hist = (double *)malloc(hsz * sizeof(double)); sw->hist = (double *)malloc(hsz * sizeof(double));
-        if (p->qbits > 0) {
-          bw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t)); sw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t));
-          or_hist_int(bins, F, qg, qh, ridx + bw->begin, bw->count, bw->ihist);
-          for (size_t jj = 0; jj < hsz; ++jj) sw->ihist[jj] = w->ihist[jj] - bw->ihist[jj];
-          for (size_t jj = 0; jj < hsz; jj += 2) {
-            bw->hist[jj] = (double)bw->ihist[jj] * inv_sg; bw->hist[jj + 1] = (double)bw->ihist[jj + 1] * inv_sh;
-            sw->hist[jj] = (double)sw->ihist[jj] * inv_sg; sw->hist[jj + 1] = (double)sw->ihist[jj + 1] * inv_sh;
+      /* pass 0: nodes big enough for a row-parallel build, one after the other;
+       * pass 1: the remaining (small) nodes in parallel, each built serially into its own buffer */
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma omp parallel for schedule(dynamic, 1) if (pass == 1)
+        for (int32_t j = 0; j < n_pairs; ++j) {
+          NodeWork *w = &level[pair_parent[j]];
+          NodeWork *wl = &next[2 * j], *wr = &next[2 * j + 1];
+          NodeWork *bw = (wl->H < wr->H) ? wl : wr, *sw = (bw == wl) ? wr : wl;
+          int big = bw->count >= 2 * (int64_t)OR_ROWS_PER_THREAD;
+          if (big != (pass == 0)) continue;
+          bw->hist = (double *)malloc(hsz * sizeof(double)); sw->hist = (double *)malloc(hsz * sizeof(double));
+          if (p->qbits > 0) {
+            bw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t)); sw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t));
+            or_hist_int(bins, F, qg, qh, ridx + bw->begin, bw->count, bw->ihist);
+            for (size_t jj = 0; jj < hsz; ++jj) sw->ihist[jj] = w->ihist[jj] - bw->ihist[jj];
+            for (size_t jj = 0; jj < hsz; jj += 2) {
+              bw->hist[jj] = (double)bw->ihist[jj] * inv_sg; bw->hist[jj + 1] = (double)bw->ihist[jj + 1] * inv_sh;
+              sw->hist[jj] = (double)sw->ihist[jj] * inv_sg; sw->hist[jj + 1] = (double)sw->ihist[jj + 1] * inv_sh;
+            }
+          } else {
+            hist_f64(bins, F, g, h, gstride, ridx + bw->begin, bw->count, bw->hist);
+            for (size_t jj = 0; jj < hsz; ++jj) sw->hist[jj] = w->hist[jj] - bw->hist[jj];
           }
-        } else {
-          hist_f64(bins, F, g, h, gstride, ridx + bw->begin, bw->count, bw->hist);
-          for (size_t jj = 0; jj < hsz; ++jj) sw->hist[jj] = w->hist[jj] - bw->hist[jj];
         }
       }
     }

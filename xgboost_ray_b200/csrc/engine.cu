@@ -19,6 +19,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b2hist.h"
@@ -61,11 +62,11 @@ int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, c
                       cudaStream_t);
 int b2_launch_fill(float*, int64_t, float, int, cudaStream_t);
 int b2_launch_transform(int, int, float*, int64_t, int, cudaStream_t);
-int b2_launch_extract_keys(const float*, int64_t, int, int, float, uint32_t*, int64_t, unsigned long long*, int,
-                           cudaStream_t);
+int b2_extract_batch();
+int b2_launch_extract_keys(const float*, int64_t, int, int, int, float, uint32_t*, int64_t, int, cudaStream_t);
 size_t b2_sort_temp_bytes(int64_t);
-int b2_sketch_column(const uint32_t*, uint32_t*, int64_t, int64_t, void*, size_t, int32_t*, int32_t*, float*, long long*,
-                     int32_t*, int, float*, int32_t*, float*, int, cudaStream_t);
+int b2_sketch_column(const uint32_t*, uint32_t*, int64_t, long long, void*, size_t, int32_t*, int32_t*, float*, long long*,
+                     int32_t*, long long*, int, float*, int32_t*, float*, int32_t*, int, cudaStream_t);
 int b2_launch_bin(const float*, int64_t, int, float, const int32_t*, const float*, const int32_t*, int, uint8_t*, uint8_t*,
                   int64_t, int, cudaStream_t);
 }
@@ -141,6 +142,69 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   ~DevBuf() { release(); }
 };
+
+// ---------------------------------------------------------------- host -> device ingest
+// Pageable host memory goes through the driver's single bounce buffer at ~10-13 GB/s.  Here T
+// worker threads copy 16 MiB slices into their own pinned staging buffers and issue the DMA on
+// their own streams, so host memcpy and PCIe transfers of different slices overlap.
+struct PinnedPool {
+  static constexpr int kWorkers = 4, kSlots = 2;
+  static constexpr size_t kSlice = (size_t)16 << 20;
+  void* buf[kWorkers][kSlots] = {};
+  cudaStream_t stream[kWorkers] = {};
+  cudaEvent_t done[kWorkers][kSlots] = {};
+  bool ready = false;
+  std::mutex mu;
+  void init() {
+    if (ready) return;
+    for (int w = 0; w < kWorkers; ++w) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&stream[w], cudaStreamNonBlocking));
+      for (int k = 0; k < kSlots; ++k) {
+        CUDA_CHECK(cudaMallocHost(&buf[w][k], kSlice));
+        CUDA_CHECK(cudaEventCreateWithFlags(&done[w][k], cudaEventDisableTiming));
+      }
+    }
+    ready = true;
+  }
+};
+std::map<int, PinnedPool*> g_pools;
+
+void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes < ((size_t)64 << 20)) {
+    if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  PinnedPool* pool;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    PinnedPool*& p = g_pools[ctx->device];
+    if (!p) p = new PinnedPool();
+    pool = p;
+  }
+  std::lock_guard<std::mutex> lk(pool->mu);   // one bulk upload per device at a time
+  pool->init();
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // dst allocation / earlier work is complete
+  const size_t n_slices = (bytes + PinnedPool::kSlice - 1) / PinnedPool::kSlice;
+  std::atomic<int> failed{0};
+  auto worker = [&](int w) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { failed = 1; return; }
+    int use = 0;
+    for (size_t i = w; i < n_slices; i += PinnedPool::kWorkers, ++use) {
+      const int k = use % PinnedPool::kSlots;
+      const size_t off = i * PinnedPool::kSlice, len = std::min(PinnedPool::kSlice, bytes - off);
+      if (use >= PinnedPool::kSlots && cudaEventSynchronize(pool->done[w][k]) != cudaSuccess) { failed = 1; return; }
+      memcpy(pool->buf[w][k], (const char*)src + off, len);
+      if (cudaMemcpyAsync((char*)dst + off, pool->buf[w][k], len, cudaMemcpyHostToDevice, pool->stream[w]) != cudaSuccess ||
+          cudaEventRecord(pool->done[w][k], pool->stream[w]) != cudaSuccess) { failed = 1; return; }
+    }
+    if (cudaStreamSynchronize(pool->stream[w]) != cudaSuccess) failed = 1;
+  };
+  std::vector<std::thread> th;
+  for (int w = 0; w < PinnedPool::kWorkers; ++w) th.emplace_back(worker, w);
+  for (auto& t : th) t.join();
+  if (failed.load()) fail("pipelined host->device upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
 
 // ---------------------------------------------------------------- NCCL (dlopen'ed)
 typedef struct ncclComm* ncclComm_t;
@@ -266,70 +330,72 @@ void upload_cuts(Matrix* m) {
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
-// GPU sketch: exact global summary per feature -> cuts (sketch.cu).  Multi-GPU: the column keys of
-// every rank are allgathered (padded to the largest shard) so all ranks compute identical cuts.
+// GPU sketch: exact global summary per feature -> cuts (sketch.cu).  No host round trip per feature.
+// Multi-GPU: the column keys of every rank are allgathered (padded to the largest shard); feature f is
+// sorted and pruned only by its owner rank f % world, and the cut tables are merged with one integer
+// allreduce (non-owners contribute zeros), so every rank ends up with identical global cuts.
 void make_cuts(Matrix* m, Comm* comm, int max_bin) {
   Ctx* ctx = m->ctx; cudaStream_t s = ctx->stream;
   if (max_bin < 2 || max_bin > 256) fail("max_bin must be in [2, 256] (uint8 bin matrix), got %d", max_bin);
   if (!m->has_raw) fail("matrix has no raw data to sketch");
-  const int world = comm ? comm->world : 1;
-  // largest shard
+  const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  // largest shard and global row count
   DevBuf<long long> d_cnt; d_cnt.ensure(2);
-  long long h_n = m->n, h_max = m->n;
+  long long h_cnt[2] = {m->n, m->n};
   if (world > 1) {
-    CUDA_CHECK(cudaMemcpyAsync(d_cnt.p, &h_n, sizeof(long long), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(d_cnt.p, h_cnt, sizeof(h_cnt), cudaMemcpyHostToDevice, s));
     allreduce(comm, d_cnt.p, 1, kNcclInt64, kNcclMax, s);
-    CUDA_CHECK(cudaMemcpyAsync(&h_max, d_cnt.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    allreduce(comm, d_cnt.p + 1, 1, kNcclInt64, kNcclSum, s);
+    CUDA_CHECK(cudaMemcpyAsync(h_cnt, d_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
   }
-  const int64_t n_pad = h_max, n_total = n_pad * world;
+  const int64_t n_pad = h_cnt[0], n_total = n_pad * world; const long long n_global = h_cnt[1];
+  const int B = b2_extract_batch(); const int F = m->F;
   DevBuf<uint32_t> keys_local, keys_all, keys_sorted;
-  DevBuf<int32_t> flags, idx, m_scratch; DevBuf<float> uval; DevBuf<long long> rmin;
-  DevBuf<unsigned long long> d_nmiss; DevBuf<float> d_cuts, d_mins; DevBuf<int32_t> d_ncuts;
+  DevBuf<int32_t> flags, idx, m_scratch; DevBuf<float> uval; DevBuf<long long> rmin, nvalid;
+  DevBuf<int32_t> d_tab;   // [F*256 cut bits][F n_cuts][F min bits][F has_missing]
   DevBuf<uint8_t> temp;
   const size_t nt = (size_t)std::max<int64_t>(n_total, 1);
-  keys_local.ensure((size_t)std::max<int64_t>(n_pad, 1)); keys_all.ensure(nt); keys_sorted.ensure(nt);
-  flags.ensure(nt); idx.ensure(nt); uval.ensure(nt); rmin.ensure(nt); m_scratch.ensure(1);
+  keys_local.ensure((size_t)std::max<int64_t>(n_pad, 1) * B);
+  if (world > 1) keys_all.ensure(nt);
+  keys_sorted.ensure(nt); flags.ensure(nt); idx.ensure(nt); uval.ensure(nt); rmin.ensure(nt); m_scratch.ensure(1); nvalid.ensure(1);
   const size_t temp_bytes = b2_sort_temp_bytes(n_total > 0 ? n_total : 1);
   temp.ensure(temp_bytes ? temp_bytes : 1);
-  const int F = m->F;
-  d_nmiss.ensure((size_t)F); d_cuts.ensure((size_t)F * 256); d_mins.ensure((size_t)F); d_ncuts.ensure((size_t)F);
-  CUDA_CHECK(cudaMemsetAsync(d_nmiss.p, 0, (size_t)F * sizeof(unsigned long long), s));
-  std::vector<unsigned long long> nmiss(F, 0);
-  long long n_global = m->n;
-  if (world > 1) {
-    CUDA_CHECK(cudaMemcpyAsync(d_cnt.p, &h_n, sizeof(long long), cudaMemcpyHostToDevice, s));
-    allreduce(comm, d_cnt.p, 1, kNcclInt64, kNcclSum, s);
-    CUDA_CHECK(cudaMemcpyAsync(&n_global, d_cnt.p, sizeof(long long), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
-  }
-  for (int f = 0; f < F; ++f) {
-    LAUNCH_CHECK(b2_launch_extract_keys(m->raw.p, m->n, F, f, m->missing, keys_local.p, n_pad, d_nmiss.p + f, ctx->num_sms, s));
-    const uint32_t* kin = keys_local.p;
-    if (world > 1) {
-      NCCL_CHECK(nccl()->AllGather(keys_local.p, keys_all.p, (size_t)n_pad, kNcclUint32, comm->comm, s));
-      allreduce(comm, d_nmiss.p + f, 1, kNcclUint64, kNcclSum, s);
-      kin = keys_all.p;
+  const size_t tab_n = (size_t)F * 256 + 3 * (size_t)F;
+  d_tab.ensure(tab_n);
+  CUDA_CHECK(cudaMemsetAsync(d_tab.p, 0, tab_n * sizeof(int32_t), s));
+  float* d_cuts = (float*)d_tab.p; int32_t* d_ncuts = d_tab.p + (size_t)F * 256;
+  float* d_mins = (float*)(d_ncuts + F); int32_t* d_hasmiss = d_ncuts + 2 * (size_t)F;
+  for (int f0 = 0; f0 < F; f0 += B) {
+    const int nf = std::min(B, F - f0);
+    LAUNCH_CHECK(b2_launch_extract_keys(m->raw.p, m->n, F, f0, nf, m->missing, keys_local.p, n_pad, ctx->num_sms, s));
+    for (int j = 0; j < nf; ++j) {
+      const int f = f0 + j;
+      const uint32_t* kin = keys_local.p + (size_t)j * n_pad;
+      if (world > 1) {
+        NCCL_CHECK(nccl()->AllGather(kin, keys_all.p, (size_t)n_pad, kNcclUint32, comm->comm, s));
+        kin = keys_all.p;
+        if (f % world != rank) continue;   // the owner rank sketches this feature
+      }
+      LAUNCH_CHECK(b2_sketch_column(kin, keys_sorted.p, n_total, n_global, temp.p, temp_bytes, flags.p, idx.p, uval.p, rmin.p,
+                                    m_scratch.p, nvalid.p, max_bin, d_cuts + (size_t)f * 256, d_ncuts + f, d_mins + f,
+                                    d_hasmiss + f, ctx->num_sms, s));
     }
-    CUDA_CHECK(cudaMemcpyAsync(&nmiss[f], d_nmiss.p + f, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    const int64_t n_valid = (int64_t)n_global - (int64_t)nmiss[f];
-    const int cap = (nmiss[f] > 0 && max_bin > 255) ? 255 : max_bin;
-    LAUNCH_CHECK(b2_sketch_column(kin, keys_sorted.p, n_total, n_valid, temp.p, temp_bytes, flags.p, idx.p, uval.p, rmin.p,
-                                  m_scratch.p, cap, d_cuts.p + (size_t)f * 256, d_ncuts.p + f, d_mins.p + f, ctx->num_sms, s));
   }
-  std::vector<float> h_cuts((size_t)F * 256), h_mins(F);
-  std::vector<int32_t> h_nc(F);
-  CUDA_CHECK(cudaMemcpyAsync(h_cuts.data(), d_cuts.p, h_cuts.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaMemcpyAsync(h_mins.data(), d_mins.p, (size_t)F * sizeof(float), cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaMemcpyAsync(h_nc.data(), d_ncuts.p, (size_t)F * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  // merge the per-owner tables: exact because every entry is written by exactly one rank (others hold 0 bits)
+  allreduce(comm, d_tab.p, tab_n, kNcclInt32, kNcclSum, s);
+  std::vector<int32_t> h_tab(tab_n);
+  CUDA_CHECK(cudaMemcpyAsync(h_tab.data(), d_tab.p, tab_n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
+  const float* h_cuts = (const float*)h_tab.data(); const int32_t* h_nc = h_tab.data() + (size_t)F * 256;
+  const float* h_mins = (const float*)(h_nc + F); const int32_t* h_hm = h_nc + 2 * (size_t)F;
   m->cut_ptrs.assign(F + 1, 0);
-  m->cut_vals.clear(); m->min_vals = h_mins; m->has_missing.assign(F, 0);
+  m->cut_vals.clear(); m->min_vals.assign(h_mins, h_mins + F); m->has_missing.assign(F, 0);
   for (int f = 0; f < F; ++f) {
+    if (h_nc[f] < 1 || h_nc[f] > 256) fail("sketch produced %d cuts for feature %d", h_nc[f], f);
     m->cut_ptrs[f + 1] = m->cut_ptrs[f] + h_nc[f];
-    m->cut_vals.insert(m->cut_vals.end(), h_cuts.begin() + (size_t)f * 256, h_cuts.begin() + (size_t)f * 256 + h_nc[f]);
-    m->has_missing[f] = nmiss[f] > 0 ? 1 : 0;
+    m->cut_vals.insert(m->cut_vals.end(), h_cuts + (size_t)f * 256, h_cuts + (size_t)f * 256 + h_nc[f]);
+    m->has_missing[f] = h_hm[f] ? 1 : 0;
   }
   m->max_bin = max_bin;
 }
@@ -941,8 +1007,7 @@ int B2_MatrixCreateFromDense(const float* data, int64_t n_rows, int32_t n_cols, 
   Matrix* m = new Matrix(); m->kind = kMatrix; m->ctx = ctx; m->n = n_rows; m->F = n_cols; m->missing = missing;
   try {
     m->raw.ensure((size_t)std::max<int64_t>(n_rows * n_cols, 1));
-    if (n_rows > 0) CUDA_CHECK(cudaMemcpyAsync(m->raw.p, data, (size_t)n_rows * n_cols * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    upload_pipelined(ctx, m->raw.p, data, (size_t)n_rows * n_cols * sizeof(float));
   } catch (...) { delete m; throw; }
   m->has_raw = true;
   *out = (B2Handle)m;
@@ -991,8 +1056,7 @@ int B2_MatrixEnsureRaw(B2Handle mh, const float* data) {
   CUDA_CHECK(cudaSetDevice(m->ctx->device));
   if (m->has_raw) return 0;
   m->raw.ensure((size_t)std::max<int64_t>(m->n * m->F, 1));
-  if (m->n > 0) CUDA_CHECK(cudaMemcpyAsync(m->raw.p, data, (size_t)m->n * m->F * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
-  CUDA_CHECK(cudaStreamSynchronize(m->ctx->stream));
+  upload_pipelined(m->ctx, m->raw.p, data, (size_t)m->n * m->F * sizeof(float));
   m->has_raw = true;
   API_END
 }

@@ -25,44 +25,56 @@ __device__ __forceinline__ bool is_missing(float x, float missing, int missing_i
   return isnan(x) || (!missing_is_nan && x == missing);
 }
 
-__global__ void extract_keys_kernel(const float* __restrict__ X, int64_t n, int F, int f, float missing,
-                                    int missing_is_nan, uint32_t* __restrict__ keys, int64_t n_padded,
-                                    unsigned long long* __restrict__ n_missing) {
-  unsigned long long cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (int64_t)gridDim.x * blockDim.x) {
+// keys of kBatch consecutive feature columns in one pass: thread (row, j) reads X[row][f0+j], so a warp
+// reads 4 rows x 32 contiguous bytes (whole sectors) instead of one float per 4*F-byte row.
+constexpr int kExtractBatch = 8;
+__global__ void extract_keys_kernel(const float* __restrict__ X, int64_t n, int F, int f0, int nf, float missing,
+                                    int missing_is_nan, uint32_t* __restrict__ keys /*[kBatch][n_padded]*/, int64_t n_padded) {
+  const int64_t total = n_padded * kExtractBatch;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / kExtractBatch; const int j = (int)(t % kExtractBatch);
+    if (j >= nf) continue;
     uint32_t k = 0xffffffffu;
     if (i < n) {
-      float x = X[i * F + f];
-      if (is_missing(x, missing, missing_is_nan)) cnt++;
-      else { if (x == 0.0f) x = 0.0f; k = f2key(x); }
+      float x = X[i * F + f0 + j];
+      if (!is_missing(x, missing, missing_is_nan)) { if (x == 0.0f) x = 0.0f; k = f2key(x); }
     }
-    keys[i] = k;
+    keys[(int64_t)j * n_padded + i] = k;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_missing, cnt);
 }
 
-__global__ void head_flags_kernel(const uint32_t* __restrict__ keys, int64_t n_valid, int32_t* __restrict__ flags) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_valid; i += (int64_t)gridDim.x * blockDim.x)
-    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+// n_valid = number of keys below the missing/padding sentinel 0xffffffff in the sorted array
+__global__ void count_valid_kernel(const uint32_t* __restrict__ sorted, int64_t n_total, long long* __restrict__ n_valid) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int64_t lo = 0, hi = n_total;
+  while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (sorted[mid] == 0xffffffffu) hi = mid; else lo = mid + 1; }
+  *n_valid = lo;
+}
+
+__global__ void head_flags_kernel(const uint32_t* __restrict__ keys, int64_t n_total, int32_t* __restrict__ flags) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x)
+    flags[i] = (keys[i] != 0xffffffffu && (i == 0 || keys[i] != keys[i - 1])) ? 1 : 0;
 }
 __global__ void scatter_unique_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ flags,
-                                      const int32_t* __restrict__ idx, int64_t n_valid, float* __restrict__ uval,
+                                      const int32_t* __restrict__ idx, int64_t n_total, float* __restrict__ uval,
                                       long long* __restrict__ rmin, int32_t* __restrict__ m_out) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_valid; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
     if (flags[i]) { uval[idx[i]] = key2f(keys[i]); rmin[idx[i]] = i; }
-    if (i == n_valid - 1) *m_out = idx[i] + flags[i];
+    if (i == n_total - 1) *m_out = idx[i] + flags[i];
   }
 }
 
 // One block.  WQSummary::SetPrune + HistogramCuts::AddCutPoint on the exact summary (A.2).
 __global__ void __launch_bounds__(256)
 prune_cuts_kernel(const float* __restrict__ uval, const long long* __restrict__ rmin, const int32_t* __restrict__ m_ptr,
-                  long long n_valid, int max_bin_cap, float* __restrict__ cut_out /*[256]*/, int32_t* __restrict__ n_cut_out,
-                  float* __restrict__ min_out) {
+                  const long long* __restrict__ n_valid_ptr, long long n_global, int max_bin, float* __restrict__ cut_out /*[256]*/,
+                  int32_t* __restrict__ n_cut_out, float* __restrict__ min_out, int32_t* __restrict__ has_missing_out) {
   __shared__ int sel[260];
   __shared__ int choice[260];
+  const long long n_valid = *n_valid_ptr;
+  const bool any_missing = n_valid < n_global;
+  const int max_bin_cap = (any_missing && max_bin > 255) ? 255 : max_bin;   // bin 255 is the missing sentinel
+  if (threadIdx.x == 0) *has_missing_out = any_missing ? 1 : 0;
   const int m = n_valid > 0 ? *m_ptr : 0;
   if (m == 0) {
     if (threadIdx.x == 0) {
@@ -161,11 +173,13 @@ static inline int sk_grid(int64_t n, int num_sms) {
 
 extern "C" {
 
-int b2_launch_extract_keys(const float* X, int64_t n, int F, int f, float missing, uint32_t* keys, int64_t n_padded,
-                           unsigned long long* n_missing, int num_sms, cudaStream_t s) {
+int b2_extract_batch() { return b2::kExtractBatch; }
+
+int b2_launch_extract_keys(const float* X, int64_t n, int F, int f0, int nf, float missing, uint32_t* keys, int64_t n_padded,
+                           int num_sms, cudaStream_t s) {
   if (n_padded <= 0) return 0;
-  b2::extract_keys_kernel<<<sk_grid(n_padded, num_sms), 256, 0, s>>>(X, n, F, f, missing, missing != missing ? 1 : 0, keys,
-                                                                    n_padded, n_missing);
+  b2::extract_keys_kernel<<<sk_grid(n_padded * b2::kExtractBatch, num_sms), 256, 0, s>>>(X, n, F, f0, nf, missing,
+                                                                                      missing != missing ? 1 : 0, keys, n_padded);
   return (int)cudaGetLastError();
 }
 
@@ -177,23 +191,25 @@ size_t b2_sort_temp_bytes(int64_t n) {
   return bytes > scan_bytes ? bytes : scan_bytes;
 }
 
-// keys_in [n_total] (any order, 0xffffffff = missing/padding) -> cuts of one feature.
+// keys_in [n_total] (any order, 0xffffffff = missing/padding) -> cuts of one feature, no host round trip:
+// n_valid is found on the device, the 255-bin cap of features with missing values is applied on the device.
 // Scratch: keys_sorted [n_total], flags/idx int32 [n_total], uval float [n_total], rmin int64 [n_total].
-int b2_sketch_column(const uint32_t* keys_in, uint32_t* keys_sorted, int64_t n_total, int64_t n_valid, void* temp,
+int b2_sketch_column(const uint32_t* keys_in, uint32_t* keys_sorted, int64_t n_total, long long n_global, void* temp,
                      size_t temp_bytes, int32_t* flags, int32_t* idx, float* uval, long long* rmin, int32_t* m_scratch,
-                     int max_bin_cap, float* cut_out, int32_t* n_cut_out, float* min_out, int num_sms, cudaStream_t s) {
+                     long long* n_valid_scratch, int max_bin, float* cut_out, int32_t* n_cut_out, float* min_out,
+                     int32_t* has_missing_out, int num_sms, cudaStream_t s) {
   cudaError_t e;
   if (n_total > 0) {
     e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_in, keys_sorted, n_total, 0, 32, s);
     if (e != cudaSuccess) return (int)e;
-  }
-  if (n_valid > 0) {
-    b2::head_flags_kernel<<<sk_grid(n_valid, num_sms), 256, 0, s>>>(keys_sorted, n_valid, flags);
-    e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, flags, idx, n_valid, s);
+    b2::head_flags_kernel<<<sk_grid(n_total, num_sms), 256, 0, s>>>(keys_sorted, n_total, flags);
+    e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, flags, idx, n_total, s);
     if (e != cudaSuccess) return (int)e;
-    b2::scatter_unique_kernel<<<sk_grid(n_valid, num_sms), 256, 0, s>>>(keys_sorted, flags, idx, n_valid, uval, rmin, m_scratch);
+    b2::scatter_unique_kernel<<<sk_grid(n_total, num_sms), 256, 0, s>>>(keys_sorted, flags, idx, n_total, uval, rmin, m_scratch);
   }
-  b2::prune_cuts_kernel<<<1, 256, 0, s>>>(uval, rmin, m_scratch, n_valid, max_bin_cap, cut_out, n_cut_out, min_out);
+  b2::count_valid_kernel<<<1, 32, 0, s>>>(keys_sorted, n_total, n_valid_scratch);
+  b2::prune_cuts_kernel<<<1, 256, 0, s>>>(uval, rmin, m_scratch, n_valid_scratch, n_global, max_bin, cut_out, n_cut_out, min_out,
+                                         has_missing_out);
   return (int)cudaGetLastError();
 }
 
