@@ -53,7 +53,8 @@ struct TileScan {
 __global__ void __launch_bounds__(kCtlThreads)
 decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt, const B2NodeSeg* __restrict__ seg_cur,
               B2NodeSeg* __restrict__ seg_nxt, const B2EvalNode* __restrict__ ev_cur, B2EvalNode* __restrict__ ev_nxt,
-              const B2SplitCand* __restrict__ cands, int n_groups, int can_split, B2TreeDev tree,
+              const B2SplitCand* __restrict__ cands, int cands_per_node, int cand_ranks, int cand_rank_stride, int can_split,
+              B2TreeDev tree,
               B2SplitWork* __restrict__ split_work, int32_t* __restrict__ pair_parent_hist, B2LeafDev* __restrict__ leaves,
               int32_t* __restrict__ n_leaves, const uint8_t* __restrict__ has_missing, const int32_t* __restrict__ qexp,
               int qbits, B2CtlParams p) {
@@ -75,11 +76,12 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
     if (in) {
       nd = ev_cur[i]; sg = seg_cur[i];
       if (can_split) {
-        for (int g = 0; g < n_groups; ++g) {
-          const B2SplitCand c = cands[(size_t)i * n_groups + g];
-          if (c.feature < 0) continue;
-          if (best.feature < 0 || c.loss_chg > best.loss_chg || (c.loss_chg == best.loss_chg && c.order < best.order)) best = c;
-        }
+        for (int w = 0; w < cand_ranks; ++w)
+          for (int g = 0; g < cands_per_node; ++g) {
+            const B2SplitCand c = cands[(size_t)w * cand_rank_stride + (size_t)i * cands_per_node + g];
+            if (c.feature < 0) continue;
+            if (best.feature < 0 || c.loss_chg > best.loss_chg || (c.loss_chg == best.loss_chg && c.order < best.order)) best = c;
+          }
         if (best.feature >= 0)
           expand = best.loss_chg > 1e-6f && best.left_h != 0 && (nd.sum_h - best.left_h) != 0 && !(best.loss_chg < p.gamma);
       }
@@ -253,11 +255,11 @@ __global__ void root_record_kernel(B2TreeDev tree, const B2EvalNode* ev0) {
 
 extern "C" {
 int b2_launch_decide(B2LevelCtl* ctl_cur, B2LevelCtl* ctl_nxt, const B2NodeSeg* seg_cur, B2NodeSeg* seg_nxt,
-                     const B2EvalNode* ev_cur, B2EvalNode* ev_nxt, const B2SplitCand* cands, int n_groups, int can_split,
-                     B2TreeDev tree, B2SplitWork* split_work, int32_t* pair_parent_hist, B2LeafDev* leaves, int32_t* n_leaves,
+                     const B2EvalNode* ev_cur, B2EvalNode* ev_nxt, const B2SplitCand* cands, int cands_per_node, int cand_ranks,
+                     int cand_rank_stride, int can_split, B2TreeDev tree, B2SplitWork* split_work, int32_t* pair_parent_hist, B2LeafDev* leaves, int32_t* n_leaves,
                      const uint8_t* has_missing, const int32_t* qexp, int qbits, B2CtlParams p, cudaStream_t s) {
-  b2::decide_kernel<<<1, b2::kCtlThreads, 0, s>>>(ctl_cur, ctl_nxt, seg_cur, seg_nxt, ev_cur, ev_nxt, cands, n_groups, can_split,
-                                                 tree, split_work, pair_parent_hist, leaves, n_leaves, has_missing, qexp, qbits, p);
+  b2::decide_kernel<<<1, b2::kCtlThreads, 0, s>>>(ctl_cur, ctl_nxt, seg_cur, seg_nxt, ev_cur, ev_nxt, cands, cands_per_node,
+                                                 cand_ranks, cand_rank_stride, can_split, tree, split_work, pair_parent_hist, leaves, n_leaves, has_missing, qexp, qbits, p);
   return (int)cudaGetLastError();
 }
 int b2_launch_finalize_level(const B2LevelCtl* ctl_cur, B2LevelCtl* ctl_nxt, B2NodeSeg* seg_nxt, B2EvalNode* ev_nxt,

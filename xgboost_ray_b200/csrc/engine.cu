@@ -28,12 +28,13 @@
 // ---------------------------------------------------------------- kernel launchers (other TUs)
 extern "C" {
 int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
-                   const B2LevelCtl*, long long*, int, cudaStream_t);
+                   const B2LevelCtl*, long long*, int, int, int, cudaStream_t);
 size_t b2_hist_scratch_elems(int, int);
 int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, const B2LevelCtl*, cudaStream_t);
 int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
-                          const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, const B2LevelCtl*, cudaStream_t);
-int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, cudaStream_t);
+                          const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, const B2LevelCtl*, int, int,
+                          cudaStream_t);
+int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, int, cudaStream_t);
 int b2_part_chunk_rows();
 int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, const B2LevelCtl*, int, int32_t*,
                         int, cudaStream_t);
@@ -42,7 +43,7 @@ int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const voi
 int b2_launch_pred_update(float*, int, int, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const float*, int,
                           cudaStream_t);
 int b2_launch_decide(B2LevelCtl*, B2LevelCtl*, const B2NodeSeg*, B2NodeSeg*, const B2EvalNode*, B2EvalNode*, const B2SplitCand*,
-                     int, int, B2TreeDev, B2SplitWork*, int32_t*, B2LeafDev*, int32_t*, const uint8_t*, const int32_t*, int,
+                     int, int, int, int, B2TreeDev, B2SplitWork*, int32_t*, B2LeafDev*, int32_t*, const uint8_t*, const int32_t*, int,
                      B2CtlParams, cudaStream_t);
 int b2_launch_finalize_level(const B2LevelCtl*, B2LevelCtl*, B2NodeSeg*, B2EvalNode*, const B2SplitWork*, const int32_t*,
                              const int32_t*, B2HistWork*, int32_t*, int, int, int, int, int, long long*, cudaStream_t);
@@ -217,6 +218,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommAbort)(ncclComm_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -233,7 +235,7 @@ NcclApi* nccl() {
     api.lib = h;
 #define LOAD(field, sym) *(void**)(&api.field) = dlsym(h, sym); if (!api.field) err = std::string("missing symbol ") + sym;
     LOAD(GetUniqueId, "ncclGetUniqueId") LOAD(CommInitRank, "ncclCommInitRank") LOAD(AllReduce, "ncclAllReduce")
-    LOAD(AllGather, "ncclAllGather") LOAD(CommAbort, "ncclCommAbort") LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(AllGather, "ncclAllGather") LOAD(ReduceScatter, "ncclReduceScatter") LOAD(CommAbort, "ncclCommAbort") LOAD(CommDestroy, "ncclCommDestroy")
     LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
   });
@@ -473,6 +475,10 @@ struct Booster : HandleBase {
   DevBuf<int2> q;                // [n]
   DevBuf<int32_t> ridx[2];
   DevBuf<long long> hist[2];
+  DevBuf<long long> hist_build;     // reduce-scatter send buffer [shards][node_cap][slice] (only when shards > 1)
+  DevBuf<B2SplitCand> d_cands_all;  // allgathered candidates [shards][nodes][cpn]
+  int shards = 1, log2_shards = 0, sp = 32, cpn = 1;
+  size_t slice_elems = 0;
   DevBuf<long long> hist_scratch;   // CTA-private int64 window accumulators (kept all-zero between launches)
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
@@ -645,12 +651,21 @@ void ensure_ctl_tables(Booster* b) {
   b->t_i32.ensure(L.i32_count); b->t_f32.ensure(L.f32_count); b->t_i64.ensure(L.i64_count);
   b->d_ctl.ensure(3);
   for (int k = 0; k < 2; ++k) { b->d_seg[k].ensure(lcap); b->d_ev[k].ensure(lcap); }
-  b->d_hist_work.ensure(half); b->d_split_work.ensure(half); b->d_cands.ensure(half * G);
+  b->d_hist_work.ensure(half); b->d_split_work.ensure(half);
   b->d_counters.ensure(2 * half); b->d_triples.ensure(3 * half); b->d_pair_parent.ensure(half);
   b->d_leaves.ensure(L.max_nodes); b->d_seg_work.ensure(L.max_nodes);
   b->d_leaf_sums.ensure(2 * lcap); b->d_leaf_values.ensure(lcap);
   b->node_elems = (size_t)G * B2_GROUP_ELEMS;
-  b->hist[0].ensure(half * b->node_elems); b->hist[1].ensure(half * b->node_elems);
+  // feature-slot sharding of the histogram exchange: rank r owns slots s with s % shards == r
+  const int world = b->comm ? b->comm->world : 1;
+  b->shards = (world > 1 && world <= 32 && (32 % world) == 0) ? world : 1;
+  b->log2_shards = 0; while ((1 << b->log2_shards) < b->shards) b->log2_shards++;
+  b->sp = B2_GROUP_SLOTS / b->shards;
+  b->slice_elems = (size_t)G * 2 * B2_BINS * b->sp;
+  b->cpn = (G * b->sp + 31) / 32;
+  b->hist[0].ensure(half * b->slice_elems); b->hist[1].ensure(half * b->slice_elems);
+  if (b->shards > 1) { b->hist_build.ensure(half * b->node_elems); b->d_cands_all.ensure(half * b->cpn * b->shards); }
+  b->d_cands.ensure(half * b->cpn);
   const size_t se = b2_hist_scratch_elems(G, b->ctx->num_sms);
   b->hist_scratch.ensure(se);
   CUDA_CHECK(cudaMemsetAsync(b->hist_scratch.p, 0, se * sizeof(long long), b->ctx->stream));
@@ -661,6 +676,22 @@ void record_hist_launch(Booster* b, cudaEvent_t& e0, cudaEvent_t& e1, bool begin
   if (!b->p.profile) return;
   if (begin) { e0 = get_event(b); e1 = get_event(b); CUDA_CHECK(cudaEventRecord(e0, b->ctx->stream)); }
   else { CUDA_CHECK(cudaEventRecord(e1, b->ctx->stream)); b->hist_events.push_back({e0, e1}); }
+}
+
+// Histogram exchange of `nb` built nodes: reduce-scatter of the build buffer into the owned slices of the
+// level buffer (shards == world), or in-place allreduce (shards == 1, any world size).
+long long* build_target(Booster* b, long long* level_buf) { return b->shards > 1 ? b->hist_build.p : level_buf; }
+void exchange_hist(Booster* b, long long* level_buf, int nb) {
+  cudaStream_t s = b->ctx->stream;
+  if (!b->comm || b->comm->world <= 1) return;
+  if (b->comm->aborted.load()) fail("communicator aborted");
+  if (b->shards > 1) {
+    NCCL_CHECK(nccl()->ReduceScatter(b->hist_build.p, level_buf, (size_t)nb * b->slice_elems, kNcclInt64, kNcclSum, b->comm->comm, s));
+    b->t.allreduce_bytes += (double)nb * b->node_elems * 8 * (b->shards - 1) / b->shards;
+  } else {
+    NCCL_CHECK(nccl()->AllReduce(level_buf, level_buf, (size_t)nb * b->node_elems, kNcclInt64, kNcclSum, b->comm->comm, s));
+    b->t.allreduce_bytes += (double)nb * b->node_elems * 8;
+  }
 }
 
 // Grow one tree for class k from gh[k] (already on device); updates margin[:, k].  No host
@@ -701,7 +732,9 @@ void grow_tree(Booster* b, int k, int slot) {
   LAUNCH_CHECK(b2_launch_tree_init(tree, ctl, b->d_seg[0].p, b->d_ev[0].p, d_n_leaves, (int)n, s));
   mark_phase(b, 0);
   // ---- root histogram (no gather; row count known on the host)
-  CUDA_CHECK(cudaMemsetAsync(b->hist[0].p, 0, b->node_elems * sizeof(long long), s));
+  const int sh = b->log2_shards;
+  const int shard_rank = b->shards > 1 ? b->comm->rank : 0;
+  CUDA_CHECK(cudaMemsetAsync(build_target(b, b->hist[0].p), 0, b->node_elems * sizeof(long long), s));
   {
     const int chunk_rows = pick_chunk_rows(b, n);
     const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
@@ -711,16 +744,15 @@ void grow_tree(Booster* b, int k, int slot) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
       LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
-                                  b->hist[0].p, nullptr, b->hist_scratch.p, ctx->num_sms, s));
+                                  build_target(b, b->hist[0].p), nullptr, b->hist_scratch.p, sh, 1, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       b->t.hist_launches++; b->t.kernel_launches++;
     }
   }
   mark_phase(b, 1);
-  allreduce(b->comm, b->hist[0].p, b->node_elems, kNcclInt64, kNcclSum, s);
+  exchange_hist(b, b->hist[0].p, 1);
   mark_phase(b, 2);
-  b->t.allreduce_bytes += (double)b->node_elems * 8;
-  LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_ev[0].p, b->d_qexp.p, p.qbits, dp, s));
+  LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_ev[0].p, b->d_qexp.p, p.qbits, dp, sh, s));
   LAUNCH_CHECK(b2_launch_root_record(tree, b->d_ev[0].p, s));
   b->t.kernel_launches += 3;
   int hb = 0;  // hist buffer holding the current level
@@ -728,13 +760,21 @@ void grow_tree(Booster* b, int k, int slot) {
     const int cur = d & 1, nxt = cur ^ 1;
     const int max_nodes_level = 1 << d;
     const bool can_split = d < D;
+    const B2SplitCand* cands_for_decide = b->d_cands.p;
     if (can_split) {
       LAUNCH_CHECK(b2_launch_eval_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_group_first.p, m->d_group_size.p,
-                                         m->d_nbins.p, m->d_has_missing.p, b->d_qexp.p, p.qbits, dp, b->d_cands.p, ctl + cur, s));
+                                         m->d_nbins.p, m->d_has_missing.p, b->d_qexp.p, p.qbits, dp, b->d_cands.p, ctl + cur, sh,
+                                         shard_rank, s));
       b->t.kernel_launches++;
+      if (b->shards > 1) {   // every rank scanned only its own slots: gather the per-node candidates
+        const size_t bytes = (size_t)max_nodes_level * b->cpn * sizeof(B2SplitCand);
+        NCCL_CHECK(nccl()->AllGather(b->d_cands.p, b->d_cands_all.p, bytes, kNcclUint8, b->comm->comm, s));
+        cands_for_decide = b->d_cands_all.p;
+      }
     }
     LAUNCH_CHECK(b2_launch_decide(ctl + cur, ctl + nxt, b->d_seg[cur].p, b->d_seg[nxt].p, b->d_ev[cur].p, b->d_ev[nxt].p,
-                                  b->d_cands.p, G, can_split ? 1 : 0, tree, b->d_split_work.p, b->d_pair_parent.p, b->d_leaves.p,
+                                  cands_for_decide, b->cpn, b->shards, max_nodes_level * b->cpn, can_split ? 1 : 0, tree,
+                                  b->d_split_work.p, b->d_pair_parent.p, b->d_leaves.p,
                                   d_n_leaves, m->d_has_missing.p, b->d_qexp.p, p.qbits, cp, s));
     b->t.kernel_launches++;
     mark_phase(b, 4);
@@ -752,17 +792,17 @@ void grow_tree(Booster* b, int k, int slot) {
     if (need_hist) {
       // ---- histograms of level d+1: built children in slots [0, 2^d), siblings in [2^d, 2^(d+1))
       const int nh = hb ^ 1;
-      CUDA_CHECK(cudaMemsetAsync(b->hist[nh].p, 0, (size_t)max_nodes_level * b->node_elems * sizeof(long long), s));
+      long long* tgt = build_target(b, b->hist[nh].p);
+      CUDA_CHECK(cudaMemsetAsync(tgt, 0, (size_t)max_nodes_level * b->node_elems * sizeof(long long), s));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
-      LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G,
-                                  b->hist[nh].p, ctl + nxt, b->hist_scratch.p, ctx->num_sms, s));
+      LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt,
+                                  ctl + nxt, b->hist_scratch.p, sh, max_nodes_level, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       mark_phase(b, 1);
-      allreduce(b->comm, b->hist[nh].p, (size_t)max_nodes_level * b->node_elems, kNcclInt64, kNcclSum, s);
+      exchange_hist(b, b->hist[nh].p, max_nodes_level);
       mark_phase(b, 2);
-      b->t.allreduce_bytes += (double)max_nodes_level * b->node_elems * 8;
-      LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[hb].p, b->hist[nh].p, b->d_triples.p, max_nodes_level, (int64_t)b->node_elems,
+      LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[hb].p, b->hist[nh].p, b->d_triples.p, max_nodes_level, (int64_t)b->slice_elems,
                                            ctl + nxt, s));
       b->t.hist_launches++; b->t.kernel_launches += 2;
       mark_phase(b, 3);
@@ -1302,7 +1342,7 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
   CUDA_CHECK(cudaEventRecord(e0, s));
   if (n_sel > 0)
     LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
-                                window_rows, m.n_groups, d_hist.p, nullptr, d_scratch.p, ctx->num_sms, s));
+                                window_rows, m.n_groups, d_hist.p, nullptr, d_scratch.p, 0, 1, ctx->num_sms, s));
   CUDA_CHECK(cudaEventRecord(e1, s));
   std::vector<long long> h(node_elems);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), d_hist.p, node_elems * sizeof(long long), cudaMemcpyDeviceToHost, s));

@@ -120,7 +120,22 @@ __device__ __forceinline__ void accumulate_row(const RowData& d, uint32_t smem_g
 }
 
 // shared cell e = bin*64 + plane*32 + slot  ->  global cell plane*8192 + bin*32 + slot
-__device__ __forceinline__ int global_cell(int e) { return ((e >> 5) & 1) * B2_PLANE_ELEMS + (e >> 6) * B2_GROUP_SLOTS + (e & 31); }
+// Global histogram layout (feature-slot sharded for the reduce-scatter):
+//   int64 [shards][node_cap][group][plane][256 bins][sp]   sp = 32 / shards, slot s lives on shard s % shards at s / shards.
+// shards == 1 degenerates to [node][group][plane][bin][32].
+struct HistTarget {
+  unsigned long long* base;   // build buffer
+  int log2_shards;            // shards = 1 << log2_shards
+  int node_cap;               // node slots per shard in this launch's buffer
+  int n_groups;
+};
+__device__ __forceinline__ size_t target_index(const HistTarget& t, int node_slot, int group, int e) {
+  const int bin = e >> 6, plane = (e >> 5) & 1, slot = e & 31;
+  const int shards = 1 << t.log2_shards, sp = B2_GROUP_SLOTS >> t.log2_shards;
+  const int r = slot & (shards - 1), sl = slot >> t.log2_shards;
+  const size_t slice_elems = (size_t)t.n_groups * 2 * B2_BINS * sp;
+  return ((size_t)r * t.node_cap + node_slot) * slice_elems + ((size_t)(group * 2 + plane) * B2_BINS + bin) * sp + sl;
+}
 
 // window flush: move the int32 partial sums into this CTA's PRIVATE int64 scratch (plain coalesced
 // read-modify-write in L2, no atomics: only this CTA touches its scratch block)
@@ -136,11 +151,12 @@ __device__ __forceinline__ void flush_to_scratch(int32_t* s_hist, long long* scr
   }
 }
 // node flush: shared (+ scratch if it was used) -> global int64 histogram with atomics
-__device__ __forceinline__ void flush_planes(int32_t* s_hist, long long* scratch, bool scratch_dirty, unsigned long long* out) {
+__device__ __forceinline__ void flush_planes(int32_t* s_hist, long long* scratch, bool scratch_dirty, const HistTarget& t,
+                                             int node_slot, int group) {
   for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) {
     long long v = s_hist[e];
     if (scratch_dirty) { v += scratch[e]; scratch[e] = 0; }
-    if (v != 0) atomicAdd(out + global_cell(e), (unsigned long long)v);
+    if (v != 0) atomicAdd(t.base + target_index(t, node_slot, group, e), (unsigned long long)v);
     s_hist[e] = 0;
   }
 }
@@ -150,7 +166,10 @@ __global__ void __launch_bounds__(kHistThreads, 3)
 hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                   const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
                   int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
-                  const B2LevelCtl* __restrict__ ctl, long long* __restrict__ scratch_all, int debug_mode) {
+                  const B2LevelCtl* __restrict__ ctl, long long* __restrict__ scratch_all, int log2_shards, int node_cap,
+                  int debug_mode) {
+  HistTarget target; target.base = (unsigned long long*)hist; target.log2_shards = log2_shards; target.node_cap = node_cap;
+  target.n_groups = n_groups;
   if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
   extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][32]
   __shared__ int s_cur_work;
@@ -186,7 +205,7 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
       // (A CTA-private int64 scratch with plain read-modify-write was measured 30 % SLOWER: 256 KB of
       // L2 traffic per window per CTA evicts the streamed rows; RED.64 moves half the bytes.)
       __syncthreads();
-      flush_planes(s_hist, scratch, false, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
+      flush_planes(s_hist, scratch, false, target, __ldg(&work[cur].hist_index), group);
       __syncthreads();
       rows_in_window = 0;
     }
@@ -225,7 +244,7 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
   }
   if (cur >= 0) {
     __syncthreads();
-    flush_planes(s_hist, scratch, scratch_dirty, (unsigned long long*)(hist + ((size_t)__ldg(&work[cur].hist_index) * n_groups + group) * B2_GROUP_ELEMS));
+    flush_planes(s_hist, scratch, scratch_dirty, target, __ldg(&work[cur].hist_index), group);
   }
   (void)s_cur_work;
 }
@@ -259,7 +278,8 @@ size_t b2_hist_scratch_elems(int n_groups, int num_sms) {
 
 int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const int32_t* ridx,
                    const B2HistWork* work, int n_work, int total_chunks, int chunk_rows, int window_rows,
-                   int n_groups, long long* hist, const B2LevelCtl* ctl, long long* scratch, int num_sms, cudaStream_t stream) {
+                   int n_groups, long long* hist, const B2LevelCtl* ctl, long long* scratch, int log2_shards, int node_cap,
+                   int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   static int debug_mode = -1;
   if (debug_mode < 0) { const char* e = getenv("B2_HIST_DEBUG_MODE"); debug_mode = e ? atoi(e) : 0; }
@@ -279,10 +299,10 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
   dim3 grid(n_groups * n_streams), block(b2::kHistThreads);
   if (ridx)
     b2::hist_build_kernel<true><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                              chunk_rows, window_rows, n_groups, hist, ctl, scratch, debug_mode);
+                                                              chunk_rows, window_rows, n_groups, hist, ctl, scratch, log2_shards, node_cap, debug_mode);
   else
     b2::hist_build_kernel<false><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                               chunk_rows, window_rows, n_groups, hist, ctl, scratch, debug_mode);
+                                                               chunk_rows, window_rows, n_groups, hist, ctl, scratch, log2_shards, node_cap, debug_mode);
   return (int)cudaGetLastError();
 }
 

@@ -42,8 +42,12 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
                    const int32_t* __restrict__ group_first, const int32_t* __restrict__ group_size,
                    const int32_t* __restrict__ nbins, const uint8_t* __restrict__ has_missing,
                    const int32_t* __restrict__ qexp, int qbits, B2TrainParamDev p, B2SplitCand* __restrict__ cands,
-                   const B2LevelCtl* __restrict__ ctl) {
-  const int node = blockIdx.x / n_groups, group = blockIdx.x % n_groups;
+                   const B2LevelCtl* __restrict__ ctl, int log2_shards, int shard_rank) {
+  // This rank owns sp = 32 >> log2_shards slots of every group (slot s is owned by s % shards): the
+  // G*sp owned "virtual slots" of a node are covered by cpn = ceil(G*sp/32) CTAs.
+  const int sp = B2_GROUP_SLOTS >> log2_shards;
+  const int cpn = (n_groups * sp + 31) >> 5;
+  const int node = blockIdx.x / cpn, cta_in_node = blockIdx.x % cpn;
   if (ctl && node >= ctl->n_nodes) return;
   const int s = threadIdx.x & 31, q = threadIdx.x >> 5;
   __shared__ long long cs_g[kEvalChunks][32], cs_h[kEvalChunks][32];
@@ -52,10 +56,15 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
   // inverse scales: 2^(e - qbits)
   p.inv_scale_g = ldexp(1.0, qexp[0] - qbits);
   p.inv_scale_h = ldexp(1.0, qexp[1] - qbits);
-  const long long* hg = level_hist + ((size_t)nd.hist_index * n_groups + group) * B2_GROUP_ELEMS;
-  const long long* hh = hg + B2_PLANE_ELEMS;
-  const bool active = s < group_size[group];
-  const int f = group_first[group] + s;
+  const int v = cta_in_node * 32 + s;                      // virtual slot
+  const bool v_ok = v < n_groups * sp;
+  const int group = v_ok ? v / sp : 0, sl = v_ok ? v % sp : 0;
+  const int slot = (sl << log2_shards) + shard_rank;       // real slot inside the group
+  const size_t slice_elems = (size_t)n_groups * 2 * B2_BINS * sp;
+  const long long* hg = level_hist + (size_t)nd.hist_index * slice_elems + (size_t)(group * 2) * B2_BINS * sp + sl;
+  const long long* hh = hg + (size_t)B2_BINS * sp;
+  const bool active = v_ok && slot < group_size[group];
+  const int f = group_first[group] + slot;
   const int nf = active ? nbins[f] : 0;
   const bool fmiss = active ? (has_missing[f] != 0) : false;
 
@@ -64,7 +73,7 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
 #pragma unroll
     for (int i = 0; i < kEvalBinsPerChunk; ++i) {
       int b = q * kEvalBinsPerChunk + i;
-      if (b < nf) { sg += hg[b * 32 + s]; sh += hh[b * 32 + s]; }
+      if (b < nf) { sg += hg[b * sp]; sh += hh[b * sp]; }
     }
   }
   cs_g[q][s] = sg; cs_h[q][s] = sh;
@@ -87,7 +96,7 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
       const int b = q * kEvalBinsPerChunk + i;
       if (b >= nf) break;
       const long long eg_excl = pg, eh_excl = ph;
-      pg += hg[b * 32 + s]; ph += hh[b * 32 + s];
+      pg += hg[b * sp]; ph += hh[b * sp];
       {  // forward: left = prefix inclusive, missing -> right
         const double lh_d = __dmul_rn(__ll2double_rn(ph), p.inv_scale_h);
         if (lh_d >= p.min_child_weight) {
@@ -128,7 +137,7 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
   unsigned long long kmax = 0;
 #pragma unroll 8
   for (int i = 0; i < kEvalChunks; ++i) kmax = wkey[i] > kmax ? wkey[i] : kmax;
-  B2SplitCand* out = cands + (size_t)node * n_groups + group;
+  B2SplitCand* out = cands + (size_t)node * cpn + cta_in_node;
   if (kmax == 0) {
     if (threadIdx.x == 0) {
       out->loss_chg = 0.0f; out->feature = -1; out->bin = 0; out->default_left = 0; out->left_g = 0; out->left_h = 0;
@@ -144,11 +153,14 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
 // root totals: sum of all 256 bins of slot 0 / group 0 (every row lands in exactly one bin, the
 // missing sentinel included) -> nodes[0].sum_g/h and root_gain
 __global__ void root_totals_kernel(const long long* __restrict__ level_hist, int n_groups, B2EvalNode* nodes,
-                                   const int32_t* __restrict__ qexp, int qbits, B2TrainParamDev p) {
+                                   const int32_t* __restrict__ qexp, int qbits, B2TrainParamDev p, int log2_shards) {
   __shared__ long long sg[256], sh[256];
-  const long long* hg = level_hist + (size_t)nodes[0].hist_index * n_groups * B2_GROUP_ELEMS;
-  sg[threadIdx.x] = hg[threadIdx.x * 32];
-  sh[threadIdx.x] = hg[B2_PLANE_ELEMS + threadIdx.x * 32];
+  const int sp = B2_GROUP_SLOTS >> log2_shards;
+  const size_t slice_elems = (size_t)n_groups * 2 * B2_BINS * sp;
+  // any owned slot works (padding slots too): every row lands in exactly one bin of every slot
+  const long long* hg = level_hist + (size_t)nodes[0].hist_index * slice_elems;
+  sg[threadIdx.x] = hg[(size_t)threadIdx.x * sp];
+  sh[threadIdx.x] = hg[(size_t)(B2_BINS + threadIdx.x) * sp];
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) { sg[threadIdx.x] += sg[threadIdx.x + o]; sh[threadIdx.x] += sh[threadIdx.x + o]; }
@@ -169,15 +181,17 @@ extern "C" {
 int b2_launch_eval_splits(const long long* level_hist, int n_groups, const B2EvalNode* nodes, int n_nodes,
                           const int32_t* group_first, const int32_t* group_size, const int32_t* nbins,
                           const uint8_t* has_missing, const int32_t* qexp, int qbits, B2TrainParamDev p,
-                          B2SplitCand* cands, const B2LevelCtl* ctl, cudaStream_t stream) {
+                          B2SplitCand* cands, const B2LevelCtl* ctl, int log2_shards, int shard_rank, cudaStream_t stream) {
   if (n_nodes <= 0) return 0;   // with ctl: n_nodes is the upper bound of the level
-  b2::eval_splits_kernel<<<n_nodes * n_groups, 32 * b2::kEvalChunks, 0, stream>>>(level_hist, n_groups, nodes, group_first, group_size,
-                                                               nbins, has_missing, qexp, qbits, p, cands, ctl);
+  const int sp = B2_GROUP_SLOTS >> log2_shards, cpn = (n_groups * sp + 31) >> 5;
+  b2::eval_splits_kernel<<<n_nodes * cpn, 32 * b2::kEvalChunks, 0, stream>>>(level_hist, n_groups, nodes, group_first, group_size,
+                                                                         nbins, has_missing, qexp, qbits, p, cands, ctl,
+                                                                         log2_shards, shard_rank);
   return (int)cudaGetLastError();
 }
 int b2_launch_root_totals(const long long* level_hist, int n_groups, B2EvalNode* nodes, const int32_t* qexp, int qbits,
-                          B2TrainParamDev p, cudaStream_t stream) {
-  b2::root_totals_kernel<<<1, 256, 0, stream>>>(level_hist, n_groups, nodes, qexp, qbits, p);
+                          B2TrainParamDev p, int log2_shards, cudaStream_t stream) {
+  b2::root_totals_kernel<<<1, 256, 0, stream>>>(level_hist, n_groups, nodes, qexp, qbits, p, log2_shards);
   return (int)cudaGetLastError();
 }
 }
