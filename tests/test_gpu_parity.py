@@ -53,11 +53,12 @@ def test_hist_kernel_adversarial_and_windows(eng, oracle):
     bins[:, 0] = 9          # constant feature: every row hits the same cell
     bins[:, 1] = bins[:, 1] & 1   # binary feature
     bins[:, 2] = 255
-    qg = np.full(n, (1 << 18), np.int32)     # extreme values: a window of 8191 rows just fits int32
+    qg = np.full(n, (1 << 18), np.int32)     # extreme values: the guard interval for 18 bits is 2^12 rows
     qg[::2] = -(1 << 18)
+    qg[: n // 2] = (1 << 18)                 # long same-sign runs on the constant feature: its cell saturates
     qh = np.full(n, (1 << 18), np.int32)
     ref = oracle.hist_int(bins, qg, qh)
-    for window, chunk in ((8191, 512), (1024, 256), (8191, 8192)):
+    for window, chunk in ((4096, 512), (1024, 256), (4096, 4096), (4096, 8192)):
         got, _ = eng.hist_build_raw(bins, qg, qh, window_rows=window, chunk_rows=chunk)
         assert np.array_equal(ref, got), (window, chunk)
 

@@ -597,9 +597,9 @@ float h_calc_weight(const Params& p, double G, double H) {
 }
 
 int window_rows_for(int qbits) {
-  // |q| <= 2^qbits, int32 cell: rows * 2^qbits <= 2^31 - 1
-  long long w = ((1LL << 31) - 1) >> qbits;
-  return (int)std::min<long long>(w, 1LL << 30);
+  // overflow-guard interval of the histogram kernel: |q| <= 2^qbits, so 2^(30-qbits) rows add less than 2^30
+  // to a cell that was below 2^30 at the last check (hist_kernel.cu flush_large_cells)
+  return 1 << (30 - qbits);
 }
 
 int pick_chunk_rows(Booster* b, int64_t rows) {
@@ -1331,7 +1331,7 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
   const size_t node_elems = (size_t)m.n_groups * B2_GROUP_ELEMS;
   d_hist.ensure(node_elems);
   CUDA_CHECK(cudaMemsetAsync(d_hist.p, 0, node_elems * sizeof(long long), s));
-  if (window_rows <= 0) window_rows = 8192;
+  if (window_rows <= 0) window_rows = 4096;
   if (chunk_rows <= 0) chunk_rows = 2048;
   if (chunk_rows > window_rows) chunk_rows = window_rows;
   B2HistWork w{0, (int32_t)n_sel, 0, 0};
