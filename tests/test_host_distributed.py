@@ -93,3 +93,29 @@ def test_validation_errors():
     # engine error propagates as a training failure (main.py:770-785)
     with pytest.raises(RuntimeError):
         train(dict(TOY_PARAMS, objective="rank:pairwise"), RayDMatrix(X_TOY, Y_TOY), ray_params=RayParams(num_actors=1))
+
+
+@pytest.mark.timeout(300)
+def test_sklearn_estimators():
+    """Subset of xgboost_ray/tests/test_sklearn.py: accuracy bars on digits (2-class err < 0.1, :115-141)
+    and multiclass, regression fit, RayDMatrix input (test_sklearn_matrix.py)."""
+    from sklearn.datasets import load_digits
+    from xgboost_ray_b200 import RayDMatrix, RayParams
+    from xgboost_ray_b200.sklearn import RayXGBClassifier, RayXGBRegressor
+    d = load_digits(n_class=2)
+    X, y = d.data.astype(np.float32), d.target
+    clf = RayXGBClassifier(n_estimators=10, max_depth=4).fit(X[::2], y[::2], ray_params=RayParams(num_actors=2))
+    pred = clf.predict(X[1::2], ray_params=RayParams(num_actors=2))
+    assert np.mean(pred != y[1::2]) < 0.1
+    proba = clf.predict_proba(X[1::2], ray_params=RayParams(num_actors=1))
+    assert proba.shape == (len(X[1::2]), 2) and np.allclose(proba.sum(axis=1), 1.0, atol=1e-5)
+    d3 = load_digits(n_class=3)
+    clf3 = RayXGBClassifier(n_estimators=5, max_depth=3).fit(d3.data.astype(np.float32), d3.target + 10,
+                                                             ray_params=RayParams(num_actors=2))
+    p3 = clf3.predict(d3.data.astype(np.float32), ray_params=RayParams(num_actors=2))
+    assert set(np.unique(p3)) <= {10, 11, 12} and np.mean(p3 != d3.target + 10) < 0.1
+    rng = np.random.RandomState(0)
+    Xr = rng.uniform(0, 10, size=(500, 5)).astype(np.float32)
+    yr = (Xr[:, 0] * 2 + Xr[:, 1]).astype(np.float32)
+    reg = RayXGBRegressor(n_estimators=20, max_depth=4).fit(RayDMatrix(Xr, yr), ray_params=RayParams(num_actors=2))
+    assert np.mean((reg.predict(RayDMatrix(Xr), ray_params=RayParams(num_actors=2)) - yr) ** 2) < 1.0
