@@ -149,23 +149,23 @@ struct DevBuf {
 // worker threads copy 16 MiB slices into their own pinned staging buffers and issue the DMA on
 // their own streams, so host memcpy and PCIe transfers of different slices overlap.
 struct PinnedPool {
-  static constexpr int kWorkers = 4, kSlots = 2;
-  static constexpr size_t kSlice = (size_t)16 << 20;
+  static constexpr int kWorkers = 16, kSlots = 2;   // upper bound; B2_UPLOAD_WORKERS picks how many are used
+  static constexpr size_t kSlice = (size_t)8 << 20;
   void* buf[kWorkers][kSlots] = {};
   cudaStream_t stream[kWorkers] = {};
   cudaEvent_t done[kWorkers][kSlots] = {};
   bool ready = false;
   std::mutex mu;
-  void init() {
-    if (ready) return;
-    for (int w = 0; w < kWorkers; ++w) {
+  int n_init = 0;
+  void init(int n) {
+    for (int w = n_init; w < n; ++w) {
       CUDA_CHECK(cudaStreamCreateWithFlags(&stream[w], cudaStreamNonBlocking));
       for (int k = 0; k < kSlots; ++k) {
         CUDA_CHECK(cudaMallocHost(&buf[w][k], kSlice));
         CUDA_CHECK(cudaEventCreateWithFlags(&done[w][k], cudaEventDisableTiming));
       }
+      n_init = w + 1;
     }
-    ready = true;
   }
 };
 std::map<int, PinnedPool*> g_pools;
@@ -184,14 +184,22 @@ void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
     pool = p;
   }
   std::lock_guard<std::mutex> lk(pool->mu);   // one bulk upload per device at a time
-  pool->init();
   CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // dst allocation / earlier work is complete
   const size_t n_slices = (bytes + PinnedPool::kSlice - 1) / PinnedPool::kSlice;
+  static int n_workers = 0;
+  if (n_workers == 0) {
+    const char* e = getenv("B2_UPLOAD_WORKERS");
+    n_workers = e ? atoi(e) : 8;
+    if (n_workers < 1) n_workers = 1;
+    if (n_workers > PinnedPool::kWorkers) n_workers = PinnedPool::kWorkers;
+  }
+  const int W = n_workers;
+  pool->init(W);
   std::atomic<int> failed{0};
   auto worker = [&](int w) {
     if (cudaSetDevice(ctx->device) != cudaSuccess) { failed = 1; return; }
     int use = 0;
-    for (size_t i = w; i < n_slices; i += PinnedPool::kWorkers, ++use) {
+    for (size_t i = w; i < n_slices; i += W, ++use) {
       const int k = use % PinnedPool::kSlots;
       const size_t off = i * PinnedPool::kSlice, len = std::min(PinnedPool::kSlice, bytes - off);
       if (use >= PinnedPool::kSlots && cudaEventSynchronize(pool->done[w][k]) != cudaSuccess) { failed = 1; return; }
@@ -202,7 +210,7 @@ void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (cudaStreamSynchronize(pool->stream[w]) != cudaSuccess) failed = 1;
   };
   std::vector<std::thread> th;
-  for (int w = 0; w < PinnedPool::kWorkers; ++w) th.emplace_back(worker, w);
+  for (int w = 0; w < W; ++w) th.emplace_back(worker, w);
   for (auto& t : th) t.join();
   if (failed.load()) fail("pipelined host->device upload failed: %s", cudaGetErrorString(cudaGetLastError()));
 }
