@@ -19,6 +19,7 @@ COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-st
           "-Xcompiler", "-fPIC,-ffp-contract=off", "-ccbin", "/usr/bin/g++"]
 SOURCES = {
     "hist_kernel.cu": [],
+    "hist_tma_kernel.cu": [],
     "split_kernel.cu": ["--fmad=false"],
     "partition_kernel.cu": ["--fmad=false"],
     "control_kernel.cu": ["--fmad=false"],
@@ -37,7 +38,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "b2hist.h"), __file__]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "hist_common.cuh"), os.path.join(HERE, "..", "include", "b2hist.h"), __file__]
     jobs = []
     objs = []
     for src, extra in SOURCES.items():

@@ -30,6 +30,9 @@ extern "C" {
 int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
                    const B2LevelCtl*, long long*, int, int, int, cudaStream_t);
 size_t b2_hist_scratch_elems(int, int);
+int b2_make_bins_tensor_map(void*, const uint8_t*, int64_t, int);
+int b2_launch_hist_tma(const void*, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
+                       const B2LevelCtl*, int, int, int64_t, int, cudaStream_t);
 int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, const B2LevelCtl*, cudaStream_t);
 int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
                           const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, const B2LevelCtl*, int, int,
@@ -289,6 +292,8 @@ struct Matrix : HandleBase {
   DevBuf<float> raw;     // [n][F], optional
   bool has_raw = false;
   DevBuf<uint8_t> bins;  // [n][row_stride]
+  alignas(64) unsigned char tmap[128];   // TMA tensor map over bins (box {32 B, 1 row}, tile::gather4)
+  bool has_tmap = false;
   DevBuf<uint8_t> bins_col;  // [F][col_stride] feature-major copy for the row partition
   int64_t col_stride = 0;
   bool quantized = false;
@@ -421,6 +426,7 @@ void bin_matrix(Matrix* m) {
   LAUNCH_CHECK(b2_launch_bin(m->raw.p, m->n, m->F, m->missing, m->d_cut_ptrs.p, m->d_cut_vals.p, m->d_feat_byte.p,
                              m->row_stride, m->bins.p, m->bins_col.p, m->col_stride, ctx->num_sms, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
+  m->has_tmap = b2_make_bins_tensor_map(m->tmap, m->bins.p, m->n, m->row_stride) == 0;
   m->quantized = true;
 }
 
@@ -686,6 +692,12 @@ void record_hist_launch(Booster* b, cudaEvent_t& e0, cudaEvent_t& e1, bool begin
   else { CUDA_CHECK(cudaEventRecord(e1, b->ctx->stream)); b->hist_events.push_back({e0, e1}); }
 }
 
+bool use_tma_hist() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B2_HIST_TMA"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v == 1;
+}
+
 // Histogram exchange of `nb` built nodes: reduce-scatter of the build buffer into the owned slices of the
 // level buffer (shards == world), or in-place allreduce (shards == 1, any world size).
 long long* build_target(Booster* b, long long* level_buf) { return b->shards > 1 ? b->hist_build.p : level_buf; }
@@ -751,8 +763,12 @@ void grow_tree(Booster* b, int k, int slot) {
       CUDA_CHECK(cudaMemcpyAsync(b->d_hist_work.p, &w, sizeof(w), cudaMemcpyHostToDevice, s));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
-      LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
-                                  build_target(b, b->hist[0].p), nullptr, b->hist_scratch.p, sh, 1, ctx->num_sms, s));
+      if (use_tma_hist() && m->has_tmap)
+        LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
+                                        build_target(b, b->hist[0].p), nullptr, sh, 1, n, ctx->num_sms, s));
+      else
+        LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
+                                    build_target(b, b->hist[0].p), nullptr, b->hist_scratch.p, sh, 1, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       b->t.hist_launches++; b->t.kernel_launches++;
     }
@@ -804,8 +820,12 @@ void grow_tree(Booster* b, int k, int slot) {
       CUDA_CHECK(cudaMemsetAsync(tgt, 0, (size_t)max_nodes_level * b->node_elems * sizeof(long long), s));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
-      LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt,
-                                  ctl + nxt, b->hist_scratch.p, sh, max_nodes_level, ctx->num_sms, s));
+      if (use_tma_hist() && m->has_tmap)
+        LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt, ctl + nxt, sh,
+                                        max_nodes_level, n, ctx->num_sms, s));
+      else
+        LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt,
+                                    ctl + nxt, b->hist_scratch.p, sh, max_nodes_level, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       mark_phase(b, 1);
       exchange_hist(b, b->hist[nh].p, max_nodes_level);
@@ -1349,8 +1369,15 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
   cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, s));
   if (n_sel > 0)
-    LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
-                                window_rows, m.n_groups, d_hist.p, nullptr, d_scratch.p, 0, 1, ctx->num_sms, s));
+  {
+    alignas(64) unsigned char tm[128];
+    if (use_tma_hist() && b2_make_bins_tensor_map(tm, d_bins.p, n_rows, m.row_stride) == 0)
+      LAUNCH_CHECK(b2_launch_hist_tma(tm, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows, window_rows, m.n_groups,
+                                      d_hist.p, nullptr, 0, 1, n_rows, ctx->num_sms, s));
+    else
+      LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
+                                  window_rows, m.n_groups, d_hist.p, nullptr, d_scratch.p, 0, 1, ctx->num_sms, s));
+  }
   CUDA_CHECK(cudaEventRecord(e1, s));
   std::vector<long long> h(node_elems);
   CUDA_CHECK(cudaMemcpyAsync(h.data(), d_hist.p, node_elems * sizeof(long long), cudaMemcpyDeviceToHost, s));
