@@ -30,8 +30,8 @@ extern "C" {
 int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
                    const B2LevelCtl*, long long*, int, int, int, cudaStream_t);
 size_t b2_hist_scratch_elems(int, int);
-int b2_make_bins_tensor_map(void*, const uint8_t*, int64_t, int);
-int b2_launch_hist_tma(const void*, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
+int b2_make_bins_tensor_map(void*, const uint8_t*, int64_t, int, int);
+int b2_launch_hist_tma(const void*, const void*, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
                        const B2LevelCtl*, int, int, int64_t, int, cudaStream_t);
 int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, const B2LevelCtl*, cudaStream_t);
 int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
@@ -293,6 +293,7 @@ struct Matrix : HandleBase {
   bool has_raw = false;
   DevBuf<uint8_t> bins;  // [n][row_stride]
   alignas(64) unsigned char tmap[128];   // TMA tensor map over bins (box {32 B, 1 row}, tile::gather4)
+  alignas(64) unsigned char tmap_tile[128];   // box {32 B, 64 rows} for the contiguous root stage
   bool has_tmap = false;
   DevBuf<uint8_t> bins_col;  // [F][col_stride] feature-major copy for the row partition
   int64_t col_stride = 0;
@@ -426,7 +427,8 @@ void bin_matrix(Matrix* m) {
   LAUNCH_CHECK(b2_launch_bin(m->raw.p, m->n, m->F, m->missing, m->d_cut_ptrs.p, m->d_cut_vals.p, m->d_feat_byte.p,
                              m->row_stride, m->bins.p, m->bins_col.p, m->col_stride, ctx->num_sms, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
-  m->has_tmap = b2_make_bins_tensor_map(m->tmap, m->bins.p, m->n, m->row_stride) == 0;
+  m->has_tmap = b2_make_bins_tensor_map(m->tmap, m->bins.p, m->n, m->row_stride, 1) == 0 &&
+                b2_make_bins_tensor_map(m->tmap_tile, m->bins.p, m->n, m->row_stride, 64) == 0;
   m->quantized = true;
 }
 
@@ -764,7 +766,7 @@ void grow_tree(Booster* b, int k, int slot) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
       if (use_tma_hist() && m->has_tmap)
-        LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
+        LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, m->tmap_tile, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
                                         build_target(b, b->hist[0].p), nullptr, sh, 1, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
@@ -821,7 +823,7 @@ void grow_tree(Booster* b, int k, int slot) {
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
       if (use_tma_hist() && m->has_tmap)
-        LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt, ctl + nxt, sh,
+        LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, m->tmap_tile, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt, ctl + nxt, sh,
                                         max_nodes_level, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt,
@@ -1370,9 +1372,10 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
   CUDA_CHECK(cudaEventRecord(e0, s));
   if (n_sel > 0)
   {
-    alignas(64) unsigned char tm[128];
-    if (use_tma_hist() && b2_make_bins_tensor_map(tm, d_bins.p, n_rows, m.row_stride) == 0)
-      LAUNCH_CHECK(b2_launch_hist_tma(tm, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows, window_rows, m.n_groups,
+    alignas(64) unsigned char tm[128]; alignas(64) unsigned char tt[128];
+    if (use_tma_hist() && b2_make_bins_tensor_map(tm, d_bins.p, n_rows, m.row_stride, 1) == 0 &&
+        b2_make_bins_tensor_map(tt, d_bins.p, n_rows, m.row_stride, 64) == 0)
+      LAUNCH_CHECK(b2_launch_hist_tma(tm, tt, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows, window_rows, m.n_groups,
                                       d_hist.p, nullptr, 0, 1, n_rows, ctx->num_sms, s));
     else
       LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,

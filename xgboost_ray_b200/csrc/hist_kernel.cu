@@ -24,8 +24,8 @@
 
 namespace b2 {
 
-template <bool kGather>
-__global__ void __launch_bounds__(kHistThreads, 3)
+template <bool kGather, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                   const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
                   int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
@@ -150,28 +150,37 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
                    int n_groups, long long* hist, const B2LevelCtl* ctl, long long* scratch, int log2_shards, int node_cap,
                    int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
-  static int debug_mode = -1;
+  static int debug_mode = -1, wide = -1;
   if (debug_mode < 0) { const char* e = getenv("B2_HIST_DEBUG_MODE"); debug_mode = e ? atoi(e) : 0; }
+  // 2 CTAs x 16 warps per SM by default (measured 6 % faster in training than 3 x 8, profiles/r01_hist_threads_ab.txt)
+  if (wide < 0) { const char* e = getenv("B2_HIST_THREADS"); wide = (e && atoi(e) == 256) ? 0 : 1; }
   const int smem = B2_GROUP_ELEMS * (int)sizeof(int32_t);  // 64 KiB
   if (!attr_set) {
-    cudaFuncSetAttribute(b2::hist_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(b2::hist_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(b2::hist_build_kernel<true, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(b2::hist_build_kernel<false, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(b2::hist_build_kernel<true, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(b2::hist_build_kernel<false, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_set = true;
   }
   // with ctl the work list / chunk counts live in device memory (sync-free level loop) and the grid is the
   // full persistent grid; without it they are host values
   if (!ctl && (total_chunks <= 0 || n_work <= 0)) return 0;
   if (!ctl && chunk_rows > window_rows) return (int)cudaErrorInvalidValue;  // a chunk must fit one int32 window
-  int n_streams = (num_sms * 3) / n_groups;
+  const int ctas_per_sm = wide ? 2 : 3;
+  int n_streams = (num_sms * ctas_per_sm) / n_groups;
   if (n_streams < 1) n_streams = 1;
   if (!ctl && n_streams > total_chunks) n_streams = total_chunks;
-  dim3 grid(n_groups * n_streams), block(b2::kHistThreads);
-  if (ridx)
-    b2::hist_build_kernel<true><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                              chunk_rows, window_rows, n_groups, hist, ctl, scratch, log2_shards, node_cap, debug_mode);
-  else
-    b2::hist_build_kernel<false><<<grid, block, smem, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                               chunk_rows, window_rows, n_groups, hist, ctl, scratch, log2_shards, node_cap, debug_mode);
+  dim3 grid(n_groups * n_streams), block(wide ? 512 : 256);
+#define B2_HIST_ARGS bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows, window_rows, n_groups, hist, ctl, scratch, \
+                     log2_shards, node_cap, debug_mode
+  if (wide) {
+    if (ridx) b2::hist_build_kernel<true, 512, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+    else b2::hist_build_kernel<false, 512, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+  } else {
+    if (ridx) b2::hist_build_kernel<true, 256, 3><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+    else b2::hist_build_kernel<false, 256, 3><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+  }
+#undef B2_HIST_ARGS
   return (int)cudaGetLastError();
 }
 

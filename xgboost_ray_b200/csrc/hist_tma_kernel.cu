@@ -38,6 +38,10 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tma
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
+__device__ __forceinline__ void tma_tile(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int col, int row) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(tmap), "r"(bar), "r"(col), "r"(row) : "memory");
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumerWarps * 32) : "memory"); }
 
 // the CTA's sequence of 64-row blocks; every warp walks it identically
@@ -70,7 +74,8 @@ struct BlockIter {
 
 template <bool kGather>
 __global__ void __launch_bounds__(kTmaThreads, 3)
-hist_build_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int2* __restrict__ gpair, const int32_t* __restrict__ ridx,
+hist_build_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tile,
+                      const int2* __restrict__ gpair, const int32_t* __restrict__ ridx,
                       const B2HistWork* __restrict__ work, int n_work, int total_chunks, int chunk_rows, int window_rows,
                       int n_groups, long long* __restrict__ hist, const B2LevelCtl* __restrict__ ctl, int log2_shards, int node_cap,
                       int64_t n_rows_total) {
@@ -97,22 +102,35 @@ hist_build_tma_kernel(const __grid_constant__ CUtensorMap tmap, const int2* __re
   it.init(work, n_work, total_chunks, chunk_rows, stream, n_streams);
 
   if (warp == kTmaConsumerWarps) {
-    // ===================== producer warp: 16 lanes x gather4 = one 64-row stage
+    // ===================== producer warp
+    // root (contiguous rows): ONE tile-mode instruction per 64-row stage (rows past the matrix end are
+    // zero filled and still counted); gathered levels: 16 lanes x gather4, with the row ids of the NEXT
+    // stage already in flight so the producer never waits on the ridx load.
+    auto load_idx = [&](const BlockIter& b, int* idx) {
+      if (b.done() || lane >= kStageRows / 4) { idx[0] = idx[1] = idx[2] = idx[3] = 0; return; }
+      const int r = b.blk * kStageRows + lane * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int rr = r + j; if (rr >= b.nrows) rr = b.nrows - 1;   // tail rows repeat the last row (consumers add zero)
+        idx[j] = __ldg(ridx + b.pos0 + rr);
+      }
+    };
+    int idx[4] = {0, 0, 0, 0}, nidx[4];
+    if (kGather) load_idx(it, idx);
+    BlockIter nx = it;
     for (; !it.done(); it.next()) {
+      if (kGather) { nx.next(); load_idx(nx, nidx); }
       const int s = it.k % kStages, use = it.k / kStages;
       mbar_wait(empty_a + s * 8, (use & 1) ^ 1);           // first use of a slot passes immediately
       if (lane == 0) mbar_expect_tx(full_a + s * 8, kStageBytes);
       __syncwarp();
-      if (lane < kStageRows / 4) {
-        const int r = it.blk * kStageRows + lane * 4;
-        int idx[4];
+      if (kGather) {
+        if (lane < kStageRows / 4)
+          tma_gather4(stage_a + s * kStageBytes + lane * 128, &tmap, full_a + s * 8, group * B2_GROUP_SLOTS, idx[0], idx[1], idx[2], idx[3]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          int rr = r + j; if (rr >= it.nrows) rr = it.nrows - 1;     // tail rows repeat the last row (consumers add zero)
-          const int64_t pos = it.pos0 + rr;
-          idx[j] = kGather ? __ldg(ridx + pos) : (int)pos;
-        }
-        tma_gather4(stage_a + s * kStageBytes + lane * 128, &tmap, full_a + s * 8, group * B2_GROUP_SLOTS, idx[0], idx[1], idx[2], idx[3]);
+        for (int j = 0; j < 4; ++j) idx[j] = nidx[j];
+      } else if (lane == 0) {
+        tma_tile(stage_a + s * kStageBytes, &tmap_tile, full_a + s * 8, group * B2_GROUP_SLOTS, (int)(it.pos0 + it.blk * kStageRows));
       }
     }
     return;
@@ -202,8 +220,9 @@ typedef CUresult (*B2EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // tensor map over the row-major bin matrix uint8 [n_rows][row_stride], box {32 bytes, 1 row} for tile::gather4.
-// out must point to 128 bytes, 64-byte aligned.  Returns 0 on success.
-int b2_make_bins_tensor_map(void* out, const uint8_t* bins, int64_t n_rows, int row_stride) {
+// out must point to 128 bytes, 64-byte aligned.  box_rows = 1 for tile::gather4, 64 for the tile-mode root stage.
+// Returns 0 on success.
+int b2_make_bins_tensor_map(void* out, const uint8_t* bins, int64_t n_rows, int row_stride, int box_rows) {
   static B2EncodeFn encode = nullptr;
   if (!encode) {
     cudaDriverEntryPointQueryResult q;
@@ -211,7 +230,7 @@ int b2_make_bins_tensor_map(void* out, const uint8_t* bins, int64_t n_rows, int 
   }
   cuuint64_t gdim[2] = {(cuuint64_t)row_stride, (cuuint64_t)(n_rows > 0 ? n_rows : 1)};
   cuuint64_t gstride[1] = {(cuuint64_t)row_stride};
-  cuuint32_t box[2] = {B2_GROUP_SLOTS, 1};
+  cuuint32_t box[2] = {B2_GROUP_SLOTS, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = encode((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)bins, gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -219,7 +238,7 @@ int b2_make_bins_tensor_map(void* out, const uint8_t* bins, int64_t n_rows, int 
   return (int)r;
 }
 
-int b2_launch_hist_tma(const void* tmap, const int2* gpair, const int32_t* ridx, const B2HistWork* work, int n_work,
+int b2_launch_hist_tma(const void* tmap, const void* tmap_tile, const int2* gpair, const int32_t* ridx, const B2HistWork* work, int n_work,
                        int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* hist, const B2LevelCtl* ctl,
                        int log2_shards, int node_cap, int64_t n_rows_total, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
@@ -235,12 +254,13 @@ int b2_launch_hist_tma(const void* tmap, const int2* gpair, const int32_t* ridx,
   if (!ctl && n_streams > total_chunks) n_streams = total_chunks;
   dim3 grid(n_groups * n_streams), block(b2::kTmaThreads);
   const CUtensorMap* tm = (const CUtensorMap*)tmap;
+  const CUtensorMap* tt = (const CUtensorMap*)tmap_tile;
   if (ridx)
-    b2::hist_build_tma_kernel<true><<<grid, block, b2::kTmaSmemBytes, stream>>>(*tm, gpair, ridx, work, n_work, total_chunks, chunk_rows,
+    b2::hist_build_tma_kernel<true><<<grid, block, b2::kTmaSmemBytes, stream>>>(*tm, *tt, gpair, ridx, work, n_work, total_chunks, chunk_rows,
                                                                            window_rows, n_groups, hist, ctl, log2_shards, node_cap,
                                                                            n_rows_total);
   else
-    b2::hist_build_tma_kernel<false><<<grid, block, b2::kTmaSmemBytes, stream>>>(*tm, gpair, ridx, work, n_work, total_chunks, chunk_rows,
+    b2::hist_build_tma_kernel<false><<<grid, block, b2::kTmaSmemBytes, stream>>>(*tm, *tt, gpair, ridx, work, n_work, total_chunks, chunk_rows,
                                                                             window_rows, n_groups, hist, ctl, log2_shards, node_cap,
                                                                             n_rows_total);
   return (int)cudaGetLastError();
