@@ -377,6 +377,20 @@ static void *pool_get(size_t bytes) {
   if (bytes > g_pool_bytes) { free(g_pool); g_pool = malloc(bytes); g_pool_bytes = g_pool ? bytes : 0; }
   return g_pool;
 }
+/* persistent scratch slots (per-tree / per-level buffers): large malloc/free pairs are mmap/munmap calls and
+ * fresh pages fault on first touch -- with 100+ threads that serialises on the kernel's mmap lock */
+#define OR_N_SLOTS 16
+static void *g_slot[OR_N_SLOTS];
+static size_t g_slot_bytes[OR_N_SLOTS];
+static void *slot_get(int slot, size_t bytes) {
+  if (bytes > g_slot_bytes[slot]) {
+    free(g_slot[slot]);
+    g_slot[slot] = malloc(bytes + (bytes >> 2));
+    g_slot_bytes[slot] = g_slot[slot] ? bytes + (bytes >> 2) : 0;
+  }
+  return g_slot[slot];
+}
+enum { SLOT_RIDX = 0, SLOT_RTMP, SLOT_QG, SLOT_QH, SLOT_G, SLOT_H, SLOT_HIST0, SLOT_HIST1, SLOT_IHIST0, SLOT_IHIST1 };
 #define OR_ROWS_PER_THREAD 32768
 static int hist_threads(int64_t nrows) {
 #ifdef _OPENMP
@@ -650,13 +664,13 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
   int32_t F = c->n_features;
   size_t hsz = (size_t)F * 512;
   OrTree *t = tree_new();
-  int32_t *ridx = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
-  int32_t *rtmp = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+  int32_t *ridx = (int32_t *)slot_get(SLOT_RIDX, (size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+  int32_t *rtmp = (int32_t *)slot_get(SLOT_RTMP, (size_t)(n > 0 ? n : 1) * sizeof(int32_t));
   for (int64_t i = 0; i < n; ++i) ridx[i] = (int32_t)i;
   int32_t *qg = NULL, *qh = NULL; int32_t eg = 0, eh = 0; double inv_sg = 1.0, inv_sh = 1.0;
   if (p->qbits > 0) {
-    qg = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
-    qh = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    qg = (int32_t *)slot_get(SLOT_QG, (size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    qh = (int32_t *)slot_get(SLOT_QH, (size_t)(n > 0 ? n : 1) * sizeof(int32_t));
     or_quantize(g, n, gstride, p->qbits, qg, &eg);
     or_quantize(h, n, gstride, p->qbits, qh, &eh);
     inv_sg = ldexp(1.0, eg - p->qbits); inv_sh = ldexp(1.0, eh - p->qbits);
@@ -664,9 +678,11 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
   int32_t cap_level = 1; NodeWork *level = (NodeWork *)calloc(1, sizeof(NodeWork)); int32_t n_level = 1;
   level[0].nid = tree_add_node(t, -1); level[0].depth = 0; level[0].begin = 0; level[0].count = n;
   /* root histogram */
-  level[0].hist = (double *)malloc(hsz * sizeof(double));
+  /* node histograms of a level live in one of two persistent arenas (ping-pong by level parity) */
+  int arena = 0;
+  level[0].hist = (double *)slot_get(SLOT_HIST0, hsz * sizeof(double));
   if (p->qbits > 0) {
-    level[0].ihist = (int64_t *)malloc(hsz * sizeof(int64_t));
+    level[0].ihist = (int64_t *)slot_get(SLOT_IHIST0, hsz * sizeof(int64_t));
     or_hist_int(bins, F, qg, qh, NULL, n, level[0].ihist);
     for (size_t j = 0; j < hsz; j += 2) {
       level[0].hist[j] = (double)level[0].ihist[j] * inv_sg;
@@ -749,6 +765,11 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
     /* phase C: histograms of the children (A.5): build the smaller-hessian child from rows,
      * sibling = parent - built.  Node-parallel when there are many nodes, row-parallel otherwise. */
     if (n_pairs > 0 && ((level[pair_parent[0]].depth + 1 < p->max_depth) || p->max_depth == 0)) {
+      const int na = arena ^ 1;
+      double *hblock = (double *)slot_get(na ? SLOT_HIST1 : SLOT_HIST0, (size_t)n_next * hsz * sizeof(double));
+      int64_t *iblock = p->qbits > 0 ? (int64_t *)slot_get(na ? SLOT_IHIST1 : SLOT_IHIST0, (size_t)n_next * hsz * sizeof(int64_t)) : NULL;
+      for (int32_t q = 0; q < n_next; ++q) { next[q].hist = hblock + (size_t)q * hsz; next[q].ihist = iblock ? iblock + (size_t)q * hsz : NULL; }
+      arena = na;
       /* pass 0: nodes big enough for a row-parallel build, one after the other;
        * pass 1: the remaining (small) nodes in parallel, each built serially into its own buffer */
       for (int pass = 0; pass < 2; ++pass) {
@@ -759,9 +780,7 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
           NodeWork *bw = (wl->H < wr->H) ? wl : wr, *sw = (bw == wl) ? wr : wl;
           int big = bw->count >= 2 * (int64_t)OR_ROWS_PER_THREAD;
           if (big != (pass == 0)) continue;
-          bw->hist = (double *)malloc(hsz * sizeof(double)); sw->hist = (double *)malloc(hsz * sizeof(double));
           if (p->qbits > 0) {
-            bw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t)); sw->ihist = (int64_t *)malloc(hsz * sizeof(int64_t));
             or_hist_int(bins, F, qg, qh, ridx + bw->begin, bw->count, bw->ihist);
             for (size_t jj = 0; jj < hsz; ++jj) sw->ihist[jj] = w->ihist[jj] - bw->ihist[jj];
             for (size_t jj = 0; jj < hsz; jj += 2) {
@@ -776,10 +795,9 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
       }
     }
     free(expand_flag); free(pair_parent);
-    for (int32_t k = 0; k < n_level; ++k) { free(level[k].hist); free(level[k].ihist); }
     free(level); level = next; n_level = n_next;
   }
-  free(level); free(ridx); free(rtmp); free(qg); free(qh);
+  free(level);
   return t;
 }
 
@@ -818,8 +836,8 @@ int or_boost_one_round(OrModel *m, const OrCuts *c, const uint8_t *bins, int64_t
   float *g = NULL, *h = NULL;
   const float *gg = custom_g, *hh = custom_h;
   if (!custom_g) {
-    g = (float *)malloc((size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
-    h = (float *)malloc((size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
+    g = (float *)slot_get(SLOT_G, (size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
+    h = (float *)slot_get(SLOT_H, (size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
     or_gradients(m->p.objective, K, margin, label, weight, n, g, h);
     gg = g; hh = h;
   }
@@ -827,7 +845,6 @@ int or_boost_one_round(OrModel *m, const OrCuts *c, const uint8_t *bins, int64_t
     OrTree *t = grow_tree(&m->p, c, bins, n, gg + k, hh + k, K, margin + k, K);
     model_push(m, t);
   }
-  free(g); free(h);
   return 0;
 }
 
