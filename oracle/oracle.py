@@ -82,11 +82,38 @@ def lib():
     return _lib
 
 
-def use_all_cores():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use every host core it can."""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    lib().or_set_num_threads(n)
-    return lib().or_num_threads()
+def use_all_cores(calibrate=True):
+    """Pick the OpenMP thread count for the CPU baseline legs.  torchrun exports OMP_NUM_THREADS=1, and on
+    shared hosts asking for every logical CPU can be far slower than a smaller team (measured on the B200
+    box: 32 threads 0.26 s/round, 128 threads 8 s/round, profiles/r01_oracle_threads.txt), so the candidates
+    {all, 64, 32, 16} are timed on a small synthetic round and the fastest is used.  Returns the count."""
+    n_all = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    L = lib()
+    cands = sorted({c for c in (n_all, 64, 32, 16) if 1 <= c <= n_all} | {min(n_all, 8)}, reverse=True)
+    if not calibrate or len(cands) == 1:
+        L.or_set_num_threads(n_all)
+        return L.or_num_threads()
+    rng = np.random.RandomState(0)
+    n, f = 400_000, 32
+    X = rng.uniform(0, 10, size=(n, f)).astype(np.float32)
+    y = (X[:, 0] + X[:, 1]).astype(np.float32)
+    L.or_set_num_threads(min(n_all, 16))
+    cuts = Cuts.from_data(X, 256)
+    bins = cuts.bin(X)
+    best, best_t = cands[-1], float("inf")
+    import time
+    for c in cands:
+        L.or_set_num_threads(c)
+        b = Booster({"objective": "reg:squarederror", "max_depth": 6, "hist_qbits": 0}, cuts)
+        b.init_margin(n)
+        b.boost(bins, y)
+        t0 = time.perf_counter()
+        b.boost(bins, y)
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.95:      # prefer the larger team unless a smaller one is clearly faster
+            best, best_t = c, min(dt, best_t)
+    L.or_set_num_threads(best)
+    return L.or_num_threads()
 
 
 def _fp(a):
