@@ -271,3 +271,42 @@ def test_errors_surface(eng):
         eng.train({"objective": "reg:squarederror"}, eng.DMatrix(X), 1, verbose_eval=False)  # no labels
     with pytest.raises(eng.XGBoostError):
         eng.train({"max_bin": 1000}, eng.DMatrix(X, label=X[:, 0]), 1, verbose_eval=False)
+
+
+# ------------------------------------------------------------------ edge cases of the device-driven level loop
+@pytest.mark.parametrize("case", ["constant_label", "depth1", "tiny", "wide200", "small_bins", "multiclass_missing",
+                                  "deep_sparse_tree"])
+def test_edge_cases_identical(eng, oracle, case):
+    rng = np.random.RandomState(17)
+    w = None
+    if case == "constant_label":          # no split is ever valid: every tree is a single leaf
+        X = make_data(3000, 6, 1); y = np.full(3000, 2.5, np.float32)
+        params = {"objective": "reg:squarederror", "max_depth": 5, "base_score": 0.5}
+    elif case == "depth1":
+        X = make_data(5000, 9, 2); y = (X[:, 4] > 3).astype(np.float32)
+        params = {"objective": "binary:logistic", "max_depth": 1, "base_score": 0.5}
+    elif case == "tiny":                  # fewer rows than one warp iteration / one stage
+        X = make_data(13, 3, 3); y = X[:, 0].astype(np.float32)
+        params = {"objective": "reg:squarederror", "max_depth": 4, "base_score": 0.5, "min_child_weight": 0.0}
+    elif case == "wide200":               # 7 feature groups
+        X = make_data(6000, 200, 4); y = (X[:, 150] + X[:, 7] * 0.5 + rng.normal(size=6000)).astype(np.float32)
+        params = {"objective": "reg:squarederror", "max_depth": 4, "base_score": 0.5}
+    elif case == "small_bins":
+        X = make_data(8000, 10, 5); y = (np.sin(X[:, 0]) + X[:, 1]).astype(np.float32)
+        params = {"objective": "reg:squarederror", "max_depth": 6, "base_score": 0.5, "max_bin": 16}
+    elif case == "multiclass_missing":
+        X = make_data(5000, 7, 6, "mixed", nan_frac=0.2); y = rng.randint(0, 3, size=5000).astype(np.float32)
+        w = rng.uniform(0.1, 3.0, size=5000).astype(np.float32)
+        params = {"objective": "multi:softprob", "num_class": 3, "max_depth": 5, "base_score": 0.5, "alpha": 0.1}
+    else:                                  # gamma prunes most branches: ragged trees, many early leaves
+        X = make_data(20000, 8, 7); y = (X[:, 0] > 9.5).astype(np.float32) * 5 + rng.normal(scale=0.05, size=20000).astype(np.float32)
+        params = {"objective": "reg:squarederror", "max_depth": 10, "base_score": 0.5, "gamma": 5.0, "eta": 0.5}
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 3, weight=w)
+    assert_same_model(ebst, obst)
+    K = int(params.get("num_class", 1))
+    m = ebst.predict(dm, output_margin=True, training=True).reshape(len(X), K)
+    assert np.max(np.abs(m - obst.margin)) <= 1e-5
+    if case == "constant_label":
+        assert all(len(t["left"]) == 1 for t in ebst.get_trees())
+    if case == "deep_sparse_tree":
+        assert any(1 < len(t["left"]) < 2 ** 11 - 1 for t in ebst.get_trees())
