@@ -59,3 +59,31 @@ def test_two_gpu_toy_matrix(oracle):
     bst = train(params, RayDMatrix(x, y), num_boost_round=2, ray_params=RayParams(num_actors=2))
     assert list(predict(bst, RayDMatrix(x), ray_params=RayParams(num_actors=2))) == list(y)
     assert bst.num_trees() == 8
+
+
+@pytest.mark.timeout(900)
+def test_config_c1_breast_cancer_two_actors(oracle):
+    """BASELINE config C1: breast_cancer, binary:logistic, tree_method=hist, RayParams(num_actors=2) -- here on
+    two GPU actors; the model must equal the oracle's and the committed golden fixture's split sequence."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import os
+    from sklearn.datasets import load_breast_cancer
+    from xgboost_ray_b200 import RayDMatrix, RayParams, predict, train
+    X, y = load_breast_cancer(return_X_y=True)
+    X = X.astype(np.float32)
+    params = {"objective": "binary:logistic", "tree_method": "hist", "max_depth": 6, "eta": 0.3, "base_score": 0.5}
+    res = {}
+    d = RayDMatrix(X, y.astype(np.float32))
+    bst = train(params, d, num_boost_round=5, evals=[(d, "train")], evals_result=res,
+                ray_params=RayParams(num_actors=2, cpus_per_actor=1))
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "breast_cancer_logistic.json")))
+    for t, g in zip(bst.get_trees(), gold["trees"]):
+        assert [int(v) for v in t["split_feature"]] == g["split_feature"]
+        assert [int(v) for v in t["split_bin"]] == g["split_bin"]
+        leaf = np.asarray(g["split_feature"]) < 0
+        assert np.max(np.abs(t["value"][leaf] - np.asarray(g["value"], np.float32)[leaf])) <= 1e-5
+    p = predict(bst, RayDMatrix(X), ray_params=RayParams(num_actors=2))
+    assert np.mean((p > 0.5) == (y > 0.5)) > 0.98
+    assert res["train"]["logloss"][-1] < res["train"]["logloss"][0]

@@ -310,3 +310,22 @@ def test_edge_cases_identical(eng, oracle, case):
         assert all(len(t["left"]) == 1 for t in ebst.get_trees())
     if case == "deep_sparse_tree":
         assert any(1 < len(t["left"]) < 2 ** 11 - 1 for t in ebst.get_trees())
+
+
+def test_config_c2_shape_higgs_like(eng, oracle):
+    """BASELINE config C2 at test size: 28 fp32 features (21 N(0,1) + 7 heavy-tailed exp(N)), binary:logistic,
+    256 bins, depth 6, one GPU -- one feature group, heavy ties in none, long tails in some cuts."""
+    rng = np.random.RandomState(1234)
+    n = 200_000
+    X = rng.normal(size=(n, 28)).astype(np.float32)
+    X[:, 21:] = np.exp(X[:, 21:])
+    wv = rng.normal(size=8).astype(np.float32)
+    logit = X[:, :8] @ wv + 0.5 * X[:, 0] * X[:, 1]
+    y = (rng.uniform(size=n) < 1.0 / (1.0 + np.exp(-logit))).astype(np.float32)
+    params = {"objective": "binary:logistic", "max_depth": 6, "eta": 0.3, "base_score": 0.5, "max_bin": 256,
+              "eval_metric": ["logloss", "error"]}
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 8)
+    assert_same_model(ebst, obst)
+    p = ebst.predict(eng.DMatrix(X[:5000]))
+    assert np.max(np.abs(p - obst.predict(X[:5000]))) <= 1e-5
+    assert np.mean((p > 0.5) == (y[:5000] > 0.5)) > 0.7
