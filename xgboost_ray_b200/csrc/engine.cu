@@ -28,8 +28,7 @@
 // ---------------------------------------------------------------- kernel launchers (other TUs)
 extern "C" {
 int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
-                   const B2LevelCtl*, long long*, int, int, int, cudaStream_t);
-size_t b2_hist_scratch_elems(int, int);
+                   const B2LevelCtl*, int, int, int, cudaStream_t);
 int b2_make_bins_tensor_map(void*, const uint8_t*, int64_t, int, int);
 int b2_launch_hist_tma(const void*, const void*, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
                        const B2LevelCtl*, int, int, int64_t, int, cudaStream_t);
@@ -495,7 +494,6 @@ struct Booster : HandleBase {
   DevBuf<B2SplitCand> d_cands_all;  // allgathered candidates [shards][nodes][cpn]
   int shards = 1, log2_shards = 0, sp = 32, cpn = 1;
   size_t slice_elems = 0;
-  DevBuf<long long> hist_scratch;   // CTA-private int64 window accumulators (kept all-zero between launches)
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
   // device-resident control tables of the sync-free level loop (control_kernel.cu)
@@ -682,9 +680,6 @@ void ensure_ctl_tables(Booster* b) {
   b->hist[0].ensure(half * b->slice_elems); b->hist[1].ensure(half * b->slice_elems);
   if (b->shards > 1) { b->hist_build.ensure(half * b->node_elems); b->d_cands_all.ensure(half * b->cpn * b->shards); }
   b->d_cands.ensure(half * b->cpn);
-  const size_t se = b2_hist_scratch_elems(G, b->ctx->num_sms);
-  b->hist_scratch.ensure(se);
-  CUDA_CHECK(cudaMemsetAsync(b->hist_scratch.p, 0, se * sizeof(long long), b->ctx->stream));
   CUDA_CHECK(cudaMemsetAsync(b->t_i64.p, 0, L.i64_count * 8, b->ctx->stream));
 }
 
@@ -770,7 +765,7 @@ void grow_tree(Booster* b, int k, int slot) {
                                         build_target(b, b->hist[0].p), nullptr, sh, 1, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
-                                    build_target(b, b->hist[0].p), nullptr, b->hist_scratch.p, sh, 1, ctx->num_sms, s));
+                                    build_target(b, b->hist[0].p), nullptr, sh, 1, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       b->t.hist_launches++; b->t.kernel_launches++;
     }
@@ -827,7 +822,7 @@ void grow_tree(Booster* b, int k, int slot) {
                                         max_nodes_level, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt,
-                                    ctl + nxt, b->hist_scratch.p, sh, max_nodes_level, ctx->num_sms, s));
+                                    ctl + nxt, sh, max_nodes_level, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       mark_phase(b, 1);
       exchange_hist(b, b->hist[nh].p, max_nodes_level);
@@ -1347,10 +1342,7 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
     for (int f = 0; f < n_cols; ++f) padded[(size_t)i * m.row_stride + m.feat_byte[f]] = bins[i * n_cols + f];
   std::vector<int2> gp((size_t)std::max<int64_t>(n_rows, 1));
   for (int64_t i = 0; i < n_rows; ++i) gp[i] = make_int2(qg[i], qh[i]);
-  DevBuf<uint8_t> d_bins; DevBuf<int2> d_gp; DevBuf<int32_t> d_ridx; DevBuf<long long> d_hist, d_scratch; DevBuf<B2HistWork> d_work;
-  const size_t se = b2_hist_scratch_elems(m.n_groups, ctx->num_sms);
-  d_scratch.ensure(se);
-  CUDA_CHECK(cudaMemsetAsync(d_scratch.p, 0, se * sizeof(long long), s));
+  DevBuf<uint8_t> d_bins; DevBuf<int2> d_gp; DevBuf<int32_t> d_ridx; DevBuf<long long> d_hist; DevBuf<B2HistWork> d_work;
   d_bins.ensure(padded.size()); d_gp.ensure(gp.size());
   CUDA_CHECK(cudaMemcpyAsync(d_bins.p, padded.data(), padded.size(), cudaMemcpyHostToDevice, s));
   CUDA_CHECK(cudaMemcpyAsync(d_gp.p, gp.data(), gp.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
@@ -1379,7 +1371,7 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
                                       d_hist.p, nullptr, 0, 1, n_rows, ctx->num_sms, s));
     else
       LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
-                                  window_rows, m.n_groups, d_hist.p, nullptr, d_scratch.p, 0, 1, ctx->num_sms, s));
+                                  window_rows, m.n_groups, d_hist.p, nullptr, 0, 1, ctx->num_sms, s));
   }
   CUDA_CHECK(cudaEventRecord(e1, s));
   std::vector<long long> h(node_elems);

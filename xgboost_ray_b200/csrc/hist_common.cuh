@@ -37,21 +37,6 @@ struct RowData {
   int2 gp;
 };
 
-template <bool kGather>
-__device__ __forceinline__ RowData load_row(const uint8_t* __restrict__ bins, const int2* __restrict__ gpair,
-                                            const int32_t* __restrict__ ridx, int64_t pos, bool valid,
-                                            int row_stride, int lane_byte_off) {
-  RowData d;
-  d.bins = make_uint4(0, 0, 0, 0);
-  d.gp = make_int2(0, 0);
-  if (valid) {
-    int64_t rid = kGather ? (int64_t)__ldg(ridx + pos) : pos;
-    d.bins = ldg_nc_v4(bins + rid * row_stride + lane_byte_off);
-    d.gp = __ldg(gpair + rid);
-  }
-  return d;
-}
-
 // row id of chunk-row r (or -1 past the end of the chunk); root level: identity
 template <bool kGather>
 __device__ __forceinline__ int64_t fetch_rid(const int32_t* __restrict__ ridx, int64_t pos0, int r, int nrows) {
@@ -118,19 +103,6 @@ __device__ __forceinline__ size_t target_index(const HistTarget& t, int node_slo
   return ((size_t)r * t.node_cap + node_slot) * slice_elems + ((size_t)(group * 2 + plane) * B2_BINS + bin) * sp + sl;
 }
 
-// window flush: move the int32 partial sums into this CTA's PRIVATE int64 scratch (plain coalesced
-// read-modify-write in L2, no atomics: only this CTA touches its scratch block)
-__device__ __forceinline__ void flush_to_scratch(int32_t* s_hist, long long* scratch) {
-  for (int e = threadIdx.x * 4; e < B2_GROUP_ELEMS; e += blockDim.x * 4) {
-    int4 v = *reinterpret_cast<int4*>(s_hist + e);
-    if ((v.x | v.y | v.z | v.w) != 0) {
-      longlong2 a = *reinterpret_cast<longlong2*>(scratch + e), b = *reinterpret_cast<longlong2*>(scratch + e + 2);
-      a.x += v.x; a.y += v.y; b.x += v.z; b.y += v.w;
-      *reinterpret_cast<longlong2*>(scratch + e) = a; *reinterpret_cast<longlong2*>(scratch + e + 2) = b;
-      *reinterpret_cast<int4*>(s_hist + e) = make_int4(0, 0, 0, 0);
-    }
-  }
-}
 // lazy window flush: only cells whose magnitude reached 2^30 are moved to the global histogram.  Called
 // (between barriers) at least every `window_rows` = 2^(30 - qbits) rows, during which a cell can grow by
 // less than 2^30, so no int32 cell can overflow; for well spread bins nothing is flushed at all.
@@ -147,14 +119,11 @@ __device__ __forceinline__ void flush_large_cells(int32_t* s_hist, const HistTar
     }
   }
 }
-// node flush: shared (+ scratch if it was used) -> global int64 histogram with atomics
-__device__ __forceinline__ void flush_planes(int32_t* s_hist, long long* scratch, bool scratch_dirty, const HistTarget& t,
-                                             int node_slot, int group) {
+// node flush: shared int32 partial sums -> global int64 histogram (RED.64), cells are left zeroed
+__device__ __forceinline__ void flush_planes(int32_t* s_hist, const HistTarget& t, int node_slot, int group) {
   for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) {
-    long long v = s_hist[e];
-    if (scratch_dirty) { v += scratch[e]; scratch[e] = 0; }
-    if (v != 0) atomicAdd(t.base + target_index(t, node_slot, group, e), (unsigned long long)v);
-    s_hist[e] = 0;
+    const long long v = s_hist[e];
+    if (v != 0) { atomicAdd(t.base + target_index(t, node_slot, group, e), (unsigned long long)v); s_hist[e] = 0; }
   }
 }
 

@@ -29,13 +29,11 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
 hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                   const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
                   int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
-                  const B2LevelCtl* __restrict__ ctl, long long* __restrict__ scratch_all, int log2_shards, int node_cap,
-                  int debug_mode) {
+                  const B2LevelCtl* __restrict__ ctl, int log2_shards, int node_cap, int debug_mode) {
   HistTarget target; target.base = (unsigned long long*)hist; target.log2_shards = log2_shards; target.node_cap = node_cap;
   target.n_groups = n_groups;
   if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
   extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][32]
-  __shared__ int s_cur_work;
   const int group = blockIdx.x % n_groups;
   const int stream = blockIdx.x / n_groups;
   const int n_streams = gridDim.x / n_groups;
@@ -50,8 +48,6 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
 
   int cur = -1;          // work index whose partial sums are in shared memory
   int rows_in_window = 0;
-  bool scratch_dirty = false;
-  long long* scratch = scratch_all + (size_t)blockIdx.x * B2_GROUP_ELEMS;
   for (int chunk = stream; chunk < total_chunks; chunk += n_streams) {
     // locate the node of this chunk (uniform across the CTA): last w with chunk_begin <= chunk
     int lo = 0, hi = n_work - 1;
@@ -66,13 +62,13 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
     if (cur >= 0 && w != cur) {
       // node change: add the partial sums to the global int64 histogram
       __syncthreads();
-      flush_planes(s_hist, scratch, false, target, __ldg(&work[cur].hist_index), group);
+      flush_planes(s_hist, target, __ldg(&work[cur].hist_index), group);
       __syncthreads();
       rows_in_window = 0;
     } else if (cur >= 0 && rows_in_window + nrows > window_rows) {
       // same node, overflow guard interval reached: flush only the (rare) cells at or above 2^30
-      // (measured alternatives: flushing all cells with RED.64 every window cost 17 % of the kernel; a
-      // CTA-private int64 scratch with plain read-modify-write was 30 % slower still)
+      // (measured alternatives, profiles/r01_summary.md: flushing all cells with RED.64 every window cost 17 % of the
+      // kernel; a CTA-private int64 scratch with plain read-modify-write was 30 % slower still)
       __syncthreads();
       flush_large_cells(s_hist, target, __ldg(&work[cur].hist_index), group);
       __syncthreads();
@@ -113,9 +109,8 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
   }
   if (cur >= 0) {
     __syncthreads();
-    flush_planes(s_hist, scratch, scratch_dirty, target, __ldg(&work[cur].hist_index), group);
+    flush_planes(s_hist, target, __ldg(&work[cur].hist_index), group);
   }
-  (void)s_cur_work;
 }
 
 // ---------------------------------------------------------------- sibling = parent - built
@@ -138,17 +133,10 @@ __global__ void hist_subtract_kernel(const long long* __restrict__ parent_level,
 extern "C" {
 
 // Launch on `stream`.  grid = n_groups * n_streams persistent CTAs; returns the cudaError.
-// scratch: zero-initialised int64 [b2_hist_scratch_elems(n_groups, num_sms)], kept all-zero between launches
-size_t b2_hist_scratch_elems(int n_groups, int num_sms) {
-  int n_streams = (num_sms * 3) / n_groups;
-  if (n_streams < 1) n_streams = 1;
-  return (size_t)n_groups * n_streams * B2_GROUP_ELEMS;
-}
-
 int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const int32_t* ridx,
                    const B2HistWork* work, int n_work, int total_chunks, int chunk_rows, int window_rows,
-                   int n_groups, long long* hist, const B2LevelCtl* ctl, long long* scratch, int log2_shards, int node_cap,
-                   int num_sms, cudaStream_t stream) {
+                   int n_groups, long long* hist, const B2LevelCtl* ctl, int log2_shards, int node_cap, int num_sms,
+                   cudaStream_t stream) {
   static bool attr_set = false;
   static int debug_mode = -1, wide = -1;
   if (debug_mode < 0) { const char* e = getenv("B2_HIST_DEBUG_MODE"); debug_mode = e ? atoi(e) : 0; }
@@ -171,8 +159,8 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
   if (n_streams < 1) n_streams = 1;
   if (!ctl && n_streams > total_chunks) n_streams = total_chunks;
   dim3 grid(n_groups * n_streams), block(wide ? 512 : 256);
-#define B2_HIST_ARGS bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows, window_rows, n_groups, hist, ctl, scratch, \
-                     log2_shards, node_cap, debug_mode
+#define B2_HIST_ARGS bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows, window_rows, n_groups, hist, ctl, log2_shards, \
+                     node_cap, debug_mode
   if (wide) {
     if (ridx) b2::hist_build_kernel<true, 512, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
     else b2::hist_build_kernel<false, 512, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
