@@ -29,29 +29,57 @@ PARAMS = {"objective": "reg:squarederror", "max_depth": 8, "eta": 0.3, "lambda":
           "min_child_weight": 1.0, "max_bin": 256, "base_score": 0.5, "tree_method": "hist"}
 
 
-def synth_block(block, rows, cols, seed=1234):
-    """Deterministic block of the C3 dataset: x~U[0,10), y = sum_{j<10} a_j x_j + sin(x_10) + N(0,0.1)."""
+WORKLOADS = {   # SURVEY.md 8(d); C3 is the configuration the metric is quoted on, the others are opt-in (--workload)
+    "C2": {"rows": 11_000_000, "cols": 28, "depth": 6, "objective": "binary:logistic"},
+    "C3": {"rows": 10_000_000, "cols": 100, "depth": 8, "objective": "reg:squarederror"},
+    "C4": {"rows": 100_000_000, "cols": 50, "depth": 10, "objective": "binary:logistic"},
+}
+
+
+def synth_block(block, rows, cols, seed=1234, workload="C3"):
+    """Deterministic block of a synthetic dataset.
+    C3: x~U[0,10), y = sum_{j<10} a_j x_j + sin(x_10) + N(0,0.1).
+    C2: 3/4 of the columns N(0,1), the rest exp(N(0,1)) (HIGGS-like); label ~ Bernoulli(sigmoid(w.x[:8] + 0.5 x0 x1)).
+    C4: x~U[0,10); label as C2 on centred features."""
     rng = np.random.default_rng([seed, block])
-    X = rng.random((rows, cols), dtype=np.float32) * np.float32(10.0)
     a = np.random.default_rng(seed).normal(size=10).astype(np.float32)
-    k = min(10, cols)
-    y = X[:, :k] @ a[:k]
-    if cols > 10:
-        y = y + np.sin(X[:, 10])
-    y = y + rng.normal(scale=0.1, size=rows).astype(np.float32)
-    return X, y.astype(np.float32)
+    if workload == "C3":
+        X = rng.random((rows, cols), dtype=np.float32) * np.float32(10.0)
+        k = min(10, cols)
+        y = X[:, :k] @ a[:k]
+        if cols > 10:
+            y = y + np.sin(X[:, 10])
+        y = y + rng.normal(scale=0.1, size=rows).astype(np.float32)
+        return X, y.astype(np.float32)
+    if workload == "C2":
+        X = rng.standard_normal((rows, cols), dtype=np.float32)
+        heavy = cols - (3 * cols) // 4
+        np.exp(X[:, cols - heavy:], out=X[:, cols - heavy:])
+        Z = X
+    else:
+        X = rng.random((rows, cols), dtype=np.float32) * np.float32(10.0)
+        Z = (X[:, :8] - np.float32(5.0)) * np.float32(0.4)
+    k = min(8, cols)
+    s = Z[:, :k] @ a[:k] + np.float32(0.5) * Z[:, 0] * Z[:, 1]
+    y = (rng.random(rows, dtype=np.float32) < 1.0 / (1.0 + np.exp(-s))).astype(np.float32)
+    return X, y
 
 
-def synth_shard(n_rows, cols, rank, world, block_rows=1_000_000):
+def synth_shard(n_rows, cols, rank, world, block_rows=1_000_000, workload="C3"):
     """Rows rank, rank+world, ... of the global matrix (INTERLEAVED sharding, matrix.py:1100)."""
-    xs, ys = [], []
+    n_local = len(range(rank, n_rows, world))
+    Xs = np.empty((n_local, cols), dtype=np.float32)
+    ys = np.empty(n_local, dtype=np.float32)
+    at = 0
     for b, start in enumerate(range(0, n_rows, block_rows)):
         rows = min(block_rows, n_rows - start)
-        X, y = synth_block(b, rows, cols)
+        X, y = synth_block(b, rows, cols, workload=workload)
         first = (rank - start) % world
-        xs.append(X[first::world])
-        ys.append(y[first::world])
-    return np.ascontiguousarray(np.concatenate(xs)), np.ascontiguousarray(np.concatenate(ys))
+        m = len(range(first, rows, world))
+        Xs[at:at + m] = X[first::world]
+        ys[at:at + m] = y[first::world]
+        at += m
+    return Xs, ys
 
 
 class ClockSampler(threading.Thread):
@@ -104,10 +132,11 @@ def hist_traffic_per_launch():
     p = os.path.join(ROOT, "profiles", "hist_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            d = json.load(open(p))
+            return d.get("dram_bytes_per_launch"), d.get("algorithmic_bytes_per_launch_same_capture")
         except Exception:
-            return None
-    return None
+            return None, None
+    return None, None
 
 
 def run_reference(args, rank, world):
@@ -117,8 +146,8 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     O.build()
     cores = O.use_all_cores()
-    X, y = synth_shard(args.rows, args.cols, 0, 1)
-    params = dict(PARAMS, max_depth=args.depth, hist_qbits=0)   # qbits=0: float64 histograms = XGBoost CPU hist
+    X, y = synth_shard(args.rows, args.cols, 0, 1, workload=args.workload)
+    params = dict(PARAMS, max_depth=args.depth, hist_qbits=0, objective=args.objective)   # qbits=0: float64 histograms = XGBoost CPU hist
     t0 = time.time()
     cuts = O.Cuts.from_data(X, 256)
     bins = cuts.bin(X)
@@ -135,7 +164,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "boosting rounds/sec", "value": v, "unit": "rounds/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3 synthetic %dx%d reg:squarederror depth %d 256 bins" % (args.rows, args.cols, args.depth),
+            "config": {"workload": "%s synthetic %dx%d %s depth %d 256 bins" % (args.workload, args.rows, args.cols, args.objective, args.depth),
                        "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256},
             "cpu_baseline": {"value": v, "unit": "rounds/s", "cores": cores, "kind": "port",
                              "sample": "full workload, %d timed rounds; CPU quantisation %.1fs not in the timed region" % (args.steps, t_quant)},
@@ -150,9 +179,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=10_000_000)
-    ap.add_argument("--cols", type=int, default=100)
-    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS), help="SURVEY.md 8(d) configuration (default C3, the headline)")
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--cols", type=int, default=None)
+    ap.add_argument("--depth", type=int, default=None)
     ap.add_argument("--qbits", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -160,6 +190,11 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    args.rows = args.rows or wl["rows"]
+    args.cols = args.cols or wl["cols"]
+    args.depth = args.depth or wl["depth"]
+    args.objective = wl["objective"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,7 +210,7 @@ def main():
     os.environ["B2_DEVICE"] = str(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    params = dict(PARAMS, max_depth=args.depth, profile=args.profile)
+    params = dict(PARAMS, max_depth=args.depth, profile=args.profile, objective=args.objective)
     if args.qbits is not None:
         params["hist_qbits"] = args.qbits
 
@@ -198,7 +233,7 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         comm_args["b2_uid"] = uid[0]
 
-    X, y = synth_shard(args.rows, args.cols, rank, world)
+    X, y = synth_shard(args.rows, args.cols, rank, world, workload=args.workload)
     sampler = ClockSampler(local_rank)
     with E.CommunicatorContext(**comm_args):
         # ================= device-resident arm: matrix quantised and resident before timing
@@ -226,7 +261,7 @@ def main():
         hist_ms = max_over_ranks(timers["hist_ms"])
         ms_per_step = 1e3 * wall / args.steps
         value = args.steps / wall
-        final_rmse = float(bst.eval_set([(dm, "train")], 0).split(":")[-1])
+        final_metric = bst.eval_set([(dm, "train")], 0).split("\t", 1)[-1]
         del bst
 
         # ================= e2e arm: host buffers -> xgb.train replacement, copies inside the timed region
@@ -246,7 +281,7 @@ def main():
                    "h2d_bytes_per_step": int((X.nbytes + y.nbytes) / args.steps),
                    "d2h_bytes_per_step": 8, "seconds_total": e2e_wall, "seconds_upload": t_up, "seconds_quantise": t_q,
                    "api": "xgboost_ray_b200.engine.train (the xgb.train replacement an actor calls, host numpy in)",
-                   "final_train_rmse": res["train"]["rmse"][-1]}
+                   "final_train_metric": {k: v[-1] for k, v in res["train"].items()}}
             del b2, d2
 
         # ================= CPU baseline (rank 0, N=1): oracle port on the host cores, bounded sample
@@ -274,6 +309,8 @@ def main():
             dist.destroy_process_group()
         return
     peak, peak_kind = measured_peak()
+    # ncu --set full capture of one boosting round (C3): dram bytes per launch and the algorithmic bytes of the SAME launches
+    traffic, traffic_alg = hist_traffic_per_launch() if args.workload == "C3" else (None, None)
     hist_bytes_per_launch = timers["hist_bytes"] / max(1, timers["hist_launches"])
     hist_ms_per_launch = hist_ms / max(1, timers["hist_launches"])
     achieved = hist_bytes_per_launch / (hist_ms_per_launch * 1e-3) / 1e9 if hist_ms_per_launch > 0 else 0.0
@@ -281,16 +318,16 @@ def main():
         "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int64 fixed-point histograms (int32 shared-memory cells), f64 gain", "data": "synthetic",
-        "config": {"workload": "C3 synthetic %dx%d reg:squarederror depth %d 256 bins, rows INTERLEAVED over %d rank(s)" % (
-                       args.rows, args.cols, args.depth, world),
+        "config": {"workload": "%s synthetic %dx%d %s depth %d 256 bins, rows INTERLEAVED over %d rank(s)" % (
+                       args.workload, args.rows, args.cols, args.objective, args.depth, world),
                    "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256, "parallelism": "dp%d" % world,
                    "hist_qbits": params.get("hist_qbits", 18), "l2": "inputs_larger_than_l2",
-                   "device_ms_per_step": dev_ms / args.steps, "phase_ms_per_step": {k: v / args.steps for k, v in timers.get("phase_ms", {}).items()}, "quantise_seconds": t_quant, "final_train_rmse": final_rmse},
+                   "device_ms_per_step": dev_ms / args.steps, "phase_ms_per_step": {k: v / args.steps for k, v in timers.get("phase_ms", {}).items()}, "quantise_seconds": t_quant, "final_train_metric": final_metric},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_kind, "kernel": "b2::hist_build_kernel",
                      "algorithmic_bytes_per_launch": hist_bytes_per_launch, "ms_per_launch": hist_ms_per_launch,
                      "launches": timers["hist_launches"], "share_of_step": hist_ms / max(dev_ms, 1e-9),
-                     "traffic": hist_traffic_per_launch()},
+                     "traffic": traffic, "traffic_capture_algorithmic_bytes": traffic_alg},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timers["kernel_launches"]),
         "clocks": sampler.summary(),
     }

@@ -22,28 +22,43 @@
 
 #include "hist_common.cuh"
 
+#ifndef B2_HIST_DEFAULT_VARIANT
+#define B2_HIST_DEFAULT_VARIANT 2
+#endif
+
 namespace b2 {
 
-template <bool kGather, int kThreads, int kMinBlocks>
+// kGPC = feature groups per CTA.  1: 64 KiB of histogram, two lanes per row, 16 rows per warp step.
+// 2: 128 KiB (one 1024-thread CTA per SM); FOUR lanes read 64 contiguous bytes of a row (one L1 wavefront
+// instead of two) and the row id / gradient pair loads are shared by both groups, which removes about a
+// quarter of the L1TEX wavefronts per row -- the pipe this kernel is bound by (profiles/r01_summary.md).
+template <bool kGather, int kThreads, int kMinBlocks, int kGPC>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                   const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
                   int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
                   const B2LevelCtl* __restrict__ ctl, int log2_shards, int node_cap, int debug_mode) {
+  constexpr int kLanesPerRow = 2 * kGPC;
+  constexpr int kRowsPerWarp = 32 / kLanesPerRow;
   HistTarget target; target.base = (unsigned long long*)hist; target.log2_shards = log2_shards; target.node_cap = node_cap;
   target.n_groups = n_groups;
   if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
-  extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][32]
-  const int group = blockIdx.x % n_groups;
-  const int stream = blockIdx.x / n_groups;
-  const int n_streams = gridDim.x / n_groups;
+  extern __shared__ __align__(16) int32_t s_hist[];  // [kGPC][256][2][32]
+  const int n_cta_groups = (n_groups + kGPC - 1) / kGPC;
+  const int group0 = (blockIdx.x % n_cta_groups) * kGPC;
+  const int stream = blockIdx.x / n_cta_groups;
+  const int n_streams = gridDim.x / n_cta_groups;
   if (stream >= total_chunks) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int rot = lane >> 1, half = lane & 1;
-  const int lane_byte_off = group * 32 + half * 16;
-  const uint32_t smem_g = (uint32_t)__cvta_generic_to_shared(s_hist);
+  // lane -> (row of the warp step, group of the CTA, 16-byte half of the group slice).  rot is distinct for the
+  // 16 (row, group) pairs of a warp, so at every step the 32 lanes hit 32 different banks (bank = slot).
+  const int sub = lane / kLanesPerRow, gsel = (lane % kLanesPerRow) >> 1, half = lane & 1;
+  const int rot = sub * kGPC + gsel;
+  const bool active = group0 + gsel < n_groups;
+  const int lane_byte_off = (group0 + gsel) * 32 + half * 16;
+  const uint32_t smem_g = (uint32_t)__cvta_generic_to_shared(s_hist) + gsel * (B2_GROUP_ELEMS * 4);
 
-  for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) s_hist[e] = 0;
+  for (int e = threadIdx.x; e < kGPC * B2_GROUP_ELEMS; e += blockDim.x) s_hist[e] = 0;
   __syncthreads();
 
   int cur = -1;          // work index whose partial sums are in shared memory
@@ -62,7 +77,9 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
     if (cur >= 0 && w != cur) {
       // node change: add the partial sums to the global int64 histogram
       __syncthreads();
-      flush_planes(s_hist, target, __ldg(&work[cur].hist_index), group);
+#pragma unroll
+      for (int gs = 0; gs < kGPC; ++gs)
+        if (group0 + gs < n_groups) flush_planes(s_hist + gs * B2_GROUP_ELEMS, target, __ldg(&work[cur].hist_index), group0 + gs);
       __syncthreads();
       rows_in_window = 0;
     } else if (cur >= 0 && rows_in_window + nrows > window_rows) {
@@ -70,46 +87,52 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
       // (measured alternatives, profiles/r01_summary.md: flushing all cells with RED.64 every window cost 17 % of the
       // kernel; a CTA-private int64 scratch with plain read-modify-write was 30 % slower still)
       __syncthreads();
-      flush_large_cells(s_hist, target, __ldg(&work[cur].hist_index), group);
+#pragma unroll
+      for (int gs = 0; gs < kGPC; ++gs)
+        if (group0 + gs < n_groups) flush_large_cells(s_hist + gs * B2_GROUP_ELEMS, target, __ldg(&work[cur].hist_index), group0 + gs);
       __syncthreads();
       rows_in_window = 0;
     }
     cur = w;
     rows_in_window += nrows;
     const int64_t pos0 = (int64_t)seg_begin + row0;
-    const int iter_rows = n_warps * kRowsPerWarpIter;
+    const int iter_rows = n_warps * kRowsPerWarp;
     // 3-stage register pipeline: while stage k is accumulated, the loads of the next two
     // iterations are in flight, and (gather) the row ids of three more iterations behind them,
     // so no load waits on the ridx -> bins dependency.
-    const int r0 = warp * kRowsPerWarpIter + rot;
-    int64_t id0 = fetch_rid<kGather>(ridx, pos0, r0, nrows);
-    int64_t id1 = fetch_rid<kGather>(ridx, pos0, r0 + iter_rows, nrows);
-    int64_t id2 = fetch_rid<kGather>(ridx, pos0, r0 + 2 * iter_rows, nrows);
+    const int rbase = warp * kRowsPerWarp;
+    const int r0 = rbase + sub;
+    const int lim = active ? nrows : 0;   // lanes of a group past the last one (odd group count) load nothing
+    int64_t id0 = fetch_rid<kGather>(ridx, pos0, r0, lim);
+    int64_t id1 = fetch_rid<kGather>(ridx, pos0, r0 + iter_rows, lim);
+    int64_t id2 = fetch_rid<kGather>(ridx, pos0, r0 + 2 * iter_rows, lim);
     unsigned sink = 0;
 #define B2_LOAD(id) (debug_mode == 2 ? fake_row(id) : load_row_id(bins, gpair, id, row_stride, lane_byte_off))
     RowData s0 = B2_LOAD(id0);
-    id0 = fetch_rid<kGather>(ridx, pos0, r0 + 3 * iter_rows, nrows);
+    id0 = fetch_rid<kGather>(ridx, pos0, r0 + 3 * iter_rows, lim);
     RowData s1 = B2_LOAD(id1);
-    id1 = fetch_rid<kGather>(ridx, pos0, r0 + 4 * iter_rows, nrows);
+    id1 = fetch_rid<kGather>(ridx, pos0, r0 + 4 * iter_rows, lim);
     RowData s2 = B2_LOAD(id2);
-    id2 = fetch_rid<kGather>(ridx, pos0, r0 + 5 * iter_rows, nrows);
-    for (int r = r0 - rot; r < nrows; r += 3 * iter_rows) {   // warp-uniform trip count
-      accumulate_row(s0, smem_g, rot, half, debug_mode, &sink);
+    id2 = fetch_rid<kGather>(ridx, pos0, r0 + 5 * iter_rows, lim);
+    for (int r = rbase; r < nrows; r += 3 * iter_rows) {   // warp-uniform trip count
+      if (kGPC == 1 || active) accumulate_row(s0, smem_g, rot, half, debug_mode, &sink);
       s0 = B2_LOAD(id0);
-      id0 = fetch_rid<kGather>(ridx, pos0, r + rot + 6 * iter_rows, nrows);
-      if (r + iter_rows < nrows) accumulate_row(s1, smem_g, rot, half, debug_mode, &sink);
+      id0 = fetch_rid<kGather>(ridx, pos0, r + sub + 6 * iter_rows, lim);
+      if (r + iter_rows < nrows && (kGPC == 1 || active)) accumulate_row(s1, smem_g, rot, half, debug_mode, &sink);
       s1 = B2_LOAD(id1);
-      id1 = fetch_rid<kGather>(ridx, pos0, r + rot + 7 * iter_rows, nrows);
-      if (r + 2 * iter_rows < nrows) accumulate_row(s2, smem_g, rot, half, debug_mode, &sink);
+      id1 = fetch_rid<kGather>(ridx, pos0, r + sub + 7 * iter_rows, lim);
+      if (r + 2 * iter_rows < nrows && (kGPC == 1 || active)) accumulate_row(s2, smem_g, rot, half, debug_mode, &sink);
       s2 = B2_LOAD(id2);
-      id2 = fetch_rid<kGather>(ridx, pos0, r + rot + 8 * iter_rows, nrows);
+      id2 = fetch_rid<kGather>(ridx, pos0, r + sub + 8 * iter_rows, lim);
     }
 #undef B2_LOAD
     if (sink == 0x9e3779b9u) s_hist[threadIdx.x] = (int)sink;
   }
   if (cur >= 0) {
     __syncthreads();
-    flush_planes(s_hist, target, __ldg(&work[cur].hist_index), group);
+#pragma unroll
+    for (int gs = 0; gs < kGPC; ++gs)
+      if (group0 + gs < n_groups) flush_planes(s_hist + gs * B2_GROUP_ELEMS, target, __ldg(&work[cur].hist_index), group0 + gs);
   }
 }
 
@@ -138,35 +161,50 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
                    int n_groups, long long* hist, const B2LevelCtl* ctl, int log2_shards, int node_cap, int num_sms,
                    cudaStream_t stream) {
   static bool attr_set = false;
-  static int debug_mode = -1, wide = -1;
+  static int debug_mode = -1, variant = -1;
   if (debug_mode < 0) { const char* e = getenv("B2_HIST_DEBUG_MODE"); debug_mode = e ? atoi(e) : 0; }
-  // 2 CTAs x 16 warps per SM by default (measured 6 % faster in training than 3 x 8, profiles/r01_hist_threads_ab.txt)
-  if (wide < 0) { const char* e = getenv("B2_HIST_THREADS"); wide = (e && atoi(e) == 256) ? 0 : 1; }
-  const int smem = B2_GROUP_ELEMS * (int)sizeof(int32_t);  // 64 KiB
+  // variants (B2_HIST_VARIANT): 0 = 256 threads x 3 CTAs/SM, one group per CTA
+  //                             1 = 512 threads x 2 CTAs/SM, one group per CTA
+  //                             2 = 1024 threads x 1 CTA/SM, two groups per CTA (default; A/B in profiles/r01_summary.md)
+  if (variant < 0) {
+    const char* e = getenv("B2_HIST_VARIANT");
+    variant = e ? atoi(e) : B2_HIST_DEFAULT_VARIANT;
+    const char* t = getenv("B2_HIST_THREADS");   // older spelling of variant 0
+    if (!e && t && atoi(t) == 256) variant = 0;
+    if (variant < 0 || variant > 2) variant = B2_HIST_DEFAULT_VARIANT;
+  }
+  const int gpc = variant == 2 ? 2 : 1;
+  const int smem = gpc * B2_GROUP_ELEMS * (int)sizeof(int32_t);  // 64 KiB per group
   if (!attr_set) {
-    cudaFuncSetAttribute(b2::hist_build_kernel<true, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(b2::hist_build_kernel<false, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(b2::hist_build_kernel<true, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(b2::hist_build_kernel<false, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(b2::hist_build_kernel<true, 256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 4);
+    cudaFuncSetAttribute(b2::hist_build_kernel<false, 256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 4);
+    cudaFuncSetAttribute(b2::hist_build_kernel<true, 512, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 4);
+    cudaFuncSetAttribute(b2::hist_build_kernel<false, 512, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 4);
+    cudaFuncSetAttribute(b2::hist_build_kernel<true, 1024, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
+    cudaFuncSetAttribute(b2::hist_build_kernel<false, 1024, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
     attr_set = true;
   }
   // with ctl the work list / chunk counts live in device memory (sync-free level loop) and the grid is the
   // full persistent grid; without it they are host values
   if (!ctl && (total_chunks <= 0 || n_work <= 0)) return 0;
   if (!ctl && chunk_rows > window_rows) return (int)cudaErrorInvalidValue;  // a chunk must fit one int32 window
-  const int ctas_per_sm = wide ? 2 : 3;
-  int n_streams = (num_sms * ctas_per_sm) / n_groups;
+  const int ctas_per_sm = variant == 0 ? 3 : variant == 1 ? 2 : 1;
+  const int n_cta_groups = (n_groups + gpc - 1) / gpc;
+  int n_streams = (num_sms * ctas_per_sm) / n_cta_groups;
   if (n_streams < 1) n_streams = 1;
   if (!ctl && n_streams > total_chunks) n_streams = total_chunks;
-  dim3 grid(n_groups * n_streams), block(wide ? 512 : 256);
+  dim3 grid(n_cta_groups * n_streams), block(variant == 0 ? 256 : variant == 1 ? 512 : 1024);
 #define B2_HIST_ARGS bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows, window_rows, n_groups, hist, ctl, log2_shards, \
                      node_cap, debug_mode
-  if (wide) {
-    if (ridx) b2::hist_build_kernel<true, 512, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
-    else b2::hist_build_kernel<false, 512, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+  if (variant == 2) {
+    if (ridx) b2::hist_build_kernel<true, 1024, 1, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+    else b2::hist_build_kernel<false, 1024, 1, 2><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+  } else if (variant == 1) {
+    if (ridx) b2::hist_build_kernel<true, 512, 2, 1><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+    else b2::hist_build_kernel<false, 512, 2, 1><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
   } else {
-    if (ridx) b2::hist_build_kernel<true, 256, 3><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
-    else b2::hist_build_kernel<false, 256, 3><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+    if (ridx) b2::hist_build_kernel<true, 256, 3, 1><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
+    else b2::hist_build_kernel<false, 256, 3, 1><<<grid, block, smem, stream>>>(B2_HIST_ARGS);
   }
 #undef B2_HIST_ARGS
   return (int)cudaGetLastError();
