@@ -47,6 +47,12 @@ int B2_MatrixCreateFromDense(const float* data, int64_t n_rows, int32_t n_cols, 
                              B2Handle* out);
 /* field: "label" | "weight" | "base_margin" (len n_rows, or n_rows*num_class for base_margin) */
 int B2_MatrixSetFloatInfo(B2Handle m, const char* field, const float* values, int64_t len);
+/* feature types: is_cat[f] != 0 marks feature f categorical (xgb.DMatrix(feature_types=[...'c'...],
+ * enable_categorical=True), forwarded by _get_dmatrix, xgboost_ray/main.py:365-376 / matrix.py:159,193).  Must be
+ * called before B2_MatrixQuantize.  A categorical value is its category code: an integer in [0, 255]
+ * ([0, 254] when the feature has missing values); its bin is the code, its cuts are 0..max code. */
+int B2_MatrixSetFeatureTypes(B2Handle m, const uint8_t* is_cat, int32_t len);
+int B2_MatrixGetFeatureTypes(B2Handle m, uint8_t* is_cat /*[n_cols]*/);
 int B2_MatrixNumRow(B2Handle m, int64_t* out);
 int B2_MatrixNumCol(B2Handle m, int32_t* out);
 /* GPU quantile sketch (global over `comm`, 0 = single process) + binning into the device uint8
@@ -90,6 +96,11 @@ int B2_BoosterAddTree(B2Handle b, int32_t n_nodes, const int32_t* left, const in
                       const int32_t* parent, const int32_t* split_feature, const int32_t* split_bin,
                       const float* split_cond, const uint8_t* default_left, const float* value,
                       const float* base_weight, const float* loss_chg, const double* sum_hess);
+/* categorical part of a tree (model JSON fields split_type / categories*): split_type[i] = 1
+ * for a categorical split; cat_bits[i*8 + (c >> 5)] bit (c & 31) set = category c goes RIGHT.  Set* is called
+ * after B2_BoosterAddTree when a model with categorical splits is loaded. */
+int B2_BoosterGetTreeCategories(B2Handle b, int32_t tree, uint8_t* split_type /*[n]*/, uint32_t* cat_bits /*[n*8]*/);
+int B2_BoosterSetTreeCategories(B2Handle b, int32_t tree, const uint8_t* split_type, const uint32_t* cat_bits);
 /* JSON object with accumulated device timings / counters of the hot path (since last reset):
  * hist_ms, hist_launches, hist_rows, hist_bytes, kernel_launches, round_ms, allreduce_bytes ... */
 int B2_BoosterGetTimers(B2Handle b, int32_t reset, char* out, int64_t out_cap);

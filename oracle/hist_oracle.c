@@ -26,6 +26,11 @@
  *   A.8  row partition    (src/tree/common_row_partitioner.h)
  *   A.9  prediction       (src/predictor/cpu_predictor.cc)
  *   A.10 metrics          (src/metric/elementwise_metric.cu, multiclass_metric.cu)
+ *   A.2/A.6/A.8 categorical features (src/common/categorical.h, evaluate_splits.h
+ *                          EnumerateOneHot / EnumeratePart): bin = category code, one-hot
+ *                          splits below max_cat_to_onehot categories, otherwise categories
+ *                          sorted by leaf weight and scanned from both ends; the split stores
+ *                          the set of categories that go RIGHT
  *
  * Deliberate, documented deviations (DESIGN.md "Oracle decisions"):
  *   - sketch ranks are exact (int64) instead of fp32 GK summaries: the exact summary
@@ -67,6 +72,8 @@ typedef struct {
   float base_score;      /* probability space for logistic */
   int32_t qbits;         /* 0 => float64 histogram */
   int32_t nthread;       /* 0 => omp default */
+  int32_t max_cat_to_onehot;  /* categorical: one-hot splits when n_categories < this (xgboost default 4) */
+  int32_t max_cat_threshold;  /* categorical: at most this many categories scanned per direction (default 64) */
 } OrParams;
 
 typedef struct {
@@ -76,6 +83,7 @@ typedef struct {
   float *cut_vals;      /* [cut_ptrs[F]] */
   float *min_vals;      /* [F] */
   uint8_t *has_missing; /* [F] */
+  uint8_t *is_cat;      /* [F] 1 = categorical feature: cuts are the codes 0..max, bin = code */
 } OrCuts;
 
 typedef struct {
@@ -90,6 +98,8 @@ typedef struct {
   float *loss_chg;
   double *sum_hess;
   double *sum_grad;
+  uint8_t *is_cat_split;  /* 1 = categorical split: categories (= bins) whose bit is set go right */
+  uint32_t *cat_bits;     /* [cap][8] bit b of word b>>5 (LSB first) = category b */
 } OrTree;
 
 typedef struct {
@@ -238,17 +248,44 @@ static int make_cuts_feature(const uint32_t *sorted_keys, int64_t cnt, int max_n
   return nc;
 }
 
-OrCuts *or_cuts_create(const float *X, int64_t n, int32_t F, float missing, int32_t max_bin) {
+void or_cuts_free(OrCuts *c);
+
+/* is_cat (may be NULL): categorical features get the cuts [0, 1, ..., max code] (HistogramCuts::AddCategories,
+ * src/common/quantile.cc); a code must be an integer in [0, 255] ([0, 254] if the feature has missing values,
+ * bin 255 being the sentinel).  Returns NULL on an invalid category value. */
+OrCuts *or_cuts_create_cat(const float *X, int64_t n, int32_t F, float missing, int32_t max_bin, const uint8_t *is_cat) {
   if (max_bin < 2 || max_bin > 256) return NULL;
   OrCuts *c = (OrCuts *)calloc(1, sizeof(OrCuts));
   c->n_features = F; c->max_bin = max_bin;
   c->cut_ptrs = (int32_t *)calloc((size_t)F + 1, sizeof(int32_t));
   c->min_vals = (float *)calloc((size_t)F, sizeof(float));
   c->has_missing = (uint8_t *)calloc((size_t)F, 1);
+  c->is_cat = (uint8_t *)calloc((size_t)F, 1);
+  if (is_cat) memcpy(c->is_cat, is_cat, (size_t)F);
   float *tmpc = (float *)malloc((size_t)F * 256 * sizeof(float));
   int32_t *ncut = (int32_t *)calloc((size_t)F, sizeof(int32_t));
+  int invalid = 0;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int32_t f = 0; f < F; ++f) {
+    if (c->is_cat[f]) {
+      int miss = 0; int32_t mx = -1; int bad = 0;
+      for (int64_t i = 0; i < n; ++i) {
+        float x = X[i * F + f];
+        if (is_missing(x, missing)) { miss = 1; continue; }
+        if (!(x >= 0.0f) || x > 255.0f || x != (float)(int32_t)x) { bad = 1; continue; }
+        if ((int32_t)x > mx) mx = (int32_t)x;
+      }
+      if (miss && mx > 254) bad = 1;
+      if (bad) {
+#pragma omp atomic write
+        invalid = 1;
+      }
+      c->has_missing[f] = (uint8_t)miss;
+      c->min_vals[f] = -1e-5f;
+      ncut[f] = mx < 0 ? 1 : mx + 1;
+      for (int32_t k = 0; k < ncut[f]; ++k) tmpc[(size_t)f * 256 + k] = (float)k;
+      continue;
+    }
     uint32_t *keys = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
     uint32_t *tmp = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
     int64_t cnt = 0; int miss = 0;
@@ -270,8 +307,14 @@ OrCuts *or_cuts_create(const float *X, int64_t n, int32_t F, float missing, int3
   for (int32_t f = 0; f < F; ++f)
     memcpy(c->cut_vals + c->cut_ptrs[f], tmpc + (size_t)f * 256, (size_t)ncut[f] * sizeof(float));
   free(tmpc); free(ncut);
+  if (invalid) { or_cuts_free(c); return NULL; }
   return c;
 }
+OrCuts *or_cuts_create(const float *X, int64_t n, int32_t F, float missing, int32_t max_bin) {
+  return or_cuts_create_cat(X, n, F, missing, max_bin, NULL);
+}
+void or_cuts_set_cat(OrCuts *c, const uint8_t *is_cat) { memcpy(c->is_cat, is_cat, (size_t)c->n_features); }
+void or_cuts_get_cat(const OrCuts *c, uint8_t *is_cat) { memcpy(is_cat, c->is_cat, (size_t)c->n_features); }
 
 /* build cuts from caller-supplied arrays (e.g. downloaded from the device path) */
 OrCuts *or_cuts_from_arrays(int32_t F, int32_t max_bin, const int32_t *ptrs, const float *vals,
@@ -286,12 +329,13 @@ OrCuts *or_cuts_from_arrays(int32_t F, int32_t max_bin, const int32_t *ptrs, con
   memcpy(c->min_vals, mins, (size_t)F * sizeof(float));
   c->has_missing = (uint8_t *)calloc((size_t)F, 1);
   if (has_missing) memcpy(c->has_missing, has_missing, (size_t)F);
+  c->is_cat = (uint8_t *)calloc((size_t)F, 1);
   return c;
 }
 
 void or_cuts_free(OrCuts *c) {
   if (!c) return;
-  free(c->cut_ptrs); free(c->cut_vals); free(c->min_vals); free(c->has_missing); free(c);
+  free(c->cut_ptrs); free(c->cut_vals); free(c->min_vals); free(c->has_missing); free(c->is_cat); free(c);
 }
 int32_t or_cuts_total(const OrCuts *c) { return c->cut_ptrs[c->n_features]; }
 void or_cuts_get(const OrCuts *c, int32_t *ptrs, float *vals, float *mins, uint8_t *has_missing) {
@@ -311,6 +355,11 @@ void or_bin_matrix(const OrCuts *c, const float *X, int64_t n, float missing, ui
       if (is_missing(x, missing)) { bins[i * F + f] = OR_MISSING_BIN; continue; }
       const float *cv = c->cut_vals + c->cut_ptrs[f];
       int32_t nf = c->cut_ptrs[f + 1] - c->cut_ptrs[f];
+      if (c->is_cat[f]) {  /* bin = category code; codes the cuts have not seen clamp like numeric values */
+        int32_t b = x >= 0.0f ? (x > 255.0f ? 255 : (int32_t)x) : 0;
+        bins[i * F + f] = (uint8_t)(b >= nf ? nf - 1 : b);
+        continue;
+      }
       int32_t lo = 0, hi = nf;
       while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (cv[mid] > x) hi = mid; else lo = mid + 1; }
       if (lo >= nf) lo = nf - 1;
@@ -505,7 +554,11 @@ static float calc_weight(const OrParams *p, double G, double H) {
 typedef struct {
   float loss_chg; int32_t feature; int32_t bin; float cond; int default_left;
   double GL, HL, GR, HR; int valid;
+  int is_cat; uint32_t cat_bits[8];   /* categorical split: categories (bins) that go right */
 } SplitCand;
+
+static void bits_set(uint32_t *b, int i) { b[i >> 5] |= 1u << (i & 31); }
+static int bits_test(const uint32_t *b, int i) { return (int)((b[i >> 5] >> (i & 31)) & 1u); }
 
 /* SplitEntry::Update / NeedReplace (src/tree/param.h) */
 static int need_replace(const SplitCand *best, float new_chg, int32_t feat) {
@@ -513,6 +566,76 @@ static int need_replace(const SplitCand *best, float new_chg, int32_t feat) {
   if (!best->valid) return new_chg > best->loss_chg; /* best->loss_chg initialised 0 */
   if (best->feature <= feat) return new_chg > best->loss_chg;
   return !(best->loss_chg > new_chg);
+}
+
+#define OR_TRY_CAT(chg_, lg_, lh_, rg_, rh_, bin_, cond_, dl_)                                    \
+  if (need_replace(best, (chg_), f)) {                                                           \
+    best->loss_chg = (chg_); best->feature = f; best->bin = (bin_); best->cond = (cond_);        \
+    best->default_left = (dl_); best->GL = (lg_); best->HL = (lh_); best->GR = (rg_); best->HR = (rh_); \
+    best->valid = 1; best->is_cat = 1; memset(best->cat_bits, 0, sizeof(best->cat_bits));       \
+    updated = 1;                                                                                 \
+  }
+
+/* EnumerateOneHot (evaluate_splits.h): one category against the rest; the chosen category goes right.
+ * Per category: first with the missing rows on the left (default_left), then with them on the right. */
+static void eval_cat_onehot(const OrParams *p, const float *cv, const double *hf, int32_t nf, int32_t f, double G,
+                            double H, float root_gain, SplitCand *best) {
+  const double mcw = (double)p->min_child_weight;
+  double fg = 0.0, fh = 0.0;
+  for (int32_t i = 0; i < nf; ++i) { fg += hf[i * 2]; fh += hf[i * 2 + 1]; }
+  const double mg = G - fg, mh = H - fh;   /* missing rows of this node */
+  for (int32_t i = 0; i < nf; ++i) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const double rg = pass ? hf[i * 2] + mg : hf[i * 2], rh = pass ? hf[i * 2 + 1] + mh : hf[i * 2 + 1];
+      const double lg = G - rg, lh = H - rh;
+      if (lh >= mcw && rh >= mcw) {
+        float chg = (float)(calc_gain(p, lg, lh) + calc_gain(p, rg, rh) - (double)root_gain);
+        int updated = 0;
+        OR_TRY_CAT(chg, lg, lh, rg, rh, i, cv[i], pass ? 0 : 1)
+        if (updated) bits_set(best->cat_bits, i);
+      }
+    }
+  }
+}
+
+/* EnumeratePart<+1>, <-1> (evaluate_splits.h): categories stable-sorted by leaf weight; forward the
+ * lightest k categories go right (missing left), backward the heaviest k go left (missing right); at most
+ * min(max_cat_threshold, n) - 1 steps per direction, so neither side is ever empty of categories. */
+static void eval_cat_partition(const OrParams *p, const double *hf, int32_t nf, int32_t f, double G, double H,
+                               float root_gain, SplitCand *best) {
+  const double mcw = (double)p->min_child_weight;
+  float w[256]; int32_t idx[256];
+  for (int32_t i = 0; i < nf; ++i) { w[i] = calc_weight(p, hf[i * 2], hf[i * 2 + 1]); idx[i] = i; }
+  for (int32_t i = 1; i < nf; ++i) {   /* stable insertion sort, ascending weight */
+    int32_t v = idx[i], j = i - 1;
+    while (j >= 0 && w[idx[j]] > w[v]) { idx[j + 1] = idx[j]; --j; }
+    idx[j + 1] = v;
+  }
+  const int32_t n_bins = p->max_cat_threshold < nf ? p->max_cat_threshold : nf;
+  const float nanv = (float)NAN;
+  double rg = 0.0, rh = 0.0;
+  for (int32_t it = 0; it < n_bins - 1; ++it) {
+    rg += hf[idx[it] * 2]; rh += hf[idx[it] * 2 + 1];
+    const double lg = G - rg, lh = H - rh;
+    if (lh >= mcw && rh >= mcw) {
+      float chg = (float)(calc_gain(p, lg, lh) + calc_gain(p, rg, rh) - (double)root_gain);
+      int updated = 0;
+      OR_TRY_CAT(chg, lg, lh, rg, rh, -1, nanv, 1)
+      if (updated) for (int32_t k = 0; k <= it; ++k) bits_set(best->cat_bits, idx[k]);
+    }
+  }
+  double lg = 0.0, lh = 0.0;
+  for (int32_t t = 0; t < n_bins - 1; ++t) {
+    const int32_t i = nf - 1 - t;
+    lg += hf[idx[i] * 2]; lh += hf[idx[i] * 2 + 1];
+    const double rg2 = G - lg, rh2 = H - lh;
+    if (lh >= mcw && rh2 >= mcw) {
+      float chg = (float)(calc_gain(p, lg, lh) + calc_gain(p, rg2, rh2) - (double)root_gain);
+      int updated = 0;
+      OR_TRY_CAT(chg, lg, lh, rg2, rh2, -1, nanv, 0)
+      if (updated) for (int32_t k = 0; k < i; ++k) bits_set(best->cat_bits, idx[k]);
+    }
+  }
 }
 
 /* hist for this node as doubles [F][256][2]; total (G,H) */
@@ -525,6 +648,11 @@ static void evaluate_node(const OrParams *p, const OrCuts *c, const double *hist
     const double *hf = hist + (size_t)f * 512;
     int32_t nf = c->cut_ptrs[f + 1] - c->cut_ptrs[f];
     const float *cv = c->cut_vals + c->cut_ptrs[f];
+    if (c->is_cat[f]) {
+      if (nf < p->max_cat_to_onehot) eval_cat_onehot(p, cv, hf, nf, f, G, H, root_gain, best);
+      else eval_cat_partition(p, hf, nf, f, G, H, root_gain, best);
+      continue;
+    }
     /* forward: missing -> right */
     double eg = 0.0, eh = 0.0;
     for (int32_t i = 0; i < nf; ++i) {
@@ -536,7 +664,7 @@ static void evaluate_node(const OrParams *p, const OrCuts *c, const double *hist
           if (need_replace(best, chg, f)) {
             best->loss_chg = chg; best->feature = f; best->bin = i; best->cond = cv[i];
             best->default_left = 0; best->GL = eg; best->HL = eh; best->GR = rg; best->HR = rh;
-            best->valid = 1;
+            best->valid = 1; best->is_cat = 0;
           }
         }
       }
@@ -554,7 +682,7 @@ static void evaluate_node(const OrParams *p, const OrCuts *c, const double *hist
               best->loss_chg = chg; best->feature = f; best->bin = i - 1; /* rows with bin<=i-1 go left */
               best->cond = (i == 0) ? c->min_vals[f] : cv[i - 1];
               best->default_left = 1; best->GL = lg; best->HL = lh; best->GR = bg; best->HR = bh;
-              best->valid = 1;
+              best->valid = 1; best->is_cat = 0;
             }
           }
         }
@@ -571,13 +699,15 @@ static OrTree *tree_new(void) {
   ALLOC(left, int32_t); ALLOC(right, int32_t); ALLOC(parent, int32_t); ALLOC(split_feature, int32_t);
   ALLOC(split_bin, int32_t); ALLOC(split_cond, float); ALLOC(default_left, uint8_t); ALLOC(value, float);
   ALLOC(base_weight, float); ALLOC(loss_chg, float); ALLOC(sum_hess, double); ALLOC(sum_grad, double);
+  ALLOC(is_cat_split, uint8_t);
+  t->cat_bits = (uint32_t *)calloc((size_t)t->cap * 8, sizeof(uint32_t));
 #undef ALLOC
   return t;
 }
 static void tree_free(OrTree *t) {
   free(t->left); free(t->right); free(t->parent); free(t->split_feature); free(t->split_bin);
   free(t->split_cond); free(t->default_left); free(t->value); free(t->base_weight); free(t->loss_chg);
-  free(t->sum_hess); free(t->sum_grad); free(t);
+  free(t->sum_hess); free(t->sum_grad); free(t->is_cat_split); free(t->cat_bits); free(t);
 }
 static int32_t tree_add_node(OrTree *t, int32_t parent) {
   if (t->n_nodes == t->cap) {
@@ -586,6 +716,8 @@ static int32_t tree_add_node(OrTree *t, int32_t parent) {
     GROW(left, int32_t); GROW(right, int32_t); GROW(parent, int32_t); GROW(split_feature, int32_t);
     GROW(split_bin, int32_t); GROW(split_cond, float); GROW(default_left, uint8_t); GROW(value, float);
     GROW(base_weight, float); GROW(loss_chg, float); GROW(sum_hess, double); GROW(sum_grad, double);
+    GROW(is_cat_split, uint8_t);
+    t->cat_bits = (uint32_t *)realloc(t->cat_bits, (size_t)nc * 8 * sizeof(uint32_t));
 #undef GROW
     t->cap = nc;
   }
@@ -593,6 +725,7 @@ static int32_t tree_add_node(OrTree *t, int32_t parent) {
   t->left[id] = t->right[id] = -1; t->parent[id] = parent; t->split_feature[id] = -1; t->split_bin[id] = -1;
   t->split_cond[id] = 0; t->default_left[id] = 0; t->value[id] = 0; t->base_weight[id] = 0;
   t->loss_chg[id] = 0; t->sum_hess[id] = 0; t->sum_grad[id] = 0;
+  t->is_cat_split[id] = 0; memset(t->cat_bits + (size_t)id * 8, 0, 32);
   return id;
 }
 
@@ -608,9 +741,12 @@ typedef struct {
 /* A.8 stable partition of ridx[begin, begin+count) into [left | right]; returns #left.
  * Block-parallel (count, prefix, scatter) for large segments. */
 static int64_t partition_segment(int32_t *ridx, int32_t *rtmp, int64_t begin, int64_t count, const uint8_t *bins,
-                                 int32_t F, int32_t feature, int32_t split_bin, int has_missing, int default_left) {
+                                 int32_t F, int32_t feature, int32_t split_bin, int has_missing, int default_left,
+                                 const uint32_t *cat_bits /* NULL = numeric split */) {
 #define GO_LEFT(row) ((bins[(int64_t)(row) * F + feature] == OR_MISSING_BIN && has_missing) \
-                          ? default_left : ((int32_t)bins[(int64_t)(row) * F + feature] <= split_bin))
+                          ? default_left                                                      \
+                          : (cat_bits ? !bits_test(cat_bits, bins[(int64_t)(row) * F + feature]) \
+                                      : ((int32_t)bins[(int64_t)(row) * F + feature] <= split_bin)))
 #ifdef _OPENMP
   int nt = omp_in_parallel() ? 1 : omp_get_max_threads();
 #else
@@ -751,11 +887,14 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
       t->left[nid] = l; t->right[nid] = r; t->split_feature[nid] = s->feature; t->split_bin[nid] = s->bin;
       t->split_cond[nid] = s->cond; t->default_left[nid] = (uint8_t)s->default_left;
       t->loss_chg[nid] = s->loss_chg; t->value[nid] = t->base_weight[nid];
+      t->is_cat_split[nid] = (uint8_t)s->is_cat;
+      if (s->is_cat) memcpy(t->cat_bits + (size_t)nid * 8, s->cat_bits, 32);
       t->sum_grad[l] = s->GL; t->sum_hess[l] = s->HL; t->sum_grad[r] = s->GR; t->sum_hess[r] = s->HR;
       t->base_weight[l] = calc_weight(p, s->GL, s->HL); t->base_weight[r] = calc_weight(p, s->GR, s->HR);
       /* A.8 partition (stable): left iff non-missing && bin <= split_bin, missing -> default */
+      /* categorical: rows whose category is in the set go right (A.8) */
       int64_t nl = partition_segment(ridx, rtmp, w->begin, w->count, bins, F, s->feature, s->bin,
-                                     c->has_missing[s->feature], s->default_left);
+                                     c->has_missing[s->feature], s->default_left, s->is_cat ? s->cat_bits : NULL);
       int64_t nr = w->count - nl;
       NodeWork *wl = &next[n_next++], *wr = &next[n_next++];
       wl->nid = l; wl->depth = w->depth + 1; wl->begin = w->begin; wl->count = nl; wl->G = s->GL; wl->H = s->HL;
@@ -861,7 +1000,14 @@ void or_tree_get(const OrModel *m, int32_t ti, int32_t *left, int32_t *right, in
   memcpy(loss_chg, t->loss_chg, n * 4); memcpy(sum_hess, t->sum_hess, n * 8);
 }
 
-/* A.9 prediction on raw floats: x < split_cond -> left; missing -> default */
+/* categorical part of a tree: split_type [n] (1 = categorical), cat_bits [n][8] */
+void or_tree_get_cat(const OrModel *m, int32_t ti, uint8_t *split_type, uint32_t *cat_bits) {
+  const OrTree *t = m->trees[ti]; size_t n = (size_t)t->n_nodes;
+  memcpy(split_type, t->is_cat_split, n); memcpy(cat_bits, t->cat_bits, n * 32);
+}
+
+/* A.9 prediction on raw floats: x < split_cond -> left; missing -> default.  Categorical node
+ * (common/categorical.h Decision): category in the set -> right; not in the set, negative or beyond the set -> left */
 void or_predict_margin(const OrModel *m, const float *X, int64_t n, float missing, int32_t tree_begin,
                        int32_t tree_end, const float *base_margin, float *out) {
   int K = m->p.num_class; int32_t F = m->n_features;
@@ -875,6 +1021,10 @@ void or_predict_margin(const OrModel *m, const float *X, int64_t n, float missin
       while (t->split_feature[nid] >= 0) {
         float x = X[i * F + t->split_feature[nid]];
         if (is_missing(x, missing)) nid = t->default_left[nid] ? t->left[nid] : t->right[nid];
+        else if (t->is_cat_split[nid]) {
+          const int in_set = x >= 0.0f && x < 256.0f && bits_test(t->cat_bits + (size_t)nid * 8, (int)x);
+          nid = in_set ? t->right[nid] : t->left[nid];
+        }
         else nid = (x < t->split_cond[nid]) ? t->left[nid] : t->right[nid];
       }
       out[i * K + (ti % K)] += t->value[nid];

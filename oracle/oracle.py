@@ -26,7 +26,8 @@ class OrParams(C.Structure):
     _fields_ = [("objective", C.c_int32), ("num_class", C.c_int32), ("max_depth", C.c_int32),
                 ("max_bin", C.c_int32), ("eta", C.c_float), ("gamma", C.c_float),
                 ("min_child_weight", C.c_float), ("lambda_", C.c_float), ("alpha", C.c_float),
-                ("base_score", C.c_float), ("qbits", C.c_int32), ("nthread", C.c_int32)]
+                ("base_score", C.c_float), ("qbits", C.c_int32), ("nthread", C.c_int32),
+                ("max_cat_to_onehot", C.c_int32), ("max_cat_threshold", C.c_int32)]
 
 
 def build(force=False):
@@ -49,6 +50,11 @@ def lib():
                           C.POINTER(C.c_double))
         L.or_cuts_create.restype = C.c_void_p
         L.or_cuts_create.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_int32]
+        L.or_cuts_create_cat.restype = C.c_void_p
+        L.or_cuts_create_cat.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, bp]
+        L.or_cuts_set_cat.argtypes = [C.c_void_p, bp]
+        L.or_cuts_get_cat.argtypes = [C.c_void_p, bp]
+        L.or_tree_get_cat.argtypes = [C.c_void_p, C.c_int32, bp, C.POINTER(C.c_uint32)]
         L.or_cuts_from_arrays.restype = C.c_void_p
         L.or_cuts_from_arrays.argtypes = [C.c_int32, C.c_int32, ip, fp, fp, bp]
         L.or_cuts_free.argtypes = [C.c_void_p]
@@ -147,24 +153,31 @@ class Cuts:
         self.has_missing = np.zeros(n_features, np.uint8)
         L.or_cuts_get(handle, _ip(self.ptrs), _fp(self.vals), _fp(self.mins), _bp(self.has_missing))
         self.vals = self.vals[:tot]
+        self.is_cat = np.zeros(n_features, np.uint8)
+        L.or_cuts_get_cat(handle, _bp(self.is_cat))
 
     @classmethod
-    def from_data(cls, X, max_bin=256, missing=np.nan):
+    def from_data(cls, X, max_bin=256, missing=np.nan, is_cat=None):
+        """is_cat: optional bool/uint8 [F]; categorical features get the cuts 0..max code (bin = code)."""
         X = _f32(X)
         n, f = X.shape
-        h = lib().or_cuts_create(_fp(X), n, f, float(missing), max_bin)
+        ic = None if is_cat is None else np.ascontiguousarray(is_cat, np.uint8)
+        h = lib().or_cuts_create_cat(_fp(X), n, f, float(missing), max_bin, _bp(ic))
         if not h:
-            raise ValueError("or_cuts_create failed (max_bin must be in [2,256])")
+            raise ValueError("or_cuts_create failed (max_bin must be in [2,256]; category codes must be integers "
+                             "in [0,255], [0,254] for a feature with missing values)")
         return cls(h, f, max_bin)
 
     @classmethod
-    def from_arrays(cls, ptrs, vals, mins, has_missing, max_bin=256):
+    def from_arrays(cls, ptrs, vals, mins, has_missing, max_bin=256, is_cat=None):
         ptrs = np.ascontiguousarray(ptrs, np.int32)
         vals = _f32(vals)
         mins = _f32(mins)
         hm = np.ascontiguousarray(has_missing, np.uint8)
         f = len(ptrs) - 1
         h = lib().or_cuts_from_arrays(f, max_bin, _ip(ptrs), _fp(vals), _fp(mins), _bp(hm))
+        if is_cat is not None:
+            lib().or_cuts_set_cat(h, _bp(np.ascontiguousarray(is_cat, np.uint8)))
         return cls(h, f, max_bin)
 
     def bin(self, X, missing=np.nan):
@@ -198,12 +211,19 @@ def make_params(params):
     p.base_score = float(params.get("base_score", 0.5))
     p.qbits = int(params.get("hist_qbits", 18))
     p.nthread = int(params.get("nthread", 0))
+    p.max_cat_to_onehot = int(params.get("max_cat_to_onehot", 4))
+    p.max_cat_threshold = int(params.get("max_cat_threshold", 64))
     return p
 
 
 class Tree:
     FIELDS = ("left", "right", "parent", "split_feature", "split_bin", "split_cond", "default_left",
-              "value", "base_weight", "loss_chg", "sum_hess")
+              "value", "base_weight", "loss_chg", "sum_hess", "split_type", "cat_bits")
+
+    def categories(self, nid):
+        """Sorted category codes that go RIGHT at categorical node nid."""
+        w = self.cat_bits[nid]
+        return [b for b in range(256) if (int(w[b >> 5]) >> (b & 31)) & 1]
 
     def __init__(self, **kw):
         for k in self.FIELDS:
@@ -260,11 +280,13 @@ class Booster:
                  split_feature=np.zeros(nn, np.int32), split_bin=np.zeros(nn, np.int32),
                  split_cond=np.zeros(nn, np.float32), default_left=np.zeros(nn, np.uint8),
                  value=np.zeros(nn, np.float32), base_weight=np.zeros(nn, np.float32),
-                 loss_chg=np.zeros(nn, np.float32), sum_hess=np.zeros(nn, np.float64))
+                 loss_chg=np.zeros(nn, np.float32), sum_hess=np.zeros(nn, np.float64),
+                 split_type=np.zeros(nn, np.uint8), cat_bits=np.zeros((nn, 8), np.uint32))
         L.or_tree_get(self.h, i, _ip(a["left"]), _ip(a["right"]), _ip(a["parent"]), _ip(a["split_feature"]),
                       _ip(a["split_bin"]), _fp(a["split_cond"]), _bp(a["default_left"]), _fp(a["value"]),
                       _fp(a["base_weight"]), _fp(a["loss_chg"]),
                       a["sum_hess"].ctypes.data_as(C.POINTER(C.c_double)))
+        L.or_tree_get_cat(self.h, i, _bp(a["split_type"]), a["cat_bits"].ctypes.data_as(C.POINTER(C.c_uint32)))
         return Tree(**a)
 
     def trees(self):
@@ -307,10 +329,10 @@ class Booster:
             pass
 
 
-def train(params, X, y, num_boost_round, weight=None, missing=np.nan, cuts=None, base_margin=None):
+def train(params, X, y, num_boost_round, weight=None, missing=np.nan, cuts=None, base_margin=None, is_cat=None):
     """Convenience: cuts -> bins -> rounds.  Returns (Booster, bins)."""
     X = _f32(X)
-    cuts = cuts or Cuts.from_data(X, int(params.get("max_bin", 256)), missing)
+    cuts = cuts or Cuts.from_data(X, int(params.get("max_bin", 256)), missing, is_cat=is_cat)
     bins = cuts.bin(X, missing)
     bst = Booster(params, cuts)
     bst.init_margin(X.shape[0], base_margin)

@@ -87,3 +87,36 @@ def test_config_c1_breast_cancer_two_actors(oracle):
     p = predict(bst, RayDMatrix(X), ray_params=RayParams(num_actors=2))
     assert np.mean((p > 0.5) == (y > 0.5)) > 0.98
     assert res["train"]["logloss"][-1] < res["train"]["logloss"][0]
+
+
+@pytest.mark.timeout(900)
+def test_two_gpu_categorical_identical_to_one_gpu_and_oracle(oracle):
+    """Categorical splits (config C5's feature kind): the category-set candidates travel through the candidate
+    allgather; 1 GPU, 2 GPUs and the oracle agree."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from xgboost_ray_b200 import RayDMatrix, RayParams, predict, train
+    rng = np.random.RandomState(9)
+    n = 40001
+    xn = rng.uniform(0, 10, size=(n, 30))
+    cats = np.column_stack([rng.randint(0, c, size=n) for c in (3, 4, 16, 64, 250)])
+    x = np.column_stack([xn, cats]).astype(np.float32)
+    x[rng.uniform(size=x.shape) < 0.03] = np.nan
+    y = ((np.nan_to_num(x[:, 0]) > 5) * 1.0 + (np.nan_to_num(x[:, 32]) % 3 == 0) * 2.0 + (np.nan_to_num(x[:, 34]) % 5 < 2) * 1.0
+         + rng.normal(scale=0.2, size=n)).astype(np.float32)
+    types = ["q"] * 30 + ["c"] * 5
+    params = {"objective": "reg:squarederror", "max_depth": 6, "eta": 0.3, "base_score": 0.5}
+    kw = dict(feature_types=types, enable_categorical=True)
+    b1 = train(params, RayDMatrix(x, y, **kw), num_boost_round=4, ray_params=RayParams(num_actors=1))
+    b2 = train(params, RayDMatrix(x, y, **kw), num_boost_round=4, ray_params=RayParams(num_actors=2))
+    assert _dump(b1) == _dump(b2)
+    ob, _ = oracle.train(params, x, y, 4, is_cat=[0] * 30 + [1] * 5)
+    n_cat_nodes = 0
+    for i, t in enumerate(b2.get_trees()):
+        o = ob.tree(i)
+        assert np.array_equal(t["split_feature"], o.split_feature) and np.array_equal(t["split_bin"], o.split_bin)
+        assert np.array_equal(t["split_type"], o.split_type) and np.array_equal(t["cat_bits"], o.cat_bits)
+        n_cat_nodes += int(t["split_type"].sum())
+    assert n_cat_nodes > 0
+    p2 = predict(b2, RayDMatrix(x, **kw), ray_params=RayParams(num_actors=2))
+    assert np.max(np.abs(p2 - ob.predict(x))) <= 1e-5

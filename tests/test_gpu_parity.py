@@ -141,7 +141,11 @@ def assert_same_model(eng_bst, or_bst, leaf_tol=LEAF_TOL):
         assert np.array_equal(t["split_feature"], o.split_feature), "tree %d split features" % i
         assert np.array_equal(t["split_bin"], o.split_bin), "tree %d split bins" % i
         assert np.array_equal(t["default_left"], o.default_left), "tree %d default directions" % i
-        assert np.array_equal(t["split_cond"].view(np.uint32), o.split_cond.view(np.uint32)), "tree %d conds" % i
+        nanc = np.isnan(o.split_cond)      # partition-based categorical splits store NaN
+        assert np.array_equal(np.isnan(t["split_cond"]), nanc), "tree %d NaN conds" % i
+        assert np.array_equal(t["split_cond"][~nanc].view(np.uint32), o.split_cond[~nanc].view(np.uint32)), "tree %d conds" % i
+        assert np.array_equal(t["split_type"], o.split_type), "tree %d split types" % i
+        assert np.array_equal(t["cat_bits"], o.cat_bits), "tree %d category sets" % i
         leaf = o.split_feature < 0
         assert np.max(np.abs(t["value"][leaf] - o.value[leaf])) <= leaf_tol, "tree %d leaf values" % i
         assert np.allclose(t["loss_chg"], o.loss_chg, rtol=0, atol=0), "tree %d loss_chg" % i
@@ -331,3 +335,109 @@ def test_config_c2_shape_higgs_like(eng, oracle):
     p = ebst.predict(eng.DMatrix(X[:5000]))
     assert np.max(np.abs(p - obst.predict(X[:5000]))) <= 1e-5
     assert np.mean((p > 0.5) == (y[:5000] > 0.5)) > 0.7
+
+
+# ------------------------------------------------------------------ categorical features (A.2 / A.6 / A.8, config C5)
+CAT_TYPES = ["q", "q", "q", "c", "c", "c"]
+IS_CAT = [0, 0, 0, 1, 1, 1]
+
+
+def make_cat_data(n, seed, nan_frac=0.0):
+    rng = np.random.RandomState(seed)
+    Xn = rng.uniform(0, 10, size=(n, 3))
+    X = np.column_stack([Xn, rng.randint(0, 3, size=n), rng.randint(0, 20, size=n), rng.randint(0, 200, size=n)]).astype(np.float32)
+    score = (Xn[:, 0] > 5) * 1.0 + (X[:, 3] == 2) * 1.5 + (X[:, 4] % 3 == 0) * 2.0 + (X[:, 5] % 7 < 2) * 1.0
+    if nan_frac > 0:
+        X[rng.uniform(size=X.shape) < nan_frac] = np.nan
+    return X, score.astype(np.float32), rng
+
+
+def run_both_cat(eng, oracle, params, X, y, rounds):
+    obst, _ = oracle.train(params, X, y, rounds, is_cat=IS_CAT)
+    dm = eng.DMatrix(X, label=y, feature_types=CAT_TYPES, enable_categorical=True)
+    ebst = eng.train(params, dm, num_boost_round=rounds, verbose_eval=False)
+    return ebst, obst, dm
+
+
+@pytest.mark.parametrize("nan_frac", [0.0, 0.1])
+def test_categorical_cuts_and_bins_bit_exact(eng, oracle, nan_frac):
+    X, _, _ = make_cat_data(20000, 31, nan_frac)
+    cuts = oracle.Cuts.from_data(X, 256, is_cat=IS_CAT)
+    dm = eng.DMatrix(X, feature_types=CAT_TYPES, enable_categorical=True)
+    dm._ensure_quantized(256)
+    ptrs, vals, mins, hm = dm.get_cuts()
+    assert np.array_equal(ptrs, cuts.ptrs) and np.array_equal(vals.view(np.uint32), cuts.vals.view(np.uint32))
+    assert np.array_equal(hm, cuts.has_missing)
+    assert np.array_equal(dm.get_bins(), cuts.bin(X))
+
+
+@pytest.mark.parametrize("objective,extra", [
+    ("reg:squarederror", {}), ("reg:squarederror", {"max_cat_to_onehot": 1}), ("reg:squarederror", {"max_cat_threshold": 8}),
+    ("reg:squarederror", {"max_cat_to_onehot": 32, "min_child_weight": 50}), ("binary:logistic", {}),
+])
+@pytest.mark.parametrize("nan_frac", [0.0, 0.08])
+def test_categorical_trees_identical(eng, oracle, objective, extra, nan_frac):
+    X, score, rng = make_cat_data(30000, 33, nan_frac)
+    y = score + rng.normal(scale=0.3, size=len(score)).astype(np.float32)
+    if objective == "binary:logistic":
+        y = (y > 2.5).astype(np.float32)
+    params = dict({"objective": objective, "max_depth": 6, "eta": 0.3, "base_score": 0.5}, **extra)
+    ebst, obst, dm = run_both_cat(eng, oracle, params, X, y, 5)
+    assert_same_model(ebst, obst)
+    types = np.concatenate([t["split_type"][t["split_feature"] >= 0] for t in ebst.get_trees()])
+    assert types.any() and not types.all()                      # both numeric and categorical splits were chosen
+    assert np.max(np.abs(ebst.predict(dm, output_margin=True) - obst.predict(X, output_margin=True))) <= LEAF_TOL
+
+
+def test_categorical_multiclass_and_model_io(eng, oracle, tmp_path):
+    import pickle
+    X, score, rng = make_cat_data(20000, 35, 0.05)
+    y = np.clip(np.round(score), 0, 4).astype(np.float32)
+    params = {"objective": "multi:softprob", "num_class": 5, "max_depth": 5, "eta": 0.4}
+    ebst, obst, dm = run_both_cat(eng, oracle, params, X, y, 3)
+    assert_same_model(ebst, obst)
+    Xt = X[:500].copy()
+    Xt[:50, 4] = 150.0           # categories the training data never had in this column
+    Xt[50:60, 5] = 231.0
+    dt = eng.DMatrix(Xt, feature_types=CAT_TYPES, enable_categorical=True)
+    want = obst.predict(Xt)
+    got = ebst.predict(dt)
+    assert np.max(np.abs(got - want)) <= LEAF_TOL
+    # JSON model round trip (categories / categories_nodes / categories_segments / categories_sizes / split_type)
+    f = str(tmp_path / "cat.json")
+    ebst.save_model(f)
+    import json
+    tr = json.load(open(f))["learner"]["gradient_booster"]["model"]["trees"]
+    assert any(t["categories_nodes"] for t in tr) and all(len(t["split_type"]) == len(t["left_children"]) for t in tr)
+    for t in tr:
+        assert sum(t["categories_sizes"]) == len(t["categories"]) and sum(t["split_type"]) == len(t["categories_nodes"])
+    b2 = eng.Booster(model_file=f)
+    assert np.array_equal(b2.predict(dt), got)
+    b3 = pickle.loads(pickle.dumps(ebst))
+    assert np.array_equal(b3.predict(dt), got)
+    assert b3.get_dump(dump_format="json") == ebst.get_dump(dump_format="json")
+    assert any(":{" in d for d in ebst.get_dump())              # text dump lists the category set
+
+
+def test_categorical_pandas_category_dtype(eng, oracle):
+    import pandas as pd
+    X, score, rng = make_cat_data(5000, 37, 0.0)
+    df = pd.DataFrame({"a": X[:, 0], "b": X[:, 1], "c": X[:, 2],
+                       "k3": pd.Categorical(X[:, 3].astype(int)), "k20": pd.Categorical(X[:, 4].astype(int)),
+                       "k200": pd.Categorical(X[:, 5].astype(int))})
+    with pytest.raises(eng.XGBoostError):
+        eng.DMatrix(df, label=score)
+    codes = np.column_stack([X[:, :3]] + [df[c].cat.codes.to_numpy() for c in ("k3", "k20", "k200")]).astype(np.float32)
+    params = {"objective": "reg:squarederror", "max_depth": 4, "eta": 0.5}
+    obst, _ = oracle.train(params, codes, score, 3, is_cat=IS_CAT)
+    ebst = eng.train(params, eng.DMatrix(df, label=score, enable_categorical=True), num_boost_round=3, verbose_eval=False)
+    assert_same_model(ebst, obst)
+
+
+def test_categorical_invalid_codes_error(eng):
+    X = np.array([[0.0, 1.0], [1.0, 2.5]], np.float32)
+    dm = eng.DMatrix(X, label=[0, 1], feature_types=["q", "c"], enable_categorical=True)
+    with pytest.raises(eng.XGBoostError, match="category codes"):
+        dm._ensure_quantized(256)
+    with pytest.raises(eng.XGBoostError, match="enable_categorical"):
+        eng.DMatrix(X, feature_types=["q", "c"])

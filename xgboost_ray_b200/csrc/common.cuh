@@ -35,7 +35,8 @@ struct B2SplitWork {
   int32_t default_left;   // direction of the missing sentinel (only if feature has missing)
   int32_t has_missing;
   int32_t chunk_begin;    // prefix of ceil(seg_count / PART_CHUNK)
-  int32_t pad;
+  int32_t is_cat;         // categorical split: rows whose bin (= category code) has its bit set go RIGHT
+  uint32_t cat_bits[8];   // bit (b & 31) of word b >> 5
 };
 
 // candidate split written by the evaluation kernel, one per (node, group)
@@ -46,7 +47,8 @@ struct B2SplitCand {
   int32_t default_left;
   int64_t left_g, left_h; // fixed-point sums of the left child
   uint32_t order;        // enumeration order key for tie-breaking
-  int32_t pad;
+  int32_t is_cat;        // categorical candidate: bin = category for a one-hot split, -1 for a partition split
+  uint32_t cat_bits[8];  // categories that go right
 };
 
 struct B2EvalNode {
@@ -61,6 +63,8 @@ struct B2TreeNodeDev {
   float cond;
   float value;
   int32_t default_left;
+  int32_t cat_slot;      // -1 numeric split, else row of the model's category-set table ([slot][8] words)
+  int32_t pad;
 };
 
 // ---- device-resident control tables of the sync-free level loop (control_kernel.cu)
@@ -81,7 +85,8 @@ struct B2SegWork {  // generic chunked (segment, id) descriptor
   int32_t buf, pad0, pad1, pad2;
 };
 struct B2TreeDev {            // arrays of capacity max_nodes
-  int32_t *left, *right, *parent, *feature, *split_bin, *default_left;
+  int32_t *left, *right, *parent, *feature, *split_bin, *default_left, *split_type;
+  uint32_t* cat_bits;         // [max_nodes][8], written only for categorical splits
   float* loss_chg;
   long long *sum_g, *sum_h;   // fixed-point node totals
   float *leaf_weight, *leaf_value;
@@ -92,4 +97,5 @@ struct B2CtlParams { double mcw, lambda, alpha; float gamma, eta; };
 struct B2TrainParamDev {
   double min_child_weight, lambda, alpha;
   double inv_scale_g, inv_scale_h;
+  int32_t max_cat_to_onehot, max_cat_threshold;
 };

@@ -69,7 +69,7 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
     const int i = base + threadIdx.x;
     const bool in = i < n;
     B2SplitCand best; best.feature = -1; best.loss_chg = 0.f; best.order = 0xffffffffu; best.bin = 0; best.default_left = 0;
-    best.left_g = 0; best.left_h = 0;
+    best.left_g = 0; best.left_h = 0; best.is_cat = 0;
     B2EvalNode nd; nd.sum_g = 0; nd.sum_h = 0; nd.hist_index = 0; nd.root_gain = 0.f;
     B2NodeSeg sg; sg.nid = 0; sg.begin = 0; sg.count = 0; sg.buf = 0;
     bool expand = false;
@@ -99,13 +99,21 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
       const int nid = sg.nid;
       tree.left[nid] = l; tree.right[nid] = r; tree.feature[nid] = best.feature; tree.split_bin[nid] = best.bin;
       tree.default_left[nid] = best.default_left; tree.loss_chg[nid] = best.loss_chg;
+      tree.split_type[nid] = best.is_cat;
+      if (best.is_cat) {
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) tree.cat_bits[(size_t)nid * 8 + w8] = best.cat_bits[w8];
+      }
       tree.left[l] = -1; tree.right[l] = -1; tree.feature[l] = -1; tree.parent[l] = nid;
       tree.left[r] = -1; tree.right[r] = -1; tree.feature[r] = -1; tree.parent[r] = nid;
       const long long lg = best.left_g, lh = best.left_h, rg = nd.sum_g - lg, rh = nd.sum_h - lh;
       tree.sum_g[l] = lg; tree.sum_h[l] = lh; tree.sum_g[r] = rg; tree.sum_h[r] = rh;
       B2SplitWork sw;
       sw.seg_begin = sg.begin; sw.seg_count = sg.count; sw.feature = best.feature; sw.split_bin = best.bin;
-      sw.default_left = best.default_left; sw.has_missing = has_missing[best.feature]; sw.chunk_begin = chunk_begin; sw.pad = 0;
+      sw.default_left = best.default_left; sw.has_missing = has_missing[best.feature]; sw.chunk_begin = chunk_begin;
+      sw.is_cat = best.is_cat;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) sw.cat_bits[w8] = best.is_cat ? best.cat_bits[w8] : 0u;
       split_work[rank] = sw;
       pair_parent_hist[rank] = nd.hist_index;
       const double GL = __dmul_rn(__ll2double_rn(lg), inv_sg), HL = __dmul_rn(__ll2double_rn(lh), inv_sh);

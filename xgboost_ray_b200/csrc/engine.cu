@@ -34,8 +34,13 @@ int b2_launch_hist_tma(const void*, const void*, const int2*, const int32_t*, co
                        const B2LevelCtl*, int, int, int64_t, int, cudaStream_t);
 int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, const B2LevelCtl*, cudaStream_t);
 int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
-                          const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, const B2LevelCtl*, int, int,
-                          cudaStream_t);
+                          const uint8_t*, const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, int, const B2LevelCtl*,
+                          int, int, cudaStream_t);
+int b2_cat_ctas();
+int b2_launch_eval_cat_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, int, const int32_t*, const int32_t*,
+                              const int32_t*, int, B2TrainParamDev, B2SplitCand*, int, int, const B2LevelCtl*, int, int,
+                              cudaStream_t);
+int b2_launch_cat_stats(const float*, int64_t, int, float, const int32_t*, int, int32_t*, int, cudaStream_t);
 int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, int, cudaStream_t);
 int b2_part_chunk_rows();
 int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, const B2LevelCtl*, int, int32_t*,
@@ -61,8 +66,8 @@ int b2_launch_absmax(const float2*, int64_t, uint32_t*, int, cudaStream_t);
 int b2_launch_quant_exponent(const uint32_t*, int32_t*, cudaStream_t);
 int b2_launch_quantize(const float2*, int64_t, const int32_t*, int, int2*, int, cudaStream_t);
 int b2_launch_metric(int, int, const float*, const float*, const float*, int64_t, double*, int, cudaStream_t);
-int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, const int32_t*, int, int, int, float*, int,
-                      cudaStream_t);
+int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, const int32_t*, const uint32_t*, int, int, int,
+                      float*, int, cudaStream_t);
 int b2_launch_fill(float*, int64_t, float, int, cudaStream_t);
 int b2_launch_transform(int, int, float*, int64_t, int, cudaStream_t);
 int b2_extract_batch();
@@ -70,8 +75,8 @@ int b2_launch_extract_keys(const float*, int64_t, int, int, int, float, uint32_t
 size_t b2_sort_temp_bytes(int64_t);
 int b2_sketch_column(const uint32_t*, uint32_t*, int64_t, long long, void*, size_t, int32_t*, int32_t*, float*, long long*,
                      int32_t*, long long*, int, float*, int32_t*, float*, int32_t*, int, cudaStream_t);
-int b2_launch_bin(const float*, int64_t, int, float, const int32_t*, const float*, const int32_t*, int, uint8_t*, uint8_t*,
-                  int64_t, int, cudaStream_t);
+int b2_launch_bin(const float*, int64_t, int, float, const int32_t*, const float*, const int32_t*, const uint8_t*, int, uint8_t*,
+                  uint8_t*, int64_t, int, cudaStream_t);
 }
 
 namespace {
@@ -303,9 +308,12 @@ struct Matrix : HandleBase {
   std::vector<float> cut_vals, min_vals;
   std::vector<uint8_t> has_missing;
   std::vector<int32_t> nbins;
-  DevBuf<int32_t> d_group_first, d_group_size, d_feat_byte, d_cut_ptrs, d_nbins;
+  std::vector<uint8_t> is_cat;        // [F] 1 = categorical feature (B2_MatrixSetFeatureTypes); empty = all numeric
+  std::vector<int32_t> cat_feats;     // ids of the categorical features
+  DevBuf<int32_t> d_group_first, d_group_size, d_feat_byte, d_cut_ptrs, d_nbins, d_cat_feats;
   DevBuf<float> d_cut_vals;
-  DevBuf<uint8_t> d_has_missing;
+  DevBuf<uint8_t> d_has_missing, d_is_cat;
+  bool any_cat() const { return !cat_feats.empty(); }
   DevBuf<float> label, weight, base_margin;
   int64_t n_label = 0, n_weight = 0, n_base_margin = 0;
 };
@@ -342,6 +350,8 @@ void upload_cuts(Matrix* m) {
   upload(m->d_feat_byte, m->feat_byte, s); upload(m->d_cut_ptrs, m->cut_ptrs, s);
   upload(m->d_cut_vals, m->cut_vals, s); upload(m->d_nbins, m->nbins, s);
   upload(m->d_has_missing, m->has_missing, s);
+  if (m->is_cat.empty()) m->is_cat.assign(m->F, 0);
+  upload(m->d_is_cat, m->is_cat, s); upload(m->d_cat_feats, m->cat_feats, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
@@ -381,11 +391,16 @@ void make_cuts(Matrix* m, Comm* comm, int max_bin) {
   CUDA_CHECK(cudaMemsetAsync(d_tab.p, 0, tab_n * sizeof(int32_t), s));
   float* d_cuts = (float*)d_tab.p; int32_t* d_ncuts = d_tab.p + (size_t)F * 256;
   float* d_mins = (float*)(d_ncuts + F); int32_t* d_hasmiss = d_ncuts + 2 * (size_t)F;
+  if (m->is_cat.empty()) m->is_cat.assign(F, 0);
   for (int f0 = 0; f0 < F; f0 += B) {
     const int nf = std::min(B, F - f0);
+    bool any_numeric = false;
+    for (int j = 0; j < nf; ++j) any_numeric = any_numeric || !m->is_cat[f0 + j];
+    if (!any_numeric) continue;
     LAUNCH_CHECK(b2_launch_extract_keys(m->raw.p, m->n, F, f0, nf, m->missing, keys_local.p, n_pad, ctx->num_sms, s));
     for (int j = 0; j < nf; ++j) {
       const int f = f0 + j;
+      if (m->is_cat[f]) continue;   // categorical: cuts are the codes 0..max (below)
       const uint32_t* kin = keys_local.p + (size_t)j * n_pad;
       if (world > 1) {
         NCCL_CHECK(nccl()->AllGather(kin, keys_all.p, (size_t)n_pad, kNcclUint32, comm->comm, s));
@@ -401,7 +416,33 @@ void make_cuts(Matrix* m, Comm* comm, int max_bin) {
   allreduce(comm, d_tab.p, tab_n, kNcclInt32, kNcclSum, s);
   std::vector<int32_t> h_tab(tab_n);
   CUDA_CHECK(cudaMemcpyAsync(h_tab.data(), d_tab.p, tab_n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  // categorical features: global max code / has-missing / invalid flags (allreduce max)
+  const int n_cat = (int)m->cat_feats.size();
+  std::vector<int32_t> h_cat((size_t)std::max(n_cat, 1) * 3, 0);
+  DevBuf<int32_t> d_cat, d_catf;
+  if (n_cat > 0) {
+    for (int i = 0; i < n_cat; ++i) { h_cat[i * 3] = -1; h_cat[i * 3 + 1] = 0; h_cat[i * 3 + 2] = 0; }
+    d_cat.ensure((size_t)n_cat * 3); d_catf.ensure((size_t)n_cat);
+    CUDA_CHECK(cudaMemcpyAsync(d_cat.p, h_cat.data(), (size_t)n_cat * 3 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(d_catf.p, m->cat_feats.data(), (size_t)n_cat * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    LAUNCH_CHECK(b2_launch_cat_stats(m->raw.p, m->n, F, m->missing, d_catf.p, n_cat, d_cat.p, ctx->num_sms, s));
+    allreduce(comm, d_cat.p, (size_t)n_cat * 3, kNcclInt32, kNcclMax, s);
+    CUDA_CHECK(cudaMemcpyAsync(h_cat.data(), d_cat.p, (size_t)n_cat * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
   CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int i = 0; i < n_cat; ++i) {
+    const int f = m->cat_feats[i], mx = h_cat[i * 3], miss = h_cat[i * 3 + 1];
+    if (h_cat[i * 3 + 2] || (miss && mx > 254))
+      fail("categorical feature %d: category codes must be integers in [0, %d]%s", f, miss ? 254 : 255,
+           miss ? " (the feature has missing values; bin 255 is the missing sentinel)" : "");
+    int32_t* t = h_tab.data();
+    float* cuts_f = (float*)t + (size_t)f * 256;
+    const int nc = mx < 0 ? 1 : mx + 1;
+    for (int k = 0; k < nc; ++k) cuts_f[k] = (float)k;
+    t[(size_t)F * 256 + f] = nc;
+    ((float*)(t + (size_t)F * 256 + F))[f] = -1e-5f;
+    t[(size_t)F * 256 + 2 * (size_t)F + f] = miss;
+  }
   const float* h_cuts = (const float*)h_tab.data(); const int32_t* h_nc = h_tab.data() + (size_t)F * 256;
   const float* h_mins = (const float*)(h_nc + F); const int32_t* h_hm = h_nc + 2 * (size_t)F;
   m->cut_ptrs.assign(F + 1, 0);
@@ -424,7 +465,8 @@ void bin_matrix(Matrix* m) {
   m->col_stride = (std::max<int64_t>(m->n, 1) + 127) & ~(int64_t)127;
   m->bins_col.ensure((size_t)m->col_stride * m->F);
   LAUNCH_CHECK(b2_launch_bin(m->raw.p, m->n, m->F, m->missing, m->d_cut_ptrs.p, m->d_cut_vals.p, m->d_feat_byte.p,
-                             m->row_stride, m->bins.p, m->bins_col.p, m->col_stride, ctx->num_sms, s));
+                             m->any_cat() ? m->d_is_cat.p : nullptr, m->row_stride, m->bins.p, m->bins_col.p, m->col_stride,
+                             ctx->num_sms, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   m->has_tmap = b2_make_bins_tensor_map(m->tmap, m->bins.p, m->n, m->row_stride, 1) == 0 &&
                 b2_make_bins_tensor_map(m->tmap_tile, m->bins.p, m->n, m->row_stride, 64) == 0;
@@ -444,6 +486,7 @@ struct Params {
   int profile = 1;
   int num_feature = 0;
   int device = 0;
+  int max_cat_to_onehot = 4, max_cat_threshold = 64;   // xgboost defaults (src/tree/param.h)
 };
 
 struct TreeHost {
@@ -451,11 +494,14 @@ struct TreeHost {
   std::vector<float> cond, value, base_weight, loss_chg;
   std::vector<double> sum_hess;
   std::vector<uint8_t> default_left;
+  std::vector<uint8_t> split_type;        // 1 = categorical split
+  std::vector<uint32_t> cat_bits;         // [n][8] categories that go right (all zero for numeric nodes)
+  bool any_cat = false;
   int add(int par) {
     int id = (int)left.size();
     left.push_back(-1); right.push_back(-1); parent.push_back(par); feature.push_back(-1); split_bin.push_back(-1);
     cond.push_back(0.f); value.push_back(0.f); base_weight.push_back(0.f); loss_chg.push_back(0.f); sum_hess.push_back(0.0);
-    default_left.push_back(0);
+    default_left.push_back(0); split_type.push_back(0); cat_bits.insert(cat_bits.end(), 8, 0u);
     return id;
   }
   int size() const { return (int)left.size(); }
@@ -483,6 +529,7 @@ struct Booster : HandleBase {
   // device model cache for prediction
   DevBuf<B2TreeNodeDev> d_nodes; DevBuf<int32_t> d_tree_offset; int d_trees_synced = 0;
   std::vector<B2TreeNodeDev> h_nodes; std::vector<int32_t> h_tree_offset;
+  DevBuf<uint32_t> d_cat_table; std::vector<uint32_t> h_cat_table;   // [categorical nodes][8]
   // training state
   bool margin_ready = false;
   DevBuf<float> margin;          // [n][K]
@@ -492,7 +539,9 @@ struct Booster : HandleBase {
   DevBuf<long long> hist[2];
   DevBuf<long long> hist_build;     // reduce-scatter send buffer [shards][node_cap][slice] (only when shards > 1)
   DevBuf<B2SplitCand> d_cands_all;  // allgathered candidates [shards][nodes][cpn]
-  int shards = 1, log2_shards = 0, sp = 32, cpn = 1;
+  int shards = 1, log2_shards = 0, sp = 32, cpn = 1;   // cpn = candidates per node (numeric CTAs + categorical CTAs)
+  int cpn_num = 1;
+  DevBuf<uint32_t> t_cat;                  // [max_nodes][8] category sets of the tree being grown
   size_t slice_elems = 0;
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
@@ -583,6 +632,8 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
     else if (k == "profile") p->profile = i();
     else if (k == "num_feature") p->num_feature = i();
     else if (k == "device") p->device = i();
+    else if (k == "max_cat_to_onehot") p->max_cat_to_onehot = i();
+    else if (k == "max_cat_threshold") p->max_cat_threshold = i();
     else if (k == "max_bin") { if (max_bin_out) *max_bin_out = i(); }
     // unknown keys (nthread, tree_method, verbosity, ...) are accepted and ignored, like xgboost
   }
@@ -590,6 +641,8 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
   if (p->objective == kObjSoftprob && p->num_class < 2) fail("multi:softprob needs num_class >= 2");
   if (p->max_depth < 1 || p->max_depth > 14) fail("max_depth must be in [1, 14], got %d", p->max_depth);
   if (p->qbits < 8 || p->qbits > 24) fail("hist_qbits must be in [8, 24], got %d", p->qbits);
+  if (p->max_cat_to_onehot < 1) fail("max_cat_to_onehot must be >= 1, got %d", p->max_cat_to_onehot);
+  if (p->max_cat_threshold < 1) fail("max_cat_threshold must be >= 1, got %d", p->max_cat_threshold);
 }
 
 float base_margin_value(const Params& p) {
@@ -631,18 +684,19 @@ int pick_chunk_rows(Booster* b, int64_t rows) {
 // layout of the per-tree read-back block (device t_* buffers are copied verbatim into one pinned block)
 struct TreeLayout {
   size_t max_nodes, i32_count, f32_count, i64_count, bytes;
-  size_t off_f32, off_i64, off_qexp;
+  size_t off_f32, off_i64, off_qexp, off_cat;
 };
 TreeLayout tree_layout(int max_depth) {
   TreeLayout L;
   L.max_nodes = ((size_t)1 << (max_depth + 1));
-  L.i32_count = 6 * L.max_nodes + 2;
+  L.i32_count = 7 * L.max_nodes + 2;
   L.f32_count = 3 * L.max_nodes;
   L.i64_count = 2 * L.max_nodes + (size_t)max_depth + 2;
   L.off_f32 = L.i32_count * 4;
   L.off_i64 = (L.off_f32 + L.f32_count * 4 + 7) & ~(size_t)7;
   L.off_qexp = L.off_i64 + L.i64_count * 8;
-  L.bytes = L.off_qexp + 16;
+  L.off_cat = L.off_qexp + 16;
+  L.bytes = L.off_cat + L.max_nodes * 8 * sizeof(uint32_t);
   return L;
 }
 B2TreeDev tree_dev(Booster* b) {
@@ -650,7 +704,9 @@ B2TreeDev tree_dev(Booster* b) {
   B2TreeDev t;
   int32_t* i = b->t_i32.p; const size_t m = L.max_nodes;
   t.left = i; t.right = i + m; t.parent = i + 2 * m; t.feature = i + 3 * m; t.split_bin = i + 4 * m; t.default_left = i + 5 * m;
-  t.n_nodes = i + 6 * m;
+  t.split_type = i + 6 * m;
+  t.n_nodes = i + 7 * m;
+  t.cat_bits = b->t_cat.p;
   t.loss_chg = b->t_f32.p; t.leaf_weight = b->t_f32.p + m; t.leaf_value = b->t_f32.p + 2 * m;
   t.sum_g = b->t_i64.p; t.sum_h = b->t_i64.p + m;
   return t;
@@ -663,6 +719,7 @@ void ensure_ctl_tables(Booster* b) {
   const TreeLayout L = tree_layout(D);
   const size_t lcap = (size_t)1 << D, half = (size_t)1 << (D > 0 ? D - 1 : 0);
   b->t_i32.ensure(L.i32_count); b->t_f32.ensure(L.f32_count); b->t_i64.ensure(L.i64_count);
+  b->t_cat.ensure(b->train->any_cat() ? L.max_nodes * 8 : 8);
   b->d_ctl.ensure(3);
   for (int k = 0; k < 2; ++k) { b->d_seg[k].ensure(lcap); b->d_ev[k].ensure(lcap); }
   b->d_hist_work.ensure(half); b->d_split_work.ensure(half);
@@ -676,7 +733,8 @@ void ensure_ctl_tables(Booster* b) {
   b->log2_shards = 0; while ((1 << b->log2_shards) < b->shards) b->log2_shards++;
   b->sp = B2_GROUP_SLOTS / b->shards;
   b->slice_elems = (size_t)G * 2 * B2_BINS * b->sp;
-  b->cpn = (G * b->sp + 31) / 32;
+  b->cpn_num = (G * b->sp + 31) / 32;
+  b->cpn = b->cpn_num + (b->train->any_cat() ? b2_cat_ctas() : 0);
   b->hist[0].ensure(half * b->slice_elems); b->hist[1].ensure(half * b->slice_elems);
   if (b->shards > 1) { b->hist_build.ensure(half * b->node_elems); b->d_cands_all.ensure(half * b->cpn * b->shards); }
   b->d_cands.ensure(half * b->cpn);
@@ -736,6 +794,7 @@ void grow_tree(Booster* b, int k, int slot) {
   B2TrainParamDev dp;
   dp.min_child_weight = (double)p.min_child_weight; dp.lambda = (double)p.lambda; dp.alpha = (double)p.alpha;
   dp.inv_scale_g = dp.inv_scale_h = 1.0;
+  dp.max_cat_to_onehot = p.max_cat_to_onehot; dp.max_cat_threshold = p.max_cat_threshold;
   B2CtlParams cp; cp.mcw = dp.min_child_weight; cp.lambda = dp.lambda; cp.alpha = dp.alpha; cp.gamma = p.gamma; cp.eta = p.eta;
   const B2TreeDev tree = tree_dev(b);
   int32_t* d_n_leaves = tree.n_nodes + 1;
@@ -784,9 +843,15 @@ void grow_tree(Booster* b, int k, int slot) {
     const B2SplitCand* cands_for_decide = b->d_cands.p;
     if (can_split) {
       LAUNCH_CHECK(b2_launch_eval_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_group_first.p, m->d_group_size.p,
-                                         m->d_nbins.p, m->d_has_missing.p, b->d_qexp.p, p.qbits, dp, b->d_cands.p, ctl + cur, sh,
-                                         shard_rank, s));
+                                         m->d_nbins.p, m->d_has_missing.p, m->any_cat() ? m->d_is_cat.p : nullptr, b->d_qexp.p,
+                                         p.qbits, dp, b->d_cands.p, b->cpn, ctl + cur, sh, shard_rank, s));
       b->t.kernel_launches++;
+      if (m->any_cat()) {
+        LAUNCH_CHECK(b2_launch_eval_cat_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_cat_feats.p,
+                                               (int)m->cat_feats.size(), m->d_feat_byte.p, m->d_nbins.p, b->d_qexp.p, p.qbits, dp,
+                                               b->d_cands.p, b->cpn, b->cpn_num, ctl + cur, sh, shard_rank, s));
+        b->t.kernel_launches++;
+      }
       if (b->shards > 1) {   // every rank scanned only its own slots: gather the per-node candidates
         const size_t bytes = (size_t)max_nodes_level * b->cpn * sizeof(B2SplitCand);
         NCCL_CHECK(nccl()->AllGather(b->d_cands.p, b->d_cands_all.p, bytes, kNcclUint8, b->comm->comm, s));
@@ -858,6 +923,7 @@ void grow_tree(Booster* b, int k, int slot) {
   CUDA_CHECK(cudaMemcpyAsync(st + L.off_f32, b->t_f32.p, L.f32_count * 4, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaMemcpyAsync(st + L.off_i64, b->t_i64.p, L.i64_count * 8, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaMemcpyAsync(st + L.off_qexp, b->d_qexp.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (m->any_cat()) CUDA_CHECK(cudaMemcpyAsync(st + L.off_cat, b->t_cat.p, L.max_nodes * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
 }
 
 // after the stream is synchronised: turn read-back block `slot` into a host tree (A.7 bookkeeping)
@@ -869,7 +935,8 @@ void materialize_tree(Booster* b, int slot) {
   const float* f32 = (const float*)(st + L.off_f32);
   const long long* i64 = (const long long*)(st + L.off_i64);
   const int32_t* qexp = (const int32_t*)(st + L.off_qexp);
-  const int nn = i32[6 * mx];
+  const int nn = i32[7 * mx];
+  const uint32_t* cat = (const uint32_t*)(st + L.off_cat);
   if (nn < 1 || (size_t)nn > mx) fail("corrupt tree read-back (n_nodes=%d)", nn);
   const double inv_sg = ldexp(1.0, qexp[0] - p.qbits), inv_sh = ldexp(1.0, qexp[1] - p.qbits);
   TreeHost t;
@@ -881,6 +948,12 @@ void materialize_tree(Booster* b, int slot) {
     if (t.feature[i] >= 0) {
       const int f = t.feature[i], bin = i32[4 * mx + i];
       t.split_bin[i] = bin; t.default_left[i] = (uint8_t)i32[5 * mx + i]; t.loss_chg[i] = f32[i];
+      if (m->any_cat() && i32[6 * mx + i]) {
+        // categorical split: one-hot keeps the category as split condition, a partition split stores NaN (RegTree::ExpandCategorical)
+        t.split_type[i] = 1; t.any_cat = true;
+        for (int w8 = 0; w8 < 8; ++w8) t.cat_bits[(size_t)i * 8 + w8] = cat[(size_t)i * 8 + w8];
+        t.cond[i] = bin >= 0 ? (float)bin : NAN;
+      } else
       t.cond[i] = bin < 0 ? m->min_vals[f] : m->cut_vals[m->cut_ptrs[f] + bin];
       t.base_weight[i] = h_calc_weight(p, G, H);
       t.value[i] = t.base_weight[i];
@@ -903,14 +976,21 @@ void materialize_tree(Booster* b, int slot) {
 
 void sync_device_trees(Booster* b) {
   if (b->d_trees_synced == (int)b->trees.size()) return;
-  b->h_nodes.clear(); b->h_tree_offset.clear();
+  b->h_nodes.clear(); b->h_tree_offset.clear(); b->h_cat_table.clear();
   for (auto& t : b->trees) {
     b->h_tree_offset.push_back((int32_t)b->h_nodes.size());
-    for (int i = 0; i < t.size(); ++i)
-      b->h_nodes.push_back(B2TreeNodeDev{t.left[i], t.right[i], t.feature[i], t.cond[i], t.value[i], (int32_t)t.default_left[i]});
+    for (int i = 0; i < t.size(); ++i) {
+      int32_t cat_slot = -1;
+      if (t.feature[i] >= 0 && t.split_type[i]) {
+        cat_slot = (int32_t)(b->h_cat_table.size() / 8);
+        b->h_cat_table.insert(b->h_cat_table.end(), t.cat_bits.begin() + (size_t)i * 8, t.cat_bits.begin() + (size_t)i * 8 + 8);
+      }
+      b->h_nodes.push_back(B2TreeNodeDev{t.left[i], t.right[i], t.feature[i], t.cond[i], t.value[i], (int32_t)t.default_left[i],
+                                         cat_slot, 0});
+    }
   }
   cudaStream_t s = b->ctx->stream;
-  upload(b->d_nodes, b->h_nodes, s); upload(b->d_tree_offset, b->h_tree_offset, s);
+  upload(b->d_nodes, b->h_nodes, s); upload(b->d_tree_offset, b->h_tree_offset, s); upload(b->d_cat_table, b->h_cat_table, s);
   CUDA_CHECK(cudaStreamSynchronize(s));
   b->d_trees_synced = (int)b->trees.size();
 }
@@ -933,7 +1013,7 @@ void ensure_train_margin(Booster* b) {
   if (!b->trees.empty()) {
     if (!m->has_raw) fail("continuing training from existing trees needs the raw data of the train matrix (B2_MatrixEnsureRaw)");
     sync_device_trees(b);
-    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, 0, (int)b->trees.size(),
+    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, 0, (int)b->trees.size(),
                                    b->p.num_class, b->margin.p, b->ctx->num_sms, b->ctx->stream));
   }
   b->margin_ready = true;
@@ -1000,7 +1080,7 @@ float* eval_margin(Booster* b, Matrix* m) {
   const int nt = (int)b->trees.size();
   if (c->n_trees_applied < nt) {
     sync_device_trees(b);
-    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, c->n_trees_applied, nt, K,
+    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, c->n_trees_applied, nt, K,
                                    c->margin.p, b->ctx->num_sms, b->ctx->stream));
     c->n_trees_applied = nt;
   }
@@ -1094,6 +1174,22 @@ int B2_MatrixSetFloatInfo(B2Handle mh, const char* field, const float* values, i
   *cnt = len;
   API_END
 }
+int B2_MatrixSetFeatureTypes(B2Handle mh, const uint8_t* is_cat, int32_t len) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  if (m->quantized) fail("feature types must be set before the matrix is quantised");
+  if (len != m->F) fail("feature types: %d entries for %d features", len, m->F);
+  m->is_cat.assign(is_cat, is_cat + len);
+  m->cat_feats.clear();
+  for (int f = 0; f < m->F; ++f) { m->is_cat[f] = m->is_cat[f] ? 1 : 0; if (m->is_cat[f]) m->cat_feats.push_back(f); }
+  API_END
+}
+int B2_MatrixGetFeatureTypes(B2Handle mh, uint8_t* is_cat) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  for (int f = 0; f < m->F; ++f) is_cat[f] = m->is_cat.empty() ? 0 : m->is_cat[f];
+  API_END
+}
 int B2_MatrixNumRow(B2Handle mh, int64_t* out) { API_BEGIN *out = from_handle<Matrix>(mh, kMatrix, "matrix")->n; API_END }
 int B2_MatrixNumCol(B2Handle mh, int32_t* out) { API_BEGIN *out = from_handle<Matrix>(mh, kMatrix, "matrix")->F; API_END }
 
@@ -1108,6 +1204,7 @@ int B2_MatrixQuantize(B2Handle mh, B2Handle commh, int32_t max_bin, B2Handle ref
     if (!r->quantized) fail("reference matrix is not quantised");
     if (r->F != m->F) fail("reference matrix has %d features, this one %d", r->F, m->F);
     m->cut_ptrs = r->cut_ptrs; m->cut_vals = r->cut_vals; m->min_vals = r->min_vals; m->has_missing = r->has_missing; m->max_bin = r->max_bin;
+    m->is_cat = r->is_cat; m->cat_feats = r->cat_feats;
   } else {
     make_cuts(m, comm, max_bin);
   }
@@ -1229,7 +1326,7 @@ int B2_BoosterPredict(B2Handle bh, B2Handle mh, int32_t output_margin, int32_t t
   DevBuf<float> tmp; tmp.ensure((size_t)std::max<int64_t>(out_len, 1));
   init_margin(b, tmp.p, m);
   sync_device_trees(b);
-  LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, tree_begin, tree_end, K, tmp.p,
+  LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, tree_begin, tree_end, K, tmp.p,
                                  b->ctx->num_sms, s));
   if (!output_margin) LAUNCH_CHECK(b2_launch_transform(b->p.objective, K, tmp.p, m->n, b->ctx->num_sms, s));
   if (out_len > 0) CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, out_len * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1299,6 +1396,28 @@ int B2_BoosterAddTree(B2Handle bh, int32_t n_nodes, const int32_t* left, const i
   }
   b->trees.push_back(std::move(t));
   b->margin_ready = false;
+  API_END
+}
+int B2_BoosterGetTreeCategories(B2Handle bh, int32_t tree, uint8_t* split_type, uint32_t* cat_bits) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  if (tree < 0 || tree >= (int)b->trees.size()) fail("tree index %d out of range", tree);
+  const TreeHost& t = b->trees[tree]; const size_t n = t.size();
+  memcpy(split_type, t.split_type.data(), n); memcpy(cat_bits, t.cat_bits.data(), n * 8 * sizeof(uint32_t));
+  API_END
+}
+int B2_BoosterSetTreeCategories(B2Handle bh, int32_t tree, const uint8_t* split_type, const uint32_t* cat_bits) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  if (tree < 0 || tree >= (int)b->trees.size()) fail("tree index %d out of range", tree);
+  TreeHost& t = b->trees[tree]; const size_t n = t.size();
+  for (size_t i = 0; i < n; ++i) {
+    t.split_type[i] = split_type[i] ? 1 : 0;
+    if (t.split_type[i]) t.any_cat = true;
+    for (int w8 = 0; w8 < 8; ++w8) t.cat_bits[i * 8 + w8] = split_type[i] ? cat_bits[i * 8 + w8] : 0u;
+  }
+  b->d_trees_synced = 0; b->margin_ready = false;
+  for (auto& kv : b->eval_cache) if (kv.second) kv.second->n_trees_applied = 0, kv.second->n = -1;
   API_END
 }
 int B2_BoosterGetTimers(B2Handle bh, int32_t reset, char* out, int64_t out_cap) {

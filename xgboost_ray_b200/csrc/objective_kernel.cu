@@ -149,9 +149,12 @@ __global__ void metric_kernel(int metric, int K, const float* __restrict__ margi
 
 // A.9 traversal on raw floats: x < cond -> left, missing -> default.  nodes of all trees are
 // concatenated; tree_offset[t] is the first node of tree t; tree t adds to class t % K.
+// Categorical node (cat_slot >= 0; common/categorical.h Decision): category in the node's set -> right;
+// not in the set, negative or beyond the set -> left.
 __global__ void predict_kernel(const float* __restrict__ X, int64_t n, int F, float missing, int missing_is_nan,
                                const B2TreeNodeDev* __restrict__ nodes, const int32_t* __restrict__ tree_offset,
-                               int tree_begin, int tree_end, int K, float* __restrict__ out) {
+                               const uint32_t* __restrict__ cat_table, int tree_begin, int tree_end, int K,
+                               float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float* x = X + i * F;
     for (int t = tree_begin; t < tree_end; ++t) {
@@ -161,7 +164,12 @@ __global__ void predict_kernel(const float* __restrict__ X, int64_t n, int F, fl
       while (nd.feature >= 0) {
         const float v = x[nd.feature];
         const bool miss = isnan(v) || (!missing_is_nan && v == missing);
-        nid = miss ? (nd.default_left ? nd.left : nd.right) : (v < nd.cond ? nd.left : nd.right);
+        if (miss) nid = nd.default_left ? nd.left : nd.right;
+        else if (nd.cat_slot >= 0) {
+          bool in_set = false;
+          if (v >= 0.0f && v < 256.0f) { const int c = (int)v; in_set = (cat_table[(size_t)nd.cat_slot * 8 + (c >> 5)] >> (c & 31)) & 1u; }
+          nid = in_set ? nd.right : nd.left;
+        } else nid = v < nd.cond ? nd.left : nd.right;
         nd = tn[nid];
       }
       out[i * K + (t % K)] += nd.value;
@@ -230,11 +238,11 @@ int b2_launch_metric(int metric, int K, const float* margin, const float* label,
   return (int)cudaGetLastError();
 }
 int b2_launch_predict(const float* X, int64_t n, int F, float missing, const B2TreeNodeDev* nodes,
-                      const int32_t* tree_offset, int tree_begin, int tree_end, int K, float* out, int num_sms,
-                      cudaStream_t s) {
+                      const int32_t* tree_offset, const uint32_t* cat_table, int tree_begin, int tree_end, int K, float* out,
+                      int num_sms, cudaStream_t s) {
   if (n <= 0 || tree_end <= tree_begin) return 0;
   b2::predict_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(X, n, F, missing, missing != missing ? 1 : 0, nodes, tree_offset,
-                                                         tree_begin, tree_end, K, out);
+                                                         cat_table, tree_begin, tree_end, K, out);
   return (int)cudaGetLastError();
 }
 int b2_launch_fill(float* out, int64_t n, float v, int num_sms, cudaStream_t s) {

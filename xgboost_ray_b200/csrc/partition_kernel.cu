@@ -40,7 +40,10 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       const bool valid = r < nrows;
       rid[it] = valid ? __ldg(ridx_in + w.seg_begin + row0 + r) : 0;
       int b = valid ? (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid[it]) : 0;
-      bool l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : (b <= w.split_bin);
+      bool l;
+      if (w.has_missing && b == B2_MISSING_BIN) l = w.default_left != 0;
+      else if (w.is_cat) l = ((__ldg(&work[lo].cat_bits[b >> 5]) >> (b & 31)) & 1u) == 0u;   // category in the set -> right
+      else l = b <= w.split_bin;
       left[it] = valid && l;
       bal[it] = __ballot_sync(0xffffffffu, left[it]);
       if (lane == 0) s_warp_left[warp][it] = __popc(bal[it]);

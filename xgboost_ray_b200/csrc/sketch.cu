@@ -139,18 +139,39 @@ prune_cuts_kernel(const float* __restrict__ uval, const long long* __restrict__ 
   }
 }
 
+// Categorical columns (HistogramCuts::AddCategories, src/common/quantile.cc): the cuts are the codes 0..max, so
+// the only statistics needed are the largest code, whether a value is missing and whether a value is not a
+// valid code.  stats [n_cat][3] int32 = {max code (init -1), has_missing, invalid}; merged with an allreduce(max).
+__global__ void cat_stats_kernel(const float* __restrict__ X, int64_t n, int F, float missing, int missing_is_nan,
+                                 const int32_t* __restrict__ cat_feats, int n_cat, int32_t* __restrict__ stats) {
+  const int64_t total = n * n_cat;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = e / n_cat; const int ci = (int)(e - row * n_cat);
+    const float x = X[row * F + cat_feats[ci]];
+    if (is_missing(x, missing, missing_is_nan)) { if (stats[ci * 3 + 1] == 0) atomicMax(&stats[ci * 3 + 1], 1); continue; }
+    if (!(x >= 0.0f) || x > 255.0f || x != (float)(int)x) { atomicMax(&stats[ci * 3 + 2], 1); continue; }
+    const int c = (int)x;
+    if (stats[ci * 3] < c) atomicMax(&stats[ci * 3], c);
+  }
+}
+
 // bin = upper_bound(cuts_f, x) clamped; missing -> 255.  One thread per matrix element.
+// Categorical feature: bin = category code (clamped to the codes the cuts know).
 __global__ void bin_kernel(const float* __restrict__ X, int64_t n, int F, float missing, int missing_is_nan,
                            const int32_t* __restrict__ cut_ptrs, const float* __restrict__ cut_vals,
-                           const int32_t* __restrict__ feat_byte, int row_stride, uint8_t* __restrict__ bins,
-                           uint8_t* __restrict__ bins_col, int64_t col_stride) {
+                           const int32_t* __restrict__ feat_byte, const uint8_t* __restrict__ is_cat, int row_stride,
+                           uint8_t* __restrict__ bins, uint8_t* __restrict__ bins_col, int64_t col_stride) {
   const int64_t total = n * F;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = e / F; const int f = (int)(e - row * F);
     const float x = X[e];
     int b;
     if (is_missing(x, missing, missing_is_nan)) b = B2_MISSING_BIN;
-    else {
+    else if (is_cat && is_cat[f]) {
+      const int nf = cut_ptrs[f + 1] - cut_ptrs[f];
+      b = x >= 0.0f ? (x > 255.0f ? 255 : (int)x) : 0;
+      if (b >= nf) b = nf - 1;
+    } else {
       const int p0 = cut_ptrs[f], nf = cut_ptrs[f + 1] - p0;
       const float* cv = cut_vals + p0;
       int lo = 0, hi = nf;
@@ -214,11 +235,19 @@ int b2_sketch_column(const uint32_t* keys_in, uint32_t* keys_sorted, int64_t n_t
 }
 
 int b2_launch_bin(const float* X, int64_t n, int F, float missing, const int32_t* cut_ptrs, const float* cut_vals,
-                  const int32_t* feat_byte, int row_stride, uint8_t* bins, uint8_t* bins_col, int64_t col_stride, int num_sms,
-                  cudaStream_t s) {
+                  const int32_t* feat_byte, const uint8_t* is_cat, int row_stride, uint8_t* bins, uint8_t* bins_col,
+                  int64_t col_stride, int num_sms, cudaStream_t s) {
   if (n <= 0) return 0;
   b2::bin_kernel<<<sk_grid(n * F, num_sms), 256, 0, s>>>(X, n, F, missing, missing != missing ? 1 : 0, cut_ptrs, cut_vals,
-                                                        feat_byte, row_stride, bins, bins_col, col_stride);
+                                                        feat_byte, is_cat, row_stride, bins, bins_col, col_stride);
+  return (int)cudaGetLastError();
+}
+// stats must be initialised to {-1, 0, 0} per categorical feature
+int b2_launch_cat_stats(const float* X, int64_t n, int F, float missing, const int32_t* cat_feats, int n_cat, int32_t* stats,
+                        int num_sms, cudaStream_t s) {
+  if (n <= 0 || n_cat <= 0) return 0;
+  b2::cat_stats_kernel<<<sk_grid(n * n_cat, num_sms), 256, 0, s>>>(X, n, F, missing, missing != missing ? 1 : 0, cat_feats, n_cat,
+                                                                  stats);
   return (int)cudaGetLastError();
 }
 }

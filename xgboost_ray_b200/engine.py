@@ -47,6 +47,8 @@ ABI = {
     "B2_CommFree": (C.c_int, [_H]),
     "B2_MatrixCreateFromDense": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
     "B2_MatrixSetFloatInfo": (C.c_int, [_H, C.c_char_p, _FP, C.c_int64]),
+    "B2_MatrixSetFeatureTypes": (C.c_int, [_H, _BP, C.c_int32]),
+    "B2_MatrixGetFeatureTypes": (C.c_int, [_H, _BP]),
     "B2_MatrixNumRow": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "B2_MatrixNumCol": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "B2_MatrixQuantize": (C.c_int, [_H, _H, C.c_int32, _H, C.c_int32]),
@@ -66,6 +68,8 @@ ABI = {
     "B2_BoosterTreeNumNodes": (C.c_int, [_H, C.c_int32, _IP]),
     "B2_BoosterGetTree": (C.c_int, [_H, C.c_int32, _IP, _IP, _IP, _IP, _IP, _FP, _BP, _FP, _FP, _FP, _DP]),
     "B2_BoosterAddTree": (C.c_int, [_H, C.c_int32, _IP, _IP, _IP, _IP, _IP, _FP, _BP, _FP, _FP, _FP, _DP]),
+    "B2_BoosterGetTreeCategories": (C.c_int, [_H, C.c_int32, _BP, C.POINTER(C.c_uint32)]),
+    "B2_BoosterSetTreeCategories": (C.c_int, [_H, C.c_int32, _BP, C.POINTER(C.c_uint32)]),
     "B2_BoosterGetTimers": (C.c_int, [_H, C.c_int32, C.c_char_p, C.c_int64]),
     "B2_BoosterCancel": (C.c_int, [_H]),
     "B2_BoosterFree": (C.c_int, [_H]),
@@ -194,12 +198,27 @@ class DMatrix:
     def __init__(self, data, label=None, weight=None, base_margin=None, missing=None, feature_names=None,
                  feature_types=None, nthread=None, enable_categorical=False, max_bin=None, ref=None,
                  device=None, **kwargs):
-        if enable_categorical:
-            raise XGBoostError("categorical features are not supported by the B200 engine yet")
         if hasattr(data, "values") and not isinstance(data, np.ndarray):  # pandas
             if feature_names is None and hasattr(data, "columns"):
                 feature_names = [str(c) for c in data.columns]
-            data = data.values
+            cat_cols = [str(dt) == "category" for dt in getattr(data, "dtypes", [])]
+            if any(cat_cols):
+                # xgboost's pandas adapter: category dtype -> codes, -1 (NaN) -> missing; needs enable_categorical
+                if not enable_categorical:
+                    raise XGBoostError("DataFrame has `category` columns: pass enable_categorical=True")
+                cols = []
+                for c, is_c in zip(data.columns, cat_cols):
+                    if is_c:
+                        codes = data[c].cat.codes.to_numpy().astype(np.float32)
+                        codes[codes < 0] = np.nan
+                        cols.append(codes)
+                    else:
+                        cols.append(data[c].to_numpy().astype(np.float32))
+                if feature_types is None:
+                    feature_types = ["c" if is_c else "q" for is_c in cat_cols]
+                data = np.stack(cols, axis=1) if cols else np.zeros((len(data), 0), np.float32)
+            else:
+                data = data.values
         data = np.asarray(data)
         if data.ndim == 1:
             data = data.reshape(-1, 1)
@@ -209,7 +228,8 @@ class DMatrix:
         self.missing = float("nan") if missing is None else float(missing)
         self.device = _default_device() if device is None else int(device)
         self.feature_names = list(feature_names) if feature_names is not None else None
-        self.feature_types = feature_types
+        self.feature_types = list(feature_types) if feature_types is not None else None
+        self.enable_categorical = bool(enable_categorical)
         self.max_bin = max_bin
         self.ref = ref
         self._quantized = False
@@ -221,6 +241,14 @@ class DMatrix:
         n, f = self._host.shape
         _check(lib().B2_MatrixCreateFromDense(_fp(self._host), n, f, self.missing, self.device, C.byref(h)))
         self.handle = h.value
+        if self.feature_types is not None:
+            if len(self.feature_types) != f:
+                raise XGBoostError("feature_types has %d entries for %d features" % (len(self.feature_types), f))
+            is_cat = np.array([1 if str(t) == "c" else 0 for t in self.feature_types], np.uint8)
+            if is_cat.any():
+                if not enable_categorical:
+                    raise XGBoostError("feature_types marks categorical features: pass enable_categorical=True")
+                _check(lib().B2_MatrixSetFeatureTypes(self.handle, _bp(is_cat), f))
         self.set_info(label=label, weight=weight, base_margin=base_margin)
 
     # -- info
@@ -343,7 +371,7 @@ _TREE_FIELDS = ("left", "right", "parent", "split_feature", "split_bin", "split_
                 "base_weight", "loss_chg", "sum_hess")
 _ENGINE_KEYS = ("objective", "num_class", "max_depth", "eta", "learning_rate", "gamma", "min_split_loss",
                 "min_child_weight", "lambda", "reg_lambda", "alpha", "reg_alpha", "base_score", "hist_qbits",
-                "hist_chunk_rows", "profile")
+                "hist_chunk_rows", "profile", "max_cat_to_onehot", "max_cat_threshold")
 
 
 def _params_dict(params):
@@ -362,6 +390,7 @@ class Booster:
         self._trees = []          # list of dict of numpy arrays (host copy for pickling / dumps)
         self._attrs = {}
         self.feature_names = None
+        self.feature_types = None
         self.n_features = None
         self.best_iteration = None
         self.best_score = None
@@ -395,6 +424,8 @@ class Booster:
         self.n_features = dtrain.num_col()
         if self.feature_names is None:
             self.feature_names = dtrain.feature_names
+        if getattr(self, "feature_types", None) is None:
+            self.feature_types = dtrain.feature_types
         if old_trees:
             dtrain._ensure_raw()
             self._push_trees(old_trees)
@@ -422,6 +453,13 @@ class Booster:
                 _bp(np.ascontiguousarray(t["default_left"], np.uint8)), _fp(_f32c(t["value"])),
                 _fp(_f32c(t["base_weight"])), _fp(_f32c(t["loss_chg"])),
                 np.ascontiguousarray(t["sum_hess"], np.float64).ctypes.data_as(_DP)))
+            st = t.get("split_type")
+            if st is not None and np.any(st):
+                nt = C.c_int32(0)
+                _check(lib().B2_BoosterNumTrees(self.handle, C.byref(nt)))
+                _check(lib().B2_BoosterSetTreeCategories(
+                    self.handle, nt.value - 1, _bp(np.ascontiguousarray(st, np.uint8)),
+                    np.ascontiguousarray(t["cat_bits"], np.uint32).ctypes.data_as(C.POINTER(C.c_uint32))))
 
     def _free(self):
         if self.handle:
@@ -462,7 +500,10 @@ class Booster:
                  split_feature=np.zeros(n, np.int32), split_bin=np.zeros(n, np.int32),
                  split_cond=np.zeros(n, np.float32), default_left=np.zeros(n, np.uint8),
                  value=np.zeros(n, np.float32), base_weight=np.zeros(n, np.float32),
-                 loss_chg=np.zeros(n, np.float32), sum_hess=np.zeros(n, np.float64))
+                 loss_chg=np.zeros(n, np.float32), sum_hess=np.zeros(n, np.float64),
+                 split_type=np.zeros(n, np.uint8), cat_bits=np.zeros((n, 8), np.uint32))
+        _check(lib().B2_BoosterGetTreeCategories(self.handle, i, _bp(t["split_type"]),
+                                                 t["cat_bits"].ctypes.data_as(C.POINTER(C.c_uint32))))
         _check(lib().B2_BoosterGetTree(self.handle, i, _ip(t["left"]), _ip(t["right"]), _ip(t["parent"]),
                                        _ip(t["split_feature"]), _ip(t["split_bin"]), _fp(t["split_cond"]),
                                        _bp(t["default_left"]), _fp(t["value"]), _fp(t["base_weight"]),
@@ -582,9 +623,15 @@ class Booster:
         for i, t in enumerate(self.get_trees()):
             n = len(t["left"])
             leaf = t["split_feature"] < 0
+            st = t.get("split_type", np.zeros(n, np.uint8))
+            cats, cat_nodes, cat_segs, cat_sizes = [], [], [], []
+            for nid in np.nonzero(np.asarray(st) & ~leaf)[0]:
+                c = _cat_list(t["cat_bits"][nid])
+                cat_nodes.append(int(nid)); cat_segs.append(len(cats)); cat_sizes.append(len(c)); cats.extend(c)
             trees.append({
                 "base_weights": [float(x) for x in t["base_weight"]],
-                "categories": [], "categories_nodes": [], "categories_segments": [], "categories_sizes": [],
+                "categories": cats, "categories_nodes": cat_nodes, "categories_segments": cat_segs,
+                "categories_sizes": cat_sizes,
                 "default_left": [int(x) for x in t["default_left"]],
                 "id": i,
                 "left_children": [int(x) for x in t["left"]],
@@ -593,7 +640,7 @@ class Booster:
                 "right_children": [int(x) for x in t["right"]],
                 "split_conditions": [float(v) if lf else float(c) for lf, v, c in zip(leaf, t["value"], t["split_cond"])],
                 "split_indices": [int(x) if x >= 0 else 0 for x in t["split_feature"]],
-                "split_type": [0] * n,
+                "split_type": [int(x) for x in st],
                 "sum_hessian": [float(x) for x in t["sum_hess"]],
                 "split_bins": [int(x) for x in t["split_bin"]],
                 "tree_param": {"num_deleted": "0", "num_feature": str(self.n_features), "num_nodes": str(n),
@@ -604,7 +651,7 @@ class Booster:
             "learner": {
                 "attributes": dict(self._attrs),
                 "feature_names": list(self.feature_names or []),
-                "feature_types": [],
+                "feature_types": list(self.feature_types or []),
                 "gradient_booster": {"name": "gbtree", "model": {
                     "gbtree_model_param": {"num_parallel_tree": "1", "num_trees": str(len(trees))},
                     "iteration_indptr": list(range(0, len(trees) + 1, K)) if K else [],
@@ -645,6 +692,7 @@ class Booster:
         self.params = params
         self.n_features = int(L["learner_model_param"]["num_feature"])
         self.feature_names = L.get("feature_names") or None
+        self.feature_types = L.get("feature_types") or None
         self._attrs = dict(L.get("attributes", {}))
         self._trees = []
         for t in L["gradient_booster"]["model"]["trees"]:
@@ -652,7 +700,16 @@ class Booster:
             leaf = left < 0
             sc = np.asarray(t["split_conditions"], np.float32)
             parent = np.asarray([p if p != 2147483647 else -1 for p in t["parents"]], np.int32)
+            st = np.asarray(t.get("split_type", [0] * len(left)), np.uint8)
+            bits = np.zeros((len(left), 8), np.uint32)
+            for nid, seg, size in zip(t.get("categories_nodes", []), t.get("categories_segments", []),
+                                      t.get("categories_sizes", [])):
+                for c in t["categories"][seg:seg + size]:
+                    if not 0 <= int(c) < 256:
+                        raise XGBoostError("model has category %r outside [0, 255]" % (c,))
+                    bits[nid, int(c) >> 5] |= np.uint32(1 << (int(c) & 31))
             self._trees.append(dict(
+                split_type=st, cat_bits=bits,
                 left=left, right=np.asarray(t["right_children"], np.int32), parent=parent,
                 split_feature=np.where(leaf, -1, np.asarray(t["split_indices"], np.int32)).astype(np.int32),
                 split_bin=np.asarray(t.get("split_bins", [-1] * len(left)), np.int32),
@@ -673,6 +730,7 @@ class Booster:
         self._trees = []
         self._attrs = {}
         self.feature_names = None
+        self.feature_types = None
         self.n_features = None
         self.load_model(state["raw"])
         self.best_iteration = state.get("best_iteration")
@@ -739,6 +797,16 @@ def _fname(names, f):
     return names[f] if names else "f%d" % f
 
 
+def _cat_list(words):
+    """Sorted categories of a 256-bit category set (8 uint32 words, LSB first)."""
+    return [b for b in range(256) if (int(words[b >> 5]) >> (b & 31)) & 1]
+
+
+def _is_cat_node(t, nid):
+    st = t.get("split_type")
+    return st is not None and bool(st[nid])
+
+
 def _dump_json(t, nid, depth, names, with_stats):
     if t["split_feature"][nid] < 0:
         d = {"nodeid": int(nid), "leaf": float(t["value"][nid])}
@@ -746,9 +814,14 @@ def _dump_json(t, nid, depth, names, with_stats):
             d["cover"] = float(t["sum_hess"][nid])
         return d
     l, r = int(t["left"][nid]), int(t["right"][nid])
-    d = {"nodeid": int(nid), "depth": depth, "split": _fname(names, int(t["split_feature"][nid])),
-         "split_condition": float(t["split_cond"][nid]), "yes": l, "no": r,
-         "missing": l if t["default_left"][nid] else r}
+    if _is_cat_node(t, nid):   # xgboost's dump: the listed categories go to "yes" = the right child
+        d = {"nodeid": int(nid), "depth": depth, "split": _fname(names, int(t["split_feature"][nid])),
+             "split_condition": _cat_list(t["cat_bits"][nid]), "yes": r, "no": l,
+             "missing": l if t["default_left"][nid] else r}
+    else:
+        d = {"nodeid": int(nid), "depth": depth, "split": _fname(names, int(t["split_feature"][nid])),
+             "split_condition": float(t["split_cond"][nid]), "yes": l, "no": r,
+             "missing": l if t["default_left"][nid] else r}
     if with_stats:
         d["gain"] = float(t["loss_chg"][nid])
         d["cover"] = float(t["sum_hess"][nid])
@@ -765,9 +838,14 @@ def _dump_text(t, nid, depth, names, with_stats, lines):
         lines.append(s + "\n")
         return
     l, r = int(t["left"][nid]), int(t["right"][nid])
-    s = "%s%d:[%s<%.9g] yes=%d,no=%d,missing=%d" % (ind, nid, _fname(names, int(t["split_feature"][nid])),
-                                                   float(t["split_cond"][nid]), l, r,
-                                                   l if t["default_left"][nid] else r)
+    if _is_cat_node(t, nid):
+        s = "%s%d:[%s:{%s}] yes=%d,no=%d,missing=%d" % (ind, nid, _fname(names, int(t["split_feature"][nid])),
+                                                        ",".join(str(c) for c in _cat_list(t["cat_bits"][nid])), r, l,
+                                                        l if t["default_left"][nid] else r)
+    else:
+        s = "%s%d:[%s<%.9g] yes=%d,no=%d,missing=%d" % (ind, nid, _fname(names, int(t["split_feature"][nid])),
+                                                       float(t["split_cond"][nid]), l, r,
+                                                       l if t["default_left"][nid] else r)
     if with_stats:
         s += ",gain=%.9g,cover=%.9g" % (float(t["loss_chg"][nid]), float(t["sum_hess"][nid]))
     lines.append(s + "\n")
