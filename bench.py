@@ -33,7 +33,16 @@ WORKLOADS = {   # SURVEY.md 8(d); C3 is the configuration the metric is quoted o
     "C2": {"rows": 11_000_000, "cols": 28, "depth": 6, "objective": "binary:logistic"},
     "C3": {"rows": 10_000_000, "cols": 100, "depth": 8, "objective": "reg:squarederror"},
     "C4": {"rows": 100_000_000, "cols": 50, "depth": 10, "objective": "binary:logistic"},
+    "C5": {"rows": 50_000_000, "cols": 200, "depth": 6, "objective": "multi:softprob", "num_class": 10},
 }
+
+
+def feature_types(workload, cols):
+    """C5: the last quarter of the columns is categorical with cardinalities 4/16/64/256 cycling."""
+    if workload != "C5":
+        return None
+    n_cat = cols // 4
+    return ["q"] * (cols - n_cat) + ["c"] * n_cat
 
 
 def synth_block(block, rows, cols, seed=1234, workload="C3"):
@@ -51,6 +60,23 @@ def synth_block(block, rows, cols, seed=1234, workload="C3"):
             y = y + np.sin(X[:, 10])
         y = y + rng.normal(scale=0.1, size=rows).astype(np.float32)
         return X, y.astype(np.float32)
+    if workload == "C5":
+        n_cat = cols // 4
+        n_num = cols - n_cat
+        X = np.empty((rows, cols), np.float32)
+        X[:, :n_num] = rng.random((rows, n_num), dtype=np.float32) * np.float32(10.0)
+        cards = [(4, 16, 64, 256)[j % 4] for j in range(n_cat)]
+        for j, c in enumerate(cards):
+            X[:, n_num + j] = rng.integers(0, c, size=rows)
+        wrng = np.random.default_rng(seed + 5)
+        k_num, k_cat = min(20, n_num), min(8, n_cat)
+        W = wrng.normal(size=(k_num, 10)).astype(np.float32)
+        score = (X[:, :k_num] - np.float32(5.0)) @ W
+        for j in range(k_cat):
+            eff = wrng.normal(scale=4.0, size=(cards[j], 10)).astype(np.float32)
+            score += eff[X[:, n_num + j].astype(np.int64)]
+        score += rng.normal(scale=1.0, size=score.shape).astype(np.float32)
+        return X, score.argmax(axis=1).astype(np.float32)
     if workload == "C2":
         X = rng.standard_normal((rows, cols), dtype=np.float32)
         heavy = cols - (3 * cols) // 4
@@ -148,8 +174,11 @@ def run_reference(args, rank, world):
     cores = O.use_all_cores()
     X, y = synth_shard(args.rows, args.cols, 0, 1, workload=args.workload)
     params = dict(PARAMS, max_depth=args.depth, hist_qbits=0, objective=args.objective)   # qbits=0: float64 histograms = XGBoost CPU hist
+    if args.num_class:
+        params["num_class"] = args.num_class
+    is_cat = [1 if t == "c" else 0 for t in args.feature_types] if args.feature_types else None
     t0 = time.time()
-    cuts = O.Cuts.from_data(X, 256)
+    cuts = O.Cuts.from_data(X, 256, is_cat=is_cat)
     bins = cuts.bin(X)
     t_quant = time.time() - t0
     bst = O.Booster(params, cuts)
@@ -195,6 +224,8 @@ def main():
     args.cols = args.cols or wl["cols"]
     args.depth = args.depth or wl["depth"]
     args.objective = wl["objective"]
+    args.num_class = wl.get("num_class")
+    args.feature_types = feature_types(args.workload, args.cols)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -211,6 +242,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     params = dict(PARAMS, max_depth=args.depth, profile=args.profile, objective=args.objective)
+    if args.num_class:
+        params["num_class"] = args.num_class
+    dm_kw = {"feature_types": args.feature_types, "enable_categorical": True} if args.feature_types else {}
     if args.qbits is not None:
         params["hist_qbits"] = args.qbits
 
@@ -239,7 +273,7 @@ def main():
         # ================= device-resident arm: matrix quantised and resident before timing
         if rank == 0:
             sampler.start()      # NVML init takes longer than a short timed region; samples are reset below
-        dm = E.DMatrix(X, label=y)
+        dm = E.DMatrix(X, label=y, **dm_kw)
         t0 = time.time()
         dm._ensure_quantized(256)
         t_quant = time.time() - t0
@@ -269,7 +303,7 @@ def main():
         if not args.no_e2e:
             barrier()
             t0 = time.perf_counter()
-            d2 = E.DMatrix(X, label=y)                      # host -> device upload
+            d2 = E.DMatrix(X, label=y, **dm_kw)             # host -> device upload
             t_up = time.perf_counter() - t0
             d2._ensure_quantized(256)                       # GPU sketch + binning (train() would do it itself)
             t_q = time.perf_counter() - t0 - t_up
@@ -291,7 +325,8 @@ def main():
             O.build()
             O.use_all_cores()
             ptrs, vals, mins, hm = dm.get_cuts()
-            cuts = O.Cuts.from_arrays(ptrs, vals, mins, hm, 256)
+            is_cat = [1 if t == "c" else 0 for t in args.feature_types] if args.feature_types else None
+            cuts = O.Cuts.from_arrays(ptrs, vals, mins, hm, 256, is_cat=is_cat)
             bins = dm.get_bins()
             ob = O.Booster(dict(params, hist_qbits=0), cuts)
             ob.init_margin(X.shape[0])

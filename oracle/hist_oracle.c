@@ -74,6 +74,8 @@ typedef struct {
   int32_t nthread;       /* 0 => omp default */
   int32_t max_cat_to_onehot;  /* categorical: one-hot splits when n_categories < this (xgboost default 4) */
   int32_t max_cat_threshold;  /* categorical: at most this many categories scanned per direction (default 64) */
+  float scale_pos_weight;     /* binary:logistic: weight multiplier of the positive rows (A.4), default 1 */
+  float max_delta_step;       /* 0 = off; otherwise |leaf weight| is clipped and the gain uses the clipped weight (A.7) */
 } OrParams;
 
 typedef struct {
@@ -370,11 +372,19 @@ void or_bin_matrix(const OrCuts *c, const float *X, int64_t n, float missing, ui
 
 /* ------------------------------------------------------------------ A.4 gradients */
 /* margin [n*K] row-major, out g,h [n*K] */
+void or_gradients_spw(int32_t objective, int32_t K, const float *margin, const float *label,
+                      const float *weight, int64_t n, float scale_pos_weight, float *g, float *h);
 void or_gradients(int32_t objective, int32_t K, const float *margin, const float *label,
                   const float *weight, int64_t n, float *g, float *h) {
+  or_gradients_spw(objective, K, margin, label, weight, n, 1.0f, g, h);
+}
+/* scale_pos_weight (regression_obj.cu, RegLossObj::GetGradient): w *= scale_pos_weight for rows with label 1 */
+void or_gradients_spw(int32_t objective, int32_t K, const float *margin, const float *label,
+                      const float *weight, int64_t n, float scale_pos_weight, float *g, float *h) {
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
     float w = weight ? weight[i] : 1.0f;
+    if (objective == OR_OBJ_LOGISTIC && label[i] == 1.0f) w = w * scale_pos_weight;
     if (objective == OR_OBJ_SQUAREDERROR) {
       g[i] = (margin[i] - label[i]) * w;
       h[i] = 1.0f * w;
@@ -540,16 +550,25 @@ static double thr_l1(double g, double a) {
   if (g < -a) return g + a;
   return 0.0;
 }
-static double calc_gain(const OrParams *p, double G, double H) {
+/* CalcWeight / CalcGain / CalcGainGivenWeight (src/tree/param.h) */
+static double calc_weight_d(const OrParams *p, double G, double H) {
   if (H < (double)p->min_child_weight || H <= 0.0) return 0.0;
   double t = p->alpha == 0.0f ? G : thr_l1(G, (double)p->alpha);
-  return (t * t) / (H + (double)p->lambda);
+  double dw = -t / (H + (double)p->lambda);
+  if (p->max_delta_step != 0.0f && fabs(dw) > (double)p->max_delta_step) dw = copysign((double)p->max_delta_step, dw);
+  return dw;
 }
-static float calc_weight(const OrParams *p, double G, double H) {
-  if (H < (double)p->min_child_weight || H <= 0.0) return 0.0f;
-  double t = p->alpha == 0.0f ? G : thr_l1(G, (double)p->alpha);
-  return (float)(-t / (H + (double)p->lambda));
+static double calc_gain(const OrParams *p, double G, double H) {
+  if (H < (double)p->min_child_weight || H <= 0.0) return 0.0;
+  if (p->max_delta_step == 0.0f) {
+    double t = p->alpha == 0.0f ? G : thr_l1(G, (double)p->alpha);
+    return (t * t) / (H + (double)p->lambda);
+  }
+  const double w = calc_weight_d(p, G, H);
+  const double ret = -((2.0 * G) * w + (H + (double)p->lambda) * (w * w));
+  return p->alpha == 0.0f ? ret : ret + (double)p->alpha * fabs(w);
 }
+static float calc_weight(const OrParams *p, double G, double H) { return (float)calc_weight_d(p, G, H); }
 
 typedef struct {
   float loss_chg; int32_t feature; int32_t bin; float cond; int default_left;
@@ -977,7 +996,7 @@ int or_boost_one_round(OrModel *m, const OrCuts *c, const uint8_t *bins, int64_t
   if (!custom_g) {
     g = (float *)slot_get(SLOT_G, (size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
     h = (float *)slot_get(SLOT_H, (size_t)(n * K > 0 ? n * K : 1) * sizeof(float));
-    or_gradients(m->p.objective, K, margin, label, weight, n, g, h);
+    or_gradients_spw(m->p.objective, K, margin, label, weight, n, m->p.scale_pos_weight, g, h);
     gg = g; hh = h;
   }
   for (int k = 0; k < K; ++k) {

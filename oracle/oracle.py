@@ -27,7 +27,8 @@ class OrParams(C.Structure):
                 ("max_bin", C.c_int32), ("eta", C.c_float), ("gamma", C.c_float),
                 ("min_child_weight", C.c_float), ("lambda_", C.c_float), ("alpha", C.c_float),
                 ("base_score", C.c_float), ("qbits", C.c_int32), ("nthread", C.c_int32),
-                ("max_cat_to_onehot", C.c_int32), ("max_cat_threshold", C.c_int32)]
+                ("max_cat_to_onehot", C.c_int32), ("max_cat_threshold", C.c_int32),
+                ("scale_pos_weight", C.c_float), ("max_delta_step", C.c_float)]
 
 
 def build(force=False):
@@ -213,6 +214,8 @@ def make_params(params):
     p.nthread = int(params.get("nthread", 0))
     p.max_cat_to_onehot = int(params.get("max_cat_to_onehot", 4))
     p.max_cat_threshold = int(params.get("max_cat_threshold", 64))
+    p.scale_pos_weight = float(params.get("scale_pos_weight", 1.0))
+    p.max_delta_step = float(params.get("max_delta_step", 0.0))
     return p
 
 

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden.make_golden import CASES, case_data
+from tests.golden.make_golden import CASES, FEATURE_TYPES, case_data
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -16,7 +16,8 @@ def test_engine_reproduces_golden(name):
     from xgboost_ray_b200 import engine as E
     want = json.load(open(os.path.join(GOLD, name + ".json")))
     x, y, w, params, rounds = case_data(name)
-    dm = E.DMatrix(x, label=y, weight=w)
+    kw = {"feature_types": FEATURE_TYPES[name], "enable_categorical": True} if name in FEATURE_TYPES else {}
+    dm = E.DMatrix(x, label=y, weight=w, **kw)
     bst = E.train(params, dm, num_boost_round=rounds, verbose_eval=False)
     ptrs, vals, mins, hm = dm.get_cuts()
     assert [int(v) for v in ptrs] == want["cut_ptrs"]
@@ -29,7 +30,12 @@ def test_engine_reproduces_golden(name):
     for t, g in zip(trees, want["trees"]):
         for k in ("left", "right", "split_feature", "split_bin", "default_left"):
             assert [int(v) for v in t[k]] == g[k], k
+        if "split_type" in g:
+            assert [int(v) for v in t["split_type"]] == g["split_type"]
+            cats = {str(i): [c for c in range(256) if (int(t["cat_bits"][i][c >> 5]) >> (c & 31)) & 1]
+                    for i in range(len(t["left"])) if t["split_type"][i]}
+            assert cats == g["categories"]
         leaf = np.asarray(g["split_feature"]) < 0
         assert np.max(np.abs(t["value"][leaf] - np.asarray(g["value"], np.float32)[leaf])) <= 1e-5
-    pred = np.asarray(bst.predict(E.DMatrix(x[:64])), np.float64).reshape(-1)
+    pred = np.asarray(bst.predict(E.DMatrix(x[:64], **kw)), np.float64).reshape(-1)
     assert np.max(np.abs(pred - np.asarray(want["pred_head"]))) <= 1e-5

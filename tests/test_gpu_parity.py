@@ -441,3 +441,23 @@ def test_categorical_invalid_codes_error(eng):
         dm._ensure_quantized(256)
     with pytest.raises(eng.XGBoostError, match="enable_categorical"):
         eng.DMatrix(X, feature_types=["q", "c"])
+
+
+@pytest.mark.parametrize("extra", [{"scale_pos_weight": 4.0}, {"max_delta_step": 0.7}, {"max_delta_step": 1.5, "alpha": 0.5},
+                                   {"scale_pos_weight": 0.25, "max_delta_step": 0.3, "min_child_weight": 3.0}])
+def test_trees_identical_scale_pos_weight_and_max_delta_step(eng, oracle, extra):
+    X = make_data(20000, 20, 61, "uniform", nan_frac=0.03)
+    rng = np.random.RandomState(62)
+    y = ((np.nan_to_num(X[:, 0]) + np.nan_to_num(X[:, 3]) + rng.normal(size=len(X))) > 13).astype(np.float32)   # ~10 % positives
+    params = dict({"objective": "binary:logistic", "max_depth": 5, "eta": 0.3, "base_score": 0.5}, **extra)
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 4)
+    assert_same_model(ebst, obst)
+
+
+def test_unsupported_parameters_fail_loudly(eng):
+    X = make_data(100, 3, 1)
+    dm = eng.DMatrix(X, label=X[:, 0])
+    for bad in ({"subsample": 0.5}, {"colsample_bytree": 0.5}, {"grow_policy": "lossguide"}, {"max_leaves": 8},
+                {"monotone_constraints": "(1,0,0)"}, {"num_parallel_tree": 4}, {"max_bin": 1024}):
+        with pytest.raises(eng.XGBoostError, match="not supported"):
+            eng.train(dict({"objective": "reg:squarederror"}, **bad), dm, num_boost_round=1, verbose_eval=False)

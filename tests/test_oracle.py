@@ -21,6 +21,7 @@ def test_oracle_reproduces_golden(oracle, name):
         for k in ("left", "right", "split_feature", "split_bin", "default_left"):
             assert a[k] == b[k], k
         assert np.allclose(a["value"], b["value"], rtol=0, atol=1e-7)
+        assert a.get("split_type") == b.get("split_type") and a.get("categories") == b.get("categories")
     assert np.allclose(got["pred_head"], want["pred_head"], rtol=0, atol=1e-6)
 
 
@@ -143,3 +144,32 @@ def test_empty_and_tiny_inputs(oracle):
     bst, _ = oracle.train({"objective": "reg:squarederror", "max_depth": 3, "base_score": 0.5}, x, np.ones(1, np.float32), 2)
     assert bst.num_trees == 2 and all(t.n_nodes == 1 for t in bst.trees())
     assert abs(bst.predict(x)[0] - (0.5 + 0.075 + 0.06375)) < 1e-6    # -G/(H+lambda)*eta twice
+
+
+def test_scale_pos_weight_known_answer(oracle):
+    """A.4: positive rows' gradient pairs are multiplied by scale_pos_weight (binary:logistic)."""
+    x = np.zeros((10, 1), np.float32)                 # constant feature: the tree is a single leaf
+    y = np.array([1, 1, 1, 0, 0, 0, 0, 0, 0, 0], np.float32)
+    spw, lam = 3.0, 1.0
+    b, _ = oracle.train({"objective": "binary:logistic", "max_depth": 2, "eta": 1.0, "base_score": 0.5, "lambda": lam,
+                         "scale_pos_weight": spw}, x, y, 1)
+    G = 0.5 * (7 - spw * 3); H = 0.25 * (7 + spw * 3)
+    assert b.tree(0).n_nodes == 1 and abs(b.tree(0).value[0] - (-G / (H + lam))) < 1e-6
+
+
+def test_max_delta_step_known_answer(oracle):
+    """A.7: the leaf weight is clipped to +-max_delta_step (before eta); the split gain uses the clipped weights."""
+    rng = np.random.RandomState(0)
+    x = rng.uniform(0, 1, size=(200, 1)).astype(np.float32)
+    y = np.where(x[:, 0] > 0.5, 10.0, -10.0).astype(np.float32)
+    p = {"objective": "reg:squarederror", "max_depth": 1, "eta": 0.5, "base_score": 0.0, "lambda": 0.0}
+    free, _ = oracle.train(p, x, y, 1)
+    clip, _ = oracle.train(dict(p, max_delta_step=2.0), x, y, 1)
+    tf, tc = free.tree(0), clip.tree(0)
+    assert tf.split_bin[0] == tc.split_bin[0]
+    assert sorted(tf.value[1:3]) == [-5.0, 5.0] and sorted(tc.value[1:3]) == [-1.0, 1.0]
+    # gain with clipped weights: -(2 G w + H w^2); children: G = -+10 n_c, H = n_c, w = +-2 -> 36 n_c each;
+    # root: G = -sum(y), H = 200, w = clip(-G/H, +-2)
+    G = -float(y.sum()); w = float(np.clip(-G / 200.0, -2.0, 2.0))
+    root_gain = -(2.0 * G * w + 200.0 * w * w)
+    assert abs(tc.loss_chg[0] - (36.0 * 200 - root_gain)) < 1e-2

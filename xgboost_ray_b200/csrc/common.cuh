@@ -92,10 +92,38 @@ struct B2TreeDev {            // arrays of capacity max_nodes
   float *leaf_weight, *leaf_value;
   int32_t* n_nodes;
 };
-struct B2CtlParams { double mcw, lambda, alpha; float gamma, eta; };
+struct B2CtlParams { double mcw, lambda, alpha, max_delta_step; float gamma, eta; };
 
 struct B2TrainParamDev {
   double min_child_weight, lambda, alpha;
   double inv_scale_g, inv_scale_h;
+  double max_delta_step;   // 0 = off (CalcWeight clips to +-max_delta_step, CalcGain uses the clipped weight)
   int32_t max_cat_to_onehot, max_cat_threshold;
 };
+
+// ---- CalcWeight / CalcGain / CalcGainGivenWeight (xgboost src/tree/param.h) with explicit
+// IEEE round-to-nearest operations: the kernels, the host code and the CPU oracle evaluate the same sequence.
+#ifdef __CUDACC__
+__device__ __forceinline__ double b2_thr_l1(double g, double a) {
+  if (g > a) return __dadd_rn(g, -a);
+  if (g < -a) return __dadd_rn(g, a);
+  return 0.0;
+}
+__device__ __forceinline__ double b2_calc_weight(double G, double H, double mcw, double lambda, double alpha, double mds) {
+  if (H < mcw || H <= 0.0) return 0.0;
+  const double t = (alpha == 0.0) ? G : b2_thr_l1(G, alpha);
+  double dw = __ddiv_rn(-t, __dadd_rn(H, lambda));
+  if (mds != 0.0 && fabs(dw) > mds) dw = copysign(mds, dw);
+  return dw;
+}
+__device__ __forceinline__ double b2_calc_gain(double G, double H, double mcw, double lambda, double alpha, double mds) {
+  if (H < mcw || H <= 0.0) return 0.0;
+  if (mds == 0.0) {
+    const double t = (alpha == 0.0) ? G : b2_thr_l1(G, alpha);
+    return __ddiv_rn(__dmul_rn(t, t), __dadd_rn(H, lambda));
+  }
+  const double w = b2_calc_weight(G, H, mcw, lambda, alpha, mds);
+  const double ret = -__dadd_rn(__dmul_rn(__dmul_rn(2.0, G), w), __dmul_rn(__dadd_rn(H, lambda), __dmul_rn(w, w)));
+  return alpha == 0.0 ? ret : __dadd_rn(ret, __dmul_rn(alpha, fabs(w)));
+}
+#endif

@@ -16,20 +16,11 @@ namespace b2 {
 constexpr int kCtlThreads = 1024;
 constexpr int kPartChunkRows = 2048;  // must match partition_kernel.cu
 
-__device__ __forceinline__ double c_thr_l1(double g, double a) {
-  if (g > a) return __dadd_rn(g, -a);
-  if (g < -a) return __dadd_rn(g, a);
-  return 0.0;
+__device__ __forceinline__ double c_calc_gain(double G, double H, const B2CtlParams& p) {
+  return b2_calc_gain(G, H, p.mcw, p.lambda, p.alpha, p.max_delta_step);
 }
-__device__ __forceinline__ double c_calc_gain(double G, double H, double mcw, double lambda, double alpha) {
-  if (H < mcw || H <= 0.0) return 0.0;
-  double t = (alpha == 0.0) ? G : c_thr_l1(G, alpha);
-  return __ddiv_rn(__dmul_rn(t, t), __dadd_rn(H, lambda));
-}
-__device__ __forceinline__ float c_calc_weight(double G, double H, double mcw, double lambda, double alpha) {
-  if (H < mcw || H <= 0.0) return 0.0f;
-  double t = (alpha == 0.0) ? G : c_thr_l1(G, alpha);
-  return __double2float_rn(__ddiv_rn(-t, __dadd_rn(H, lambda)));
+__device__ __forceinline__ float c_calc_weight(double G, double H, const B2CtlParams& p) {
+  return __double2float_rn(b2_calc_weight(G, H, p.mcw, p.lambda, p.alpha, p.max_delta_step));
 }
 
 // exclusive scan of one int per item over n items handled as tiles of kCtlThreads; returns total
@@ -119,8 +110,8 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
       const double GL = __dmul_rn(__ll2double_rn(lg), inv_sg), HL = __dmul_rn(__ll2double_rn(lh), inv_sh);
       const double GR = __dmul_rn(__ll2double_rn(rg), inv_sg), HR = __dmul_rn(__ll2double_rn(rh), inv_sh);
       B2EvalNode el, er;
-      el.sum_g = lg; el.sum_h = lh; el.hist_index = -1; el.root_gain = __double2float_rn(c_calc_gain(GL, HL, p.mcw, p.lambda, p.alpha));
-      er.sum_g = rg; er.sum_h = rh; er.hist_index = -1; er.root_gain = __double2float_rn(c_calc_gain(GR, HR, p.mcw, p.lambda, p.alpha));
+      el.sum_g = lg; el.sum_h = lh; el.hist_index = -1; el.root_gain = __double2float_rn(c_calc_gain(GL, HL, p));
+      er.sum_g = rg; er.sum_h = rh; er.hist_index = -1; er.root_gain = __double2float_rn(c_calc_gain(GR, HR, p));
       ev_nxt[2 * rank] = el; ev_nxt[2 * rank + 1] = er;
       B2NodeSeg sl, sr;
       sl.nid = l; sl.buf = sg.buf ^ 1; sl.begin = sg.begin; sl.count = 0;
@@ -234,7 +225,7 @@ __global__ void leaf_values_kernel(const B2LeafDev* __restrict__ leaves, const i
   const double kg = ldexp(1.0, leaf_bits - qexp[0]), kh = ldexp(1.0, leaf_bits - qexp[1]);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double G = __ddiv_rn(__ll2double_rn(sums[2 * i]), kg), H = __ddiv_rn(__ll2double_rn(sums[2 * i + 1]), kh);
-    const float w = c_calc_weight(G, H, p.mcw, p.lambda, p.alpha);
+    const float w = c_calc_weight(G, H, p);
     const float v = __fmul_rn(w, p.eta);
     leaf_value[i] = v;
     tree.leaf_weight[leaves[i].nid] = w;

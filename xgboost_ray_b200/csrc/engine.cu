@@ -60,7 +60,7 @@ int b2_launch_leaf_values(const B2LeafDev*, const int32_t*, const long long*, co
 int b2_launch_tree_init(B2TreeDev, B2LevelCtl*, B2NodeSeg*, B2EvalNode*, int32_t*, int, cudaStream_t);
 int b2_launch_root_record(B2TreeDev, const B2EvalNode*, cudaStream_t);
 int b2_launch_iota(int32_t*, int64_t, cudaStream_t);
-int b2_launch_gradient(int, int, const float*, const float*, const float*, int64_t, float2*, int, cudaStream_t);
+int b2_launch_gradient(int, int, const float*, const float*, const float*, int64_t, float, float2*, int, cudaStream_t);
 int b2_launch_pack_custom(const float*, const float*, int, int64_t, float2*, int, cudaStream_t);
 int b2_launch_absmax(const float2*, int64_t, uint32_t*, int, cudaStream_t);
 int b2_launch_quant_exponent(const uint32_t*, int32_t*, cudaStream_t);
@@ -487,6 +487,7 @@ struct Params {
   int num_feature = 0;
   int device = 0;
   int max_cat_to_onehot = 4, max_cat_threshold = 64;   // xgboost defaults (src/tree/param.h)
+  float scale_pos_weight = 1.0f, max_delta_step = 0.0f;
 };
 
 struct TreeHost {
@@ -632,6 +633,8 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
     else if (k == "profile") p->profile = i();
     else if (k == "num_feature") p->num_feature = i();
     else if (k == "device") p->device = i();
+    else if (k == "scale_pos_weight") p->scale_pos_weight = f();
+    else if (k == "max_delta_step") p->max_delta_step = f();
     else if (k == "max_cat_to_onehot") p->max_cat_to_onehot = i();
     else if (k == "max_cat_threshold") p->max_cat_threshold = i();
     else if (k == "max_bin") { if (max_bin_out) *max_bin_out = i(); }
@@ -652,15 +655,12 @@ float base_margin_value(const Params& p) {
 
 // -- host replicas of the gain / weight formulas (A.6, A.7); same IEEE sequence as the kernels
 double h_thr_l1(double g, double a) { if (g > a) return g - a; if (g < -a) return g + a; return 0.0; }
-double h_calc_gain(const Params& p, double G, double H) {
-  if (H < (double)p.min_child_weight || H <= 0.0) return 0.0;
-  double t = p.alpha == 0.0f ? G : h_thr_l1(G, (double)p.alpha);
-  return (t * t) / (H + (double)p.lambda);
-}
 float h_calc_weight(const Params& p, double G, double H) {
   if (H < (double)p.min_child_weight || H <= 0.0) return 0.0f;
   double t = p.alpha == 0.0f ? G : h_thr_l1(G, (double)p.alpha);
-  return (float)(-t / (H + (double)p.lambda));
+  double dw = -t / (H + (double)p.lambda);
+  if (p.max_delta_step != 0.0f && fabs(dw) > (double)p.max_delta_step) dw = copysign((double)p.max_delta_step, dw);
+  return (float)dw;
 }
 
 int window_rows_for(int qbits) {
@@ -795,7 +795,8 @@ void grow_tree(Booster* b, int k, int slot) {
   dp.min_child_weight = (double)p.min_child_weight; dp.lambda = (double)p.lambda; dp.alpha = (double)p.alpha;
   dp.inv_scale_g = dp.inv_scale_h = 1.0;
   dp.max_cat_to_onehot = p.max_cat_to_onehot; dp.max_cat_threshold = p.max_cat_threshold;
-  B2CtlParams cp; cp.mcw = dp.min_child_weight; cp.lambda = dp.lambda; cp.alpha = dp.alpha; cp.gamma = p.gamma; cp.eta = p.eta;
+  dp.max_delta_step = (double)p.max_delta_step;
+  B2CtlParams cp; cp.mcw = dp.min_child_weight; cp.lambda = dp.lambda; cp.alpha = dp.alpha; cp.max_delta_step = dp.max_delta_step; cp.gamma = p.gamma; cp.eta = p.eta;
   const B2TreeDev tree = tree_dev(b);
   int32_t* d_n_leaves = tree.n_nodes + 1;
   long long* d_level_rows = b->t_i64.p + 2 * L.max_nodes;
@@ -1036,8 +1037,8 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
     LAUNCH_CHECK(b2_launch_pack_custom(b->d_custom_g.p, b->d_custom_h.p, K, n, b->gh.p, b->ctx->num_sms, s));
   } else {
     if (m->n_label != n) fail("train matrix has %lld labels for %lld rows", (long long)m->n_label, (long long)n);
-    LAUNCH_CHECK(b2_launch_gradient(b->p.objective, K, b->margin.p, m->label.p, m->n_weight ? m->weight.p : nullptr, n, b->gh.p,
-                                    b->ctx->num_sms, s));
+    LAUNCH_CHECK(b2_launch_gradient(b->p.objective, K, b->margin.p, m->label.p, m->n_weight ? m->weight.p : nullptr, n,
+                                    b->p.scale_pos_weight, b->gh.p, b->ctx->num_sms, s));
   }
   b->t.kernel_launches++;
   for (int k = 0; k < K; ++k) grow_tree(b, k, k);

@@ -43,9 +43,10 @@ __device__ __forceinline__ float b2_sigmoid(float x) {
 
 // gh layout: class-major [K][n] float2 so that each class tree reads a contiguous slice
 __global__ void gradient_kernel(int objective, int K, const float* __restrict__ margin, const float* __restrict__ label,
-                                const float* __restrict__ weight, int64_t n, float2* __restrict__ gh) {
+                                const float* __restrict__ weight, int64_t n, float scale_pos_weight, float2* __restrict__ gh) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float w = weight ? weight[i] : 1.0f;
+    float w = weight ? weight[i] : 1.0f;
+    if (objective == 1 && label[i] == 1.0f) w = __fmul_rn(w, scale_pos_weight);   // RegLossObj: positive rows
     if (objective == 0) {
       gh[i] = make_float2(__fmul_rn(__fadd_rn(margin[i], -label[i]), w), w);
     } else if (objective == 1) {
@@ -207,9 +208,9 @@ static inline int grid_for(int64_t n, int num_sms) {
 
 extern "C" {
 int b2_launch_gradient(int objective, int K, const float* margin, const float* label, const float* weight, int64_t n,
-                       float2* gh, int num_sms, cudaStream_t s) {
+                       float scale_pos_weight, float2* gh, int num_sms, cudaStream_t s) {
   if (n <= 0) return 0;
-  b2::gradient_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, K, margin, label, weight, n, gh);
+  b2::gradient_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, K, margin, label, weight, n, scale_pos_weight, gh);
   return (int)cudaGetLastError();
 }
 int b2_launch_pack_custom(const float* g, const float* h, int K, int64_t n, float2* gh, int num_sms, cudaStream_t s) {

@@ -12,15 +12,8 @@
 
 namespace b2 {
 
-__device__ __forceinline__ double thr_l1(double g, double a) {
-  if (g > a) return __dadd_rn(g, -a);
-  if (g < -a) return __dadd_rn(g, a);
-  return 0.0;
-}
 __device__ __forceinline__ double calc_gain(double G, double H, const B2TrainParamDev& p) {
-  if (H < p.min_child_weight || H <= 0.0) return 0.0;
-  double t = (p.alpha == 0.0) ? G : thr_l1(G, p.alpha);
-  return __ddiv_rn(__dmul_rn(t, t), __dadd_rn(H, p.lambda));
+  return b2_calc_gain(G, H, p.min_child_weight, p.lambda, p.alpha, p.max_delta_step);
 }
 
 struct Best {
@@ -161,9 +154,7 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
 constexpr int kCatCtas = 4;
 
 __device__ __forceinline__ float calc_weight_f(double G, double H, const B2TrainParamDev& p) {
-  if (H < p.min_child_weight || H <= 0.0) return 0.0f;
-  double t = (p.alpha == 0.0) ? G : thr_l1(G, p.alpha);
-  return __double2float_rn(__ddiv_rn(-t, __dadd_rn(H, p.lambda)));
+  return __double2float_rn(b2_calc_weight(G, H, p.min_child_weight, p.lambda, p.alpha, p.max_delta_step));
 }
 
 __global__ void __launch_bounds__(256)

@@ -371,7 +371,31 @@ _TREE_FIELDS = ("left", "right", "parent", "split_feature", "split_bin", "split_
                 "base_weight", "loss_chg", "sum_hess")
 _ENGINE_KEYS = ("objective", "num_class", "max_depth", "eta", "learning_rate", "gamma", "min_split_loss",
                 "min_child_weight", "lambda", "reg_lambda", "alpha", "reg_alpha", "base_score", "hist_qbits",
-                "hist_chunk_rows", "profile", "max_cat_to_onehot", "max_cat_threshold")
+                "hist_chunk_rows", "profile", "max_cat_to_onehot", "max_cat_threshold", "scale_pos_weight",
+                "max_delta_step")
+
+# xgboost parameters that change the trained model and that this engine does not implement: a value different
+# from the neutral one is an error, never silently ignored (a drop-in must not train a different model quietly)
+_UNSUPPORTED_NEUTRAL = {
+    "subsample": (1, 1.0), "colsample_bytree": (1, 1.0), "colsample_bylevel": (1, 1.0), "colsample_bynode": (1, 1.0),
+    "sampling_method": ("uniform",), "max_leaves": (0,), "grow_policy": ("depthwise",), "num_parallel_tree": (1,),
+    "monotone_constraints": (None, "", "()", (), []), "interaction_constraints": (None, "", "[]", (), []),
+    "multi_strategy": ("one_output_per_tree",), "refresh_leaf": (1, True), "process_type": ("default",),
+    "updater": (None, "grow_quantile_histmaker", "grow_gpu_hist"), "max_bin": tuple(range(2, 257)),
+}
+
+
+def _check_supported(params):
+    for k, neutral in _UNSUPPORTED_NEUTRAL.items():
+        if k in params and params[k] is not None:
+            v = params[k]
+            if isinstance(v, (list, tuple)) and k == "monotone_constraints" and all(int(x) == 0 for x in v):
+                continue
+            if isinstance(v, str) and k == "monotone_constraints" and set(v) <= set("(), 0"):
+                continue
+            if v not in neutral:
+                raise XGBoostError("parameter %s=%r is not supported by the B200 hist engine (supported: %s)"
+                                   % (k, v, ", ".join(repr(x) for x in neutral[:4])))
 
 
 def _params_dict(params):
@@ -407,6 +431,7 @@ class Booster:
 
     # -- engine object management
     def _param_text(self, extra=None):
+        _check_supported(self.params)
         p = {k: self.params[k] for k in _ENGINE_KEYS if k in self.params and self.params[k] is not None}
         if extra:
             p.update(extra)
