@@ -185,9 +185,22 @@ static void radix_sort_keys(uint32_t *a, uint32_t *tmp, int64_t n) {
   }
 }
 
+/* (key, integer weight) pairs sorted by key: LSD radix over the key half of key<<32 | weight */
+static void radix_sort_pairs(uint64_t *a, uint64_t *tmp, int64_t n) {
+  for (int pass = 0; pass < 4; ++pass) {
+    const int sh = 32 + 8 * pass;
+    int64_t cnt[257]; memset(cnt, 0, sizeof(cnt));
+    for (int64_t i = 0; i < n; ++i) cnt[((a[i] >> sh) & 255u) + 1]++;
+    for (int b = 0; b < 256; ++b) cnt[b + 1] += cnt[b];
+    for (int64_t i = 0; i < n; ++i) tmp[cnt[(a[i] >> sh) & 255u]++] = a[i];
+    memcpy(a, tmp, (size_t)n * sizeof(uint64_t));
+  }
+}
+
 /* One feature: exact summary (distinct values, int64 rmin/rmax) -> SetPrune -> cuts.
- * Returns number of cuts written to out_cuts (<= 256). */
-static int make_cuts_feature(const uint32_t *sorted_keys, int64_t cnt, int max_num_bins_cap,
+ * sorted_wq (NULL = every row counts 1): integer sample weights aligned with sorted_keys; ranks are then sums
+ * of weights (weighted quantile sketch).  Returns number of cuts written to out_cuts (<= 256). */
+static int make_cuts_feature(const uint32_t *sorted_keys, const int32_t *sorted_wq, int64_t cnt, int max_num_bins_cap,
                              float *out_cuts, float *out_min) {
   /* distinct summary */
   int64_t m = 0;
@@ -203,11 +216,13 @@ static int make_cuts_feature(const uint32_t *sorted_keys, int64_t cnt, int max_n
   float *val = (float *)malloc((size_t)m * sizeof(float));
   int64_t *rmin = (int64_t *)malloc((size_t)m * sizeof(int64_t));
   int64_t *rmax = (int64_t *)malloc((size_t)m * sizeof(int64_t));
-  int64_t u = -1;
+  int64_t u = -1, pre = 0;
   for (int64_t i = 0; i < cnt; ++i) {
+    const int64_t wi = sorted_wq ? (int64_t)sorted_wq[i] : 1;
     if (i == 0 || sorted_keys[i] != sorted_keys[i - 1]) {
-      ++u; val[u] = key2f(sorted_keys[i]); rmin[u] = i; rmax[u] = i + 1;
-    } else rmax[u] = i + 1;
+      ++u; val[u] = key2f(sorted_keys[i]); rmin[u] = pre; rmax[u] = pre + wi;
+    } else rmax[u] = pre + wi;
+    pre += wi;
   }
   int64_t max_num_bins = m < max_num_bins_cap ? m : max_num_bins_cap;
   int64_t maxsize = max_num_bins + 1;
@@ -255,8 +270,30 @@ void or_cuts_free(OrCuts *c);
 /* is_cat (may be NULL): categorical features get the cuts [0, 1, ..., max code] (HistogramCuts::AddCategories,
  * src/common/quantile.cc); a code must be an integer in [0, 255] ([0, 254] if the feature has missing values,
  * bin 255 being the sentinel).  Returns NULL on an invalid category value. */
+OrCuts *or_cuts_create_w(const float *X, int64_t n, int32_t F, float missing, int32_t max_bin, const uint8_t *is_cat,
+                         const float *weight);
 OrCuts *or_cuts_create_cat(const float *X, int64_t n, int32_t F, float missing, int32_t max_bin, const uint8_t *is_cat) {
+  return or_cuts_create_w(X, n, F, missing, max_bin, is_cat, NULL);
+}
+/* weight (may be NULL): sample weights -> weighted quantile sketch (SketchContainer pushes info.weights_,
+ * src/common/quantile.cc).  Weights are quantised to integers wq = rint(w * 2^(30-e)), 2^e > max w, so that the
+ * weighted ranks are exact (order independent); negative / non-finite weights are rejected (NULL). */
+OrCuts *or_cuts_create_w(const float *X, int64_t n, int32_t F, float missing, int32_t max_bin, const uint8_t *is_cat,
+                         const float *weight) {
   if (max_bin < 2 || max_bin > 256) return NULL;
+  int32_t *wq = NULL;
+  if (weight) {
+    float vmax = 0.0f;
+    for (int64_t i = 0; i < n; ++i) {
+      if (!(weight[i] >= 0.0f) || isinf(weight[i])) return NULL;
+      if (weight[i] > vmax) vmax = weight[i];
+    }
+    int e = 0;
+    if (vmax > 0.0f) frexpf(vmax, &e);
+    const float scale = ldexpf(1.0f, 30 - e);
+    wq = (int32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(int32_t));
+    for (int64_t i = 0; i < n; ++i) wq[i] = (int32_t)lrintf(weight[i] * scale);
+  }
   OrCuts *c = (OrCuts *)calloc(1, sizeof(OrCuts));
   c->n_features = F; c->max_bin = max_bin;
   c->cut_ptrs = (int32_t *)calloc((size_t)F + 1, sizeof(int32_t));
@@ -290,25 +327,41 @@ OrCuts *or_cuts_create_cat(const float *X, int64_t n, int32_t F, float missing, 
     }
     uint32_t *keys = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
     uint32_t *tmp = (uint32_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
+    int32_t *swq = NULL;
     int64_t cnt = 0; int miss = 0;
-    for (int64_t i = 0; i < n; ++i) {
-      float x = X[i * F + f];
-      if (is_missing(x, missing)) { miss = 1; continue; }
-      if (x == 0.0f) x = 0.0f; /* -0 -> +0 */
-      keys[cnt++] = f2key(x);
+    if (wq) {
+      uint64_t *pairs = (uint64_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint64_t));
+      uint64_t *ptmp = (uint64_t *)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint64_t));
+      for (int64_t i = 0; i < n; ++i) {
+        float x = X[i * F + f];
+        if (is_missing(x, missing)) { miss = 1; continue; }
+        if (x == 0.0f) x = 0.0f;
+        pairs[cnt++] = ((uint64_t)f2key(x) << 32) | (uint32_t)wq[i];
+      }
+      radix_sort_pairs(pairs, ptmp, cnt);
+      swq = (int32_t *)malloc((size_t)(cnt > 0 ? cnt : 1) * sizeof(int32_t));
+      for (int64_t i = 0; i < cnt; ++i) { keys[i] = (uint32_t)(pairs[i] >> 32); swq[i] = (int32_t)(uint32_t)pairs[i]; }
+      free(pairs); free(ptmp);
+    } else {
+      for (int64_t i = 0; i < n; ++i) {
+        float x = X[i * F + f];
+        if (is_missing(x, missing)) { miss = 1; continue; }
+        if (x == 0.0f) x = 0.0f; /* -0 -> +0 */
+        keys[cnt++] = f2key(x);
+      }
+      radix_sort_keys(keys, tmp, cnt);
     }
-    radix_sort_keys(keys, tmp, cnt);
     c->has_missing[f] = (uint8_t)miss;
     int cap = max_bin;
     if (miss && cap > 255) cap = 255;
-    ncut[f] = make_cuts_feature(keys, cnt, cap, tmpc + (size_t)f * 256, &c->min_vals[f]);
-    free(keys); free(tmp);
+    ncut[f] = make_cuts_feature(keys, swq, cnt, cap, tmpc + (size_t)f * 256, &c->min_vals[f]);
+    free(keys); free(tmp); free(swq);
   }
   for (int32_t f = 0; f < F; ++f) c->cut_ptrs[f + 1] = c->cut_ptrs[f] + ncut[f];
   c->cut_vals = (float *)malloc((size_t)(c->cut_ptrs[F] > 0 ? c->cut_ptrs[F] : 1) * sizeof(float));
   for (int32_t f = 0; f < F; ++f)
     memcpy(c->cut_vals + c->cut_ptrs[f], tmpc + (size_t)f * 256, (size_t)ncut[f] * sizeof(float));
-  free(tmpc); free(ncut);
+  free(tmpc); free(ncut); free(wq);
   if (invalid) { or_cuts_free(c); return NULL; }
   return c;
 }

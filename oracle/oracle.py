@@ -53,6 +53,8 @@ def lib():
         L.or_cuts_create.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_int32]
         L.or_cuts_create_cat.restype = C.c_void_p
         L.or_cuts_create_cat.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, bp]
+        L.or_cuts_create_w.restype = C.c_void_p
+        L.or_cuts_create_w.argtypes = [fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, bp, fp]
         L.or_cuts_set_cat.argtypes = [C.c_void_p, bp]
         L.or_cuts_get_cat.argtypes = [C.c_void_p, bp]
         L.or_tree_get_cat.argtypes = [C.c_void_p, C.c_int32, bp, C.POINTER(C.c_uint32)]
@@ -158,12 +160,14 @@ class Cuts:
         L.or_cuts_get_cat(handle, _bp(self.is_cat))
 
     @classmethod
-    def from_data(cls, X, max_bin=256, missing=np.nan, is_cat=None):
-        """is_cat: optional bool/uint8 [F]; categorical features get the cuts 0..max code (bin = code)."""
+    def from_data(cls, X, max_bin=256, missing=np.nan, is_cat=None, weight=None):
+        """is_cat: optional bool/uint8 [F]; categorical features get the cuts 0..max code (bin = code).
+        weight: optional sample weights [n] -> weighted quantile sketch."""
         X = _f32(X)
         n, f = X.shape
         ic = None if is_cat is None else np.ascontiguousarray(is_cat, np.uint8)
-        h = lib().or_cuts_create_cat(_fp(X), n, f, float(missing), max_bin, _bp(ic))
+        w = _f32(weight)
+        h = lib().or_cuts_create_w(_fp(X), n, f, float(missing), max_bin, _bp(ic), _fp(w))
         if not h:
             raise ValueError("or_cuts_create failed (max_bin must be in [2,256]; category codes must be integers "
                              "in [0,255], [0,254] for a feature with missing values)")
@@ -335,7 +339,7 @@ class Booster:
 def train(params, X, y, num_boost_round, weight=None, missing=np.nan, cuts=None, base_margin=None, is_cat=None):
     """Convenience: cuts -> bins -> rounds.  Returns (Booster, bins)."""
     X = _f32(X)
-    cuts = cuts or Cuts.from_data(X, int(params.get("max_bin", 256)), missing, is_cat=is_cat)
+    cuts = cuts or Cuts.from_data(X, int(params.get("max_bin", 256)), missing, is_cat=is_cat, weight=weight)
     bins = cuts.bin(X, missing)
     bst = Booster(params, cuts)
     bst.init_margin(X.shape[0], base_margin)

@@ -120,3 +120,26 @@ def test_two_gpu_categorical_identical_to_one_gpu_and_oracle(oracle):
     assert n_cat_nodes > 0
     p2 = predict(b2, RayDMatrix(x, **kw), ray_params=RayParams(num_actors=2))
     assert np.max(np.abs(p2 - ob.predict(x))) <= 1e-5
+
+
+@pytest.mark.timeout(900)
+def test_two_gpu_weighted_rows_identical_to_one_gpu_and_oracle(oracle):
+    """Sample weights: weighted quantile sketch (integer rank sums, merged over the ranks) + weighted gradients."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    rng = np.random.RandomState(13)
+    n, f = 30011, 12
+    x = rng.normal(size=(n, f)).astype(np.float32)
+    x[rng.uniform(size=x.shape) < 0.05] = np.nan
+    w = rng.gamma(2.0, 1.0, size=n).astype(np.float32)
+    y = (np.nan_to_num(x[:, 0]) - np.nan_to_num(x[:, 2]) + rng.normal(scale=0.3, size=n)).astype(np.float32)
+    params = {"objective": "reg:squarederror", "max_depth": 5, "eta": 0.3, "base_score": 0.5, "max_bin": 64}
+    b1 = train(params, RayDMatrix(x, y, weight=w), num_boost_round=4, ray_params=RayParams(num_actors=1))
+    b2 = train(params, RayDMatrix(x, y, weight=w), num_boost_round=4, ray_params=RayParams(num_actors=2))
+    assert _dump(b1) == _dump(b2)
+    ob, _ = oracle.train(params, x, y, 4, weight=w)
+    for i, t in enumerate(b2.get_trees()):
+        o = ob.tree(i)
+        assert np.array_equal(t["split_feature"], o.split_feature) and np.array_equal(t["split_bin"], o.split_bin)
+        assert np.array_equal(t["split_cond"].view(np.uint32), o.split_cond.view(np.uint32))   # same (weighted) cuts

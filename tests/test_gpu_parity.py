@@ -461,3 +461,24 @@ def test_unsupported_parameters_fail_loudly(eng):
                 {"monotone_constraints": "(1,0,0)"}, {"num_parallel_tree": 4}, {"max_bin": 1024}):
         with pytest.raises(eng.XGBoostError, match="not supported"):
             eng.train(dict({"objective": "reg:squarederror"}, **bad), dm, num_boost_round=1, verbose_eval=False)
+
+
+@pytest.mark.parametrize("nan_frac", [0.0, 0.1])
+@pytest.mark.parametrize("max_bin", [16, 256])
+def test_weighted_sketch_cuts_bit_exact(eng, oracle, nan_frac, max_bin):
+    X = make_data(30000, 12, 71, "mixed", nan_frac)
+    rng = np.random.RandomState(72)
+    w = rng.gamma(2.0, 1.0, size=len(X)).astype(np.float32)
+    w[::13] = 0.0                                               # zero-weight rows stay in the summary with no mass
+    cuts = oracle.Cuts.from_data(X, max_bin, weight=w)
+    dm = eng.DMatrix(X, weight=w)
+    dm._ensure_quantized(max_bin)
+    ptrs, vals, mins, hm = dm.get_cuts()
+    assert np.array_equal(ptrs, cuts.ptrs) and np.array_equal(vals.view(np.uint32), cuts.vals.view(np.uint32))
+    assert np.array_equal(mins.view(np.uint32), cuts.mins.view(np.uint32)) and np.array_equal(hm, cuts.has_missing)
+    assert np.array_equal(dm.get_bins(), cuts.bin(X))
+    unweighted = oracle.Cuts.from_data(X, max_bin)
+    assert max_bin == 256 or not np.array_equal(unweighted.vals, cuts.vals)   # the weights matter
+    bad = w.copy(); bad[5] = -2.0
+    with pytest.raises(eng.XGBoostError, match="weights"):
+        eng.DMatrix(X, weight=bad)._ensure_quantized(max_bin)

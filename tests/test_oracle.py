@@ -173,3 +173,26 @@ def test_max_delta_step_known_answer(oracle):
     G = -float(y.sum()); w = float(np.clip(-G / 200.0, -2.0, 2.0))
     root_gain = -(2.0 * G * w + 200.0 * w * w)
     assert abs(tc.loss_chg[0] - (36.0 * 200 - root_gain)) < 1e-2
+
+
+def test_weighted_sketch_known_answers(oracle):
+    """A.2 "(weighted) quantiles": sample weights are the rank increments of the sketch.  Integer weights are
+    equivalent to repeating rows, a uniform weight changes nothing, invalid weights are rejected."""
+    rng = np.random.RandomState(0)
+    n = 5000
+    X = rng.normal(size=(n, 3)).astype(np.float32)
+    X[::11, 1] = np.nan
+    base = oracle.Cuts.from_data(X, 16)
+    for w in (np.ones(n, np.float32), np.full(n, 0.37, np.float32)):
+        c = oracle.Cuts.from_data(X, 16, weight=w)
+        assert np.array_equal(c.vals, base.vals) and np.array_equal(c.ptrs, base.ptrs)
+    heavy = X[:, 0] > 0
+    dup = np.concatenate([X, X[heavy], X[heavy]])
+    c_dup = oracle.Cuts.from_data(dup, 16)
+    c_w = oracle.Cuts.from_data(X, 16, weight=np.where(heavy, 3.0, 1.0).astype(np.float32))
+    assert np.array_equal(c_dup.vals, c_w.vals) and np.array_equal(c_dup.ptrs, c_w.ptrs)
+    assert not np.array_equal(c_w.vals, base.vals)
+    for bad in (-1.0, np.nan, np.inf):
+        w = np.ones(n, np.float32); w[7] = bad
+        with pytest.raises(ValueError):
+            oracle.Cuts.from_data(X, 16, weight=w)

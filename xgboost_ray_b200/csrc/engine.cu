@@ -73,8 +73,10 @@ int b2_launch_transform(int, int, float*, int64_t, int, cudaStream_t);
 int b2_extract_batch();
 int b2_launch_extract_keys(const float*, int64_t, int, int, int, float, uint32_t*, int64_t, int, cudaStream_t);
 size_t b2_sort_temp_bytes(int64_t);
-int b2_sketch_column(const uint32_t*, uint32_t*, int64_t, long long, void*, size_t, int32_t*, int32_t*, float*, long long*,
-                     int32_t*, long long*, int, float*, int32_t*, float*, int32_t*, int, cudaStream_t);
+int b2_sketch_column(const uint32_t*, const int32_t*, uint32_t*, int32_t*, long long*, int64_t, long long, void*, size_t, int32_t*,
+                     int32_t*, float*, long long*, int32_t*, long long*, int, float*, int32_t*, float*, int32_t*, int, cudaStream_t);
+int b2_launch_weight_absmax(const float*, int64_t, uint32_t*, int, cudaStream_t);
+int b2_launch_weight_quantize(const float*, int64_t, int64_t, const uint32_t*, int32_t*, int, cudaStream_t);
 int b2_launch_bin(const float*, int64_t, int, float, const int32_t*, const float*, const int32_t*, const uint8_t*, int, uint8_t*,
                   uint8_t*, int64_t, int, cudaStream_t);
 }
@@ -383,7 +385,40 @@ void make_cuts(Matrix* m, Comm* comm, int max_bin) {
   const size_t nt = (size_t)std::max<int64_t>(n_total, 1);
   keys_local.ensure((size_t)std::max<int64_t>(n_pad, 1) * B);
   if (world > 1) keys_all.ensure(nt);
-  keys_sorted.ensure(nt); flags.ensure(nt); idx.ensure(nt); uval.ensure(nt); rmin.ensure(nt); m_scratch.ensure(1); nvalid.ensure(1);
+  keys_sorted.ensure(nt); flags.ensure(nt); idx.ensure(nt); uval.ensure(nt); rmin.ensure(nt); m_scratch.ensure(1); nvalid.ensure(2);
+  // sample weights make the sketch a weighted one (xgboost SketchContainer pushes info.weights_): quantise them to
+  // integers with a global power-of-two scale so that the weighted ranks are exact and identical on every rank
+  DevBuf<int32_t> wq_local, wq_all, wq_sorted; DevBuf<long long> wpre; DevBuf<uint32_t> d_wmax;
+  const int32_t* wq = nullptr;
+  {
+    long long h_has[1] = {m->n_weight > 0 ? 1 : 0};
+    if (world > 1) {   // a rank whose shard came without weights while others have them would desynchronise the collectives
+      CUDA_CHECK(cudaMemcpyAsync(d_cnt.p, h_has, sizeof(h_has), cudaMemcpyHostToDevice, s));
+      allreduce(comm, d_cnt.p, 1, kNcclInt64, kNcclMax, s);
+      CUDA_CHECK(cudaMemcpyAsync(h_has, d_cnt.p, sizeof(h_has), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    if (h_has[0]) {
+      if (m->n_weight != m->n) fail("sample weights are set on some ranks only (this rank has %lld for %lld rows)", (long long)m->n_weight, (long long)m->n);
+      d_wmax.ensure(2);
+      CUDA_CHECK(cudaMemsetAsync(d_wmax.p, 0, 2 * sizeof(uint32_t), s));
+      LAUNCH_CHECK(b2_launch_weight_absmax(m->weight.p, m->n, d_wmax.p, ctx->num_sms, s));
+      allreduce(comm, d_wmax.p, 2, kNcclUint32, kNcclMax, s);
+      uint32_t h_w[2];
+      CUDA_CHECK(cudaMemcpyAsync(h_w, d_wmax.p, sizeof(h_w), cudaMemcpyDeviceToHost, s));
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      if (h_w[1]) fail("sample weights must be finite and non-negative");
+      wq_local.ensure((size_t)std::max<int64_t>(n_pad, 1));
+      LAUNCH_CHECK(b2_launch_weight_quantize(m->weight.p, m->n, n_pad, d_wmax.p, wq_local.p, ctx->num_sms, s));
+      wq = wq_local.p;
+      if (world > 1) {
+        wq_all.ensure(nt);
+        NCCL_CHECK(nccl()->AllGather(wq_local.p, wq_all.p, (size_t)n_pad, kNcclInt32, comm->comm, s));
+        wq = wq_all.p;
+      }
+      wq_sorted.ensure(nt); wpre.ensure(nt);
+    }
+  }
   const size_t temp_bytes = b2_sort_temp_bytes(n_total > 0 ? n_total : 1);
   temp.ensure(temp_bytes ? temp_bytes : 1);
   const size_t tab_n = (size_t)F * 256 + 3 * (size_t)F;
@@ -407,7 +442,7 @@ void make_cuts(Matrix* m, Comm* comm, int max_bin) {
         kin = keys_all.p;
         if (f % world != rank) continue;   // the owner rank sketches this feature
       }
-      LAUNCH_CHECK(b2_sketch_column(kin, keys_sorted.p, n_total, n_global, temp.p, temp_bytes, flags.p, idx.p, uval.p, rmin.p,
+      LAUNCH_CHECK(b2_sketch_column(kin, wq, keys_sorted.p, wq_sorted.p, wpre.p, n_total, n_global, temp.p, temp_bytes, flags.p, idx.p, uval.p, rmin.p,
                                     m_scratch.p, nvalid.p, max_bin, d_cuts + (size_t)f * 256, d_ncuts + f, d_mins + f,
                                     d_hasmiss + f, ctx->num_sms, s));
     }

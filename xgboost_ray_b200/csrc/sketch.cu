@@ -64,14 +64,54 @@ __global__ void scatter_unique_kernel(const uint32_t* __restrict__ keys, const i
   }
 }
 
+// ---- weighted sketch (sample weights; WQSummary ranks are sums of weights).  Weights are quantised to integers
+// wq = rint(w * 2^(30 - e)), 2^e > max w over all ranks, so rank sums are exact int64 and independent of the order
+// of rows and of the number of GPUs (same idea as the fixed-point gradient histograms).
+__global__ void weight_absmax_kernel(const float* __restrict__ w, int64_t n, uint32_t* __restrict__ out /*[2]: max bits, invalid*/) {
+  uint32_t mx = 0, bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = w[i];
+    if (!(v >= 0.0f) || isinf(v)) bad = 1; else mx = max(mx, __float_as_uint(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); bad |= __shfl_xor_sync(0xffffffffu, bad, o); }
+  if ((threadIdx.x & 31) == 0) { if (mx) atomicMax(&out[0], mx); if (bad) atomicMax(&out[1], 1u); }
+}
+__global__ void weight_quantize_kernel(const float* __restrict__ w, int64_t n, int64_t n_padded, const uint32_t* __restrict__ absmax,
+                                       int32_t* __restrict__ wq) {
+  int e = 0;
+  const float vmax = __uint_as_float(absmax[0]);
+  if (vmax > 0.0f) frexpf(vmax, &e);
+  const float scale = ldexpf(1.0f, 30 - e);            // exact power of two
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (int64_t)gridDim.x * blockDim.x)
+    wq[i] = i < n ? __float2int_rn(__fmul_rn(w[i], scale)) : 0;
+}
+struct CastI64 { __host__ __device__ long long operator()(int32_t v) const { return (long long)v; } };
+__global__ void scatter_unique_weighted_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ flags,
+                                               const int32_t* __restrict__ idx, const long long* __restrict__ wpre,
+                                               const int32_t* __restrict__ wq_sorted, const long long* __restrict__ n_valid_ptr,
+                                               int64_t n_total, float* __restrict__ uval, long long* __restrict__ rmin,
+                                               int32_t* __restrict__ m_out, long long* __restrict__ w_total) {
+  const long long n_valid = *n_valid_ptr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (flags[i]) { uval[idx[i]] = key2f(keys[i]); rmin[idx[i]] = wpre[i]; }
+    if (i == n_total - 1) *m_out = idx[i] + flags[i];
+    if (i == n_valid - 1) *w_total = wpre[i] + wq_sorted[i];      // total weight of the non-missing values
+  }
+  if (n_valid == 0 && blockIdx.x == 0 && threadIdx.x == 0) *w_total = 0;
+}
+
 // One block.  WQSummary::SetPrune + HistogramCuts::AddCutPoint on the exact summary (A.2).
+// w_total_ptr != nullptr: rmin holds weighted ranks and *w_total_ptr the total weight (the last rmax).
 __global__ void __launch_bounds__(256)
 prune_cuts_kernel(const float* __restrict__ uval, const long long* __restrict__ rmin, const int32_t* __restrict__ m_ptr,
-                  const long long* __restrict__ n_valid_ptr, long long n_global, int max_bin, float* __restrict__ cut_out /*[256]*/,
+                  const long long* __restrict__ n_valid_ptr, const long long* __restrict__ w_total_ptr, long long n_global, int max_bin,
+                  float* __restrict__ cut_out /*[256]*/,
                   int32_t* __restrict__ n_cut_out, float* __restrict__ min_out, int32_t* __restrict__ has_missing_out) {
   __shared__ int sel[260];
   __shared__ int choice[260];
   const long long n_valid = *n_valid_ptr;
+  const long long rank_end = w_total_ptr ? *w_total_ptr : n_valid;
   const bool any_missing = n_valid < n_global;
   const int max_bin_cap = (any_missing && max_bin > 255) ? 255 : max_bin;   // bin 255 is the missing sentinel
   if (threadIdx.x == 0) *has_missing_out = any_missing ? 1 : 0;
@@ -89,7 +129,7 @@ prune_cuts_kernel(const float* __restrict__ uval, const long long* __restrict__ 
   const int max_num_bins = m < max_bin_cap ? m : max_bin_cap;
   const int maxsize = max_num_bins + 1;
   int size = 0;
-  auto RMAX = [&](int u) -> long long { return (u + 1 < m) ? rmin[u + 1] : n_valid; };
+  auto RMAX = [&](int u) -> long long { return (u + 1 < m) ? rmin[u + 1] : rank_end; };
   if (m > maxsize) {
     const double begin = (double)RMAX(0);
     const double range = __dadd_rn((double)rmin[m - 1], -begin);
@@ -205,32 +245,66 @@ int b2_launch_extract_keys(const float* X, int64_t n, int F, int f0, int nf, flo
 }
 
 size_t b2_sort_temp_bytes(int64_t n) {
-  size_t bytes = 0;
+  size_t bytes = 0, b2 = 0;
   cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n);
-  size_t scan_bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, n);
-  return bytes > scan_bytes ? bytes : scan_bytes;
+  cub::DeviceRadixSort::SortPairs(nullptr, b2, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, n);
+  bytes = bytes > b2 ? bytes : b2;
+  cub::DeviceScan::ExclusiveSum(nullptr, b2, (const int32_t*)nullptr, (int32_t*)nullptr, n);
+  bytes = bytes > b2 ? bytes : b2;
+  cub::TransformInputIterator<long long, b2::CastI64, const int32_t*> it((const int32_t*)nullptr, b2::CastI64());
+  cub::DeviceScan::ExclusiveSum(nullptr, b2, it, (long long*)nullptr, n);
+  return bytes > b2 ? bytes : b2;
+}
+
+// sample weights -> integer weights of the sketch (see weight_absmax_kernel).  absmax [2] must be zeroed; call
+// b2_launch_weight_absmax, allreduce(max) absmax over the ranks, then b2_launch_weight_quantize.
+int b2_launch_weight_absmax(const float* w, int64_t n, uint32_t* absmax, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::weight_absmax_kernel<<<sk_grid(n, num_sms), 256, 0, s>>>(w, n, absmax);
+  return (int)cudaGetLastError();
+}
+int b2_launch_weight_quantize(const float* w, int64_t n, int64_t n_padded, const uint32_t* absmax, int32_t* wq, int num_sms,
+                              cudaStream_t s) {
+  if (n_padded <= 0) return 0;
+  b2::weight_quantize_kernel<<<sk_grid(n_padded, num_sms), 256, 0, s>>>(w, n, n_padded, absmax, wq);
+  return (int)cudaGetLastError();
 }
 
 // keys_in [n_total] (any order, 0xffffffff = missing/padding) -> cuts of one feature, no host round trip:
 // n_valid is found on the device, the 255-bin cap of features with missing values is applied on the device.
 // Scratch: keys_sorted [n_total], flags/idx int32 [n_total], uval float [n_total], rmin int64 [n_total].
-int b2_sketch_column(const uint32_t* keys_in, uint32_t* keys_sorted, int64_t n_total, long long n_global, void* temp,
+// wq_in (nullable) [n_total]: integer sample weights aligned with keys_in; wq_sorted int32 [n_total], wpre int64 [n_total] and
+// n_valid_scratch [2] are then needed as extra scratch.
+int b2_sketch_column(const uint32_t* keys_in, const int32_t* wq_in, uint32_t* keys_sorted, int32_t* wq_sorted, long long* wpre,
+                     int64_t n_total, long long n_global, void* temp,
                      size_t temp_bytes, int32_t* flags, int32_t* idx, float* uval, long long* rmin, int32_t* m_scratch,
                      long long* n_valid_scratch, int max_bin, float* cut_out, int32_t* n_cut_out, float* min_out,
                      int32_t* has_missing_out, int num_sms, cudaStream_t s) {
   cudaError_t e;
   if (n_total > 0) {
-    e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_in, keys_sorted, n_total, 0, 32, s);
+    if (wq_in) e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_sorted, wq_in, wq_sorted, n_total, 0, 32, s);
+    else e = cub::DeviceRadixSort::SortKeys(temp, temp_bytes, keys_in, keys_sorted, n_total, 0, 32, s);
     if (e != cudaSuccess) return (int)e;
     b2::head_flags_kernel<<<sk_grid(n_total, num_sms), 256, 0, s>>>(keys_sorted, n_total, flags);
     e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, flags, idx, n_total, s);
     if (e != cudaSuccess) return (int)e;
-    b2::scatter_unique_kernel<<<sk_grid(n_total, num_sms), 256, 0, s>>>(keys_sorted, flags, idx, n_total, uval, rmin, m_scratch);
   }
   b2::count_valid_kernel<<<1, 32, 0, s>>>(keys_sorted, n_total, n_valid_scratch);
-  b2::prune_cuts_kernel<<<1, 256, 0, s>>>(uval, rmin, m_scratch, n_valid_scratch, n_global, max_bin, cut_out, n_cut_out, min_out,
-                                         has_missing_out);
+  if (n_total > 0) {
+    if (wq_in) {
+      cub::TransformInputIterator<long long, b2::CastI64, const int32_t*> it(wq_sorted, b2::CastI64());
+      e = cub::DeviceScan::ExclusiveSum(temp, temp_bytes, it, wpre, n_total, s);
+      if (e != cudaSuccess) return (int)e;
+      b2::scatter_unique_weighted_kernel<<<sk_grid(n_total, num_sms), 256, 0, s>>>(keys_sorted, flags, idx, wpre, wq_sorted,
+                                                                                  n_valid_scratch, n_total, uval, rmin, m_scratch,
+                                                                                  n_valid_scratch + 1);
+    } else {
+      b2::scatter_unique_kernel<<<sk_grid(n_total, num_sms), 256, 0, s>>>(keys_sorted, flags, idx, n_total, uval, rmin, m_scratch);
+    }
+  }
+  b2::prune_cuts_kernel<<<1, 256, 0, s>>>(uval, rmin, m_scratch, n_valid_scratch, (wq_in && n_total > 0) ? n_valid_scratch + 1 : nullptr,
+                                         n_global, max_bin, cut_out, n_cut_out, min_out, has_missing_out);
   return (int)cudaGetLastError();
 }
 
