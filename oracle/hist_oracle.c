@@ -76,6 +76,10 @@ typedef struct {
   int32_t max_cat_threshold;  /* categorical: at most this many categories scanned per direction (default 64) */
   float scale_pos_weight;     /* binary:logistic: weight multiplier of the positive rows (A.4), default 1 */
   float max_delta_step;       /* 0 = off; otherwise |leaf weight| is clipped and the gain uses the clipped weight (A.7) */
+  float subsample;            /* row sampling per tree (1 = off) */
+  float colsample_bytree, colsample_bylevel, colsample_bynode;   /* nested column sampling (1 = off) */
+  int32_t seed;
+  int32_t rank;               /* worker rank: part of the row-sampling hash (each worker samples its own rows) */
 } OrParams;
 
 typedef struct {
@@ -109,6 +113,7 @@ typedef struct {
   int32_t n_features;
   int32_t n_trees, cap_trees;
   OrTree **trees;
+  uint32_t *fwq;          /* feature_weights in Q16 (NULL = all 1.0) */
 } OrModel;
 
 /* ------------------------------------------------------------------ util */
@@ -597,6 +602,72 @@ static void hist_f64(const uint8_t *bins, int32_t F, const float *g, const float
   }
 }
 
+/* ------------------------------------------------------------------ sampling (subsample / colsample_* / feature_weights)
+ * XGBoost draws row and column samples from per-worker Mersenne twisters (src/common/random.h ColumnSampler,
+ * src/tree/hist/sampler.h); that stream cannot be reproduced by another implementation, so the contract is the
+ * PUBLISHED behaviour with a counter-based integer hash instead of the twister:
+ *   - a row is kept for tree t iff hash(seed, t, rank, row) < subsample * 2^32 (Bernoulli per row and tree;
+ *     dropped rows get a zero gradient pair but are still partitioned and receive the leaf value);
+ *   - bytree / bylevel / bynode are nested: each scope keeps n = max(1, int(frac * |parent set|)) features of
+ *     its parent scope's set; with feature_weights the choice is weighted sampling without replacement
+ *     (exponential race: smallest -log2(u)/w), weight 0 sorts last (test_end_to_end.py:429-467). */
+static uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+static uint32_t hash4(uint32_t seed, uint32_t a, uint32_t b, uint32_t c) {
+  uint64_t h = mix64((uint64_t)seed * 0x9e3779b97f4a7c15ull + a);
+  h = mix64(h + b);
+  h = mix64(h + c);
+  return (uint32_t)(h >> 32);
+}
+/* -log2((u | 1) / 2^32) in Q16, integer shift-and-square */
+static uint32_t neg_log2_q16(uint32_t u) {
+  u |= 1u;
+  int e = 0;
+  while (!(u & 0x80000000u)) { u <<= 1; ++e; }
+  uint64_t x = u;
+  uint32_t frac = 0;
+  for (int k = 0; k < 16; ++k) {
+    x = (x * x) >> 31;
+    frac <<= 1;
+    if (x >= (1ull << 32)) { frac |= 1u; x >>= 1; }
+  }
+  return ((uint32_t)(e + 1) << 16) - frac;
+}
+#define OR_SCOPE_TREE 1u
+#define OR_SCOPE_LEVEL(d) (16u + (uint32_t)(d))
+#define OR_SCOPE_NODE(nid) (4096u + (uint32_t)(nid))
+static uint64_t col_key(uint32_t seed, uint32_t tree, uint32_t scope, uint32_t f, uint32_t wq) {
+  if (wq == 0) return 0xffffffffffffffffull;
+  return ((uint64_t)neg_log2_q16(hash4(seed, tree, scope, f)) << 24) / wq;
+}
+/* out[f] = 1 for the n smallest keys among parent (NULL = all features); returns the number selected */
+static int select_features(uint32_t seed, uint32_t tree, uint32_t scope, const uint8_t *parent, const uint32_t *fwq,
+                           int32_t F, double frac, uint8_t *out) {
+  int n_parent = 0;
+  for (int32_t f = 0; f < F; ++f) n_parent += (!parent || parent[f]) ? 1 : 0;
+  int n_sel = (int)(frac * (double)n_parent);
+  if (n_sel < 1) n_sel = 1;
+  uint64_t *key = (uint64_t *)malloc((size_t)F * sizeof(uint64_t));
+  for (int32_t f = 0; f < F; ++f) key[f] = col_key(seed, tree, scope, (uint32_t)f, fwq ? fwq[f] : 65536u);
+  int cnt = 0;
+  for (int32_t f = 0; f < F; ++f) {
+    out[f] = 0;
+    if (parent && !parent[f]) continue;
+    int rank = 0;
+    for (int32_t g = 0; g < F; ++g) {
+      if (g == f || (parent && !parent[g])) continue;
+      rank += (key[g] < key[f] || (key[g] == key[f] && g < f)) ? 1 : 0;
+    }
+    if (rank < n_sel) { out[f] = 1; ++cnt; }
+  }
+  free(key);
+  return cnt;
+}
+
 /* ------------------------------------------------------------------ A.6 split */
 static double thr_l1(double g, double a) {
   if (g > a) return g - a;
@@ -712,11 +783,12 @@ static void eval_cat_partition(const OrParams *p, const double *hf, int32_t nf, 
 
 /* hist for this node as doubles [F][256][2]; total (G,H) */
 static void evaluate_node(const OrParams *p, const OrCuts *c, const double *hist, double G, double H,
-                          float root_gain, SplitCand *best) {
+                          float root_gain, const uint8_t *feat_mask /* NULL = all features */, SplitCand *best) {
   memset(best, 0, sizeof(*best));
   best->loss_chg = 0.0f; best->feature = 0; best->valid = 0;
   int32_t F = c->n_features;
   for (int32_t f = 0; f < F; ++f) {
+    if (feat_mask && !feat_mask[f]) continue;
     const double *hf = hist + (size_t)f * 512;
     int32_t nf = c->cut_ptrs[f + 1] - c->cut_ptrs[f];
     const float *cv = c->cut_vals + c->cut_ptrs[f];
@@ -868,10 +940,30 @@ static int64_t partition_segment(int32_t *ridx, int32_t *rtmp, int64_t begin, in
 /* grow one tree on (bins, g, h); g/h may be strided (multi-class). Appends leaf values to margin
  * cache: margin[r*mstride] += leaf. */
 static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins, int64_t n,
-                         const float *g, const float *h, int64_t gstride, float *margin, int64_t mstride) {
+                         const float *g, const float *h, int64_t gstride, float *margin, int64_t mstride,
+                         int32_t tree_index, const uint32_t *fwq) {
   int32_t F = c->n_features;
   size_t hsz = (size_t)F * 512;
   OrTree *t = tree_new();
+  /* row sampling: dropped rows keep their place in the partition but carry a zero gradient pair */
+  float *gs = NULL, *hs = NULL;
+  if (p->subsample < 1.0f) {
+    const double thr_d = (double)p->subsample * 4294967296.0;
+    const uint32_t thr = thr_d >= 4294967295.0 ? 0xffffffffu : (uint32_t)thr_d;
+    gs = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float)); hs = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+    for (int64_t i = 0; i < n; ++i) {
+      const int keep = hash4((uint32_t)p->seed, (uint32_t)tree_index, (uint32_t)p->rank, (uint32_t)i) < thr;
+      gs[i] = keep ? g[i * gstride] : 0.0f; hs[i] = keep ? h[i * gstride] : 0.0f;
+    }
+    g = gs; h = hs; gstride = 1;
+  }
+  /* column sampling: tree set, then one set per level (sampled when the level is first evaluated) */
+  const int use_cols = p->colsample_bytree < 1.0f || p->colsample_bylevel < 1.0f || p->colsample_bynode < 1.0f;
+  uint8_t *mask_tree = NULL, *mask_level = NULL, *mask_node = NULL; int level_of_mask = -1;
+  if (use_cols) {
+    mask_tree = (uint8_t *)malloc((size_t)F); mask_level = (uint8_t *)malloc((size_t)F);
+    select_features((uint32_t)p->seed, (uint32_t)tree_index, OR_SCOPE_TREE, NULL, fwq, F, (double)p->colsample_bytree, mask_tree);
+  }
   int32_t *ridx = (int32_t *)slot_get(SLOT_RIDX, (size_t)(n > 0 ? n : 1) * sizeof(int32_t));
   int32_t *rtmp = (int32_t *)slot_get(SLOT_RTMP, (size_t)(n > 0 ? n : 1) * sizeof(int32_t));
   for (int64_t i = 0; i < n; ++i) ridx[i] = (int32_t)i;
@@ -917,12 +1009,24 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
     NodeWork *next = (NodeWork *)calloc((size_t)n_level * 2, sizeof(NodeWork)); int32_t n_next = 0;
     /* phase A: evaluate all nodes of the level (node-parallel) */
     int8_t *expand_flag = (int8_t *)calloc((size_t)n_level, 1);
+    if (use_cols && n_level > 0 && level[0].depth != level_of_mask) {
+      level_of_mask = level[0].depth;
+      select_features((uint32_t)p->seed, (uint32_t)tree_index, OR_SCOPE_LEVEL(level_of_mask), mask_tree, fwq, F,
+                      (double)p->colsample_bylevel, mask_level);
+    }
+    if (use_cols && p->colsample_bynode < 1.0f) mask_node = (uint8_t *)malloc((size_t)n_level * F);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int32_t k = 0; k < n_level; ++k) {
       NodeWork *w = &level[k];
       if (w->depth < p->max_depth || p->max_depth == 0) {
         float root_gain = (float)calc_gain(p, w->G, w->H);
-        evaluate_node(p, c, w->hist, w->G, w->H, root_gain, &w->split);
+        const uint8_t *fm = mask_level;
+        if (mask_node) {
+          select_features((uint32_t)p->seed, (uint32_t)tree_index, OR_SCOPE_NODE(w->nid), mask_level, fwq, F,
+                          (double)p->colsample_bynode, mask_node + (size_t)k * F);
+          fm = mask_node + (size_t)k * F;
+        }
+        evaluate_node(p, c, w->hist, w->G, w->H, root_gain, fm, &w->split);
         SplitCand *sc = &w->split;
         expand_flag[k] = sc->valid && sc->loss_chg > OR_RT_EPS && sc->HL != 0.0 && sc->HR != 0.0 &&
                          !(sc->loss_chg < p->gamma);
@@ -1005,10 +1109,10 @@ static OrTree *grow_tree(const OrParams *p, const OrCuts *c, const uint8_t *bins
         }
       }
     }
-    free(expand_flag); free(pair_parent);
+    free(expand_flag); free(pair_parent); free(mask_node); mask_node = NULL;
     free(level); level = next; n_level = n_next;
   }
-  free(level);
+  free(level); free(gs); free(hs); free(mask_tree); free(mask_level);
   return t;
 }
 
@@ -1023,7 +1127,19 @@ OrModel *or_model_new(const OrParams *p, int32_t n_features) {
 void or_model_free(OrModel *m) {
   if (!m) return;
   for (int i = 0; i < m->n_trees; ++i) tree_free(m->trees[i]);
-  free(m->trees); free(m);
+  free(m->trees); free(m->fwq); free(m);
+}
+/* feature_weights (DMatrix.set_info(feature_weights=...), main.py:439-442): Q16, negative -> invalid (returns -1) */
+int or_model_set_feature_weights(OrModel *m, const float *fw, int32_t len) {
+  if (len != m->n_features) return -1;
+  for (int32_t f = 0; f < len; ++f) if (!(fw[f] >= 0.0f) || isinf(fw[f])) return -1;
+  free(m->fwq);
+  m->fwq = (uint32_t *)malloc((size_t)len * sizeof(uint32_t));
+  for (int32_t f = 0; f < len; ++f) {
+    double q = (double)fw[f] * 65536.0;
+    m->fwq[f] = q >= 4294967295.0 ? 0xffffffffu : (uint32_t)llrint(q);
+  }
+  return 0;
 }
 static void model_push(OrModel *m, OrTree *t) {
   if (m->n_trees == m->cap_trees) {
@@ -1053,7 +1169,7 @@ int or_boost_one_round(OrModel *m, const OrCuts *c, const uint8_t *bins, int64_t
     gg = g; hh = h;
   }
   for (int k = 0; k < K; ++k) {
-    OrTree *t = grow_tree(&m->p, c, bins, n, gg + k, hh + k, K, margin + k, K);
+    OrTree *t = grow_tree(&m->p, c, bins, n, gg + k, hh + k, K, margin + k, K, m->n_trees, m->fwq);
     model_push(m, t);
   }
   return 0;

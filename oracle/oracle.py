@@ -28,7 +28,9 @@ class OrParams(C.Structure):
                 ("min_child_weight", C.c_float), ("lambda_", C.c_float), ("alpha", C.c_float),
                 ("base_score", C.c_float), ("qbits", C.c_int32), ("nthread", C.c_int32),
                 ("max_cat_to_onehot", C.c_int32), ("max_cat_threshold", C.c_int32),
-                ("scale_pos_weight", C.c_float), ("max_delta_step", C.c_float)]
+                ("scale_pos_weight", C.c_float), ("max_delta_step", C.c_float), ("subsample", C.c_float),
+                ("colsample_bytree", C.c_float), ("colsample_bylevel", C.c_float), ("colsample_bynode", C.c_float),
+                ("seed", C.c_int32), ("rank", C.c_int32)]
 
 
 def build(force=False):
@@ -71,6 +73,8 @@ def lib():
         L.or_model_new.restype = C.c_void_p
         L.or_model_new.argtypes = [C.POINTER(OrParams), C.c_int32]
         L.or_model_free.argtypes = [C.c_void_p]
+        L.or_model_set_feature_weights.restype = C.c_int
+        L.or_model_set_feature_weights.argtypes = [C.c_void_p, fp, C.c_int32]
         L.or_base_margin.restype = C.c_float
         L.or_base_margin.argtypes = [C.POINTER(OrParams)]
         L.or_boost_one_round.restype = C.c_int
@@ -220,6 +224,12 @@ def make_params(params):
     p.max_cat_threshold = int(params.get("max_cat_threshold", 64))
     p.scale_pos_weight = float(params.get("scale_pos_weight", 1.0))
     p.max_delta_step = float(params.get("max_delta_step", 0.0))
+    p.subsample = float(params.get("subsample", 1.0))
+    p.colsample_bytree = float(params.get("colsample_bytree", 1.0))
+    p.colsample_bylevel = float(params.get("colsample_bylevel", 1.0))
+    p.colsample_bynode = float(params.get("colsample_bynode", 1.0))
+    p.seed = int(params.get("seed", params.get("random_state", 0)) or 0)
+    p.rank = int(params.get("_rank", 0))
     return p
 
 
@@ -251,6 +261,11 @@ class Booster:
         self.h = lib().or_model_new(C.byref(self.p), cuts.n_features)
         self.K = self.p.num_class
         self.margin = None
+
+    def set_feature_weights(self, fw):
+        fw = _f32(fw)
+        if lib().or_model_set_feature_weights(self.h, _fp(fw), len(fw)) != 0:
+            raise ValueError("feature_weights must have one finite non-negative value per feature")
 
     def base_margin_value(self):
         return float(lib().or_base_margin(C.byref(self.p)))
@@ -336,12 +351,15 @@ class Booster:
             pass
 
 
-def train(params, X, y, num_boost_round, weight=None, missing=np.nan, cuts=None, base_margin=None, is_cat=None):
+def train(params, X, y, num_boost_round, weight=None, missing=np.nan, cuts=None, base_margin=None, is_cat=None,
+          feature_weights=None):
     """Convenience: cuts -> bins -> rounds.  Returns (Booster, bins)."""
     X = _f32(X)
     cuts = cuts or Cuts.from_data(X, int(params.get("max_bin", 256)), missing, is_cat=is_cat, weight=weight)
     bins = cuts.bin(X, missing)
     bst = Booster(params, cuts)
+    if feature_weights is not None:
+        bst.set_feature_weights(feature_weights)
     bst.init_margin(X.shape[0], base_margin)
     for _ in range(num_boost_round):
         bst.boost(bins, y, weight)

@@ -110,9 +110,11 @@ class DMatrix:
         self.base_margin = None if base_margin is None else np.asarray(base_margin, np.float32)
         self.missing = np.nan if missing is None else missing
         self.feature_names = feature_names
+        self.feature_weights = None
 
-    def set_info(self, **kw):
-        pass
+    def set_info(self, feature_weights=None, **kw):
+        if feature_weights is not None:
+            self.feature_weights = np.asarray(feature_weights, np.float32)
 
     def get_label(self):
         return self.label if self.label is not None else np.zeros(0, np.float32)
@@ -212,6 +214,8 @@ def train(params, dtrain, num_boost_round=10, evals=(), obj=None, feval=None, ma
     bst = Booster(params)
     bst.n_features = X.shape[1]
     bst.ob = O.Booster(params, cuts)
+    if dtrain.feature_weights is not None:
+        bst.ob.set_feature_weights(dtrain.feature_weights)
     bst.ob.init_margin(X.shape[0])
     if xgb_model is not None:
         prev = xgb_model.trees() if isinstance(xgb_model, Booster) else pickle.loads(bytes(xgb_model))["trees"]

@@ -457,7 +457,7 @@ def test_trees_identical_scale_pos_weight_and_max_delta_step(eng, oracle, extra)
 def test_unsupported_parameters_fail_loudly(eng):
     X = make_data(100, 3, 1)
     dm = eng.DMatrix(X, label=X[:, 0])
-    for bad in ({"subsample": 0.5}, {"colsample_bytree": 0.5}, {"grow_policy": "lossguide"}, {"max_leaves": 8},
+    for bad in ({"sampling_method": "gradient_based"}, {"grow_policy": "lossguide"}, {"max_leaves": 8},
                 {"monotone_constraints": "(1,0,0)"}, {"num_parallel_tree": 4}, {"max_bin": 1024}):
         with pytest.raises(eng.XGBoostError, match="not supported"):
             eng.train(dict({"objective": "reg:squarederror"}, **bad), dm, num_boost_round=1, verbose_eval=False)
@@ -482,3 +482,45 @@ def test_weighted_sketch_cuts_bit_exact(eng, oracle, nan_frac, max_bin):
     bad = w.copy(); bad[5] = -2.0
     with pytest.raises(eng.XGBoostError, match="weights"):
         eng.DMatrix(X, weight=bad)._ensure_quantized(max_bin)
+
+
+# ------------------------------------------------------------------ row / column sampling (sampling.cuh)
+@pytest.mark.parametrize("extra", [
+    {"subsample": 0.5, "seed": 7}, {"colsample_bytree": 0.5}, {"colsample_bylevel": 0.4, "seed": 3},
+    {"colsample_bynode": 0.3, "seed": 11}, {"subsample": 0.8, "colsample_bytree": 0.7, "colsample_bylevel": 0.7,
+                                           "colsample_bynode": 0.5, "seed": 2024},
+])
+def test_trees_identical_with_sampling(eng, oracle, extra):
+    X = make_data(20000, 40, 81, "uniform", nan_frac=0.02)
+    rng = np.random.RandomState(82)
+    y = (np.nan_to_num(X[:, :8]).sum(axis=1) + rng.normal(size=len(X))).astype(np.float32)
+    params = dict({"objective": "reg:squarederror", "max_depth": 5, "eta": 0.3, "base_score": 0.5}, **extra)
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 4)
+    assert_same_model(ebst, obst)
+    plain, _ = oracle.train({k: v for k, v in params.items() if k in ("objective", "max_depth", "eta", "base_score")}, X, y, 1)
+    assert not np.array_equal(plain.tree(0).split_feature, obst.tree(0).split_feature) or "subsample" in extra
+
+
+def test_sampling_with_categorical_and_multiclass(eng, oracle):
+    X, score, rng = make_cat_data(20000, 83, 0.03)
+    y = np.clip(np.round(score), 0, 4).astype(np.float32)
+    params = {"objective": "multi:softprob", "num_class": 5, "max_depth": 4, "eta": 0.4, "subsample": 0.7,
+              "colsample_bynode": 0.5, "seed": 5}
+    ebst, obst, dm = run_both_cat(eng, oracle, params, X, y, 2)
+    assert_same_model(ebst, obst)
+
+
+def test_feature_weights_known_answer(eng, oracle):
+    """test_end_to_end.py:429-467: feature_weights = 0..9 with colsample_bynode=0.1 -> f0 never splits, f9 most often."""
+    rng = np.random.RandomState(1994)
+    X = rng.randn(1000, 10).astype(np.float32)
+    y = rng.randn(1000).astype(np.float32)
+    fw = np.arange(10, dtype=np.float32)
+    params = {"objective": "reg:squarederror", "colsample_bynode": 0.1, "max_depth": 6}
+    dm = eng.DMatrix(X, label=y)
+    dm.set_info(feature_weights=fw)
+    ebst = eng.train(params, dm, num_boost_round=60, verbose_eval=False)
+    fmap = ebst.get_fscore()
+    assert fmap.get("f0") is None and max(fmap.values()) == fmap.get("f9")
+    obst, _ = oracle.train(params, X, y, 60, feature_weights=fw)
+    assert_same_model(ebst, obst)

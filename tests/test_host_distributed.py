@@ -119,3 +119,23 @@ def test_sklearn_estimators():
     yr = (Xr[:, 0] * 2 + Xr[:, 1]).astype(np.float32)
     reg = RayXGBRegressor(n_estimators=20, max_depth=4).fit(RayDMatrix(Xr, yr), ray_params=RayParams(num_actors=2))
     assert np.mean((reg.predict(RayDMatrix(Xr), ray_params=RayParams(num_actors=2)) - yr) ** 2) < 1.0
+
+
+@pytest.mark.timeout(600)
+def test_feature_weights_reach_the_engine():
+    """test_end_to_end.py:429-467: RayDMatrix(feature_weights=...) is forwarded per actor (set_info, main.py:439-442);
+    weights 0..9 with colsample_bynode=0.1 -> feature 0 is never used, feature 9 most."""
+    import json
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    rng = np.random.RandomState(1994)
+    X = rng.randn(1000, 10).astype(np.float32)
+    y = rng.randn(1000).astype(np.float32)
+    fw = np.arange(10, dtype=np.float32)
+    bst = train({"objective": "reg:squarederror", "colsample_bynode": 0.1}, RayDMatrix(X, y, feature_weights=fw),
+                num_boost_round=40, ray_params=RayParams(num_actors=2, cpus_per_actor=1))
+    cnt = np.zeros(10, int)
+    for t in bst.get_dump():
+        for f in json.loads(t)["split_feature"]:
+            if f >= 0:
+                cnt[f] += 1
+    assert cnt[0] == 0 and cnt.argmax() == 9

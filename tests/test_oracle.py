@@ -196,3 +196,54 @@ def test_weighted_sketch_known_answers(oracle):
         w = np.ones(n, np.float32); w[7] = bad
         with pytest.raises(ValueError):
             oracle.Cuts.from_data(X, 16, weight=w)
+
+
+def _used_features(bst):
+    return [sorted({int(f) for f in t.split_feature if f >= 0}) for t in bst.trees()]
+
+
+def test_sampling_known_answers(oracle):
+    """subsample / colsample_* (sampling section of the oracle): fractions, nesting, determinism, weights."""
+    rng = np.random.RandomState(3)
+    n, F = 4000, 20
+    X = rng.uniform(0, 10, size=(n, F)).astype(np.float32)
+    y = (X.sum(axis=1) + rng.normal(size=n)).astype(np.float32)
+    base = {"objective": "reg:squarederror", "max_depth": 5, "eta": 0.3}
+    plain, _ = oracle.train(base, X, y, 3)
+    same, _ = oracle.train(dict(base, subsample=1.0, colsample_bytree=1.0, colsample_bylevel=1.0, colsample_bynode=1.0, seed=9), X, y, 3)
+    assert all(np.array_equal(a.split_feature, b.split_feature) for a, b in zip(plain.trees(), same.trees()))
+    # subsample: the root's hessian sum (= kept rows for squared error) is binomial around subsample * n, per tree
+    sub, _ = oracle.train(dict(base, subsample=0.25, seed=1), X, y, 4)
+    kept = [t.sum_hess[0] for t in sub.trees()]
+    assert all(abs(k - 0.25 * n) < 5 * np.sqrt(n * 0.25 * 0.75) for k in kept) and len(set(kept)) > 1
+    # bytree: int(0.5 * 20) = 10 features per tree, different trees draw different sets
+    bt, _ = oracle.train(dict(base, colsample_bytree=0.5, seed=1), X, y, 6)
+    sets = _used_features(bt)
+    assert all(len(s) <= 10 for s in sets) and len({tuple(s) for s in sets}) > 1
+    # bynode = 1/F: every node sees exactly one feature; seeds matter, same seed repeats
+    bn1, _ = oracle.train(dict(base, colsample_bynode=0.05, seed=1), X, y, 2)
+    bn2, _ = oracle.train(dict(base, colsample_bynode=0.05, seed=1), X, y, 2)
+    bn3, _ = oracle.train(dict(base, colsample_bynode=0.05, seed=2), X, y, 2)
+    assert all(np.array_equal(a.split_feature, b.split_feature) for a, b in zip(bn1.trees(), bn2.trees()))
+    assert not all(np.array_equal(a.split_feature, b.split_feature) for a, b in zip(bn1.trees(), bn3.trees()))
+    # nesting: with bytree = 0.25 (5 features) every level / node set is a subset of the tree's 5
+    nest, _ = oracle.train(dict(base, colsample_bytree=0.25, colsample_bylevel=0.6, colsample_bynode=0.7, seed=4), X, y, 5)
+    assert all(len(s) <= 5 for s in _used_features(nest))
+
+
+def test_feature_weights_known_answer(oracle):
+    """test_end_to_end.py:429-467 (xgboost feature_weights demo): weights 0..9, colsample_bynode=0.1 -> feature 0 is
+    never used and feature 9 is used most."""
+    rng = np.random.RandomState(1994)
+    X = rng.randn(1000, 10).astype(np.float32)
+    y = rng.randn(1000).astype(np.float32)
+    bst, _ = oracle.train({"objective": "reg:squarederror", "colsample_bynode": 0.1, "max_depth": 6}, X, y, 60,
+                          feature_weights=np.arange(10, dtype=np.float32))
+    cnt = np.zeros(10, int)
+    for t in bst.trees():
+        for f in t.split_feature:
+            if f >= 0:
+                cnt[f] += 1
+    assert cnt[0] == 0 and cnt.argmax() == 9
+    with pytest.raises(ValueError):
+        oracle.train({"objective": "reg:squarederror"}, X, y, 1, feature_weights=-np.ones(10, np.float32))

@@ -94,6 +94,17 @@ struct B2TreeDev {            // arrays of capacity max_nodes
 };
 struct B2CtlParams { double mcw, lambda, alpha, max_delta_step; float gamma, eta; };
 
+// column sampling of one level (sampling.cuh): level_mask = features of the level's set (nullptr = all);
+// bynode < 1 makes every node draw its own subset of that set on the device
+struct B2ColSample {
+  const uint8_t* level_mask;
+  const uint32_t* fwq;      // feature weights in Q16 (nullptr = all 1.0)
+  double bynode;
+  int32_t n_level;          // features in the level's set
+  int32_t n_features;
+  uint32_t seed, tree;
+};
+
 struct B2TrainParamDev {
   double min_child_weight, lambda, alpha;
   double inv_scale_g, inv_scale_h;

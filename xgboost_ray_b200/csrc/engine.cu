@@ -24,6 +24,7 @@
 
 #include "../../include/b2hist.h"
 #include "common.cuh"
+#include "sampling.cuh"
 
 // ---------------------------------------------------------------- kernel launchers (other TUs)
 extern "C" {
@@ -35,11 +36,12 @@ int b2_launch_hist_tma(const void*, const void*, const int2*, const int32_t*, co
 int b2_launch_hist_subtract(const long long*, long long*, const int32_t*, int, int64_t, const B2LevelCtl*, cudaStream_t);
 int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, const int32_t*, const int32_t*,
                           const uint8_t*, const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, int, const B2LevelCtl*,
-                          int, int, cudaStream_t);
+                          int, int, B2ColSample, const B2NodeSeg*, cudaStream_t);
+int b2_launch_subsample(float2*, int64_t, uint32_t, uint32_t, uint32_t, double, int, cudaStream_t);
 int b2_cat_ctas();
 int b2_launch_eval_cat_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, int, const int32_t*, const int32_t*,
                               const int32_t*, int, B2TrainParamDev, B2SplitCand*, int, int, const B2LevelCtl*, int, int,
-                              cudaStream_t);
+                              B2ColSample, const B2NodeSeg*, cudaStream_t);
 int b2_launch_cat_stats(const float*, int64_t, int, float, const int32_t*, int, int32_t*, int, cudaStream_t);
 int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, int, cudaStream_t);
 int b2_part_chunk_rows();
@@ -318,6 +320,8 @@ struct Matrix : HandleBase {
   bool any_cat() const { return !cat_feats.empty(); }
   DevBuf<float> label, weight, base_margin;
   int64_t n_label = 0, n_weight = 0, n_base_margin = 0;
+  std::vector<uint32_t> fwq;          // feature_weights in Q16 (empty = all 1.0)
+  DevBuf<uint32_t> d_fwq;
 };
 
 void setup_groups(Matrix* m) {
@@ -523,6 +527,9 @@ struct Params {
   int device = 0;
   int max_cat_to_onehot = 4, max_cat_threshold = 64;   // xgboost defaults (src/tree/param.h)
   float scale_pos_weight = 1.0f, max_delta_step = 0.0f;
+  float subsample = 1.0f, colsample_bytree = 1.0f, colsample_bylevel = 1.0f, colsample_bynode = 1.0f;
+  int seed = 0;
+  bool use_cols() const { return colsample_bytree < 1.0f || colsample_bylevel < 1.0f || colsample_bynode < 1.0f; }
 };
 
 struct TreeHost {
@@ -578,6 +585,7 @@ struct Booster : HandleBase {
   int shards = 1, log2_shards = 0, sp = 32, cpn = 1;   // cpn = candidates per node (numeric CTAs + categorical CTAs)
   int cpn_num = 1;
   DevBuf<uint32_t> t_cat;                  // [max_nodes][8] category sets of the tree being grown
+  DevBuf<uint8_t> d_col_masks;             // [max_depth][F] level feature sets of the tree being grown (column sampling)
   size_t slice_elems = 0;
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
@@ -668,6 +676,11 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
     else if (k == "profile") p->profile = i();
     else if (k == "num_feature") p->num_feature = i();
     else if (k == "device") p->device = i();
+    else if (k == "subsample") p->subsample = f();
+    else if (k == "colsample_bytree") p->colsample_bytree = f();
+    else if (k == "colsample_bylevel") p->colsample_bylevel = f();
+    else if (k == "colsample_bynode") p->colsample_bynode = f();
+    else if (k == "seed" || k == "random_state") p->seed = i();
     else if (k == "scale_pos_weight") p->scale_pos_weight = f();
     else if (k == "max_delta_step") p->max_delta_step = f();
     else if (k == "max_cat_to_onehot") p->max_cat_to_onehot = i();
@@ -679,6 +692,8 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
   if (p->objective == kObjSoftprob && p->num_class < 2) fail("multi:softprob needs num_class >= 2");
   if (p->max_depth < 1 || p->max_depth > 14) fail("max_depth must be in [1, 14], got %d", p->max_depth);
   if (p->qbits < 8 || p->qbits > 24) fail("hist_qbits must be in [8, 24], got %d", p->qbits);
+  for (float v : {p->subsample, p->colsample_bytree, p->colsample_bylevel, p->colsample_bynode})
+    if (!(v > 0.0f && v <= 1.0f)) fail("subsample / colsample_* must be in (0, 1], got %g", (double)v);
   if (p->max_cat_to_onehot < 1) fail("max_cat_to_onehot must be >= 1, got %d", p->max_cat_to_onehot);
   if (p->max_cat_threshold < 1) fail("max_cat_threshold must be >= 1, got %d", p->max_cat_threshold);
 }
@@ -816,6 +831,34 @@ void grow_tree(Booster* b, int k, int slot) {
   mark_phase(b, -1);
   // ---- fixed-point quantisation (global scale via allreduce max)
   b->d_absmax.ensure(2); b->d_qexp.ensure(2);
+  const uint32_t tree_index = (uint32_t)b->trees.size() + (uint32_t)k;   // the k-th class tree of this round
+  if (p.subsample < 1.0f) {
+    LAUNCH_CHECK(b2_launch_subsample(b->gh.p + (size_t)k * n, n, (uint32_t)p.seed, tree_index, b->comm ? (uint32_t)b->comm->rank : 0u,
+                                     (double)p.subsample, ctx->num_sms, s));
+    b->t.kernel_launches++;
+  }
+  // column sampling: the tree's feature set and one nested set per level are drawn on the host (they depend on
+  // (seed, tree, level) only, never on the data), the per-node subsets inside the split-scan kernels
+  std::vector<int> n_level_feats(D > 0 ? D : 1, m->F);
+  if (p.use_cols()) {
+    const int F = m->F;
+    const uint32_t* fwq = m->fwq.empty() ? nullptr : m->fwq.data();
+    std::vector<uint8_t> mask_tree(F), masks((size_t)std::max(D, 1) * F);
+    for (int f = 0; f < F; ++f)
+      mask_tree[f] = b2_col_selected((uint32_t)p.seed, tree_index, B2_SCOPE_TREE, f, nullptr, fwq, F, b2_sample_count((double)p.colsample_bytree, F));
+    int n_tree = 0; for (int f = 0; f < F; ++f) n_tree += mask_tree[f];
+    for (int d = 0; d < D; ++d) {
+      int cnt = 0;
+      for (int f = 0; f < F; ++f) {
+        masks[(size_t)d * F + f] = b2_col_selected((uint32_t)p.seed, tree_index, B2_SCOPE_LEVEL(d), f, mask_tree.data(), fwq, F,
+                                                   b2_sample_count((double)p.colsample_bylevel, n_tree));
+        cnt += masks[(size_t)d * F + f];
+      }
+      n_level_feats[d] = cnt;
+    }
+    b->d_col_masks.ensure(masks.size());
+    CUDA_CHECK(cudaMemcpyAsync(b->d_col_masks.p, masks.data(), masks.size(), cudaMemcpyHostToDevice, s));   // pageable source: staged before return
+  }
   CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * sizeof(uint32_t), s));
   LAUNCH_CHECK(b2_launch_absmax(gh, n, b->d_absmax.p, ctx->num_sms, s));
   allreduce(b->comm, b->d_absmax.p, 2, kNcclUint32, kNcclMax, s);
@@ -878,14 +921,19 @@ void grow_tree(Booster* b, int k, int slot) {
     const bool can_split = d < D;
     const B2SplitCand* cands_for_decide = b->d_cands.p;
     if (can_split) {
+      B2ColSample cs;
+      cs.level_mask = p.use_cols() ? b->d_col_masks.p + (size_t)d * m->F : nullptr;
+      cs.fwq = m->fwq.empty() ? nullptr : m->d_fwq.p;
+      cs.bynode = (double)p.colsample_bynode; cs.n_level = n_level_feats[d]; cs.n_features = m->F;
+      cs.seed = (uint32_t)p.seed; cs.tree = tree_index;
       LAUNCH_CHECK(b2_launch_eval_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_group_first.p, m->d_group_size.p,
                                          m->d_nbins.p, m->d_has_missing.p, m->any_cat() ? m->d_is_cat.p : nullptr, b->d_qexp.p,
-                                         p.qbits, dp, b->d_cands.p, b->cpn, ctl + cur, sh, shard_rank, s));
+                                         p.qbits, dp, b->d_cands.p, b->cpn, ctl + cur, sh, shard_rank, cs, b->d_seg[cur].p, s));
       b->t.kernel_launches++;
       if (m->any_cat()) {
         LAUNCH_CHECK(b2_launch_eval_cat_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_cat_feats.p,
                                                (int)m->cat_feats.size(), m->d_feat_byte.p, m->d_nbins.p, b->d_qexp.p, p.qbits, dp,
-                                               b->d_cands.p, b->cpn, b->cpn_num, ctl + cur, sh, shard_rank, s));
+                                               b->d_cands.p, b->cpn, b->cpn_num, ctl + cur, sh, shard_rank, cs, b->d_seg[cur].p, s));
         b->t.kernel_launches++;
       }
       if (b->shards > 1) {   // every rank scanned only its own slots: gather the per-node candidates
@@ -1203,6 +1251,20 @@ int B2_MatrixSetFloatInfo(B2Handle mh, const char* field, const float* values, i
   if (f == "label") { dst = &m->label; cnt = &m->n_label; if (len != m->n) fail("label length %lld != rows %lld", (long long)len, (long long)m->n); }
   else if (f == "weight") { dst = &m->weight; cnt = &m->n_weight; if (len != m->n && len != 0) fail("weight length %lld != rows %lld", (long long)len, (long long)m->n); }
   else if (f == "base_margin") { dst = &m->base_margin; cnt = &m->n_base_margin; if (len != 0 && (m->n == 0 || len % m->n != 0)) fail("base_margin length %lld is not a multiple of rows %lld", (long long)len, (long long)m->n); }
+  else if (f == "feature_weights") {
+    // DMatrix.set_info(feature_weights=...) (main.py:439-442): weights of the column sampler, Q16 fixed point
+    if (len != 0 && len != m->F) fail("feature_weights length %lld != features %d", (long long)len, m->F);
+    m->fwq.clear();
+    for (int64_t i = 0; i < len; ++i) {
+      if (!(values[i] >= 0.0f) || std::isinf(values[i])) fail("feature_weights must be finite and non-negative");
+      const double q = (double)values[i] * 65536.0;
+      m->fwq.push_back(q >= 4294967295.0 ? 0xffffffffu : (uint32_t)llrint(q));
+    }
+    m->d_fwq.ensure((size_t)std::max<int64_t>(len, 1));
+    if (len > 0) CUDA_CHECK(cudaMemcpyAsync(m->d_fwq.p, m->fwq.data(), len * sizeof(uint32_t), cudaMemcpyHostToDevice, m->ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(m->ctx->stream));
+    return 0;
+  }
   else fail("unknown float info field '%s'", f.c_str());
   dst->ensure((size_t)std::max<int64_t>(len, 1));
   if (len > 0) CUDA_CHECK(cudaMemcpyAsync(dst->p, values, len * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));

@@ -5,6 +5,7 @@
 // Appendix A.4, A.9, A.10).  Compiled with --fmad=false: b2_expf below is a fixed sequence of
 // IEEE-754 binary32 mul/add, replayed identically by the CPU oracle, so gradients are bit-equal.
 #include "common.cuh"
+#include "sampling.cuh"
 
 namespace b2 {
 
@@ -70,6 +71,13 @@ __global__ void gradient_kernel(int objective, int K, const float* __restrict__ 
       }
     }
   }
+}
+
+// row sampling (subsample < 1): rows whose hash falls above the threshold get a zero gradient pair for this tree
+// (sampling.cuh); they stay in the row partition and still receive the leaf value.
+__global__ void subsample_kernel(float2* __restrict__ gh, int64_t n, uint32_t seed, uint32_t tree, uint32_t rank, uint32_t thr) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (!(b2_hash4(seed, tree, rank, (uint32_t)i) < thr)) gh[i] = make_float2(0.0f, 0.0f);
 }
 
 // interleave user-supplied gradients (custom objective): g,h row-major [n][K] -> gh [K][n]
@@ -211,6 +219,12 @@ int b2_launch_gradient(int objective, int K, const float* margin, const float* l
                        float scale_pos_weight, float2* gh, int num_sms, cudaStream_t s) {
   if (n <= 0) return 0;
   b2::gradient_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, K, margin, label, weight, n, scale_pos_weight, gh);
+  return (int)cudaGetLastError();
+}
+int b2_launch_subsample(float2* gh, int64_t n, uint32_t seed, uint32_t tree, uint32_t rank, double subsample, int num_sms,
+                        cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::subsample_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(gh, n, seed, tree, rank, b2_subsample_threshold(subsample));
   return (int)cudaGetLastError();
 }
 int b2_launch_pack_custom(const float* g, const float* h, int K, int64_t n, float2* gh, int num_sms, cudaStream_t s) {

@@ -9,6 +9,7 @@
 #include <cub/block/block_scan.cuh>
 
 #include "common.cuh"
+#include "sampling.cuh"
 
 namespace b2 {
 
@@ -38,7 +39,8 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
                    const int32_t* __restrict__ nbins, const uint8_t* __restrict__ has_missing,
                    const uint8_t* __restrict__ is_cat /* nullable: categorical features are scanned by eval_cat_splits_kernel */,
                    const int32_t* __restrict__ qexp, int qbits, B2TrainParamDev p, B2SplitCand* __restrict__ cands,
-                   int cand_stride, const B2LevelCtl* __restrict__ ctl, int log2_shards, int shard_rank) {
+                   int cand_stride, const B2LevelCtl* __restrict__ ctl, int log2_shards, int shard_rank, B2ColSample cs,
+                   const B2NodeSeg* __restrict__ seg) {
   // This rank owns sp = 32 >> log2_shards slots of every group (slot s is owned by s % shards): the
   // G*sp owned "virtual slots" of a node are covered by cpn = ceil(G*sp/32) CTAs.
   const int sp = B2_GROUP_SLOTS >> log2_shards;
@@ -60,7 +62,16 @@ eval_splits_kernel(const long long* __restrict__ level_hist, int n_groups, const
   const long long* hg = level_hist + (size_t)nd.hist_index * slice_elems + (size_t)(group * 2) * B2_BINS * sp + sl;
   const long long* hh = hg + (size_t)B2_BINS * sp;
   const int f = group_first[group] + slot;
-  const bool active = v_ok && slot < group_size[group] && !(is_cat && is_cat[f]);
+  bool active = v_ok && slot < group_size[group] && !(is_cat && is_cat[f]);
+  if (active && cs.level_mask) active = cs.level_mask[f] != 0;          // colsample_bytree / bylevel
+  if (cs.bynode < 1.0) {                                                // colsample_bynode: this node's own subset
+    __shared__ uint8_t s_allowed[32];
+    if (q == 0)
+      s_allowed[s] = active && b2_col_selected(cs.seed, cs.tree, B2_SCOPE_NODE(seg[node].nid), f, cs.level_mask, cs.fwq,
+                                               cs.n_features, b2_sample_count(cs.bynode, cs.n_level));
+    __syncthreads();
+    active = active && s_allowed[s];
+  }
   const int nf = active ? nbins[f] : 0;
   const bool fmiss = active ? (has_missing[f] != 0) : false;
 
@@ -162,7 +173,7 @@ eval_cat_splits_kernel(const long long* __restrict__ level_hist, int n_groups, c
                        const int32_t* __restrict__ cat_feats, int n_cat, const int32_t* __restrict__ feat_byte,
                        const int32_t* __restrict__ nbins, const int32_t* __restrict__ qexp, int qbits, B2TrainParamDev p,
                        B2SplitCand* __restrict__ cands, int cand_stride, int cand_offset, const B2LevelCtl* __restrict__ ctl,
-                       int log2_shards, int shard_rank) {
+                       int log2_shards, int shard_rank, B2ColSample cs, const B2NodeSeg* __restrict__ seg) {
   const int node = blockIdx.x / kCatCtas, j = blockIdx.x % kCatCtas;
   if (ctl && node >= ctl->n_nodes) return;
   typedef cub::BlockScan<long long, 256> Scan;
@@ -174,6 +185,7 @@ eval_cat_splits_kernel(const long long* __restrict__ level_hist, int n_groups, c
   __shared__ unsigned long long s_best_key;
   __shared__ uint32_t s_bits[8];
   __shared__ int s_mode, s_part;             // winner of the current feature: 0 one-hot (category s_part), 1 partition (first s_part sorted)
+  __shared__ int s_skip;
   __shared__ B2SplitCand s_best;
   const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
   const int sp = B2_GROUP_SLOTS >> log2_shards, shards = 1 << log2_shards;
@@ -190,6 +202,19 @@ eval_cat_splits_kernel(const long long* __restrict__ level_hist, int n_groups, c
     const int f = cat_feats[ci];
     const int fb = feat_byte[f], group = fb >> 5, slot = fb & 31;
     if ((slot & (shards - 1)) != shard_rank) continue;          // another rank owns this slot (uniform)
+    if (cs.level_mask || cs.bynode < 1.0) {                     // column sampling (uniform decision per feature)
+      if (b == 0) {
+        bool ok = !cs.level_mask || cs.level_mask[f] != 0;
+        if (ok && cs.bynode < 1.0)
+          ok = b2_col_selected(cs.seed, cs.tree, B2_SCOPE_NODE(seg[node].nid), f, cs.level_mask, cs.fwq, cs.n_features,
+                               b2_sample_count(cs.bynode, cs.n_level));
+        s_skip = ok ? 0 : 1;
+      }
+      __syncthreads();
+      const bool skip = s_skip != 0;
+      __syncthreads();
+      if (skip) continue;
+    }
     const int sl = slot >> log2_shards;
     const long long* hg = level_hist + (size_t)nd.hist_index * slice_elems + (size_t)(group * 2) * B2_BINS * sp + sl;
     const long long* hh = hg + (size_t)B2_BINS * sp;
@@ -337,12 +362,12 @@ int b2_launch_eval_splits(const long long* level_hist, int n_groups, const B2Eva
                           const int32_t* group_first, const int32_t* group_size, const int32_t* nbins,
                           const uint8_t* has_missing, const uint8_t* is_cat, const int32_t* qexp, int qbits, B2TrainParamDev p,
                           B2SplitCand* cands, int cand_stride, const B2LevelCtl* ctl, int log2_shards, int shard_rank,
-                          cudaStream_t stream) {
+                          B2ColSample cs, const B2NodeSeg* seg, cudaStream_t stream) {
   if (n_nodes <= 0) return 0;   // with ctl: n_nodes is the upper bound of the level
   const int sp = B2_GROUP_SLOTS >> log2_shards, cpn = (n_groups * sp + 31) >> 5;
   b2::eval_splits_kernel<<<n_nodes * cpn, 32 * b2::kEvalChunks, 0, stream>>>(level_hist, n_groups, nodes, group_first, group_size,
                                                                          nbins, has_missing, is_cat, qexp, qbits, p, cands,
-                                                                         cand_stride, ctl, log2_shards, shard_rank);
+                                                                         cand_stride, ctl, log2_shards, shard_rank, cs, seg);
   return (int)cudaGetLastError();
 }
 int b2_cat_ctas() { return b2::kCatCtas; }
@@ -350,11 +375,12 @@ int b2_cat_ctas() { return b2::kCatCtas; }
 int b2_launch_eval_cat_splits(const long long* level_hist, int n_groups, const B2EvalNode* nodes, int n_nodes,
                               const int32_t* cat_feats, int n_cat, const int32_t* feat_byte, const int32_t* nbins,
                               const int32_t* qexp, int qbits, B2TrainParamDev p, B2SplitCand* cands, int cand_stride,
-                              int cand_offset, const B2LevelCtl* ctl, int log2_shards, int shard_rank, cudaStream_t stream) {
+                              int cand_offset, const B2LevelCtl* ctl, int log2_shards, int shard_rank, B2ColSample cs,
+                              const B2NodeSeg* seg, cudaStream_t stream) {
   if (n_nodes <= 0 || n_cat <= 0) return 0;
   b2::eval_cat_splits_kernel<<<n_nodes * b2::kCatCtas, 256, 0, stream>>>(level_hist, n_groups, nodes, cat_feats, n_cat, feat_byte,
                                                                         nbins, qexp, qbits, p, cands, cand_stride, cand_offset,
-                                                                        ctl, log2_shards, shard_rank);
+                                                                        ctl, log2_shards, shard_rank, cs, seg);
   return (int)cudaGetLastError();
 }
 int b2_launch_root_totals(const long long* level_hist, int n_groups, B2EvalNode* nodes, const int32_t* qexp, int qbits,

@@ -254,7 +254,8 @@ class DMatrix:
     # -- info
     def set_info(self, label=None, weight=None, base_margin=None, feature_weights=None,
                  label_lower_bound=None, label_upper_bound=None, **kw):
-        for field, v in (("label", label), ("weight", weight), ("base_margin", base_margin)):
+        for field, v in (("label", label), ("weight", weight), ("base_margin", base_margin),
+                         ("feature_weights", feature_weights)):
             if v is None:
                 continue
             if hasattr(v, "values") and not isinstance(v, np.ndarray):
@@ -372,12 +373,12 @@ _TREE_FIELDS = ("left", "right", "parent", "split_feature", "split_bin", "split_
 _ENGINE_KEYS = ("objective", "num_class", "max_depth", "eta", "learning_rate", "gamma", "min_split_loss",
                 "min_child_weight", "lambda", "reg_lambda", "alpha", "reg_alpha", "base_score", "hist_qbits",
                 "hist_chunk_rows", "profile", "max_cat_to_onehot", "max_cat_threshold", "scale_pos_weight",
-                "max_delta_step")
+                "max_delta_step", "subsample", "colsample_bytree", "colsample_bylevel", "colsample_bynode", "seed",
+                "random_state")
 
 # xgboost parameters that change the trained model and that this engine does not implement: a value different
 # from the neutral one is an error, never silently ignored (a drop-in must not train a different model quietly)
 _UNSUPPORTED_NEUTRAL = {
-    "subsample": (1, 1.0), "colsample_bytree": (1, 1.0), "colsample_bylevel": (1, 1.0), "colsample_bynode": (1, 1.0),
     "sampling_method": ("uniform",), "max_leaves": (0,), "grow_policy": ("depthwise",), "num_parallel_tree": (1,),
     "monotone_constraints": (None, "", "()", (), []), "interaction_constraints": (None, "", "[]", (), []),
     "multi_strategy": ("one_output_per_tree",), "refresh_leaf": (1, True), "process_type": ("default",),
