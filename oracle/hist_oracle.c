@@ -1235,20 +1235,33 @@ void or_transform(int32_t objective, int32_t K, float *m, int64_t n) {
   }
 }
 
-/* A.10 metrics on margins: returns (sum, wsum) so callers can combine shards.
- * metric: 0 rmse, 1 logloss, 2 error, 3 mlogloss, 4 merror */
+/* A.10 metrics on margins: returns (sum, wsum) so callers can combine shards.  Metrics see the transformed
+ * prediction (ObjFunction::EvalTransform): probability for binary:logistic, raw value for reg:squarederror.
+ * metric: 0 rmse, 1 logloss, 2 error, 3 mlogloss, 4 merror, 5 mae */
+void or_metric_sums_obj(int32_t objective, int32_t metric, int32_t K, const float *margin, const float *label,
+                        const float *weight, int64_t n, double *out_sum, double *out_wsum);
 void or_metric_sums(int32_t metric, int32_t K, const float *margin, const float *label, const float *weight,
                     int64_t n, double *out_sum, double *out_wsum) {
+  /* historical entry point: logloss / error on margins of a logistic model, rmse on raw values */
+  or_metric_sums_obj((metric == 1 || metric == 2) ? OR_OBJ_LOGISTIC : OR_OBJ_SQUAREDERROR, metric, K, margin, label, weight, n,
+                     out_sum, out_wsum);
+}
+void or_metric_sums_obj(int32_t objective, int32_t metric, int32_t K, const float *margin, const float *label,
+                        const float *weight, int64_t n, double *out_sum, double *out_wsum) {
   double s = 0.0, ws = 0.0;
   for (int64_t i = 0; i < n; ++i) {
     double w = weight ? weight[i] : 1.0; double v = 0.0;
-    if (metric == 0) { double d = (double)margin[i] - (double)label[i]; v = d * d; }
-    else if (metric == 1) {
-      float p = or_sigmoid(margin[i]); const float eps = 1e-16f; float y = label[i];
-      float pn = 1.0f - p;
-      float a = p < eps ? eps : p, b = pn < eps ? eps : pn;
-      v = -((double)y * log((double)a) + (1.0 - (double)y) * log((double)b));
-    } else if (metric == 2) { float p = or_sigmoid(margin[i]); v = (p > 0.5f) != (label[i] > 0.5f) ? 1.0 : 0.0; }
+    if (metric <= 2 || metric == 5) {
+      float p = objective == OR_OBJ_LOGISTIC ? or_sigmoid(margin[i]) : margin[i];
+      if (metric == 0) { double d = (double)p - (double)label[i]; v = d * d; }
+      else if (metric == 5) v = fabs((double)p - (double)label[i]);
+      else if (metric == 1) {
+        const float eps = 1e-16f; float y = label[i];
+        float pn = 1.0f - p;
+        float a = p < eps ? eps : p, b = pn < eps ? eps : pn;
+        v = -((double)y * log((double)a) + (1.0 - (double)y) * log((double)b));
+      } else v = (p > 0.5f) != (label[i] > 0.5f) ? 1.0 : 0.0;
+    }
     else {
       const float *r = margin + i * K; int y = (int)label[i]; float mx = r[0]; int am = 0;
       for (int k = 1; k < K; ++k) if (r[k] > mx) { mx = r[k]; am = k; }

@@ -19,7 +19,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 OBJECTIVES = {"reg:squarederror": 0, "reg:linear": 0, "binary:logistic": 1,
               "multi:softprob": 2, "multi:softmax": 2}
-METRICS = {"rmse": 0, "logloss": 1, "error": 2, "mlogloss": 3, "merror": 4}
+METRICS = {"rmse": 0, "logloss": 1, "error": 2, "mlogloss": 3, "merror": 4, "mae": 5}
 
 
 class OrParams(C.Structure):
@@ -87,6 +87,7 @@ def lib():
         L.or_predict_margin.argtypes = [C.c_void_p, fp, C.c_int64, C.c_float, C.c_int32, C.c_int32, fp, fp]
         L.or_transform.argtypes = [C.c_int32, C.c_int32, fp, C.c_int64]
         L.or_metric_sums.argtypes = [C.c_int32, C.c_int32, fp, fp, fp, C.c_int64, dp, dp]
+        L.or_metric_sums_obj.argtypes = [C.c_int32, C.c_int32, C.c_int32, fp, fp, fp, C.c_int64, dp, dp]
         L.or_expf.restype = C.c_float
         L.or_expf.argtypes = [C.c_float]
         L.or_num_threads.restype = C.c_int32
@@ -339,8 +340,8 @@ class Booster:
     def metric(self, name, margin, label, weight=None):
         margin = _f32(margin)
         s, ws = C.c_double(), C.c_double()
-        lib().or_metric_sums(METRICS[name], self.K, _fp(margin), _fp(_f32(label)), _fp(_f32(weight)),
-                             margin.shape[0], C.byref(s), C.byref(ws))
+        lib().or_metric_sums_obj(self.p.objective, METRICS[name], self.K, _fp(margin), _fp(_f32(label)),
+                                 _fp(_f32(weight)), margin.shape[0], C.byref(s), C.byref(ws))
         v = s.value / ws.value if ws.value > 0 else 0.0
         return float(np.sqrt(v)) if name == "rmse" else v
 

@@ -238,6 +238,24 @@ def test_metrics_match_oracle(eng, oracle):
     mv = obst.predict_margin(Xv)
     assert abs(res["valid"]["logloss"][-1] - obst.metric("logloss", mv, yv)) < 1e-6
     assert len(res["valid"]["logloss"]) == 4
+    # metrics see the transformed prediction: rmse / mae of a logistic model compare the PROBABILITY with the label,
+    # error / logloss of a squared-error model use the raw value (test_end_to_end.py:449 asks for "error" there)
+    res2 = {}
+    eng.train(dict(params, eval_metric=["rmse", "mae"]), dm, num_boost_round=2, evals=[(dm, "train")], evals_result=res2,
+              verbose_eval=False)
+    ob2, _ = oracle.train(params, X, y, 2)
+    p = ob2.predict(X)
+    assert abs(res2["train"]["rmse"][-1] - float(np.sqrt(np.mean((p - y) ** 2)))) < 1e-6
+    assert abs(res2["train"]["mae"][-1] - float(np.mean(np.abs(p - y)))) < 1e-6
+    assert abs(res2["train"]["rmse"][-1] - ob2.metric("rmse", ob2.margin, y)) < 1e-7
+    res3 = {}
+    reg = {"objective": "reg:squarederror", "max_depth": 3, "base_score": 0.5, "eval_metric": ["rmse", "error"]}
+    eng.train(reg, dm, num_boost_round=2, evals=[(dm, "train")], evals_result=res3, verbose_eval=False)
+    ob3, _ = oracle.train(reg, X, y, 2)
+    raw = ob3.predict(X)
+    assert abs(res3["train"]["error"][-1] - float(np.mean((raw > 0.5) != (y > 0.5)))) < 1e-9
+    with pytest.raises(eng.XGBoostError, match="does not fit"):
+        eng.train(dict(reg, eval_metric="mlogloss"), dm, num_boost_round=1, evals=[(dm, "train")], verbose_eval=False)
 
 
 def test_custom_objective_and_continuation(eng, oracle):

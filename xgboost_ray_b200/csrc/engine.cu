@@ -67,7 +67,7 @@ int b2_launch_pack_custom(const float*, const float*, int, int64_t, float2*, int
 int b2_launch_absmax(const float2*, int64_t, uint32_t*, int, cudaStream_t);
 int b2_launch_quant_exponent(const uint32_t*, int32_t*, cudaStream_t);
 int b2_launch_quantize(const float2*, int64_t, const int32_t*, int, int2*, int, cudaStream_t);
-int b2_launch_metric(int, int, const float*, const float*, const float*, int64_t, double*, int, cudaStream_t);
+int b2_launch_metric(int, int, int, const float*, const float*, const float*, int64_t, double*, int, cudaStream_t);
 int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, const int32_t*, const uint32_t*, int, int, int,
                       float*, int, cudaStream_t);
 int b2_launch_fill(float*, int64_t, float, int, cudaStream_t);
@@ -1145,7 +1145,8 @@ int metric_id(const char* name) {
   if (s == "error") return 2;
   if (s == "mlogloss") return 3;
   if (s == "merror") return 4;
-  fail("unsupported eval metric '%s' (supported: rmse, logloss, error, mlogloss, merror)", s.c_str());
+  if (s == "mae") return 5;
+  fail("unsupported eval metric '%s' (supported: rmse, mae, logloss, error, mlogloss, merror)", s.c_str());
 }
 
 // margin of matrix m under the current model (cached per matrix, only new trees are applied)
@@ -1398,7 +1399,9 @@ int B2_BoosterEvalSet(B2Handle bh, B2Handle mh, const char* metric, double* out)
   float* margin = eval_margin(b, m);
   b->d_metric.ensure(2);
   CUDA_CHECK(cudaMemsetAsync(b->d_metric.p, 0, 2 * sizeof(double), s));
-  LAUNCH_CHECK(b2_launch_metric(mid, b->p.num_class, margin, m->label.p, m->n_weight ? m->weight.p : nullptr, m->n, b->d_metric.p,
+  if ((mid == 3 || mid == 4) != (b->p.objective == kObjSoftprob))
+    fail("metric '%s' does not fit objective '%s'", metric, b->p.objective_name.c_str());
+  LAUNCH_CHECK(b2_launch_metric(b->p.objective, mid, b->p.num_class, margin, m->label.p, m->n_weight ? m->weight.p : nullptr, m->n, b->d_metric.p,
                                 b->ctx->num_sms, s));
   allreduce(b->comm, b->d_metric.p, 2, kNcclFloat64, kNcclSum, s);
   double h[2];

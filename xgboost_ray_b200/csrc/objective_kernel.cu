@@ -125,18 +125,24 @@ __global__ void quantize_kernel(const float2* __restrict__ gh, int64_t n, const 
 }
 
 // metric sums (sum loss*w, sum w) -> out[2] doubles; metric: 0 rmse 1 logloss 2 error 3 mlogloss 4 merror
-__global__ void metric_kernel(int metric, int K, const float* __restrict__ margin, const float* __restrict__ label,
+// Metrics see the TRANSFORMED prediction (ObjFunction::EvalTransform, src/learner.cc): the probability for
+// binary:logistic, the raw value for reg:squarederror.  metric: 0 rmse, 1 logloss, 2 error, 3 mlogloss, 4 merror, 5 mae.
+__global__ void metric_kernel(int objective, int metric, int K, const float* __restrict__ margin, const float* __restrict__ label,
                               const float* __restrict__ weight, int64_t n, double* __restrict__ out) {
   double s = 0.0, ws = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const double w = weight ? (double)weight[i] : 1.0;
     double v = 0.0;
-    if (metric == 0) { const double d = (double)margin[i] - (double)label[i]; v = d * d; }
-    else if (metric == 1) {
-      const float p = b2_sigmoid(margin[i]); const float eps = 1e-16f; const float y = label[i];
-      const float pn = 1.0f - p; const float a = p < eps ? eps : p, b = pn < eps ? eps : pn;
-      v = -((double)y * log((double)a) + (1.0 - (double)y) * log((double)b));
-    } else if (metric == 2) { const float p = b2_sigmoid(margin[i]); v = ((p > 0.5f) != (label[i] > 0.5f)) ? 1.0 : 0.0; }
+    if (metric <= 2 || metric == 5) {
+      const float p = objective == 1 ? b2_sigmoid(margin[i]) : margin[i];
+      if (metric == 0) { const double d = (double)p - (double)label[i]; v = d * d; }
+      else if (metric == 5) v = fabs((double)p - (double)label[i]);
+      else if (metric == 1) {
+        const float eps = 1e-16f; const float y = label[i];
+        const float pn = 1.0f - p; const float a = p < eps ? eps : p, b = pn < eps ? eps : pn;
+        v = -((double)y * log((double)a) + (1.0 - (double)y) * log((double)b));
+      } else v = ((p > 0.5f) != (label[i] > 0.5f)) ? 1.0 : 0.0;
+    }
     else {
       const float* r = margin + i * K; const int y = (int)label[i]; float mx = r[0]; int am = 0;
       for (int k = 1; k < K; ++k) if (r[k] > mx) { mx = r[k]; am = k; }
@@ -246,10 +252,10 @@ int b2_launch_quantize(const float2* gh, int64_t n, const int32_t* qexp, int qbi
   b2::quantize_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(gh, n, qexp, qbits, q);
   return (int)cudaGetLastError();
 }
-int b2_launch_metric(int metric, int K, const float* margin, const float* label, const float* weight, int64_t n,
+int b2_launch_metric(int objective, int metric, int K, const float* margin, const float* label, const float* weight, int64_t n,
                      double* out, int num_sms, cudaStream_t s) {
   if (n <= 0) return 0;
-  b2::metric_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(metric, K, margin, label, weight, n, out);
+  b2::metric_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, metric, K, margin, label, weight, n, out);
   return (int)cudaGetLastError();
 }
 int b2_launch_predict(const float* X, int64_t n, int F, float missing, const B2TreeNodeDev* nodes,
