@@ -87,6 +87,10 @@ int B2_BoosterGetTrainMargin(B2Handle b, float* out, int64_t out_len);
 /* (re)initialise the training margin cache from base_margin/base_score plus all current trees
  * (continuation from xgb_model=, main.py:1211-1220); needs the raw data of the train matrix */
 int B2_BoosterResetTrainMargin(B2Handle b);
+/* base_score of the model (probability space for binary:logistic).  When the params carried no base_score it is
+ * estimated from the labels of all workers before the first tree (xgboost >= 2.0 behaviour);
+ * is_final = 0 until that has happened. */
+int B2_BoosterGetBaseScore(B2Handle b, float* out, int32_t* is_final);
 int B2_BoosterNumTrees(B2Handle b, int32_t* out);
 int B2_BoosterTreeNumNodes(B2Handle b, int32_t tree, int32_t* out);
 int B2_BoosterGetTree(B2Handle b, int32_t tree, int32_t* left, int32_t* right, int32_t* parent,

@@ -1152,6 +1152,27 @@ float or_base_margin(const OrParams *p) {
   return p->base_score;
 }
 
+/* A.3 base_score when the user gave none (xgboost >= 2.0: ObjFunction::InitEstimation -> FitIntercept::InitEstimation,
+ * tree::FitStump): one Newton step of a stump at margin 0, -sum(g)/sum(h) (no regularisation; 0 when sum(h) <= 1e-6),
+ * then the inverse link (identity / sigmoid).  Multi-class keeps 0.5.  Sums are 40-bit fixed point (exact). */
+float or_estimate_base_score(OrModel *m, const float *label, const float *weight, int64_t n) {
+  if (m->p.objective == OR_OBJ_SOFTPROB) return m->p.base_score;
+  float *zeros = (float *)calloc((size_t)(n > 0 ? n : 1), sizeof(float));
+  float *g = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float)), *h = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+  or_gradients_spw(m->p.objective, 1, zeros, label, weight, n, m->p.scale_pos_weight, g, h);
+  float mg = 0.0f, mh = 0.0f;
+  for (int64_t i = 0; i < n; ++i) { if (fabsf(g[i]) > mg) mg = fabsf(g[i]); if (fabsf(h[i]) > mh) mh = fabsf(h[i]); }
+  const int32_t eg = or_quant_exponent(mg), eh = or_quant_exponent(mh);
+  const double kg = ldexp(1.0, OR_LEAF_BITS - eg), kh = ldexp(1.0, OR_LEAF_BITS - eh);
+  int64_t sg = 0, sh = 0;
+  for (int64_t i = 0; i < n; ++i) { sg += llrint((double)g[i] * kg); sh += llrint((double)h[i] * kh); }
+  const double G = (double)sg / kg, H = (double)sh / kh;
+  const float stump = H <= 1e-6 ? 0.0f : (float)(-G / H);
+  free(zeros); free(g); free(h);
+  m->p.base_score = m->p.objective == OR_OBJ_LOGISTIC ? or_sigmoid(stump) : stump;
+  return m->p.base_score;
+}
+
 /* One boosting round.  margin [n*K] is the prediction cache (in/out).  custom_g/custom_h
  * (may be NULL) replace the objective gradient (xgb.train(obj=...), test_xgboost_api.py:77-102). */
 int or_boost_one_round(OrModel *m, const OrCuts *c, const uint8_t *bins, int64_t n, const float *label,

@@ -73,6 +73,8 @@ def lib():
         L.or_model_new.restype = C.c_void_p
         L.or_model_new.argtypes = [C.POINTER(OrParams), C.c_int32]
         L.or_model_free.argtypes = [C.c_void_p]
+        L.or_estimate_base_score.restype = C.c_float
+        L.or_estimate_base_score.argtypes = [C.c_void_p, fp, fp, C.c_int64]
         L.or_model_set_feature_weights.restype = C.c_int
         L.or_model_set_feature_weights.argtypes = [C.c_void_p, fp, C.c_int32]
         L.or_base_margin.restype = C.c_float
@@ -263,6 +265,14 @@ class Booster:
         self.K = self.p.num_class
         self.margin = None
 
+    def estimate_base_score(self, label, weight=None):
+        """xgboost >= 2.0 default when no base_score is given (A.3); updates the model and self.p."""
+        label = _f32(label)
+        v = float(lib().or_estimate_base_score(self.h, _fp(label), _fp(_f32(weight)), len(label)))
+        self.p.base_score = v
+        self.params["base_score"] = v
+        return v
+
     def set_feature_weights(self, fw):
         fw = _f32(fw)
         if lib().or_model_set_feature_weights(self.h, _fp(fw), len(fw)) != 0:
@@ -361,6 +371,8 @@ def train(params, X, y, num_boost_round, weight=None, missing=np.nan, cuts=None,
     bst = Booster(params, cuts)
     if feature_weights is not None:
         bst.set_feature_weights(feature_weights)
+    if params.get("base_score") is None:
+        bst.estimate_base_score(y, weight)
     bst.init_margin(X.shape[0], base_margin)
     for _ in range(num_boost_round):
         bst.boost(bins, y, weight)

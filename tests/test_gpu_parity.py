@@ -542,3 +542,22 @@ def test_feature_weights_known_answer(eng, oracle):
     assert fmap.get("f0") is None and max(fmap.values()) == fmap.get("f9")
     obst, _ = oracle.train(params, X, y, 60, feature_weights=fw)
     assert_same_model(ebst, obst)
+
+
+@pytest.mark.parametrize("objective", ["reg:squarederror", "binary:logistic"])
+def test_base_score_estimated_when_not_given(eng, oracle, objective, tmp_path):
+    """A.3: without base_score the engine estimates it from the labels (all ranks) like xgboost >= 2.0 and keeps it
+    with the model."""
+    X = make_data(20000, 8, 91, "uniform", nan_frac=0.02)
+    rng = np.random.RandomState(92)
+    y = np.nan_to_num(X[:, 0]) * 2 + rng.normal(size=len(X))
+    y = (y > 14).astype(np.float32) if objective == "binary:logistic" else y.astype(np.float32)
+    w = rng.uniform(0.5, 2.0, size=len(X)).astype(np.float32)
+    params = {"objective": objective, "max_depth": 4, "eta": 0.3}
+    ebst, obst, dm = run_both(eng, oracle, params, X, y, 3, weight=w)
+    assert np.float32(ebst.params["base_score"]) == np.float32(obst.params["base_score"]) != np.float32(0.5)
+    assert_same_model(ebst, obst)
+    assert np.max(np.abs(ebst.predict(dm) - obst.predict(X))) <= LEAF_TOL
+    f = str(tmp_path / "m.json")
+    ebst.save_model(f)
+    assert np.array_equal(eng.Booster(model_file=f).predict(eng.DMatrix(X)), ebst.predict(dm))

@@ -247,3 +247,21 @@ def test_feature_weights_known_answer(oracle):
     assert cnt[0] == 0 and cnt.argmax() == 9
     with pytest.raises(ValueError):
         oracle.train({"objective": "reg:squarederror"}, X, y, 1, feature_weights=-np.ones(10, np.float32))
+
+
+def test_base_score_estimation_known_answers(oracle):
+    """A.3 (xgboost >= 2.0, no base_score given): Newton step of a stump at margin 0, then the inverse link:
+    weighted mean(y) for squared error, sigmoid(4 (mean(y) - 0.5)) for logistic; 0.5 for multi-class."""
+    rng = np.random.RandomState(0)
+    X = rng.uniform(0, 1, size=(1000, 3)).astype(np.float32)
+    y = (rng.uniform(size=1000) < 0.2).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, size=1000).astype(np.float32)
+    b, _ = oracle.train({"objective": "binary:logistic", "max_depth": 2}, X, y, 1)
+    assert abs(b.params["base_score"] - 1 / (1 + np.exp(-4 * (y.mean() - 0.5)))) < 1e-6
+    yr = (X[:, 0] * 3 + 1).astype(np.float32)
+    b, _ = oracle.train({"objective": "reg:squarederror", "max_depth": 2}, X, yr, 1, weight=w)
+    assert abs(b.params["base_score"] - float((w.astype(np.float64) * yr).sum() / w.sum())) < 1e-5
+    b, _ = oracle.train({"objective": "multi:softprob", "num_class": 3, "max_depth": 2}, X, (y * 2), 1)
+    assert b.params.get("base_score", 0.5) == 0.5
+    b, _ = oracle.train({"objective": "reg:squarederror", "max_depth": 2, "base_score": 0.5}, X, yr, 1)
+    assert b.params["base_score"] == 0.5                       # an explicit value is never replaced

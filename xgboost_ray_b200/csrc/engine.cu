@@ -38,6 +38,7 @@ int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const i
                           const uint8_t*, const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, int, const B2LevelCtl*,
                           int, int, B2ColSample, const B2NodeSeg*, cudaStream_t);
 int b2_launch_subsample(float2*, int64_t, uint32_t, uint32_t, uint32_t, double, int, cudaStream_t);
+int b2_launch_sum_fixed(const float2*, int64_t, const int32_t*, int, long long*, int, cudaStream_t);
 int b2_cat_ctas();
 int b2_launch_eval_cat_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, int, const int32_t*, const int32_t*,
                               const int32_t*, int, B2TrainParamDev, B2SplitCand*, int, int, const B2LevelCtl*, int, int,
@@ -529,6 +530,7 @@ struct Params {
   float scale_pos_weight = 1.0f, max_delta_step = 0.0f;
   float subsample = 1.0f, colsample_bytree = 1.0f, colsample_bylevel = 1.0f, colsample_bynode = 1.0f;
   int seed = 0;
+  bool base_score_set = false;   // false: estimated from the labels before the first tree (xgboost >= 2.0, A.3)
   bool use_cols() const { return colsample_bytree < 1.0f || colsample_bylevel < 1.0f || colsample_bynode < 1.0f; }
 };
 
@@ -670,7 +672,7 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
     else if (k == "min_child_weight") p->min_child_weight = f();
     else if (k == "lambda" || k == "reg_lambda") p->lambda = f();
     else if (k == "alpha" || k == "reg_alpha") p->alpha = f();
-    else if (k == "base_score") p->base_score = f();
+    else if (k == "base_score") { p->base_score = f(); p->base_score_set = true; }
     else if (k == "hist_qbits") p->qbits = i();
     else if (k == "hist_chunk_rows") p->hist_chunk_rows = i();
     else if (k == "profile") p->profile = i();
@@ -1089,9 +1091,52 @@ void init_margin(Booster* b, float* margin, Matrix* m) {
   }
 }
 
+// base_score when the user gave none (xgboost >= 2.0: ObjFunction::InitEstimation -> FitIntercept, tree::FitStump;
+// SURVEY.md A.3): one Newton step of a stump at margin 0, -sum(g)/sum(h) over ALL workers, then the inverse link.
+// Sums are 40-bit fixed-point integers, so every rank (and the oracle) computes the same value.
+void estimate_base_score(Booster* b) {
+  Matrix* m = b->train; cudaStream_t s = b->ctx->stream; Params& p = b->p;
+  if (p.base_score_set || !b->trees.empty() || p.objective == kObjSoftprob) { p.base_score_set = true; return; }
+  if (m->n_label != m->n) fail("train matrix has %lld labels for %lld rows", (long long)m->n_label, (long long)m->n);
+  const int64_t n = m->n;
+  DevBuf<float> zeros; DevBuf<float2> gh; DevBuf<long long> sums;
+  zeros.ensure((size_t)std::max<int64_t>(n, 1)); gh.ensure((size_t)std::max<int64_t>(n, 1)); sums.ensure(2);
+  CUDA_CHECK(cudaMemsetAsync(zeros.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(float), s));
+  LAUNCH_CHECK(b2_launch_gradient(p.objective, 1, zeros.p, m->label.p, m->n_weight ? m->weight.p : nullptr, n, p.scale_pos_weight,
+                                  gh.p, b->ctx->num_sms, s));
+  b->d_absmax.ensure(2); b->d_qexp.ensure(2);
+  CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * sizeof(uint32_t), s));
+  LAUNCH_CHECK(b2_launch_absmax(gh.p, n, b->d_absmax.p, b->ctx->num_sms, s));
+  allreduce(b->comm, b->d_absmax.p, 2, kNcclUint32, kNcclMax, s);
+  LAUNCH_CHECK(b2_launch_quant_exponent(b->d_absmax.p, b->d_qexp.p, s));
+  CUDA_CHECK(cudaMemsetAsync(sums.p, 0, 2 * sizeof(long long), s));
+  LAUNCH_CHECK(b2_launch_sum_fixed(gh.p, n, b->d_qexp.p, 40, sums.p, b->ctx->num_sms, s));
+  allreduce(b->comm, sums.p, 2, kNcclInt64, kNcclSum, s);
+  long long h_s[2]; int32_t h_e[2];
+  CUDA_CHECK(cudaMemcpyAsync(h_s, sums.p, sizeof(h_s), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(h_e, b->d_qexp.p, sizeof(h_e), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  const double G = (double)h_s[0] / ldexp(1.0, 40 - h_e[0]), H = (double)h_s[1] / ldexp(1.0, 40 - h_e[1]);
+  const float stump = H <= 1e-6 ? 0.0f : (float)(-G / H);
+  if (p.objective == kObjLogistic) {
+    // margin -> probability with the engine's own sigmoid (same IEEE sequence as the kernels): evaluated on the device
+    DevBuf<float> one; one.ensure(1);
+    CUDA_CHECK(cudaMemcpyAsync(one.p, &stump, sizeof(float), cudaMemcpyHostToDevice, s));
+    LAUNCH_CHECK(b2_launch_transform(kObjLogistic, 1, one.p, 1, b->ctx->num_sms, s));
+    float prob = 0.5f;
+    CUDA_CHECK(cudaMemcpyAsync(&prob, one.p, sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    p.base_score = prob;
+  } else {
+    p.base_score = stump;
+  }
+  p.base_score_set = true;
+}
+
 void ensure_train_margin(Booster* b) {
   if (b->margin_ready) return;
   Matrix* m = b->train;
+  estimate_base_score(b);
   b->margin.ensure((size_t)std::max<int64_t>(m->n * b->p.num_class, 1));
   init_margin(b, b->margin.p, m);
   if (!b->trees.empty()) {
@@ -1454,6 +1499,12 @@ int B2_BoosterResetTrainMargin(B2Handle bh) {
   b->margin_ready = false;
   ensure_train_margin(b);
   CUDA_CHECK(cudaStreamSynchronize(b->ctx->stream));
+  API_END
+}
+int B2_BoosterGetBaseScore(B2Handle bh, float* out, int32_t* is_final) {
+  API_BEGIN
+  Booster* b = from_handle<Booster>(bh, kBooster, "booster");
+  *out = b->p.base_score; *is_final = b->p.base_score_set ? 1 : 0;
   API_END
 }
 int B2_BoosterNumTrees(B2Handle bh, int32_t* out) { API_BEGIN *out = (int32_t)from_handle<Booster>(bh, kBooster, "booster")->trees.size(); API_END }

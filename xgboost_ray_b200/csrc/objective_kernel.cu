@@ -80,6 +80,25 @@ __global__ void subsample_kernel(float2* __restrict__ gh, int64_t n, uint32_t se
     if (!(b2_hash4(seed, tree, rank, (uint32_t)i) < thr)) gh[i] = make_float2(0.0f, 0.0f);
 }
 
+// exact sums of one gradient-pair array in fixed point (bits relative to the quantisation exponents): int64 atomics
+// of block partials, so the result does not depend on the order of rows, blocks or GPUs (base_score estimation)
+__global__ void sum_fixed_kernel(const float2* __restrict__ gh, int64_t n, const int32_t* __restrict__ qexp, int bits,
+                                 long long* __restrict__ out /*[2]*/) {
+  const double kg = ldexp(1.0, bits - qexp[0]), kh = ldexp(1.0, bits - qexp[1]);
+  long long ag = 0, ah = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = gh[i];
+    ag += __double2ll_rn(__dmul_rn((double)v.x, kg));
+    ah += __double2ll_rn(__dmul_rn((double)v.y, kh));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { ag += __shfl_xor_sync(0xffffffffu, ag, o); ah += __shfl_xor_sync(0xffffffffu, ah, o); }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd((unsigned long long*)&out[0], (unsigned long long)ag);
+    atomicAdd((unsigned long long*)&out[1], (unsigned long long)ah);
+  }
+}
+
 // interleave user-supplied gradients (custom objective): g,h row-major [n][K] -> gh [K][n]
 __global__ void pack_custom_kernel(const float* __restrict__ g, const float* __restrict__ h, int K, int64_t n,
                                    float2* __restrict__ gh) {
@@ -231,6 +250,11 @@ int b2_launch_subsample(float2* gh, int64_t n, uint32_t seed, uint32_t tree, uin
                         cudaStream_t s) {
   if (n <= 0) return 0;
   b2::subsample_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(gh, n, seed, tree, rank, b2_subsample_threshold(subsample));
+  return (int)cudaGetLastError();
+}
+int b2_launch_sum_fixed(const float2* gh, int64_t n, const int32_t* qexp, int bits, long long* out, int num_sms, cudaStream_t s) {
+  if (n <= 0) return 0;
+  b2::sum_fixed_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(gh, n, qexp, bits, out);
   return (int)cudaGetLastError();
 }
 int b2_launch_pack_custom(const float* g, const float* h, int K, int64_t n, float2* gh, int num_sms, cudaStream_t s) {

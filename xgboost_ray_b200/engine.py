@@ -64,6 +64,7 @@ ABI = {
     "B2_BoosterPredict": (C.c_int, [_H, _H, C.c_int32, C.c_int32, C.c_int32, _FP, C.c_int64]),
     "B2_BoosterGetTrainMargin": (C.c_int, [_H, _FP, C.c_int64]),
     "B2_BoosterResetTrainMargin": (C.c_int, [_H]),
+    "B2_BoosterGetBaseScore": (C.c_int, [_H, _FP, _IP]),
     "B2_BoosterNumTrees": (C.c_int, [_H, _IP]),
     "B2_BoosterTreeNumNodes": (C.c_int, [_H, C.c_int32, _IP]),
     "B2_BoosterGetTree": (C.c_int, [_H, C.c_int32, _IP, _IP, _IP, _IP, _IP, _FP, _BP, _FP, _FP, _FP, _DP]),
@@ -553,6 +554,16 @@ class Booster:
             self.boost(dtrain, grad, hess)
             return
         _check(lib().B2_BoosterUpdateOneIter(self.handle, int(iteration)))
+        self._sync_base_score()
+
+    def _sync_base_score(self):
+        """Without a user base_score the engine estimates it from the labels before the first tree (xgboost >= 2.0,
+        SURVEY.md A.3); keep the value with the model so that saved / pickled / predict-only boosters use it."""
+        if self.handle and self.params.get("base_score") is None:
+            v, fin = C.c_float(0), C.c_int32(0)
+            _check(lib().B2_BoosterGetBaseScore(self.handle, C.byref(v), C.byref(fin)))
+            if fin.value:
+                self.params["base_score"] = float(v.value)
 
     def boost(self, dtrain, grad, hess):
         if self._train is not dtrain:
@@ -562,6 +573,7 @@ class Booster:
         if g.size != h.size:
             raise XGBoostError("grad / hess size mismatch")
         _check(lib().B2_BoosterBoostOneIter(self.handle, _fp(g), _fp(h), g.size))
+        self._sync_base_score()
 
     def _metric_names(self):
         m = self.params.get("eval_metric")
