@@ -22,6 +22,7 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
   __shared__ int s_warp_left[kPartThreads / 32][kPartChunk / kPartThreads];
   __shared__ int s_base_left, s_base_right;
   __shared__ int s_pref[kPartThreads / 32][kPartChunk / kPartThreads];
+  __shared__ uint32_t s_cat[8];   // category set of the chunk's split (all zero for a numeric split)
   constexpr int kIters = kPartChunk / kPartThreads;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
@@ -33,6 +34,12 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
     const B2SplitWork w = work[lo];
     const int row0 = (chunk - w.chunk_begin) * kPartChunk;
     const int nrows = min(kPartChunk, w.seg_count - row0);
+    // the category set goes through shared memory so that the row loop below stays branch-free straight-line code
+    // (a divergent global load in its body kept the compiler from batching the 8 row-id / bin-byte loads: the
+    // kernel ran 1.7x slower, profiles/r01_summary.md)
+    if (threadIdx.x < 8) s_cat[threadIdx.x] = w.is_cat ? __ldg(&work[lo].cat_bits[threadIdx.x]) : 0u;
+    __syncthreads();
+    const bool is_cat = w.is_cat != 0, has_missing = w.has_missing != 0, default_left = w.default_left != 0;
     int rid[kIters]; bool left[kIters]; unsigned bal[kIters];
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
@@ -40,10 +47,9 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       const bool valid = r < nrows;
       rid[it] = valid ? __ldg(ridx_in + w.seg_begin + row0 + r) : 0;
       int b = valid ? (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid[it]) : 0;
-      bool l;
-      if (w.has_missing && b == B2_MISSING_BIN) l = w.default_left != 0;
-      else if (w.is_cat) l = ((__ldg(&work[lo].cat_bits[b >> 5]) >> (b & 31)) & 1u) == 0u;   // category in the set -> right
-      else l = b <= w.split_bin;
+      const bool in_set = ((s_cat[b >> 5] >> (b & 31)) & 1u) != 0u;              // category in the set -> right
+      const bool go_left = is_cat ? !in_set : (b <= w.split_bin);
+      const bool l = (has_missing && b == B2_MISSING_BIN) ? default_left : go_left;
       left[it] = valid && l;
       bal[it] = __ballot_sync(0xffffffffu, left[it]);
       if (lane == 0) s_warp_left[warp][it] = __popc(bal[it]);
