@@ -47,7 +47,7 @@ int b2_launch_cat_stats(const float*, int64_t, int, float, const int32_t*, int, 
 int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, int, cudaStream_t);
 int b2_part_chunk_rows();
 int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, const B2LevelCtl*, int, int32_t*,
-                        int, cudaStream_t);
+                        int, int, cudaStream_t);
 int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const int32_t*, int,
                         long long*, int, cudaStream_t);
 int b2_launch_pred_update(float*, int, int, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const float*, int,
@@ -954,7 +954,8 @@ void grow_tree(Booster* b, int k, int slot) {
     // ---- partition rows of the expanding nodes into the other index list
     CUDA_CHECK(cudaMemsetAsync(b->d_counters.p, 0, 2 * (size_t)max_nodes_level * sizeof(int32_t), s));
     LAUNCH_CHECK(b2_launch_partition(m->bins_col.p, m->col_stride, b->ridx[cur].p, b->ridx[nxt].p, b->d_split_work.p, ctl + cur,
-                                     max_part_chunks_total + max_nodes_level, b->d_counters.p, ctx->num_sms, s));
+                                     max_part_chunks_total + max_nodes_level, b->d_counters.p, m->any_cat() ? 1 : 0,
+                                     ctx->num_sms, s));
     const bool need_hist = d + 1 < D;
     LAUNCH_CHECK(b2_launch_finalize_level(ctl + cur, ctl + nxt, b->d_seg[nxt].p, b->d_ev[nxt].p, b->d_split_work.p, b->d_counters.p,
                                           b->d_pair_parent.p, b->d_hist_work.p, b->d_triples.p, max_nodes_level, need_hist ? 1 : 0,

@@ -14,6 +14,11 @@ constexpr int kPartChunk = 2048;  // rows per CTA work item
 
 typedef B2SegWork SegWork;
 
+// kCat = false: the matrix has no categorical feature; the row loop is then straight-line code whose 8 row-id loads
+// and 8 bin-byte loads the compiler batches (48 registers).  With the category test in the body it software-pipelines
+// only 2-3 deep and the kernel runs 1.7x slower (ncu launch lists in profiles/), so numeric matrices keep their own
+// instantiation.
+template <bool kCat>
 __global__ void __launch_bounds__(kPartThreads)
 partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const int32_t* __restrict__ ridx_in,
                  int32_t* __restrict__ ridx_out, const B2SplitWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl,
@@ -37,9 +42,11 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
     // the category set goes through shared memory so that the row loop below stays branch-free straight-line code
     // (a divergent global load in its body kept the compiler from batching the 8 row-id / bin-byte loads: the
     // kernel ran 1.7x slower, profiles/r01_summary.md)
-    if (threadIdx.x < 8) s_cat[threadIdx.x] = w.is_cat ? __ldg(&work[lo].cat_bits[threadIdx.x]) : 0u;
-    __syncthreads();
-    const bool is_cat = w.is_cat != 0, has_missing = w.has_missing != 0, default_left = w.default_left != 0;
+    if (kCat) {
+      if (threadIdx.x < 8) s_cat[threadIdx.x] = w.is_cat ? __ldg(&work[lo].cat_bits[threadIdx.x]) : 0u;
+      __syncthreads();
+    }
+    const bool is_cat = kCat && w.is_cat != 0, has_missing = w.has_missing != 0, default_left = w.default_left != 0;
     int rid[kIters]; bool left[kIters]; unsigned bal[kIters];
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
@@ -47,9 +54,14 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       const bool valid = r < nrows;
       rid[it] = valid ? __ldg(ridx_in + w.seg_begin + row0 + r) : 0;
       int b = valid ? (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid[it]) : 0;
-      const bool in_set = ((s_cat[b >> 5] >> (b & 31)) & 1u) != 0u;              // category in the set -> right
-      const bool go_left = is_cat ? !in_set : (b <= w.split_bin);
-      const bool l = (has_missing && b == B2_MISSING_BIN) ? default_left : go_left;
+      bool l;
+      if (kCat) {
+        const bool in_set = ((s_cat[b >> 5] >> (b & 31)) & 1u) != 0u;            // category in the set -> right
+        const bool go_left = is_cat ? !in_set : (b <= w.split_bin);
+        l = (has_missing && b == B2_MISSING_BIN) ? default_left : go_left;
+      } else {
+        l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : (b <= w.split_bin);
+      }
       left[it] = valid && l;
       bal[it] = __ballot_sync(0xffffffffu, left[it]);
       if (lane == 0) s_warp_left[warp][it] = __popc(bal[it]);
@@ -154,11 +166,14 @@ extern "C" {
 int b2_part_chunk_rows() { return b2::kPartChunk; }
 
 int b2_launch_partition(const uint8_t* bins_col, int64_t col_stride, const int32_t* ridx_in, int32_t* ridx_out,
-                        const B2SplitWork* work, const B2LevelCtl* ctl, int max_chunks, int32_t* counters, int num_sms,
-                        cudaStream_t stream) {
+                        const B2SplitWork* work, const B2LevelCtl* ctl, int max_chunks, int32_t* counters, int any_categorical,
+                        int num_sms, cudaStream_t stream) {
   if (max_chunks <= 0) return 0;
   int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
-  b2::partition_kernel<<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
+  if (any_categorical)
+    b2::partition_kernel<true><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
+  else
+    b2::partition_kernel<false><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
   return (int)cudaGetLastError();
 }
 int b2_launch_leaf_sums(const float2* gh, const int32_t* ridx0, const int32_t* ridx1, const void* work, const B2LevelCtl* ctl,
