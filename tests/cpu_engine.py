@@ -243,6 +243,12 @@ def train(params, dtrain, num_boost_round=10, evals=(), obj=None, feval=None, ma
                 Xe, ye = np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
                 v = bst.ob.metric(metric, bst._margin(Xe, np.nan), ye)
             evals_log.setdefault(name, {}).setdefault(metric, []).append(v)
+            fm = custom_metric or feval
+            if fm is not None:   # custom metric on the (union) matrix: every rank reports the same value
+                Xm, ym = (X, y) if dm is dtrain else (Xe, ye)
+                pm = bst.ob.margin.reshape(-1) if dm is dtrain and bst.ob.K == 1 else bst._margin(Xm, np.nan).reshape(-1)
+                mname, mval = fm(pm, DMatrix(Xm, ym))
+                evals_log[name].setdefault(mname, []).append(float(mval))
         if any([cb.after_iteration(bst, epoch, evals_log) for cb in callbacks]):
             break
     for cb in callbacks:

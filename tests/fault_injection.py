@@ -26,3 +26,23 @@ class RankRecorder(TrainingCallback):
         if epoch == 0:
             put_queue(("rank", get_actor_rank()))
         return False
+
+
+# ---- custom objective / metric of xgboost_ray/tests/test_xgboost_api.py:20-44 (top level: picklable for the actors)
+def squared_log(predt, dtrain):
+    import numpy as np
+    y = dtrain.get_label()
+    predt = np.asarray(predt, np.float64).copy()
+    predt[predt < -1] = -1 + 1e-6
+    grad = (np.log1p(predt) - np.log1p(y)) / (predt + 1)
+    hess = (-np.log1p(predt) + np.log1p(y) + 1) / np.power(predt + 1, 2)
+    return grad, hess
+
+
+def rmsle(predt, dtrain):
+    import numpy as np
+    y = dtrain.get_label()
+    predt = np.asarray(predt, np.float64).copy()
+    predt[predt < -1] = -1 + 1e-6
+    elements = np.power(np.log1p(y) - np.log1p(predt), 2)
+    return "PyRMSLE", float(np.sqrt(np.sum(elements) / len(y)))

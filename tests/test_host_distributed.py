@@ -139,3 +139,22 @@ def test_feature_weights_reach_the_engine():
             if f >= 0:
                 cnt[f] += 1
     assert cnt[0] == 0 and cnt.argmax() == 9
+
+
+@pytest.mark.timeout(600)
+def test_custom_objective_and_metric_two_actors():
+    """test_xgboost_api.py:77-152: a custom objective (squared log error) and a custom metric through two actors
+    give the single-process result; the rounded predictions reproduce the labels."""
+    from tests.fault_injection import rmsle, squared_log
+    from xgboost_ray_b200 import RayDMatrix, RayParams, predict, train
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+    y = np.array([0, 1, 0, 1] * 8, np.float32)
+    params = {"booster": "gbtree", "tree_method": "hist", "nthread": 1, "max_depth": 2, "seed": 1000}
+    res1, res2 = {}, {}
+    d1, d2 = RayDMatrix(x, y), RayDMatrix(x, y)
+    b1 = train(params, d1, evals=[(d1, "dtrain")], evals_result=res1, obj=squared_log, feval=rmsle, ray_params=RayParams(num_actors=1))
+    b2 = train(params, d2, evals=[(d2, "dtrain")], evals_result=res2, obj=squared_log, feval=rmsle, ray_params=RayParams(num_actors=2))
+    p1 = np.round(predict(b1, RayDMatrix(x), ray_params=RayParams(num_actors=1)))
+    p2 = np.round(predict(b2, RayDMatrix(x), ray_params=RayParams(num_actors=2)))
+    assert list(p1) == list(p2) == list(y)
+    assert np.allclose(res1["dtrain"]["PyRMSLE"], res2["dtrain"]["PyRMSLE"], atol=0.1) and len(res2["dtrain"]["PyRMSLE"]) == 10

@@ -265,3 +265,22 @@ def test_base_score_estimation_known_answers(oracle):
     assert b.params.get("base_score", 0.5) == 0.5
     b, _ = oracle.train({"objective": "reg:squarederror", "max_depth": 2, "base_score": 0.5}, X, yr, 1)
     assert b.params["base_score"] == 0.5                       # an explicit value is never replaced
+
+
+def test_custom_objective_known_answer(oracle):
+    """test_xgboost_api.py:77-102: ten rounds of the squared-log-error objective on the 4-pattern toy matrix; the
+    rounded predictions are the labels."""
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+    y = np.array([0, 1, 0, 1] * 8, np.float32)
+    cuts = oracle.Cuts.from_data(x, 256)
+    bins = cuts.bin(x)
+    b = oracle.Booster({"max_depth": 2, "objective": "reg:squarederror", "seed": 1000}, cuts)
+    assert b.estimate_base_score(y) == 0.5
+    b.init_margin(len(y))
+    for _ in range(10):
+        predt = b.margin[:, 0].astype(np.float64)
+        predt[predt < -1] = -1 + 1e-6
+        g = (np.log1p(predt) - np.log1p(y)) / (predt + 1)
+        h = (-np.log1p(predt) + np.log1p(y) + 1) / np.power(predt + 1, 2)
+        b.boost(bins, y, custom_g=g, custom_h=h)
+    assert list(np.round(b.predict(x))) == list(y)
