@@ -37,6 +37,10 @@ int B2_DeviceCount(int* out);
 int B2_GetUniqueId(uint8_t out[128]);
 int B2_CommCreate(const uint8_t uid[128], int rank, int world, int device, B2Handle* out);
 int B2_CommRank(B2Handle comm, int* rank, int* world);
+/* host-side allreduce of a few doubles over the communicator (xgb.collective.allreduce; xgboost averages custom
+ * metric values over the workers with it, python-package callback.py _allreduce_metric).  op: 0 sum, 1 max, 2 min.
+ * comm == 0 or a single-process communicator: identity. */
+int B2_CommAllReduce(B2Handle comm, double* inout, int32_t n, int32_t op);
 int B2_CommAbort(B2Handle comm);
 int B2_CommFree(B2Handle comm);
 

@@ -143,3 +143,24 @@ def test_two_gpu_weighted_rows_identical_to_one_gpu_and_oracle(oracle):
         o = ob.tree(i)
         assert np.array_equal(t["split_feature"], o.split_feature) and np.array_equal(t["split_bin"], o.split_bin)
         assert np.array_equal(t["split_cond"].view(np.uint32), o.split_cond.view(np.uint32))   # same (weighted) cuts
+
+
+@pytest.mark.timeout(900)
+def test_two_gpu_custom_objective_and_metric():
+    """test_xgboost_api.py:77-152 on two GPU actors: custom objective through B2_BoosterBoostOneIter, custom metric
+    averaged over the actors (B2_CommAllReduce, xgboost's _allreduce_metric)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tests.fault_injection import rmsle, squared_log
+    from xgboost_ray_b200 import RayDMatrix, RayParams, predict, train
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+    y = np.array([0, 1, 0, 1] * 8, np.float32)
+    params = {"booster": "gbtree", "tree_method": "hist", "max_depth": 2, "seed": 1000}
+    res1, res2 = {}, {}
+    d1, d2 = RayDMatrix(x, y), RayDMatrix(x, y)
+    b1 = train(params, d1, evals=[(d1, "dtrain")], evals_result=res1, obj=squared_log, feval=rmsle, ray_params=RayParams(num_actors=1))
+    b2 = train(params, d2, evals=[(d2, "dtrain")], evals_result=res2, obj=squared_log, feval=rmsle, ray_params=RayParams(num_actors=2))
+    assert _dump(b1) == _dump(b2)
+    p2 = np.round(predict(b2, RayDMatrix(x), ray_params=RayParams(num_actors=2)))
+    assert list(p2) == list(y)
+    assert np.allclose(res1["dtrain"]["PyRMSLE"], res2["dtrain"]["PyRMSLE"], atol=0.1)

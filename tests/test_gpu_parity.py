@@ -561,3 +561,17 @@ def test_base_score_estimated_when_not_given(eng, oracle, objective, tmp_path):
     f = str(tmp_path / "m.json")
     ebst.save_model(f)
     assert np.array_equal(eng.Booster(model_file=f).predict(eng.DMatrix(X)), ebst.predict(dm))
+
+
+def test_custom_objective_known_answer_single_process(eng):
+    """test_xgboost_api.py:77-102, single process: squared-log-error objective, rounded predictions == labels."""
+    from tests.fault_injection import rmsle, squared_log
+    x = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
+    y = np.array([0, 1, 0, 1] * 8, np.float32)
+    dm = eng.DMatrix(x, label=y)
+    res = {}
+    bst = eng.train({"tree_method": "hist", "max_depth": 2, "seed": 1000}, dm, num_boost_round=10, obj=squared_log, feval=rmsle,
+                    evals=[(dm, "dtrain")], evals_result=res, verbose_eval=False)
+    assert list(np.round(bst.predict(eng.DMatrix(x)))) == list(y)
+    assert len(res["dtrain"]["PyRMSLE"]) == 10 and res["dtrain"]["PyRMSLE"][-1] < res["dtrain"]["PyRMSLE"][0]
+    assert eng.collective.allreduce([1.0, 2.0]).tolist() == [1.0, 2.0]      # no communicator: identity

@@ -230,7 +230,7 @@ void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
 // ---------------------------------------------------------------- NCCL (dlopen'ed)
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { kNcclSum = 0, kNcclMax = 2 };
+enum { kNcclSum = 0, kNcclMax = 2, kNcclMin = 3 };   // ncclRedOp_t
 enum { kNcclUint8 = 1, kNcclInt32 = 2, kNcclUint32 = 3, kNcclInt64 = 4, kNcclUint64 = 5, kNcclFloat32 = 7, kNcclFloat64 = 8 };
 struct NcclApi {
   void* lib = nullptr;
@@ -1259,6 +1259,21 @@ int B2_CommRank(B2Handle comm, int* rank, int* world) {
   API_BEGIN
   CommH* h = from_handle<CommH>(comm, kComm, "communicator");
   *rank = h->c.rank; *world = h->c.world;
+  API_END
+}
+int B2_CommAllReduce(B2Handle comm, double* inout, int32_t n, int32_t op) {
+  API_BEGIN
+  if (n < 0 || op < 0 || op > 2) fail("invalid allreduce arguments (n=%d, op=%d)", n, op);
+  if (!comm || n == 0) return 0;                      // single process: identity
+  CommH* h = from_handle<CommH>(comm, kComm, "communicator");
+  if (h->c.world <= 1) return 0;
+  Ctx* ctx = get_ctx(h->c.device);
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  DevBuf<double> d; d.ensure((size_t)n);
+  CUDA_CHECK(cudaMemcpyAsync(d.p, inout, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  allreduce(&h->c, d.p, (size_t)n, kNcclFloat64, op == 0 ? kNcclSum : op == 1 ? kNcclMax : kNcclMin, ctx->stream);
+  CUDA_CHECK(cudaMemcpyAsync(inout, d.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   API_END
 }
 int B2_CommAbort(B2Handle comm) {

@@ -43,6 +43,7 @@ ABI = {
     "B2_GetUniqueId": (C.c_int, [_BP]),
     "B2_CommCreate": (C.c_int, [_BP, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
     "B2_CommRank": (C.c_int, [_H, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "B2_CommAllReduce": (C.c_int, [_H, _DP, C.c_int32, C.c_int32]),
     "B2_CommAbort": (C.c_int, [_H]),
     "B2_CommFree": (C.c_int, [_H]),
     "B2_MatrixCreateFromDense": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
@@ -189,6 +190,14 @@ class collective:  # namespace shim: xgb.collective.get_rank() (session.py:73)
     @staticmethod
     def get_world_size():
         return _coll.world
+
+    @staticmethod
+    def allreduce(data, op="sum"):
+        """xgb.collective.allreduce over the actors' communicator (float64; op: sum / max / min)."""
+        a = np.ascontiguousarray(np.asarray(data, np.float64)).copy()
+        flat = a.reshape(-1)
+        _check(lib().B2_CommAllReduce(_coll.handle, flat.ctypes.data_as(_DP), flat.size, {"sum": 0, "max": 1, "min": 2}[op]))
+        return a
 
 
 # ----------------------------------------------------------------------------- DMatrix
@@ -595,6 +604,9 @@ class Booster:
                 pred = self.predict(dm, output_margin=output_margin, training=(dm is self._train))
                 res = feval(pred, dm)
                 res = res if isinstance(res, list) else [res]
+                if _coll.world > 1:   # xgboost averages custom metric values over the workers (_allreduce_metric)
+                    vals = collective.allreduce([float(v) for _, v in res]) / _coll.world
+                    res = [(mname, float(v)) for (mname, _), v in zip(res, vals)]
                 for mname, val in res:
                     parts.append("%s-%s:%.6f" % (name, mname, float(val)))
         return "\t".join(parts)
