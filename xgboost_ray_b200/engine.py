@@ -211,7 +211,7 @@ class DMatrix:
         if hasattr(data, "values") and not isinstance(data, np.ndarray):  # pandas
             if feature_names is None and hasattr(data, "columns"):
                 feature_names = [str(c) for c in data.columns]
-            cat_cols = [str(dt) == "category" for dt in getattr(data, "dtypes", [])]
+            cat_cols = [str(dt) == "category" for dt in data.dtypes] if hasattr(data, "columns") else []
             if any(cat_cols):
                 # xgboost's pandas adapter: category dtype -> codes, -1 (NaN) -> missing; needs enable_categorical
                 if not enable_categorical:
