@@ -105,6 +105,16 @@ struct B2ColSample {
   uint32_t seed, tree;
 };
 
+// ---- peer mapping of the experimental NVLink histogram exchange (p2p_exchange.cu)
+#define B2_P2P_MAX_WORLD 32
+enum { kSlotHist = 0, kSlotCand = 1, kSlotRead = 2, kP2PSlots = 3 };
+struct B2P2P {
+  long long* build[B2_P2P_MAX_WORLD];      // hist_build of rank w ([shards][node_cap][slice]); own pointer for w == rank
+  B2SplitCand* cands[B2_P2P_MAX_WORLD];    // candidate table of rank w ([world][cand_cap])
+  uint32_t* flags[B2_P2P_MAX_WORLD];       // flag array of rank w ([kP2PSlots][world])
+  int32_t world, rank;
+};
+
 struct B2TrainParamDev {
   double min_child_weight, lambda, alpha;
   double inv_scale_g, inv_scale_h;

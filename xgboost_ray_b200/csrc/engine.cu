@@ -38,6 +38,11 @@ int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const i
                           const uint8_t*, const uint8_t*, const int32_t*, int, B2TrainParamDev, B2SplitCand*, int, const B2LevelCtl*,
                           int, int, B2ColSample, const B2NodeSeg*, cudaStream_t);
 int b2_launch_subsample(float2*, int64_t, uint32_t, uint32_t, uint32_t, double, int, cudaStream_t);
+int b2_p2p_flag_words(int);
+int b2_launch_p2p_signal(const void*, int, uint32_t, cudaStream_t);
+int b2_launch_p2p_wait(const void*, int, uint32_t, uint32_t*, cudaStream_t);
+int b2_launch_p2p_reduce(const void*, uint32_t, long long*, size_t, size_t, uint32_t*, int, cudaStream_t);
+int b2_launch_p2p_push_cands(const void*, const B2SplitCand*, int, int, int, cudaStream_t);
 int b2_launch_sum_fixed(const float2*, int64_t, const int32_t*, int, long long*, int, cudaStream_t);
 int b2_cat_ctas();
 int b2_launch_eval_cat_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, int, const int32_t*, const int32_t*,
@@ -588,6 +593,15 @@ struct Booster : HandleBase {
   int cpn_num = 1;
   DevBuf<uint32_t> t_cat;                  // [max_nodes][8] category sets of the tree being grown
   DevBuf<uint8_t> d_col_masks;             // [max_depth][F] level feature sets of the tree being grown (column sampling)
+  // experimental NVLink peer-memory exchange (p2p_exchange.cu; B2_EXCHANGE_P2P=1), off unless every rank mapped its peers
+  struct P2PState {
+    bool enabled = false;
+    B2P2P pp;
+    DevBuf<uint32_t> flags, err;
+    std::vector<void*> opened;
+    uint32_t hist_epoch = 0, cand_epoch = 0, pending_read = 0;
+    int cand_cap = 0;
+  } p2p;
   size_t slice_elems = 0;
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
@@ -613,6 +627,7 @@ struct Booster : HandleBase {
   std::vector<std::pair<int, cudaEvent_t>> phase_marks;   // (phase that ENDS at this event)
   cudaEvent_t round_start = nullptr, round_stop = nullptr;
   ~Booster() {
+    for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
     for (auto e : ev_pool) cudaEventDestroy(e);
     if (round_start) cudaEventDestroy(round_start);
     if (round_stop) cudaEventDestroy(round_stop);
@@ -764,6 +779,55 @@ B2TreeDev tree_dev(Booster* b) {
   return t;
 }
 
+// Map every peer's build buffer, candidate table and flag array (cudaIpc) for the experimental exchange.  All ranks
+// take the same decision: one failed mapping anywhere switches every rank back to NCCL.
+void p2p_setup(Booster* b) {
+  const char* env = getenv("B2_EXCHANGE_P2P");
+  if (!env || atoi(env) == 0 || b->shards <= 1 || b->p2p.enabled) return;
+  Comm* c = b->comm; cudaStream_t s = b->ctx->stream; const int W = c->world;
+  if (W > B2_P2P_MAX_WORLD) return;
+  Booster::P2PState& st = b->p2p;
+  st.flags.ensure((size_t)b2_p2p_flag_words(W)); st.err.ensure(1);
+  CUDA_CHECK(cudaMemsetAsync(st.flags.p, 0, (size_t)b2_p2p_flag_words(W) * sizeof(uint32_t), s));
+  CUDA_CHECK(cudaMemsetAsync(st.err.p, 0, sizeof(uint32_t), s));
+  struct Handles { cudaIpcMemHandle_t build, cands, flags; };
+  Handles mine; int ok = 1;
+  if (cudaIpcGetMemHandle(&mine.build, b->hist_build.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.cands, b->d_cands_all.p) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine.flags, st.flags.p) != cudaSuccess) { ok = 0; cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+  DevBuf<uint8_t> d_mine, d_all; d_mine.ensure(sizeof(Handles)); d_all.ensure(sizeof(Handles) * (size_t)W);
+  CUDA_CHECK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(Handles), cudaMemcpyHostToDevice, s));
+  NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(Handles), kNcclUint8, c->comm, s));   // also orders the flag memset before any signal
+  std::vector<Handles> all((size_t)W);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Handles) * (size_t)W, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  memset(&st.pp, 0, sizeof(st.pp));
+  st.pp.world = W; st.pp.rank = c->rank;
+  for (int w = 0; w < W && ok; ++w) {
+    if (w == c->rank) { st.pp.build[w] = b->hist_build.p; st.pp.cands[w] = b->d_cands_all.p; st.pp.flags[w] = st.flags.p; continue; }
+    void *pb = nullptr, *pc = nullptr, *pf = nullptr;
+    if (cudaIpcOpenMemHandle(&pb, all[w].build, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pc, all[w].cands, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pf, all[w].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    for (void* q : {pb, pc, pf}) if (q) st.opened.push_back(q);
+    st.pp.build[w] = (long long*)pb; st.pp.cands[w] = (B2SplitCand*)pc; st.pp.flags[w] = (uint32_t*)pf;
+  }
+  // agree: min over ranks of the local success flag
+  DevBuf<int32_t> d_ok; d_ok.ensure(1);
+  int32_t neg = ok ? 0 : 1;   // allreduce(max) of "failed"
+  CUDA_CHECK(cudaMemcpyAsync(d_ok.p, &neg, sizeof(neg), cudaMemcpyHostToDevice, s));
+  allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
+  CUDA_CHECK(cudaMemcpyAsync(&neg, d_ok.p, sizeof(neg), cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaStreamSynchronize(s));
+  if (neg) {
+    for (void* q : st.opened) cudaIpcCloseMemHandle(q);
+    st.opened.clear();
+    fprintf(stderr, "[b2hist] B2_EXCHANGE_P2P=1 requested but peer mapping failed on some rank; using NCCL\n");
+    return;
+  }
+  st.hist_epoch = st.cand_epoch = st.pending_read = 0;
+  st.enabled = true;
+}
+
 void ensure_ctl_tables(Booster* b) {
   const int D = b->p.max_depth; const int G = b->train->n_groups;
   if (b->ctl_depth == D) return;
@@ -791,6 +855,8 @@ void ensure_ctl_tables(Booster* b) {
   if (b->shards > 1) { b->hist_build.ensure(half * b->node_elems); b->d_cands_all.ensure(half * b->cpn * b->shards); }
   b->d_cands.ensure(half * b->cpn);
   CUDA_CHECK(cudaMemsetAsync(b->t_i64.p, 0, L.i64_count * 8, b->ctx->stream));
+  b->p2p.cand_cap = (int)(half * b->cpn);
+  p2p_setup(b);
 }
 
 void record_hist_launch(Booster* b, cudaEvent_t& e0, cudaEvent_t& e1, bool begin) {
@@ -808,10 +874,27 @@ bool use_tma_hist() {
 // Histogram exchange of `nb` built nodes: reduce-scatter of the build buffer into the owned slices of the
 // level buffer (shards == world), or in-place allreduce (shards == 1, any world size).
 long long* build_target(Booster* b, long long* level_buf) { return b->shards > 1 ? b->hist_build.p : level_buf; }
-void exchange_hist(Booster* b, long long* level_buf, int nb) {
+// before a rank zeroes its build buffer again every peer must have finished reading it (experimental P2P exchange)
+void p2p_wait_reads(Booster* b) {
+  if (!b->p2p.enabled || b->p2p.pending_read == 0) return;
+  LAUNCH_CHECK(b2_launch_p2p_wait(&b->p2p.pp, kSlotRead, b->p2p.pending_read, b->p2p.err.p, b->ctx->stream));
+  b->p2p.pending_read = 0;
+}
+void exchange_hist(Booster* b, long long* level_buf, int nb, int node_cap) {
   cudaStream_t s = b->ctx->stream;
   if (!b->comm || b->comm->world <= 1) return;
   if (b->comm->aborted.load()) fail("communicator aborted");
+  if (b->p2p.enabled) {
+    const uint32_t epoch = ++b->p2p.hist_epoch;
+    LAUNCH_CHECK(b2_launch_p2p_signal(&b->p2p.pp, kSlotHist, epoch, s));
+    LAUNCH_CHECK(b2_launch_p2p_reduce(&b->p2p.pp, epoch, level_buf, (size_t)nb * b->slice_elems, (size_t)node_cap * b->slice_elems,
+                                      b->p2p.err.p, b->ctx->num_sms, s));
+    LAUNCH_CHECK(b2_launch_p2p_signal(&b->p2p.pp, kSlotRead, epoch, s));
+    b->p2p.pending_read = epoch;
+    b->t.allreduce_bytes += (double)nb * b->node_elems * 8 * (b->shards - 1) / b->shards;
+    b->t.kernel_launches += 3;
+    return;
+  }
   if (b->shards > 1) {
     NCCL_CHECK(nccl()->ReduceScatter(b->hist_build.p, level_buf, (size_t)nb * b->slice_elems, kNcclInt64, kNcclSum, b->comm->comm, s));
     b->t.allreduce_bytes += (double)nb * b->node_elems * 8 * (b->shards - 1) / b->shards;
@@ -891,6 +974,7 @@ void grow_tree(Booster* b, int k, int slot) {
   // ---- root histogram (no gather; row count known on the host)
   const int sh = b->log2_shards;
   const int shard_rank = b->shards > 1 ? b->comm->rank : 0;
+  p2p_wait_reads(b);
   CUDA_CHECK(cudaMemsetAsync(build_target(b, b->hist[0].p), 0, b->node_elems * sizeof(long long), s));
   {
     const int chunk_rows = pick_chunk_rows(b, n);
@@ -911,7 +995,7 @@ void grow_tree(Booster* b, int k, int slot) {
     }
   }
   mark_phase(b, 1);
-  exchange_hist(b, b->hist[0].p, 1);
+  exchange_hist(b, b->hist[0].p, 1, 1);
   mark_phase(b, 2);
   LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_ev[0].p, b->d_qexp.p, p.qbits, dp, sh, s));
   LAUNCH_CHECK(b2_launch_root_record(tree, b->d_ev[0].p, s));
@@ -922,6 +1006,7 @@ void grow_tree(Booster* b, int k, int slot) {
     const int max_nodes_level = 1 << d;
     const bool can_split = d < D;
     const B2SplitCand* cands_for_decide = b->d_cands.p;
+    int cand_rank_stride = max_nodes_level * b->cpn;
     if (can_split) {
       B2ColSample cs;
       cs.level_mask = p.use_cols() ? b->d_col_masks.p + (size_t)d * m->F : nullptr;
@@ -938,14 +1023,22 @@ void grow_tree(Booster* b, int k, int slot) {
                                                b->d_cands.p, b->cpn, b->cpn_num, ctl + cur, sh, shard_rank, cs, b->d_seg[cur].p, s));
         b->t.kernel_launches++;
       }
-      if (b->shards > 1) {   // every rank scanned only its own slots: gather the per-node candidates
+      if (b->shards > 1 && b->p2p.enabled) {   // experimental: candidates stored straight into the peers' tables
+        const uint32_t epoch = ++b->p2p.cand_epoch;
+        LAUNCH_CHECK(b2_launch_p2p_push_cands(&b->p2p.pp, b->d_cands.p, max_nodes_level * b->cpn, b->p2p.cand_cap, ctx->num_sms, s));
+        LAUNCH_CHECK(b2_launch_p2p_signal(&b->p2p.pp, kSlotCand, epoch, s));
+        LAUNCH_CHECK(b2_launch_p2p_wait(&b->p2p.pp, kSlotCand, epoch, b->p2p.err.p, s));
+        cands_for_decide = b->d_cands_all.p;
+        cand_rank_stride = b->p2p.cand_cap;
+        b->t.kernel_launches += 3;
+      } else if (b->shards > 1) {   // every rank scanned only its own slots: gather the per-node candidates
         const size_t bytes = (size_t)max_nodes_level * b->cpn * sizeof(B2SplitCand);
         NCCL_CHECK(nccl()->AllGather(b->d_cands.p, b->d_cands_all.p, bytes, kNcclUint8, b->comm->comm, s));
         cands_for_decide = b->d_cands_all.p;
       }
     }
     LAUNCH_CHECK(b2_launch_decide(ctl + cur, ctl + nxt, b->d_seg[cur].p, b->d_seg[nxt].p, b->d_ev[cur].p, b->d_ev[nxt].p,
-                                  cands_for_decide, b->cpn, b->shards, max_nodes_level * b->cpn, can_split ? 1 : 0, tree,
+                                  cands_for_decide, b->cpn, b->shards, cand_rank_stride, can_split ? 1 : 0, tree,
                                   b->d_split_work.p, b->d_pair_parent.p, b->d_leaves.p,
                                   d_n_leaves, m->d_has_missing.p, b->d_qexp.p, p.qbits, cp, s));
     b->t.kernel_launches++;
@@ -966,6 +1059,7 @@ void grow_tree(Booster* b, int k, int slot) {
       // ---- histograms of level d+1: built children in slots [0, 2^d), siblings in [2^d, 2^(d+1))
       const int nh = hb ^ 1;
       long long* tgt = build_target(b, b->hist[nh].p);
+      p2p_wait_reads(b);
       CUDA_CHECK(cudaMemsetAsync(tgt, 0, (size_t)max_nodes_level * b->node_elems * sizeof(long long), s));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
       record_hist_launch(b, e0, e1, true);
@@ -977,7 +1071,7 @@ void grow_tree(Booster* b, int k, int slot) {
                                     ctl + nxt, sh, max_nodes_level, ctx->num_sms, s));
       record_hist_launch(b, e0, e1, false);
       mark_phase(b, 1);
-      exchange_hist(b, b->hist[nh].p, max_nodes_level);
+      exchange_hist(b, b->hist[nh].p, max_nodes_level, max_nodes_level);
       mark_phase(b, 2);
       LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[hb].p, b->hist[nh].p, b->d_triples.p, max_nodes_level, (int64_t)b->slice_elems,
                                            ctl + nxt, s));
@@ -1179,6 +1273,11 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
     resolve_events(b);
   } else {
     CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  if (b->p2p.enabled) {
+    uint32_t perr = 0;
+    CUDA_CHECK(cudaMemcpy(&perr, b->p2p.err.p, sizeof(perr), cudaMemcpyDeviceToHost));
+    if (perr) fail("peer-memory histogram exchange timed out waiting for another rank (flag slot %u)", perr - 1);
   }
   for (int k = 0; k < K; ++k) materialize_tree(b, k);
   b->t.rounds++;
