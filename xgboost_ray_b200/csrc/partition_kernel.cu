@@ -5,6 +5,8 @@
 // Rows of a node live in a contiguous segment of a row-index list; a split rewrites the segment
 // as [left rows | right rows] into the other (ping-pong) list.  Histogram sums are exact integers,
 // so the order of rows inside a child segment is irrelevant to the model.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2 {
@@ -18,7 +20,10 @@ typedef B2SegWork SegWork;
 // and 8 bin-byte loads the compiler batches (48 registers).  With the category test in the body it software-pipelines
 // only 2-3 deep and the kernel runs 1.7x slower (ncu launch lists in profiles/), so numeric matrices keep their own
 // instantiation.
-template <bool kCat>
+// kMode 0: numeric only.  1: category set in shared memory (the validated categorical path).  2 (experimental,
+// B2_PART_CAT_MODE=2): category set in eight uniform registers selected with a 3-level select tree, no shared-memory
+// load in the row loop.
+template <int kMode>
 __global__ void __launch_bounds__(kPartThreads)
 partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const int32_t* __restrict__ ridx_in,
                  int32_t* __restrict__ ridx_out, const B2SplitWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl,
@@ -42,9 +47,15 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
     // the category set goes through shared memory so that the row loop below stays branch-free straight-line code
     // (a divergent global load in its body kept the compiler from batching the 8 row-id / bin-byte loads: the
     // kernel ran 1.7x slower, profiles/r01_summary.md)
-    if (kCat) {
+    constexpr bool kCat = kMode != 0;
+    if (kMode == 1) {
       if (threadIdx.x < 8) s_cat[threadIdx.x] = w.is_cat ? __ldg(&work[lo].cat_bits[threadIdx.x]) : 0u;
       __syncthreads();
+    }
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
+    if (kMode == 2 && w.is_cat) {
+      const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(work[lo].cat_bits)), hi4 = __ldg(reinterpret_cast<const uint4*>(work[lo].cat_bits) + 1);
+      c0 = lo4.x; c1 = lo4.y; c2 = lo4.z; c3 = lo4.w; c4 = hi4.x; c5 = hi4.y; c6 = hi4.z; c7 = hi4.w;
     }
     const bool is_cat = kCat && w.is_cat != 0, has_missing = w.has_missing != 0, default_left = w.default_left != 0;
     int rid[kIters]; bool left[kIters]; unsigned bal[kIters];
@@ -56,7 +67,14 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       int b = valid ? (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid[it]) : 0;
       bool l;
       if (kCat) {
-        const bool in_set = ((s_cat[b >> 5] >> (b & 31)) & 1u) != 0u;            // category in the set -> right
+        uint32_t word;
+        if (kMode == 1) word = s_cat[b >> 5];
+        else {
+          const uint32_t w01 = (b & 32) ? c1 : c0, w23 = (b & 32) ? c3 : c2, w45 = (b & 32) ? c5 : c4, w67 = (b & 32) ? c7 : c6;
+          const uint32_t w03 = (b & 64) ? w23 : w01, w47 = (b & 64) ? w67 : w45;
+          word = (b & 128) ? w47 : w03;
+        }
+        const bool in_set = ((word >> (b & 31)) & 1u) != 0u;                     // category in the set -> right
         const bool go_left = is_cat ? !in_set : (b <= w.split_bin);
         l = (has_missing && b == B2_MISSING_BIN) ? default_left : go_left;
       } else {
@@ -170,10 +188,14 @@ int b2_launch_partition(const uint8_t* bins_col, int64_t col_stride, const int32
                         int num_sms, cudaStream_t stream) {
   if (max_chunks <= 0) return 0;
   int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
-  if (any_categorical)
-    b2::partition_kernel<true><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
+  static int cat_mode = -1;
+  if (cat_mode < 0) { const char* e = getenv("B2_PART_CAT_MODE"); cat_mode = (e && atoi(e) == 2) ? 2 : 1; }
+  if (any_categorical && cat_mode == 2)
+    b2::partition_kernel<2><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
+  else if (any_categorical)
+    b2::partition_kernel<1><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
   else
-    b2::partition_kernel<false><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
+    b2::partition_kernel<0><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
   return (int)cudaGetLastError();
 }
 int b2_launch_leaf_sums(const float2* gh, const int32_t* ridx0, const int32_t* ridx1, const void* work, const B2LevelCtl* ctl,
