@@ -190,6 +190,20 @@ class Booster:
                     return np.argmax(m, axis=1).astype(np.float32)
         return m[:, 0].astype(np.float32) if K == 1 else m.astype(np.float32)
 
+    def get_score(self, fmap="", importance_type="weight"):
+        cnt, tot = {}, {}
+        for t in self.trees():
+            for f, g in zip(t["split_feature"], t["loss_chg"]):
+                if f >= 0:
+                    k = "f%d" % f
+                    cnt[k] = cnt.get(k, 0) + 1
+                    tot[k] = tot.get(k, 0.0) + float(g)
+        if importance_type == "weight":
+            return cnt
+        return tot if importance_type.startswith("total") else {k: tot[k] / cnt[k] for k in tot}
+
+    get_fscore = get_score
+
     def get_dump(self, dump_format="json", **kw):
         return [json.dumps({k: np.asarray(v).tolist() for k, v in t.items()}) for t in self.trees()]
 

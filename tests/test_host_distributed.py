@@ -158,3 +158,30 @@ def test_custom_objective_and_metric_two_actors():
     p2 = np.round(predict(b2, RayDMatrix(x), ray_params=RayParams(num_actors=2)))
     assert list(p1) == list(p2) == list(y)
     assert np.allclose(res1["dtrain"]["PyRMSLE"], res2["dtrain"]["PyRMSLE"], atol=0.1) and len(res2["dtrain"]["PyRMSLE"]) == 10
+
+
+@pytest.mark.timeout(600)
+def test_sklearn_parameters_and_attributes(tmp_path):
+    """sklearn.py surface: engine parameters travel from the estimator to xgb.train, None leaves the engine default
+    (base_score=None -> estimated like xgboost >= 2.0), importances, unsupported estimators fail loudly."""
+    from xgboost_ray_b200 import RayParams
+    from xgboost_ray_b200.sklearn import (RayXGBClassifier, RayXGBRanker, RayXGBRegressor, RayXGBRFClassifier,
+                                          RayXGBRFRegressor)
+    reg = RayXGBRegressor(n_estimators=3, max_depth=3, subsample=0.8, colsample_bynode=0.5, random_state=7,
+                          max_delta_step=1.0, eval_metric="rmse")
+    p = reg.get_xgb_params()
+    assert p["subsample"] == 0.8 and p["colsample_bynode"] == 0.5 and p["seed"] == 7 and p["max_delta_step"] == 1.0
+    assert "base_score" not in p and "scale_pos_weight" not in p and p["eval_metric"] == "rmse"
+    assert RayXGBClassifier(scale_pos_weight=3.0, base_score=0.4).get_xgb_params()["scale_pos_weight"] == 3.0
+    assert set(reg.get_params()) >= {"subsample", "colsample_bytree", "enable_categorical", "early_stopping_rounds"}
+    rng = np.random.RandomState(0)
+    X = rng.uniform(0, 10, size=(600, 6)).astype(np.float32)
+    y = (X[:, 2] * 3 + rng.normal(scale=0.1, size=600)).astype(np.float32)
+    reg = RayXGBRegressor(n_estimators=8, max_depth=3, colsample_bynode=0.5, random_state=1).fit(
+        X, y, eval_set=[(X, y)], ray_params=RayParams(num_actors=2))
+    imp = reg.feature_importances_
+    assert imp.shape == (6,) and abs(imp.sum() - 1.0) < 1e-5 and imp.argmax() == 2
+    assert "validation_0" in reg.evals_result() and len(reg.evals_result()["validation_0"]["rmse"]) == 8
+    for cls in (RayXGBRFRegressor, RayXGBRFClassifier, RayXGBRanker):
+        with pytest.raises(NotImplementedError):
+            cls()

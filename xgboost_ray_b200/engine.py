@@ -814,18 +814,24 @@ class Booster:
         return self.get_score(importance_type="weight")
 
     def get_score(self, fmap="", importance_type="weight"):
-        score = {}
+        """xgboost's Booster.get_score: weight (split count), gain / cover (averages per split), total_gain / total_cover."""
+        if importance_type not in ("weight", "gain", "cover", "total_gain", "total_cover"):
+            raise XGBoostError("unknown importance_type %r" % (importance_type,))
+        cnt, tot = {}, {}
         for t in self.get_trees():
             for nid in range(len(t["left"])):
                 f = int(t["split_feature"][nid])
                 if f < 0:
                     continue
                 name = self.feature_names[f] if self.feature_names else "f%d" % f
-                if importance_type == "weight":
-                    score[name] = score.get(name, 0) + 1
-                else:
-                    score[name] = score.get(name, 0.0) + float(t["loss_chg"][nid])
-        return score
+                cnt[name] = cnt.get(name, 0) + 1
+                v = float(t["sum_hess"][nid]) if importance_type.endswith("cover") else float(t["loss_chg"][nid])
+                tot[name] = tot.get(name, 0.0) + v
+        if importance_type == "weight":
+            return cnt
+        if importance_type.startswith("total_"):
+            return tot
+        return {k: tot[k] / cnt[k] for k in tot}
 
     def get_timers(self, reset=False):
         if not self.handle:

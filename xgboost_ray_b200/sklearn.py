@@ -13,8 +13,10 @@ from sklearn.base import BaseEstimator, ClassifierMixin, RegressorMixin
 from xgboost_ray_b200.main import RayParams, predict, train
 from xgboost_ray_b200.matrix import RayDMatrix
 
+# estimator attributes forwarded to the engine as training parameters (None = leave the engine default)
 _PARAM_NAMES = ("max_depth", "learning_rate", "gamma", "min_child_weight", "reg_lambda", "reg_alpha", "max_bin",
-                "base_score", "tree_method")
+                "base_score", "tree_method", "subsample", "colsample_bytree", "colsample_bylevel", "colsample_bynode",
+                "scale_pos_weight", "max_delta_step", "max_cat_to_onehot", "max_cat_threshold", "eval_metric")
 
 
 def _check_if_params_are_ray_dmatrix(X, sample_weight, base_margin, eval_set):
@@ -35,8 +37,13 @@ def _check_if_params_are_ray_dmatrix(X, sample_weight, base_margin, eval_set):
 class RayXGBMixin(BaseEstimator):
     def __init__(self, n_estimators: int = 100, max_depth: int = 6, learning_rate: float = 0.3, gamma: float = 0.0,
                  min_child_weight: float = 1.0, reg_lambda: float = 1.0, reg_alpha: float = 0.0, max_bin: int = 256,
-                 base_score: float = 0.5, tree_method: str = "hist", objective: Optional[str] = None,
-                 n_jobs: Optional[int] = None, random_state: Optional[int] = None):
+                 base_score: Optional[float] = None, tree_method: str = "hist", objective: Optional[str] = None,
+                 n_jobs: Optional[int] = None, random_state: Optional[int] = None, subsample: Optional[float] = None,
+                 colsample_bytree: Optional[float] = None, colsample_bylevel: Optional[float] = None,
+                 colsample_bynode: Optional[float] = None, scale_pos_weight: Optional[float] = None,
+                 max_delta_step: Optional[float] = None, max_cat_to_onehot: Optional[int] = None,
+                 max_cat_threshold: Optional[int] = None, enable_categorical: bool = False, missing: float = np.nan,
+                 eval_metric=None, early_stopping_rounds: Optional[int] = None, callbacks=None):
         self.n_estimators = n_estimators
         self.max_depth = max_depth
         self.learning_rate = learning_rate
@@ -45,15 +52,30 @@ class RayXGBMixin(BaseEstimator):
         self.reg_lambda = reg_lambda
         self.reg_alpha = reg_alpha
         self.max_bin = max_bin
-        self.base_score = base_score
+        self.base_score = base_score          # None: estimated from the labels like xgboost >= 2.0
         self.tree_method = tree_method
         self.objective = objective
         self.n_jobs = n_jobs
         self.random_state = random_state
+        self.subsample = subsample
+        self.colsample_bytree = colsample_bytree
+        self.colsample_bylevel = colsample_bylevel
+        self.colsample_bynode = colsample_bynode
+        self.scale_pos_weight = scale_pos_weight
+        self.max_delta_step = max_delta_step
+        self.max_cat_to_onehot = max_cat_to_onehot
+        self.max_cat_threshold = max_cat_threshold
+        self.enable_categorical = enable_categorical
+        self.missing = missing
+        self.eval_metric = eval_metric
+        self.early_stopping_rounds = early_stopping_rounds
+        self.callbacks = callbacks
 
     def get_xgb_params(self):
-        p = {k: getattr(self, k) for k in _PARAM_NAMES}
+        p = {k: getattr(self, k) for k in _PARAM_NAMES if getattr(self, k) is not None}
         p["objective"] = self.objective
+        if self.random_state is not None:
+            p["seed"] = int(self.random_state)
         return p
 
     def _ray_params(self, ray_params):
@@ -67,7 +89,15 @@ class RayXGBMixin(BaseEstimator):
         return self._Booster
 
     def _fit(self, params, X, y, sample_weight, base_margin, eval_set, ray_params, ray_dmatrix_params, **kw):
-        ray_dmatrix_params = ray_dmatrix_params or {}
+        ray_dmatrix_params = dict(ray_dmatrix_params or {})
+        if self.enable_categorical:
+            ray_dmatrix_params.setdefault("enable_categorical", True)
+        if not (isinstance(self.missing, float) and np.isnan(self.missing)):
+            ray_dmatrix_params.setdefault("missing", self.missing)
+        if self.early_stopping_rounds is not None:
+            kw.setdefault("early_stopping_rounds", self.early_stopping_rounds)
+        if self.callbacks is not None:
+            kw.setdefault("callbacks", self.callbacks)
         train_dmatrix, evals = _check_if_params_are_ray_dmatrix(X, sample_weight, base_margin, eval_set)
         if train_dmatrix is None:
             train_dmatrix = RayDMatrix(X, y, weight=sample_weight, base_margin=base_margin, **ray_dmatrix_params)
@@ -77,6 +107,33 @@ class RayXGBMixin(BaseEstimator):
         self.additional_results_ = {}
         self._Booster = train(params, train_dmatrix, self.n_estimators, evals=evals, evals_result=self.evals_result_,
                               additional_results=self.additional_results_, ray_params=self._ray_params(ray_params), **kw)
+        self.n_features_in_ = self._Booster.n_features
+        self.best_iteration = getattr(self._Booster, "best_iteration", None)
+        self.best_score = getattr(self._Booster, "best_score", None)
+        return self
+
+    def evals_result(self):
+        return self.evals_result_
+
+    @property
+    def feature_importances_(self):
+        """Normalised average gain per feature (importance_type "gain", xgboost's default for tree boosters)."""
+        b = self.get_booster()
+        score = b.get_score(importance_type="gain")
+        out = np.zeros(self.n_features_in_, np.float32)
+        names = getattr(b, "feature_names", None)
+        for k, v in score.items():
+            idx = names.index(k) if names and k in names else int(k[1:])
+            out[idx] = v
+        tot = out.sum()
+        return out / tot if tot > 0 else out
+
+    def save_model(self, fname):
+        self.get_booster().save_model(fname)
+
+    def load_model(self, fname):
+        from xgboost_ray_b200.xgb import xgboost as _x
+        self._Booster = _x.Booster(model_file=fname)
         self.n_features_in_ = self._Booster.n_features
         return self
 
@@ -129,3 +186,24 @@ class RayXGBClassifier(RayXGBMixin, ClassifierMixin):
             return self._predict(X, ray_params, ray_dmatrix_params, output_margin=True, **kw)
         proba = self.predict_proba(X, ray_params, ray_dmatrix_params, **kw)
         return self.classes_[np.argmax(proba, axis=1)]
+
+
+class _Unsupported:
+    _why = ""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError(self._why)
+
+
+class RayXGBRFRegressor(_Unsupported):
+    """xgboost_ray/sklearn.py:563-640: random-forest mode needs num_parallel_tree > 1, which this engine does not grow."""
+    _why = "random forest estimators need num_parallel_tree > 1, which the B200 hist engine does not implement"
+
+
+class RayXGBRFClassifier(_Unsupported):
+    _why = RayXGBRFRegressor._why
+
+
+class RayXGBRanker(_Unsupported):
+    """xgboost_ray/sklearn.py:868-1083: ranking objectives (qid groups) are outside the hot path."""
+    _why = "ranking objectives (rank:pairwise / rank:ndcg, qid groups) are not implemented by the B200 hist engine"
