@@ -392,11 +392,15 @@ _UNSUPPORTED_NEUTRAL = {
     "sampling_method": ("uniform",), "max_leaves": (0,), "grow_policy": ("depthwise",), "num_parallel_tree": (1,),
     "monotone_constraints": (None, "", "()", (), []), "interaction_constraints": (None, "", "[]", (), []),
     "multi_strategy": ("one_output_per_tree",), "refresh_leaf": (1, True), "process_type": ("default",),
-    "updater": (None, "grow_quantile_histmaker", "grow_gpu_hist"), "max_bin": tuple(range(2, 257)),
+    "updater": (None, "grow_quantile_histmaker", "grow_gpu_hist"),
 }
 
 
 def _check_supported(params):
+    mb = params.get("max_bin")
+    if mb is not None and not 2 <= int(mb) <= 256:
+        raise XGBoostError("parameter max_bin=%r is not supported by the B200 hist engine: the bin matrix is uint8, "
+                           "max_bin must be in [2, 256]" % (mb,))
     for k, neutral in _UNSUPPORTED_NEUTRAL.items():
         if k in params and params[k] is not None:
             v = params[k]
