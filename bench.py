@@ -94,6 +94,11 @@ def synth_block(block, rows, cols, seed=1234, workload="C3"):
 def synth_shard(n_rows, cols, rank, world, block_rows=1_000_000, workload="C3"):
     """Rows rank, rank+world, ... of the global matrix (INTERLEAVED sharding, matrix.py:1100)."""
     n_local = len(range(rank, n_rows, world))
+    cache = os.environ.get("B2_BENCH_CACHE")   # optional .npy cache of the generated shard (A/B runs inside one gpurun call)
+    cpath = os.path.join(cache, "%s_%d_%d_%d_%d.npz" % (workload, n_rows, cols, rank, world)) if cache else None
+    if cpath and os.path.exists(cpath):
+        z = np.load(cpath)
+        return z["X"], z["y"]
     Xs = np.empty((n_local, cols), dtype=np.float32)
     ys = np.empty(n_local, dtype=np.float32)
     at = 0
@@ -105,6 +110,9 @@ def synth_shard(n_rows, cols, rank, world, block_rows=1_000_000, workload="C3"):
         Xs[at:at + m] = X[first::world]
         ys[at:at + m] = y[first::world]
         at += m
+    if cpath:
+        os.makedirs(cache, exist_ok=True)
+        np.savez(cpath, X=Xs, y=ys)
     return Xs, ys
 
 
@@ -144,6 +152,61 @@ class ClockSampler(threading.Thread):
             mask |= rs
         return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_sm),
                 "reasons": [n for n, bit in self.REASONS if mask & bit], "samples": len(sm)}
+
+
+def workload_string(args):
+    """Identical on both arms (the driver compares the config of the reference arm with ours)."""
+    return "%s synthetic %dx%d %s depth %d 256 bins" % (args.workload, args.rows, args.cols, args.objective, args.depth)
+
+
+def _sha(*arrays):
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(a if isinstance(a, (bytes, bytearray)) else np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def parity_check(E, args, rank, world, dm_kw, bst_timed, dm_timed):
+    """Outside the timed region: (1) hashes of the timed model and of its cut points -- integer histograms make them
+    independent of the GPU count, so the SCALE lines must carry the same values at N = 1/2/4/8; (2) a 200k-row, 3-round
+    sub-problem of the same workload trained on all N ranks and compared tree for tree with the fixed-point CPU oracle
+    on rank 0 (split feature / bin / default direction bit-exact, leaf values within 1e-5)."""
+    dump = "\n".join(bst_timed.get_dump(dump_format="json", with_stats=True)).encode()
+    ptrs, vals, mins, hm = dm_timed.get_cuts()
+    out = {"model_sha256": _sha(dump), "cuts_sha256": _sha(ptrs, vals, mins, hm), "oracle_match": None}
+    n_sub, rounds = min(200_000, args.rows), 3
+    Xs, ys = synth_shard(n_sub, args.cols, rank, world, workload=args.workload)
+    params = dict(PARAMS, max_depth=min(args.depth, 8), objective=args.objective, profile=0)
+    if args.num_class:
+        params["num_class"] = args.num_class
+    d = E.DMatrix(Xs, label=ys, **dm_kw)
+    b = E.train(params, d, num_boost_round=rounds, verbose_eval=False)
+    trees = b.get_trees()
+    out["sub_model_sha256"] = _sha("\n".join(b.get_dump(dump_format="json", with_stats=True)).encode())
+    if rank == 0:
+        from oracle import oracle as O
+        O.build()
+        O.use_all_cores()
+        Xf, yf = synth_shard(n_sub, args.cols, 0, 1, workload=args.workload)
+        is_cat = [1 if t == "c" else 0 for t in args.feature_types] if args.feature_types else None
+        ob, _ = O.train(params, Xf, yf, rounds, is_cat=is_cat)
+        ok = len(trees) == ob.num_trees
+        worst = 0.0
+        for i, t in enumerate(trees):
+            if not ok:
+                break
+            o = ob.tree(i)
+            ok = (np.array_equal(t["split_feature"], o.split_feature) and np.array_equal(t["split_bin"], o.split_bin)
+                  and np.array_equal(t["default_left"], o.default_left))
+            if ok:
+                leaf = o.split_feature < 0
+                worst = max(worst, float(np.max(np.abs(t["value"][leaf] - o.value[leaf]))))
+        out["oracle_match"] = bool(ok and worst <= 1e-5)
+        out["oracle_sub_problem"] = "%d rows x %d cols, %d rounds, depth %d, %d rank(s); max |leaf - oracle| %.3g" % (
+            n_sub, args.cols, rounds, params["max_depth"], world, worst)
+    del b, d
+    return out
 
 
 def measured_peak():
@@ -193,7 +256,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "boosting rounds/sec", "value": v, "unit": "rounds/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s synthetic %dx%d %s depth %d 256 bins" % (args.workload, args.rows, args.cols, args.objective, args.depth),
+            "config": {"workload": workload_string(args), "sharding": "whole matrix on the host (CPU arm)",
                        "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256},
             "cpu_baseline": {"value": v, "unit": "rounds/s", "cores": cores, "kind": "port",
                              "sample": "full workload, %d timed rounds; CPU quantisation %.1fs not in the timed region" % (args.steps, t_quant)},
@@ -215,6 +278,7 @@ def main():
     ap.add_argument("--qbits", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--profile", type=int, default=1, help="2 = per-phase CUDA-event timers (adds event records)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -296,6 +360,8 @@ def main():
         ms_per_step = 1e3 * wall / args.steps
         value = args.steps / wall
         final_metric = bst.eval_set([(dm, "train")], 0).split("\t", 1)[-1]
+        exchange_kind = "none (1 GPU)" if world == 1 else ("nccl" if os.environ.get("B2_EXCHANGE", "").lower() == "nccl" else "nvlink peer memory (nccl if peers cannot be mapped)")
+        parity = None if args.no_parity else parity_check(E, args, rank, world, dm_kw, bst, dm)
         del bst
 
         # ================= e2e arm: host buffers -> xgb.train replacement, copies inside the timed region
@@ -353,17 +419,17 @@ def main():
         "metric": "boosting rounds/sec", "value": value, "unit": "rounds/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int64 fixed-point histograms (int32 shared-memory cells), f64 gain", "data": "synthetic",
-        "config": {"workload": "%s synthetic %dx%d %s depth %d 256 bins, rows INTERLEAVED over %d rank(s)" % (
-                       args.workload, args.rows, args.cols, args.objective, args.depth, world),
+        "config": {"workload": workload_string(args), "sharding": "rows INTERLEAVED over %d rank(s)" % world,
                    "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256, "parallelism": "dp%d" % world,
                    "hist_qbits": params.get("hist_qbits", 18), "l2": "inputs_larger_than_l2",
-                   "device_ms_per_step": dev_ms / args.steps, "phase_ms_per_step": {k: v / args.steps for k, v in timers.get("phase_ms", {}).items()}, "quantise_seconds": t_quant, "final_train_metric": final_metric},
+                   "device_ms_per_step": dev_ms / args.steps, **({"phase_ms_per_step": {k: v / args.steps for k, v in timers.get("phase_ms", {}).items()}} if args.profile >= 2 else {}),
+                   "quantise_seconds": t_quant, "exchange": exchange_kind, "cuda_graph": os.environ.get("B2_GRAPH", "1") != "0", "final_train_metric": final_metric},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_kind, "kernel": "b2::hist_build_kernel",
                      "algorithmic_bytes_per_launch": hist_bytes_per_launch, "ms_per_launch": hist_ms_per_launch,
                      "launches": timers["hist_launches"], "share_of_step": hist_ms / max(dev_ms, 1e-9),
                      "traffic": traffic, "traffic_capture_algorithmic_bytes": traffic_alg},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(timers["kernel_launches"]),
+        "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(timers["kernel_launches"]),
         "clocks": sampler.summary(),
     }
     print(json.dumps(line), flush=True)

@@ -25,7 +25,7 @@ SOURCES = {
     "control_kernel.cu": ["--fmad=false"],
     "objective_kernel.cu": ["--fmad=false"],   # bit-exact gradients vs the oracle
     "sketch.cu": ["--fmad=false"],
-    "p2p_exchange.cu": [],                     # experimental NVLink peer-memory exchange (opt-in)
+    "p2p_exchange.cu": [],                     # NVLink peer-memory histogram exchange
     "engine.cu": [],
 }
 
@@ -39,7 +39,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "hist_common.cuh"), os.path.join(CSRC, "sampling.cuh"), os.path.join(HERE, "..", "include", "b2hist.h"), __file__]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "hist_common.cuh"), os.path.join(CSRC, "sampling.cuh"), os.path.join(CSRC, "p2p.cuh"), os.path.join(HERE, "..", "include", "b2hist.h"), __file__]
     jobs = []
     objs = []
     for src, extra in SOURCES.items():

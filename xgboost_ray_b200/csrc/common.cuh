@@ -76,7 +76,7 @@ struct B2LevelCtl {
   int32_t hist_total_chunks;
   int32_t hist_chunk_rows;
   int32_t n_pairs;            // (parent, built, sibling) triples of this level
-  int32_t pad;
+  int32_t leaf_base_next;     // number of leaves after this level's decide = leaf index of the next level's first node
 };
 struct B2NodeSeg { int32_t nid, begin, count, buf; };
 struct B2LeafDev { int32_t nid, buf, begin, count; };
@@ -105,14 +105,26 @@ struct B2ColSample {
   uint32_t seed, tree;
 };
 
-// ---- peer mapping of the experimental NVLink histogram exchange (p2p_exchange.cu)
-#define B2_P2P_MAX_WORLD 32
-enum { kSlotHist = 0, kSlotCand = 1, kSlotRead = 2, kP2PSlots = 3 };
+// ---- peer-memory exchange over NVLink / NVSwitch (p2p.cuh, p2p_exchange.cu, control_kernel.cu)
+// Every rank maps four regions of every peer (cudaIpc): the histogram build buffer (peers READ their owned slices out
+// of it), and three tables the peers WRITE into -- split candidates, per-tree |g|,|h| maxima + leaf sums, and epoch
+// flags.  An exchange "slot" is a lock-step sequence of epochs: all ranks run the same kernel sequence, so the n-th
+// exchange of a slot is epoch n on every rank.  The epoch counters live in device memory and are advanced by the
+// kernels themselves, which keeps the whole tree capturable in a CUDA graph.
+#define B2_P2P_MAX_WORLD 8
+enum { kSlotHist = 0, kSlotCand = 1, kSlotAbsmax = 2, kSlotLeaf = 3, kSlotClose = 4, kP2PSlots = 5 };
 struct B2P2P {
   long long* build[B2_P2P_MAX_WORLD];      // hist_build of rank w ([shards][node_cap][slice]); own pointer for w == rank
   B2SplitCand* cands[B2_P2P_MAX_WORLD];    // candidate table of rank w ([world][cand_cap])
+  long long* misc[B2_P2P_MAX_WORLD];       // misc table of rank w ([world][misc_stride] int64: [0]=absmax bits, [2..]=leaf sums)
   uint32_t* flags[B2_P2P_MAX_WORLD];       // flag array of rank w ([kP2PSlots][world])
+  uint32_t* epoch;                         // [kP2PSlots] local: last completed epoch of each slot
+  uint32_t* done;                          // [kP2PSlots] local: CTA completion counters of multi-CTA exchange kernels
+  uint32_t* err;                           // local: != 0 after a timed-out / aborted wait (1 + slot)
+  const uint32_t* abort_flag;              // local: set by B2_CommAbort through a side stream
   int32_t world, rank;
+  int32_t cand_cap, misc_stride;
+  long long spin_limit;                    // polls (each ~0.25 us) before a wait gives up
 };
 
 struct B2TrainParamDev {

@@ -7,9 +7,12 @@
 // sequence for every tree and reads the finished tree back once (SURVEY.md 3.1 "host hot spots").
 // All arithmetic that influences the model is IEEE fp64/fp32 with explicit rounding, identical to
 // the oracle's host formulas (Appendix A.6/A.7).
+#include <string.h>
+
 #include <cub/block/block_scan.cuh>
 
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace b2 {
 
@@ -48,10 +51,29 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
               B2TreeDev tree,
               B2SplitWork* __restrict__ split_work, int32_t* __restrict__ pair_parent_hist, B2LeafDev* __restrict__ leaves,
               int32_t* __restrict__ n_leaves, const uint8_t* __restrict__ has_missing, const int32_t* __restrict__ qexp,
-              int qbits, B2CtlParams p) {
+              int qbits, B2CtlParams p, int32_t* __restrict__ part_counters, const B2SplitCand* __restrict__ local_cands,
+              int use_p2p, B2P2P pp) {
   __shared__ typename TileScan::Scan::TempStorage tmp;
   __shared__ int s_node_base, s_leaf_base;
   const int n = ctl_cur->n_nodes;
+  // the partition of this level counts its left / right rows per split node with atomics: start them at zero here
+  if (part_counters) for (int i = threadIdx.x; i < 2 * n; i += kCtlThreads) part_counters[i] = 0;
+  if (use_p2p && can_split) {
+    // peer-memory candidate exchange (replaces ncclAllGather): this rank scanned only the feature slots it owns, so
+    // its per-node candidates go into region `rank` of EVERY rank's table; `cands` is this rank's own table
+    constexpr int kWords = sizeof(B2SplitCand) / 8;
+    static_assert(sizeof(B2SplitCand) % 8 == 0, "candidates are copied as 64-bit words");
+    const uint32_t epoch = p2p_next_epoch(pp, kSlotCand);
+    const int total = n * cands_per_node * kWords;
+    for (int w = 0; w < pp.world; ++w) {
+      long long* dst = reinterpret_cast<long long*>(pp.cands[w] + (size_t)pp.rank * pp.cand_cap);
+      for (int t = threadIdx.x; t < total; t += kCtlThreads) st_volatile_u64(dst + t, reinterpret_cast<const long long*>(local_cands)[t]);
+    }
+    __syncthreads();
+    p2p_signal(pp, kSlotCand, epoch);
+    p2p_wait(pp, kSlotCand, epoch);
+    p2p_finish_single(pp, kSlotCand, epoch);
+  }
   const double inv_sg = ldexp(1.0, qexp[0] - qbits), inv_sh = ldexp(1.0, qexp[1] - qbits);
   if (threadIdx.x == 0) { s_node_base = *tree.n_nodes; s_leaf_base = *n_leaves; }
   __syncthreads();
@@ -69,7 +91,13 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
       if (can_split) {
         for (int w = 0; w < cand_ranks; ++w)
           for (int g = 0; g < cands_per_node; ++g) {
-            const B2SplitCand c = cands[(size_t)w * cand_rank_stride + (size_t)i * cands_per_node + g];
+            B2SplitCand c;
+            if (use_p2p) {   // written by a peer while this kernel was already running: never the read-only / L1 path
+              constexpr int kW = sizeof(B2SplitCand) / 8;
+              const long long* src = reinterpret_cast<const long long*>(cands + (size_t)w * cand_rank_stride + (size_t)i * cands_per_node + g);
+#pragma unroll
+              for (int t = 0; t < kW; ++t) reinterpret_cast<unsigned long long*>(&c)[t] = ld_volatile_u64(src + t);
+            } else c = cands[(size_t)w * cand_rank_stride + (size_t)i * cands_per_node + g];
             if (c.feature < 0) continue;
             if (best.feature < 0 || c.loss_chg > best.loss_chg || (c.loss_chg == best.loss_chg && c.order < best.order)) best = c;
           }
@@ -123,6 +151,7 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
   if (threadIdx.x == 0) {
     const int n_split = scan_split.carry;
     ctl_cur->n_split = n_split; ctl_cur->part_chunks = scan_chunks.carry;
+    ctl_cur->leaf_base_next = s_leaf_base + scan_leaf.carry;   // leaf index of the first node of the next level (final_assign_kernel)
     ctl_nxt->n_nodes = 2 * n_split; ctl_nxt->n_split = 0; ctl_nxt->part_chunks = 0;
     ctl_nxt->hist_n_work = 0; ctl_nxt->hist_total_chunks = 0; ctl_nxt->n_pairs = 0;
     *tree.n_nodes = s_node_base + 2 * n_split;
@@ -211,7 +240,11 @@ leaf_plan_kernel(const B2LeafDev* __restrict__ leaves, const int32_t* __restrict
     int chunks = 0; B2LeafDev lf; lf.nid = 0; lf.buf = 0; lf.begin = 0; lf.count = 0;
     if (i < n) { lf = leaves[i]; chunks = (lf.count + kPartChunkRows - 1) / kPartChunkRows; }
     const int cb = scan.step(chunks);
-    if (i < n) { B2SegWork w; w.seg_begin = lf.begin; w.seg_count = lf.count; w.id = i; w.chunk_begin = cb; w.buf = lf.buf; w.pad0 = w.pad1 = w.pad2 = 0; work[i] = w; }
+    if (i < n) {
+      B2SegWork w; w.seg_begin = lf.begin; w.seg_count = lf.count; w.id = i; w.chunk_begin = cb; w.buf = lf.buf;
+      w.pad0 = lf.nid == 0 ? 1 : 0;   // the root as a leaf: its rows are the identity list (no index list was ever written)
+      w.pad1 = w.pad2 = 0; work[i] = w;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) { leaf_ctl->hist_n_work = n; leaf_ctl->hist_total_chunks = scan.carry; }
@@ -235,8 +268,10 @@ __global__ void leaf_values_kernel(const B2LeafDev* __restrict__ leaves, const i
 
 // tree-start reset: root node, counters
 __global__ void tree_init_kernel(B2TreeDev tree, B2LevelCtl* ctl0, B2NodeSeg* seg0, B2EvalNode* ev0, int32_t* n_leaves,
-                                 int n_rows) {
+                                 int n_rows, B2HistWork* hist_work0) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    B2HistWork hw; hw.seg_begin = 0; hw.seg_count = n_rows; hw.hist_index = 0; hw.chunk_begin = 0; hist_work0[0] = hw;
+    ctl0->leaf_base_next = 0;
     *tree.n_nodes = 1; *n_leaves = 0;
     tree.left[0] = -1; tree.right[0] = -1; tree.parent[0] = -1; tree.feature[0] = -1;
     ctl0->n_nodes = 1; ctl0->n_split = 0; ctl0->part_chunks = 0; ctl0->hist_n_work = 0; ctl0->hist_total_chunks = 0;
@@ -256,9 +291,13 @@ extern "C" {
 int b2_launch_decide(B2LevelCtl* ctl_cur, B2LevelCtl* ctl_nxt, const B2NodeSeg* seg_cur, B2NodeSeg* seg_nxt,
                      const B2EvalNode* ev_cur, B2EvalNode* ev_nxt, const B2SplitCand* cands, int cands_per_node, int cand_ranks,
                      int cand_rank_stride, int can_split, B2TreeDev tree, B2SplitWork* split_work, int32_t* pair_parent_hist, B2LeafDev* leaves, int32_t* n_leaves,
-                     const uint8_t* has_missing, const int32_t* qexp, int qbits, B2CtlParams p, cudaStream_t s) {
+                     const uint8_t* has_missing, const int32_t* qexp, int qbits, B2CtlParams p, int32_t* part_counters,
+                     const B2SplitCand* local_cands, const void* p2p, cudaStream_t s) {
+  B2P2P pp;
+  if (p2p) pp = *reinterpret_cast<const B2P2P*>(p2p); else memset(&pp, 0, sizeof(pp));
   b2::decide_kernel<<<1, b2::kCtlThreads, 0, s>>>(ctl_cur, ctl_nxt, seg_cur, seg_nxt, ev_cur, ev_nxt, cands, cands_per_node,
-                                                 cand_ranks, cand_rank_stride, can_split, tree, split_work, pair_parent_hist, leaves, n_leaves, has_missing, qexp, qbits, p);
+                                                 cand_ranks, cand_rank_stride, can_split, tree, split_work, pair_parent_hist, leaves, n_leaves, has_missing, qexp, qbits, p,
+                                                 part_counters, local_cands, p2p ? 1 : 0, pp);
   return (int)cudaGetLastError();
 }
 int b2_launch_finalize_level(const B2LevelCtl* ctl_cur, B2LevelCtl* ctl_nxt, B2NodeSeg* seg_nxt, B2EvalNode* ev_nxt,
@@ -280,8 +319,8 @@ int b2_launch_leaf_values(const B2LeafDev* leaves, const int32_t* n_leaves, cons
   return (int)cudaGetLastError();
 }
 int b2_launch_tree_init(B2TreeDev tree, B2LevelCtl* ctl0, B2NodeSeg* seg0, B2EvalNode* ev0, int32_t* n_leaves, int n_rows,
-                        cudaStream_t s) {
-  b2::tree_init_kernel<<<1, 32, 0, s>>>(tree, ctl0, seg0, ev0, n_leaves, n_rows);
+                        B2HistWork* hist_work0, cudaStream_t s) {
+  b2::tree_init_kernel<<<1, 32, 0, s>>>(tree, ctl0, seg0, ev0, n_leaves, n_rows, hist_work0);
   return (int)cudaGetLastError();
 }
 int b2_launch_root_record(B2TreeDev tree, const B2EvalNode* ev0, cudaStream_t s) {

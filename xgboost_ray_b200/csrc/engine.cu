@@ -18,6 +18,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
@@ -39,10 +40,15 @@ int b2_launch_eval_splits(const long long*, int, const B2EvalNode*, int, const i
                           int, int, B2ColSample, const B2NodeSeg*, cudaStream_t);
 int b2_launch_subsample(float2*, int64_t, uint32_t, uint32_t, uint32_t, double, int, cudaStream_t);
 int b2_p2p_flag_words(int);
-int b2_launch_p2p_signal(const void*, int, uint32_t, cudaStream_t);
-int b2_launch_p2p_wait(const void*, int, uint32_t, uint32_t*, cudaStream_t);
-int b2_launch_p2p_reduce(const void*, uint32_t, long long*, size_t, size_t, uint32_t*, int, cudaStream_t);
-int b2_launch_p2p_push_cands(const void*, const B2SplitCand*, int, int, int, cudaStream_t);
+int b2_launch_p2p_reduce_subtract(const void*, const long long*, long long*, const int32_t*, const B2LevelCtl*, int, int, int64_t, int,
+                                  cudaStream_t);
+int b2_launch_p2p_quant_exponent(const void*, const uint32_t*, int32_t*, cudaStream_t);
+int b2_launch_p2p_leaf_sums(const void*, const int32_t*, long long*, cudaStream_t);
+int b2_launch_p2p_close(const void*, cudaStream_t);
+int b2_launch_final_assign(const uint8_t*, int64_t, const int32_t*, const B2SplitWork*, const B2LevelCtl*, int, const float2*,
+                           const int32_t*, int, long long*, uint16_t*, int, int, cudaStream_t);
+int b2_launch_margin_update(float*, int, int, const uint16_t*, const float*, int64_t, int, cudaStream_t);
+int b2_gradient_fused_max_classes();
 int b2_launch_sum_fixed(const float2*, int64_t, const int32_t*, int, long long*, int, cudaStream_t);
 int b2_cat_ctas();
 int b2_launch_eval_cat_splits(const long long*, int, const B2EvalNode*, int, const int32_t*, int, const int32_t*, const int32_t*,
@@ -54,21 +60,21 @@ int b2_part_chunk_rows();
 int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, const B2LevelCtl*, int, int32_t*,
                         int, int, cudaStream_t);
 int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const int32_t*, int,
-                        long long*, int, cudaStream_t);
+                        long long*, uint16_t*, int, cudaStream_t);
 int b2_launch_pred_update(float*, int, int, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const float*, int,
                           cudaStream_t);
 int b2_launch_decide(B2LevelCtl*, B2LevelCtl*, const B2NodeSeg*, B2NodeSeg*, const B2EvalNode*, B2EvalNode*, const B2SplitCand*,
                      int, int, int, int, B2TreeDev, B2SplitWork*, int32_t*, B2LeafDev*, int32_t*, const uint8_t*, const int32_t*, int,
-                     B2CtlParams, cudaStream_t);
+                     B2CtlParams, int32_t*, const B2SplitCand*, const void*, cudaStream_t);
 int b2_launch_finalize_level(const B2LevelCtl*, B2LevelCtl*, B2NodeSeg*, B2EvalNode*, const B2SplitWork*, const int32_t*,
                              const int32_t*, B2HistWork*, int32_t*, int, int, int, int, int, long long*, cudaStream_t);
 int b2_launch_leaf_plan(const B2LeafDev*, const int32_t*, B2SegWork*, B2LevelCtl*, cudaStream_t);
 int b2_launch_leaf_values(const B2LeafDev*, const int32_t*, const long long*, const int32_t*, int, B2CtlParams, float*, B2TreeDev,
                           cudaStream_t);
-int b2_launch_tree_init(B2TreeDev, B2LevelCtl*, B2NodeSeg*, B2EvalNode*, int32_t*, int, cudaStream_t);
+int b2_launch_tree_init(B2TreeDev, B2LevelCtl*, B2NodeSeg*, B2EvalNode*, int32_t*, int, B2HistWork*, cudaStream_t);
 int b2_launch_root_record(B2TreeDev, const B2EvalNode*, cudaStream_t);
 int b2_launch_iota(int32_t*, int64_t, cudaStream_t);
-int b2_launch_gradient(int, int, const float*, const float*, const float*, int64_t, float, float2*, int, cudaStream_t);
+int b2_launch_gradient(int, int, const float*, const float*, const float*, int64_t, float, float2*, uint32_t*, int, cudaStream_t);
 int b2_launch_pack_custom(const float*, const float*, int, int64_t, float2*, int, cudaStream_t);
 int b2_launch_absmax(const float2*, int64_t, uint32_t*, int, cudaStream_t);
 int b2_launch_quant_exponent(const uint32_t*, int32_t*, cudaStream_t);
@@ -277,6 +283,8 @@ struct Comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1, device = 0;
   std::atomic<bool> aborted{false};
+  uint32_t* d_abort = nullptr;        // device word polled by the peer-memory waits (p2p.cuh); set by B2_CommAbort
+  cudaStream_t abort_stream = nullptr;
 };
 
 void allreduce(Comm* c, void* buf, size_t count, int dtype, int op, cudaStream_t s) {
@@ -298,7 +306,15 @@ T* from_handle(B2Handle h, int kind, const char* what) {
 
 struct CommH : HandleBase { Comm c; };
 
+// ids of the matrices that are alive: a Booster's evaluation cache is keyed by the id, never by the address (a freed
+// matrix and a new one of the same shape can share an address)
+std::mutex g_matrix_mu;
+std::set<uint64_t> g_live_matrices;
+uint64_t g_next_matrix_uid = 1;
+
 struct Matrix : HandleBase {
+  uint64_t margin_version = 0;   // bumped when base_margin changes (cached evaluation margins start from it)
+  uint64_t uid = 0;       // unique for the life of the process; 0 = not registered (stack temporaries)
   Ctx* ctx = nullptr;
   int64_t n = 0;
   int F = 0;
@@ -566,7 +582,7 @@ struct Timers {
   void reset() { *this = Timers(); }
 };
 
-struct EvalCache { DevBuf<float> margin; int n_trees_applied = 0; int64_t n = 0; };
+struct EvalCache { DevBuf<float> margin; int n_trees_applied = 0; int64_t n = 0; uint64_t margin_version = 0; };
 
 struct Booster : HandleBase {
   Ctx* ctx = nullptr;
@@ -593,15 +609,28 @@ struct Booster : HandleBase {
   int cpn_num = 1;
   DevBuf<uint32_t> t_cat;                  // [max_nodes][8] category sets of the tree being grown
   DevBuf<uint8_t> d_col_masks;             // [max_depth][F] level feature sets of the tree being grown (column sampling)
-  // experimental NVLink peer-memory exchange (p2p_exchange.cu; B2_EXCHANGE_P2P=1), off unless every rank mapped its peers
+  // NVLink peer-memory exchange (p2p.cuh, p2p_exchange.cu): on when every rank mapped its peers; B2_EXCHANGE=nccl keeps NCCL
   struct P2PState {
-    bool enabled = false;
+    bool enabled = false, tried = false;
     B2P2P pp;
-    DevBuf<uint32_t> flags, err;
+    DevBuf<uint32_t> flags, words;        // words: [kP2PSlots] epoch, [kP2PSlots] done, err, local abort stand-in
+    DevBuf<long long> misc;               // [world][misc_stride]
     std::vector<void*> opened;
-    uint32_t hist_epoch = 0, cand_epoch = 0, pending_read = 0;
     int cand_cap = 0;
   } p2p;
+  // CUDA graphs of the per-tree launch sequence, one per class tree of a round (grow_tree is sync-free and its
+  // arguments are the same for every tree, so the sequence is captured once and replayed)
+  struct TreeGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hist_ev;   // owned; recorded by the graph (external event nodes)
+    long long hist_launches = 0, kernel_launches = 0;
+    double allreduce_bytes = 0;
+  };
+  std::map<int, TreeGraph> graphs;
+  std::map<int, int> direct_trees;         // trees grown with direct launches per class slot (the first one allocates)
+  bool graph_failed = false;
+  bool absmax_fused = false;               // this round's gradient kernel already produced d_absmax[k]
+  DevBuf<uint16_t> pos;                    // [n] leaf index of every row (final_assign / leaf_sums -> margin_update)
   size_t slice_elems = 0;
   size_t node_elems = 0;
   DevBuf<uint32_t> d_absmax; DevBuf<int32_t> d_qexp;
@@ -619,7 +648,7 @@ struct Booster : HandleBase {
   std::vector<void*> staging;              // pinned host copies of finished trees, one per class tree of a round
   size_t staging_bytes = 0;
   DevBuf<float> d_custom_g, d_custom_h;
-  std::map<Matrix*, EvalCache*> eval_cache;
+  std::map<uint64_t, EvalCache*> eval_cache;   // keyed by Matrix::uid
   // profiling
   Timers t;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
@@ -627,6 +656,14 @@ struct Booster : HandleBase {
   std::vector<std::pair<int, cudaEvent_t>> phase_marks;   // (phase that ENDS at this event)
   cudaEvent_t round_start = nullptr, round_stop = nullptr;
   ~Booster() {
+    for (auto& kv : graphs) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      for (auto& pr : kv.second.hist_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    }
+    if (p2p.enabled && ctx) {   // nobody frees a mapped buffer while a peer may still read it (bounded wait)
+      b2_launch_p2p_close(&p2p.pp, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+    }
     for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
     for (auto e : ev_pool) cudaEventDestroy(e);
     if (round_start) cudaEventDestroy(round_start);
@@ -779,41 +816,58 @@ B2TreeDev tree_dev(Booster* b) {
   return t;
 }
 
-// Map every peer's build buffer, candidate table and flag array (cudaIpc) for the experimental exchange.  All ranks
-// take the same decision: one failed mapping anywhere switches every rank back to NCCL.
+// Map every peer's build buffer, candidate table, misc table and flag array (cudaIpc) for the peer-memory exchange.
+// All ranks take the same decision: one failed mapping anywhere leaves every rank on NCCL.
+int p2p_timeout_seconds() {
+  const char* e = getenv("B2_P2P_TIMEOUT_S");
+  int v = e ? atoi(e) : 60;
+  return v < 1 ? 1 : v;
+}
 void p2p_setup(Booster* b) {
-  const char* env = getenv("B2_EXCHANGE_P2P");
-  if (!env || atoi(env) == 0 || b->shards <= 1 || b->p2p.enabled) return;
+  Booster::P2PState& st = b->p2p;
+  if (st.tried || b->shards <= 1) return;
+  st.tried = true;
+  const char* env = getenv("B2_EXCHANGE");
+  if (env && (strcmp(env, "nccl") == 0 || strcmp(env, "NCCL") == 0)) return;
   Comm* c = b->comm; cudaStream_t s = b->ctx->stream; const int W = c->world;
   if (W > B2_P2P_MAX_WORLD) return;
-  Booster::P2PState& st = b->p2p;
-  st.flags.ensure((size_t)b2_p2p_flag_words(W)); st.err.ensure(1);
-  CUDA_CHECK(cudaMemsetAsync(st.flags.p, 0, (size_t)b2_p2p_flag_words(W) * sizeof(uint32_t), s));
-  CUDA_CHECK(cudaMemsetAsync(st.err.p, 0, sizeof(uint32_t), s));
-  struct Handles { cudaIpcMemHandle_t build, cands, flags; };
+  const size_t lcap = (size_t)1 << b->p.max_depth;
+  const size_t misc_stride = 2 + 2 * lcap;                       // even: 16-byte aligned regions
+  const size_t n_flags = (size_t)b2_p2p_flag_words(W), n_words = 2 * (size_t)kP2PSlots + 2;
+  st.flags.ensure(n_flags); st.words.ensure(n_words); st.misc.ensure((size_t)W * misc_stride);
+  CUDA_CHECK(cudaMemsetAsync(st.flags.p, 0, n_flags * sizeof(uint32_t), s));
+  CUDA_CHECK(cudaMemsetAsync(st.words.p, 0, n_words * sizeof(uint32_t), s));
+  CUDA_CHECK(cudaMemsetAsync(st.misc.p, 0, (size_t)W * misc_stride * sizeof(long long), s));
+  struct Handles { cudaIpcMemHandle_t build, cands, misc, flags; };
   Handles mine; int ok = 1;
   if (cudaIpcGetMemHandle(&mine.build, b->hist_build.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.cands, b->d_cands_all.p) != cudaSuccess ||
-      cudaIpcGetMemHandle(&mine.flags, st.flags.p) != cudaSuccess) { ok = 0; cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+      cudaIpcGetMemHandle(&mine.misc, st.misc.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, st.flags.p) != cudaSuccess) {
+    ok = 0; cudaGetLastError(); memset(&mine, 0, sizeof(mine));
+  }
   DevBuf<uint8_t> d_mine, d_all; d_mine.ensure(sizeof(Handles)); d_all.ensure(sizeof(Handles) * (size_t)W);
   CUDA_CHECK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(Handles), cudaMemcpyHostToDevice, s));
-  NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(Handles), kNcclUint8, c->comm, s));   // also orders the flag memset before any signal
+  NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(Handles), kNcclUint8, c->comm, s));   // also orders the memsets before any peer store
   std::vector<Handles> all((size_t)W);
   CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Handles) * (size_t)W, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   memset(&st.pp, 0, sizeof(st.pp));
-  st.pp.world = W; st.pp.rank = c->rank;
+  st.pp.world = W; st.pp.rank = c->rank; st.pp.cand_cap = st.cand_cap; st.pp.misc_stride = (int32_t)misc_stride;
+  st.pp.epoch = st.words.p; st.pp.done = st.words.p + kP2PSlots; st.pp.err = st.words.p + 2 * kP2PSlots;
+  st.pp.abort_flag = c->d_abort ? c->d_abort : st.words.p + 2 * kP2PSlots + 1;
+  st.pp.spin_limit = (long long)p2p_timeout_seconds() * 1000000LL;
   for (int w = 0; w < W && ok; ++w) {
-    if (w == c->rank) { st.pp.build[w] = b->hist_build.p; st.pp.cands[w] = b->d_cands_all.p; st.pp.flags[w] = st.flags.p; continue; }
-    void *pb = nullptr, *pc = nullptr, *pf = nullptr;
+    if (w == c->rank) { st.pp.build[w] = b->hist_build.p; st.pp.cands[w] = b->d_cands_all.p; st.pp.misc[w] = st.misc.p; st.pp.flags[w] = st.flags.p; continue; }
+    void *pb = nullptr, *pc = nullptr, *pm = nullptr, *pf = nullptr;
     if (cudaIpcOpenMemHandle(&pb, all[w].build, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
         cudaIpcOpenMemHandle(&pc, all[w].cands, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&pm, all[w].misc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
         cudaIpcOpenMemHandle(&pf, all[w].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
-    for (void* q : {pb, pc, pf}) if (q) st.opened.push_back(q);
-    st.pp.build[w] = (long long*)pb; st.pp.cands[w] = (B2SplitCand*)pc; st.pp.flags[w] = (uint32_t*)pf;
+    for (void* q : {pb, pc, pm, pf}) if (q) st.opened.push_back(q);
+    st.pp.build[w] = (long long*)pb; st.pp.cands[w] = (B2SplitCand*)pc; st.pp.misc[w] = (long long*)pm; st.pp.flags[w] = (uint32_t*)pf;
   }
-  // agree: min over ranks of the local success flag
+  // agree: max over ranks of "failed"
   DevBuf<int32_t> d_ok; d_ok.ensure(1);
-  int32_t neg = ok ? 0 : 1;   // allreduce(max) of "failed"
+  int32_t neg = ok ? 0 : 1;
   CUDA_CHECK(cudaMemcpyAsync(d_ok.p, &neg, sizeof(neg), cudaMemcpyHostToDevice, s));
   allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
   CUDA_CHECK(cudaMemcpyAsync(&neg, d_ok.p, sizeof(neg), cudaMemcpyDeviceToHost, s));
@@ -821,16 +875,21 @@ void p2p_setup(Booster* b) {
   if (neg) {
     for (void* q : st.opened) cudaIpcCloseMemHandle(q);
     st.opened.clear();
-    fprintf(stderr, "[b2hist] B2_EXCHANGE_P2P=1 requested but peer mapping failed on some rank; using NCCL\n");
+    if (getenv("B2_EXCHANGE")) fprintf(stderr, "[b2hist] peer mapping failed on some rank; histogram exchange stays on NCCL\n");
     return;
   }
-  st.hist_epoch = st.cand_epoch = st.pending_read = 0;
   st.enabled = true;
 }
 
 void ensure_ctl_tables(Booster* b) {
   const int D = b->p.max_depth; const int G = b->train->n_groups;
   if (b->ctl_depth == D) return;
+  if (b->ctl_depth != 0 && b->p2p.enabled) fail("max_depth cannot change while the peer-memory exchange is mapped");
+  for (auto& kv : b->graphs) {   // captured launch sequences hold the old table addresses
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& pr : kv.second.hist_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  }
+  b->graphs.clear(); b->direct_trees.clear();
   b->ctl_depth = D;
   const TreeLayout L = tree_layout(D);
   const size_t lcap = (size_t)1 << D, half = (size_t)1 << (D > 0 ? D - 1 : 0);
@@ -859,10 +918,26 @@ void ensure_ctl_tables(Booster* b) {
   p2p_setup(b);
 }
 
-void record_hist_launch(Booster* b, cudaEvent_t& e0, cudaEvent_t& e1, bool begin) {
+// Launch bookkeeping of one tree: with direct launches it is applied right away, a captured tree keeps it with its
+// graph and applies it on every replay.
+struct TreeStats {
+  long long hist_launches = 0, kernel_launches = 0;
+  double allreduce_bytes = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hist_ev;
+  bool capturing = false;
+};
+void record_hist_launch(Booster* b, TreeStats& st, cudaEvent_t& e0, cudaEvent_t& e1, bool begin) {
   if (!b->p.profile) return;
-  if (begin) { e0 = get_event(b); e1 = get_event(b); CUDA_CHECK(cudaEventRecord(e0, b->ctx->stream)); }
-  else { CUDA_CHECK(cudaEventRecord(e1, b->ctx->stream)); b->hist_events.push_back({e0, e1}); }
+  cudaStream_t s = b->ctx->stream;
+  if (begin) {
+    if (st.capturing) { CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); }   // owned by the graph
+    else { e0 = get_event(b); e1 = get_event(b); }
+    // inside a capture the record becomes an event-record node that every replay executes (external event)
+    CUDA_CHECK(cudaEventRecordWithFlags(e0, s, st.capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+  } else {
+    CUDA_CHECK(cudaEventRecordWithFlags(e1, s, st.capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+    st.hist_ev.push_back({e0, e1});
+  }
 }
 
 bool use_tma_hist() {
@@ -870,57 +945,69 @@ bool use_tma_hist() {
   if (v < 0) { const char* e = getenv("B2_HIST_TMA"); v = (e && atoi(e) != 0) ? 1 : 0; }
   return v == 1;
 }
-
-// Histogram exchange of `nb` built nodes: reduce-scatter of the build buffer into the owned slices of the
-// level buffer (shards == world), or in-place allreduce (shards == 1, any world size).
-long long* build_target(Booster* b, long long* level_buf) { return b->shards > 1 ? b->hist_build.p : level_buf; }
-// before a rank zeroes its build buffer again every peer must have finished reading it (experimental P2P exchange)
-void p2p_wait_reads(Booster* b) {
-  if (!b->p2p.enabled || b->p2p.pending_read == 0) return;
-  LAUNCH_CHECK(b2_launch_p2p_wait(&b->p2p.pp, kSlotRead, b->p2p.pending_read, b->p2p.err.p, b->ctx->stream));
-  b->p2p.pending_read = 0;
+bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) != 0 : dflt;
 }
-void exchange_hist(Booster* b, long long* level_buf, int nb, int node_cap) {
+
+// Where the histogram kernel of a level accumulates: the reduce-scatter / peer-read build buffer when the exchange
+// is sharded by feature slot (shards == world), else the level buffer itself (single GPU, or in-place allreduce).
+long long* build_target(Booster* b, long long* level_buf) { return b->shards > 1 ? b->hist_build.p : level_buf; }
+
+// Histogram exchange of the nodes built for one level + sibling subtraction (parent - built).
+//   peer memory : ONE kernel reads the W partial slices out of the peers' build buffers, stores built and sibling
+//   NCCL        : reduce-scatter (shards == world) or in-place allreduce, then hist_subtract_kernel
+// `triples` == nullptr: the root (nothing to subtract).
+void exchange_and_subtract(Booster* b, TreeStats& st, const long long* parent_level, long long* level_buf, const int32_t* triples,
+                           const B2LevelCtl* ctl_nxt, int nb, int node_cap) {
   cudaStream_t s = b->ctx->stream;
-  if (!b->comm || b->comm->world <= 1) return;
-  if (b->comm->aborted.load()) fail("communicator aborted");
-  if (b->p2p.enabled) {
-    const uint32_t epoch = ++b->p2p.hist_epoch;
-    LAUNCH_CHECK(b2_launch_p2p_signal(&b->p2p.pp, kSlotHist, epoch, s));
-    LAUNCH_CHECK(b2_launch_p2p_reduce(&b->p2p.pp, epoch, level_buf, (size_t)nb * b->slice_elems, (size_t)node_cap * b->slice_elems,
-                                      b->p2p.err.p, b->ctx->num_sms, s));
-    LAUNCH_CHECK(b2_launch_p2p_signal(&b->p2p.pp, kSlotRead, epoch, s));
-    b->p2p.pending_read = epoch;
-    b->t.allreduce_bytes += (double)nb * b->node_elems * 8 * (b->shards - 1) / b->shards;
-    b->t.kernel_launches += 3;
+  const bool multi = b->comm && b->comm->world > 1;
+  if (multi && b->comm->aborted.load()) fail("communicator aborted");
+  if (multi && b->p2p.enabled) {
+    LAUNCH_CHECK(b2_launch_p2p_reduce_subtract(&b->p2p.pp, parent_level, level_buf, triples, ctl_nxt, nb, node_cap,
+                                               (int64_t)b->slice_elems, b->ctx->num_sms, s));
+    st.allreduce_bytes += (double)nb * b->node_elems * 8 * (b->shards - 1) / b->shards;
+    st.kernel_launches++;
+    mark_phase(b, 2);
     return;
   }
-  if (b->shards > 1) {
+  if (multi && b->shards > 1) {
     NCCL_CHECK(nccl()->ReduceScatter(b->hist_build.p, level_buf, (size_t)nb * b->slice_elems, kNcclInt64, kNcclSum, b->comm->comm, s));
-    b->t.allreduce_bytes += (double)nb * b->node_elems * 8 * (b->shards - 1) / b->shards;
-  } else {
+    st.allreduce_bytes += (double)nb * b->node_elems * 8 * (b->shards - 1) / b->shards;
+  } else if (multi) {
     NCCL_CHECK(nccl()->AllReduce(level_buf, level_buf, (size_t)nb * b->node_elems, kNcclInt64, kNcclSum, b->comm->comm, s));
-    b->t.allreduce_bytes += (double)nb * b->node_elems * 8;
+    st.allreduce_bytes += (double)nb * b->node_elems * 8;
   }
+  mark_phase(b, 2);
+  if (triples) {
+    LAUNCH_CHECK(b2_launch_hist_subtract(parent_level, level_buf, triples, nb, (int64_t)b->slice_elems, ctl_nxt, s));
+    st.kernel_launches++;
+  }
+  mark_phase(b, 3);
 }
 
 // Grow one tree for class k from gh[k] (already on device); updates margin[:, k].  No host
 // synchronisation: every data-dependent decision is taken by the control kernels, the host
 // enqueues a fixed sequence and the finished tree is copied into pinned block `slot`.
-void grow_tree(Booster* b, int k, int slot) {
+// With st.capturing the stream is in capture mode: nothing here may allocate, touch pageable host memory or depend on
+// host state that changes from tree to tree (run_tree decides when that holds).
+void grow_tree(Booster* b, int k, int slot, TreeStats& st) {
   Matrix* m = b->train; Ctx* ctx = b->ctx; cudaStream_t s = ctx->stream; const Params& p = b->p;
   const int64_t n = m->n; const int K = p.num_class; const int G = m->n_groups; const int D = p.max_depth;
   const float2* gh = b->gh.p + (size_t)k * n;
   ensure_ctl_tables(b);
   const TreeLayout L = tree_layout(D);
+  const bool multi = b->comm && b->comm->world > 1;
+  const bool p2p = multi && b->p2p.enabled;
+  static const bool leaf_fused = env_flag("B2_LEAF_FUSED", true);
   mark_phase(b, -1);
-  // ---- fixed-point quantisation (global scale via allreduce max)
-  b->d_absmax.ensure(2); b->d_qexp.ensure(2);
+  // ---- fixed-point quantisation (global scale via max over the ranks)
   const uint32_t tree_index = (uint32_t)b->trees.size() + (uint32_t)k;   // the k-th class tree of this round
+  uint32_t* d_absmax = b->d_absmax.p + 2 * k;
   if (p.subsample < 1.0f) {
     LAUNCH_CHECK(b2_launch_subsample(b->gh.p + (size_t)k * n, n, (uint32_t)p.seed, tree_index, b->comm ? (uint32_t)b->comm->rank : 0u,
                                      (double)p.subsample, ctx->num_sms, s));
-    b->t.kernel_launches++;
+    st.kernel_launches++;
   }
   // column sampling: the tree's feature set and one nested set per level are drawn on the host (they depend on
   // (seed, tree, level) only, never on the data), the per-node subsets inside the split-scan kernels
@@ -944,15 +1031,18 @@ void grow_tree(Booster* b, int k, int slot) {
     b->d_col_masks.ensure(masks.size());
     CUDA_CHECK(cudaMemcpyAsync(b->d_col_masks.p, masks.data(), masks.size(), cudaMemcpyHostToDevice, s));   // pageable source: staged before return
   }
-  CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * sizeof(uint32_t), s));
-  LAUNCH_CHECK(b2_launch_absmax(gh, n, b->d_absmax.p, ctx->num_sms, s));
-  allreduce(b->comm, b->d_absmax.p, 2, kNcclUint32, kNcclMax, s);
-  LAUNCH_CHECK(b2_launch_quant_exponent(b->d_absmax.p, b->d_qexp.p, s));
-  b->q.ensure((size_t)std::max<int64_t>(n, 1));
+  if (!b->absmax_fused) {   // custom objective / row sampling / many classes: |g|,|h| maxima in their own pass
+    CUDA_CHECK(cudaMemsetAsync(d_absmax, 0, 2 * sizeof(uint32_t), s));
+    LAUNCH_CHECK(b2_launch_absmax(gh, n, d_absmax, ctx->num_sms, s));
+    st.kernel_launches++;
+  }
+  if (p2p) LAUNCH_CHECK(b2_launch_p2p_quant_exponent(&b->p2p.pp, d_absmax, b->d_qexp.p, s));
+  else {
+    allreduce(b->comm, d_absmax, 2, kNcclUint32, kNcclMax, s);
+    LAUNCH_CHECK(b2_launch_quant_exponent(d_absmax, b->d_qexp.p, s));
+  }
   LAUNCH_CHECK(b2_launch_quantize(gh, n, b->d_qexp.p, p.qbits, b->q.p, ctx->num_sms, s));
-  b->ridx[0].ensure((size_t)std::max<int64_t>(n, 1)); b->ridx[1].ensure((size_t)std::max<int64_t>(n, 1));
-  LAUNCH_CHECK(b2_launch_iota(b->ridx[0].p, n, s));
-  b->t.kernel_launches += 4;
+  st.kernel_launches += 2;
 
   B2TrainParamDev dp;
   dp.min_child_weight = (double)p.min_child_weight; dp.lambda = (double)p.lambda; dp.alpha = (double)p.alpha;
@@ -968,43 +1058,43 @@ void grow_tree(Booster* b, int k, int slot) {
   const int n_streams = std::max(1, ctx->num_sms * 3 / G);
   const int pchunk = b2_part_chunk_rows();
   const int max_part_chunks_total = (int)((n + pchunk - 1) / pchunk);
+  const size_t lcap = (size_t)1 << D;
+  const int max_leaf_chunks = max_part_chunks_total + (int)lcap;
 
-  LAUNCH_CHECK(b2_launch_tree_init(tree, ctl, b->d_seg[0].p, b->d_ev[0].p, d_n_leaves, (int)n, s));
+  LAUNCH_CHECK(b2_launch_tree_init(tree, ctl, b->d_seg[0].p, b->d_ev[0].p, d_n_leaves, (int)n, b->d_hist_work.p, s));
+  CUDA_CHECK(cudaMemsetAsync(b->d_leaf_sums.p, 0, 2 * lcap * sizeof(long long), s));
   mark_phase(b, 0);
   // ---- root histogram (no gather; row count known on the host)
   const int sh = b->log2_shards;
   const int shard_rank = b->shards > 1 ? b->comm->rank : 0;
-  p2p_wait_reads(b);
   CUDA_CHECK(cudaMemsetAsync(build_target(b, b->hist[0].p), 0, b->node_elems * sizeof(long long), s));
   {
     const int chunk_rows = pick_chunk_rows(b, n);
     const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
     if (n > 0) {
-      B2HistWork w{0, (int32_t)n, 0, 0};
-      CUDA_CHECK(cudaMemcpyAsync(b->d_hist_work.p, &w, sizeof(w), cudaMemcpyHostToDevice, s));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
-      record_hist_launch(b, e0, e1, true);
+      record_hist_launch(b, st, e0, e1, true);
       if (use_tma_hist() && m->has_tmap)
         LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, m->tmap_tile, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
                                         build_target(b, b->hist[0].p), nullptr, sh, 1, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
                                     build_target(b, b->hist[0].p), nullptr, sh, 1, ctx->num_sms, s));
-      record_hist_launch(b, e0, e1, false);
-      b->t.hist_launches++; b->t.kernel_launches++;
+      record_hist_launch(b, st, e0, e1, false);
+      st.hist_launches++; st.kernel_launches++;
     }
   }
   mark_phase(b, 1);
-  exchange_hist(b, b->hist[0].p, 1, 1);
-  mark_phase(b, 2);
+  exchange_and_subtract(b, st, nullptr, b->hist[0].p, nullptr, nullptr, 1, 1);
   LAUNCH_CHECK(b2_launch_root_totals(b->hist[0].p, G, b->d_ev[0].p, b->d_qexp.p, p.qbits, dp, sh, s));
   LAUNCH_CHECK(b2_launch_root_record(tree, b->d_ev[0].p, s));
-  b->t.kernel_launches += 3;
+  st.kernel_launches += 3;
   int hb = 0;  // hist buffer holding the current level
   for (int d = 0; d <= D; ++d) {
     const int cur = d & 1, nxt = cur ^ 1;
     const int max_nodes_level = 1 << d;
     const bool can_split = d < D;
+    const bool last_split_level = d == D - 1;
     const B2SplitCand* cands_for_decide = b->d_cands.p;
     int cand_rank_stride = max_nodes_level * b->cpn;
     if (can_split) {
@@ -1012,25 +1102,20 @@ void grow_tree(Booster* b, int k, int slot) {
       cs.level_mask = p.use_cols() ? b->d_col_masks.p + (size_t)d * m->F : nullptr;
       cs.fwq = m->fwq.empty() ? nullptr : m->d_fwq.p;
       cs.bynode = (double)p.colsample_bynode; cs.n_level = n_level_feats[d]; cs.n_features = m->F;
-      cs.seed = (uint32_t)p.seed; cs.tree = tree_index;
+      cs.seed = (uint32_t)p.seed; cs.tree = p.use_cols() ? tree_index : 0u;
       LAUNCH_CHECK(b2_launch_eval_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_group_first.p, m->d_group_size.p,
                                          m->d_nbins.p, m->d_has_missing.p, m->any_cat() ? m->d_is_cat.p : nullptr, b->d_qexp.p,
                                          p.qbits, dp, b->d_cands.p, b->cpn, ctl + cur, sh, shard_rank, cs, b->d_seg[cur].p, s));
-      b->t.kernel_launches++;
+      st.kernel_launches++;
       if (m->any_cat()) {
         LAUNCH_CHECK(b2_launch_eval_cat_splits(b->hist[hb].p, G, b->d_ev[cur].p, max_nodes_level, m->d_cat_feats.p,
                                                (int)m->cat_feats.size(), m->d_feat_byte.p, m->d_nbins.p, b->d_qexp.p, p.qbits, dp,
                                                b->d_cands.p, b->cpn, b->cpn_num, ctl + cur, sh, shard_rank, cs, b->d_seg[cur].p, s));
-        b->t.kernel_launches++;
+        st.kernel_launches++;
       }
-      if (b->shards > 1 && b->p2p.enabled) {   // experimental: candidates stored straight into the peers' tables
-        const uint32_t epoch = ++b->p2p.cand_epoch;
-        LAUNCH_CHECK(b2_launch_p2p_push_cands(&b->p2p.pp, b->d_cands.p, max_nodes_level * b->cpn, b->p2p.cand_cap, ctx->num_sms, s));
-        LAUNCH_CHECK(b2_launch_p2p_signal(&b->p2p.pp, kSlotCand, epoch, s));
-        LAUNCH_CHECK(b2_launch_p2p_wait(&b->p2p.pp, kSlotCand, epoch, b->p2p.err.p, s));
+      if (p2p) {   // decide_kernel stores the candidates straight into the peers' tables and waits for theirs
         cands_for_decide = b->d_cands_all.p;
         cand_rank_stride = b->p2p.cand_cap;
-        b->t.kernel_launches += 3;
       } else if (b->shards > 1) {   // every rank scanned only its own slots: gather the per-node candidates
         const size_t bytes = (size_t)max_nodes_level * b->cpn * sizeof(B2SplitCand);
         NCCL_CHECK(nccl()->AllGather(b->d_cands.p, b->d_cands_all.p, bytes, kNcclUint8, b->comm->comm, s));
@@ -1040,71 +1125,148 @@ void grow_tree(Booster* b, int k, int slot) {
     LAUNCH_CHECK(b2_launch_decide(ctl + cur, ctl + nxt, b->d_seg[cur].p, b->d_seg[nxt].p, b->d_ev[cur].p, b->d_ev[nxt].p,
                                   cands_for_decide, b->cpn, b->shards, cand_rank_stride, can_split ? 1 : 0, tree,
                                   b->d_split_work.p, b->d_pair_parent.p, b->d_leaves.p,
-                                  d_n_leaves, m->d_has_missing.p, b->d_qexp.p, p.qbits, cp, s));
-    b->t.kernel_launches++;
+                                  d_n_leaves, m->d_has_missing.p, b->d_qexp.p, p.qbits, cp, can_split ? b->d_counters.p : nullptr, b->d_cands.p,
+                                  (p2p && can_split) ? &b->p2p.pp : nullptr, s));
+    st.kernel_launches++;
     mark_phase(b, 4);
     if (!can_split) break;
-    // ---- partition rows of the expanding nodes into the other index list
-    CUDA_CHECK(cudaMemsetAsync(b->d_counters.p, 0, 2 * (size_t)max_nodes_level * sizeof(int32_t), s));
-    LAUNCH_CHECK(b2_launch_partition(m->bins_col.p, m->col_stride, b->ridx[cur].p, b->ridx[nxt].p, b->d_split_work.p, ctl + cur,
+    const int32_t* ridx_in = d == 0 ? nullptr : b->ridx[cur].p;   // the root's rows are the identity list
+    if (last_split_level && leaf_fused) {
+      // ---- the children of this level are leaves: no ordered index lists any more.  Leaves that stopped earlier are
+      // summed from their segments, rows of the nodes that split here are assigned in one pass (partition_kernel.cu)
+      LAUNCH_CHECK(b2_launch_leaf_plan(b->d_leaves.p, &ctl[cur].leaf_base_next, b->d_seg_work.p, ctl + 2, s));
+      LAUNCH_CHECK(b2_launch_leaf_sums(gh, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks, b->d_qexp.p, 40,
+                                       b->d_leaf_sums.p, b->pos.p, ctx->num_sms, s));
+      LAUNCH_CHECK(b2_launch_final_assign(m->bins_col.p, m->col_stride, ridx_in, b->d_split_work.p, ctl + cur,
+                                          max_part_chunks_total + max_nodes_level, gh, b->d_qexp.p, 40, b->d_leaf_sums.p, b->pos.p,
+                                          m->any_cat() ? 1 : 0, ctx->num_sms, s));
+      st.kernel_launches += 3;
+      mark_phase(b, 5);
+      continue;
+    }
+    // ---- partition rows of the expanding nodes into the other index list (decide zeroed the counters)
+    LAUNCH_CHECK(b2_launch_partition(m->bins_col.p, m->col_stride, ridx_in, b->ridx[nxt].p, b->d_split_work.p, ctl + cur,
                                      max_part_chunks_total + max_nodes_level, b->d_counters.p, m->any_cat() ? 1 : 0,
                                      ctx->num_sms, s));
     const bool need_hist = d + 1 < D;
     LAUNCH_CHECK(b2_launch_finalize_level(ctl + cur, ctl + nxt, b->d_seg[nxt].p, b->d_ev[nxt].p, b->d_split_work.p, b->d_counters.p,
                                           b->d_pair_parent.p, b->d_hist_work.p, b->d_triples.p, max_nodes_level, need_hist ? 1 : 0,
                                           n_streams, window, p.hist_chunk_rows, d_level_rows + d + 1, s));
-    b->t.kernel_launches += 2;
+    st.kernel_launches += 2;
     mark_phase(b, 5);
     if (need_hist) {
       // ---- histograms of level d+1: built children in slots [0, 2^d), siblings in [2^d, 2^(d+1))
       const int nh = hb ^ 1;
       long long* tgt = build_target(b, b->hist[nh].p);
-      p2p_wait_reads(b);
+      // (peer-memory exchange: every peer finished reading this rank's build buffer before it published the candidates
+      // that the decide kernel above waited for, so the buffer can be zeroed here without another handshake)
       CUDA_CHECK(cudaMemsetAsync(tgt, 0, (size_t)max_nodes_level * b->node_elems * sizeof(long long), s));
       cudaEvent_t e0 = nullptr, e1 = nullptr;
-      record_hist_launch(b, e0, e1, true);
+      record_hist_launch(b, st, e0, e1, true);
       if (use_tma_hist() && m->has_tmap)
         LAUNCH_CHECK(b2_launch_hist_tma(m->tmap, m->tmap_tile, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt, ctl + nxt, sh,
                                         max_nodes_level, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt,
                                     ctl + nxt, sh, max_nodes_level, ctx->num_sms, s));
-      record_hist_launch(b, e0, e1, false);
+      record_hist_launch(b, st, e0, e1, false);
+      st.hist_launches++; st.kernel_launches++;
       mark_phase(b, 1);
-      exchange_hist(b, b->hist[nh].p, max_nodes_level, max_nodes_level);
-      mark_phase(b, 2);
-      LAUNCH_CHECK(b2_launch_hist_subtract(b->hist[hb].p, b->hist[nh].p, b->d_triples.p, max_nodes_level, (int64_t)b->slice_elems,
-                                           ctl + nxt, s));
-      b->t.hist_launches++; b->t.kernel_launches += 2;
-      mark_phase(b, 3);
+      exchange_and_subtract(b, st, b->hist[hb].p, b->hist[nh].p, b->d_triples.p, ctl + nxt, max_nodes_level, max_nodes_level);
       hb = nh;
     }
   }
-  // ---- leaves: 40-bit fixed-point leaf sums -> allreduce -> weights -> margin update
-  const size_t lcap = (size_t)1 << D;
-  const int max_leaf_chunks = max_part_chunks_total + (int)lcap;
-  LAUNCH_CHECK(b2_launch_leaf_plan(b->d_leaves.p, d_n_leaves, b->d_seg_work.p, ctl + 2, s));
-  CUDA_CHECK(cudaMemsetAsync(b->d_leaf_sums.p, 0, 2 * lcap * sizeof(long long), s));
-  LAUNCH_CHECK(b2_launch_leaf_sums(gh, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks, b->d_qexp.p, 40,
-                                   b->d_leaf_sums.p, ctx->num_sms, s));
-  allreduce(b->comm, b->d_leaf_sums.p, 2 * lcap, kNcclInt64, kNcclSum, s);
+  // ---- leaves: 40-bit fixed-point leaf sums -> sum over the ranks -> weights -> margin update
+  if (!leaf_fused) {
+    LAUNCH_CHECK(b2_launch_leaf_plan(b->d_leaves.p, d_n_leaves, b->d_seg_work.p, ctl + 2, s));
+    LAUNCH_CHECK(b2_launch_leaf_sums(gh, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks, b->d_qexp.p, 40,
+                                     b->d_leaf_sums.p, nullptr, ctx->num_sms, s));
+    st.kernel_launches += 2;
+  }
+  if (p2p) { LAUNCH_CHECK(b2_launch_p2p_leaf_sums(&b->p2p.pp, d_n_leaves, b->d_leaf_sums.p, s)); st.kernel_launches++; }
+  else allreduce(b->comm, b->d_leaf_sums.p, 2 * lcap, kNcclInt64, kNcclSum, s);
   LAUNCH_CHECK(b2_launch_leaf_values(b->d_leaves.p, d_n_leaves, b->d_leaf_sums.p, b->d_qexp.p, 40, cp, b->d_leaf_values.p, tree, s));
-  LAUNCH_CHECK(b2_launch_pred_update(b->margin.p, K, k, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks,
-                                     b->d_leaf_values.p, ctx->num_sms, s));
-  b->t.kernel_launches += 4;
+  if (leaf_fused)
+    LAUNCH_CHECK(b2_launch_margin_update(b->margin.p, K, k, b->pos.p, b->d_leaf_values.p, n, ctx->num_sms, s));
+  else
+    LAUNCH_CHECK(b2_launch_pred_update(b->margin.p, K, k, b->ridx[0].p, b->ridx[1].p, b->d_seg_work.p, ctl + 2, max_leaf_chunks,
+                                       b->d_leaf_values.p, ctx->num_sms, s));
+  st.kernel_launches += 2;
   mark_phase(b, 6);
   // ---- read the finished tree back (pinned, asynchronous; resolved at the end of the round)
+  char* stg = (char*)b->staging[slot];
+  CUDA_CHECK(cudaMemcpyAsync(stg, b->t_i32.p, L.i32_count * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(stg + L.off_f32, b->t_f32.p, L.f32_count * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(stg + L.off_i64, b->t_i64.p, L.i64_count * 8, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemcpyAsync(stg + L.off_qexp, b->d_qexp.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (m->any_cat()) CUDA_CHECK(cudaMemcpyAsync(stg + L.off_cat, b->t_cat.p, L.max_nodes * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+}
+
+void apply_tree_stats(Booster* b, long long hist_launches, long long kernel_launches, double allreduce_bytes,
+                      const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& ev) {
+  b->t.hist_launches += hist_launches; b->t.kernel_launches += kernel_launches; b->t.allreduce_bytes += allreduce_bytes;
+  for (auto& pr : ev) b->hist_events.push_back(pr);
+}
+
+// buffers a tree needs, allocated outside of any capture
+void prepare_tree_buffers(Booster* b, int slot) {
+  Matrix* m = b->train; const int64_t n = m->n;
+  ensure_ctl_tables(b);
+  const TreeLayout L = tree_layout(b->p.max_depth);
+  const size_t rows = (size_t)std::max<int64_t>(n, 1);
+  b->d_absmax.ensure(2 * (size_t)b->p.num_class); b->d_qexp.ensure(2);
+  b->q.ensure(rows); b->ridx[0].ensure(rows); b->ridx[1].ensure(rows); b->pos.ensure(rows);
   if (b->staging_bytes != L.bytes) {
     for (void* h : b->staging) cudaFreeHost(h);
     b->staging.clear(); b->staging_bytes = L.bytes;
   }
   while ((int)b->staging.size() <= slot) { void* h = nullptr; CUDA_CHECK(cudaMallocHost(&h, L.bytes)); b->staging.push_back(h); }
-  char* st = (char*)b->staging[slot];
-  CUDA_CHECK(cudaMemcpyAsync(st, b->t_i32.p, L.i32_count * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaMemcpyAsync(st + L.off_f32, b->t_f32.p, L.f32_count * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaMemcpyAsync(st + L.off_i64, b->t_i64.p, L.i64_count * 8, cudaMemcpyDeviceToHost, s));
-  CUDA_CHECK(cudaMemcpyAsync(st + L.off_qexp, b->d_qexp.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  if (m->any_cat()) CUDA_CHECK(cudaMemcpyAsync(st + L.off_cat, b->t_cat.p, L.max_nodes * 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+}
+
+// One class tree: replay its CUDA graph when the launch sequence is the same for every tree (no row / column sampling,
+// fused |g|,|h| maxima, no per-phase profiling), otherwise enqueue the kernels one by one.  The first tree of a class
+// slot always runs with direct launches (it allocates), the second is captured, the following ones replay.
+void run_tree(Booster* b, int k) {
+  cudaStream_t s = b->ctx->stream; const Params& p = b->p;
+  prepare_tree_buffers(b, k);
+  static const bool want_graph = env_flag("B2_GRAPH", true);
+  const bool eligible = want_graph && !b->graph_failed && b->absmax_fused && p.subsample >= 1.0f && !p.use_cols() &&
+                        p.profile < 2 && !use_tma_hist();
+  auto direct = [&]() {
+    TreeStats st;
+    grow_tree(b, k, k, st);
+    apply_tree_stats(b, st.hist_launches, st.kernel_launches, st.allreduce_bytes, st.hist_ev);
+    b->direct_trees[k]++;
+  };
+  if (!eligible) { direct(); return; }
+  auto it = b->graphs.find(k);
+  if (it == b->graphs.end()) {
+    if (b->direct_trees[k] == 0) { direct(); return; }
+    TreeStats st; st.capturing = true;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      try { grow_tree(b, k, k, st); }
+      catch (const B2Error& e) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); throw; }
+      ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      for (auto& pr : st.hist_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+      b->graph_failed = true;
+      fprintf(stderr, "[b2hist] CUDA graph capture of the tree failed; continuing with direct launches\n");
+      direct();
+      return;
+    }
+    Booster::TreeGraph g;
+    g.exec = exec; g.hist_ev = st.hist_ev; g.hist_launches = st.hist_launches; g.kernel_launches = st.kernel_launches;
+    g.allreduce_bytes = st.allreduce_bytes;
+    it = b->graphs.emplace(k, std::move(g)).first;
+  }
+  CUDA_CHECK(cudaGraphLaunch(it->second.exec, s));
+  apply_tree_stats(b, it->second.hist_launches, it->second.kernel_launches, it->second.allreduce_bytes, it->second.hist_ev);
 }
 
 // after the stream is synchronised: turn read-back block `slot` into a host tree (A.7 bookkeeping)
@@ -1191,14 +1353,16 @@ void init_margin(Booster* b, float* margin, Matrix* m) {
 // Sums are 40-bit fixed-point integers, so every rank (and the oracle) computes the same value.
 void estimate_base_score(Booster* b) {
   Matrix* m = b->train; cudaStream_t s = b->ctx->stream; Params& p = b->p;
-  if (p.base_score_set || !b->trees.empty() || p.objective == kObjSoftprob) { p.base_score_set = true; return; }
+  if (p.base_score_set || p.objective == kObjSoftprob) { p.base_score_set = true; return; }
+  // existing trees were fitted around the intercept of the model they came from: never assume the default for them
+  if (!b->trees.empty()) fail("continuing from existing trees needs an explicit base_score (the source model's intercept)");
   if (m->n_label != m->n) fail("train matrix has %lld labels for %lld rows", (long long)m->n_label, (long long)m->n);
   const int64_t n = m->n;
   DevBuf<float> zeros; DevBuf<float2> gh; DevBuf<long long> sums;
   zeros.ensure((size_t)std::max<int64_t>(n, 1)); gh.ensure((size_t)std::max<int64_t>(n, 1)); sums.ensure(2);
   CUDA_CHECK(cudaMemsetAsync(zeros.p, 0, (size_t)std::max<int64_t>(n, 1) * sizeof(float), s));
   LAUNCH_CHECK(b2_launch_gradient(p.objective, 1, zeros.p, m->label.p, m->n_weight ? m->weight.p : nullptr, n, p.scale_pos_weight,
-                                  gh.p, b->ctx->num_sms, s));
+                                  gh.p, nullptr, b->ctx->num_sms, s));
   b->d_absmax.ensure(2); b->d_qexp.ensure(2);
   CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * sizeof(uint32_t), s));
   LAUNCH_CHECK(b2_launch_absmax(gh.p, n, b->d_absmax.p, b->ctx->num_sms, s));
@@ -1252,6 +1416,8 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
   if (b->p.profile) CUDA_CHECK(cudaEventRecord(b->round_start, s));
   ensure_train_margin(b);
   b->gh.ensure((size_t)std::max<int64_t>(n * K, 1));
+  b->d_absmax.ensure(2 * (size_t)K); b->d_qexp.ensure(2);
+  b->absmax_fused = false;
   if (custom_g) {
     if (len != n * K) fail("custom gradient has %lld values, expected %lld", (long long)len, (long long)(n * K));
     b->d_custom_g.ensure((size_t)std::max<int64_t>(len, 1)); b->d_custom_h.ensure((size_t)std::max<int64_t>(len, 1));
@@ -1260,11 +1426,14 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
     LAUNCH_CHECK(b2_launch_pack_custom(b->d_custom_g.p, b->d_custom_h.p, K, n, b->gh.p, b->ctx->num_sms, s));
   } else {
     if (m->n_label != n) fail("train matrix has %lld labels for %lld rows", (long long)m->n_label, (long long)n);
+    // the |g|,|h| maxima of every class tree come out of the same pass unless rows are dropped afterwards (subsample)
+    b->absmax_fused = b->p.subsample >= 1.0f && K <= b2_gradient_fused_max_classes();
+    if (b->absmax_fused) CUDA_CHECK(cudaMemsetAsync(b->d_absmax.p, 0, 2 * (size_t)K * sizeof(uint32_t), s));
     LAUNCH_CHECK(b2_launch_gradient(b->p.objective, K, b->margin.p, m->label.p, m->n_weight ? m->weight.p : nullptr, n,
-                                    b->p.scale_pos_weight, b->gh.p, b->ctx->num_sms, s));
+                                    b->p.scale_pos_weight, b->gh.p, b->absmax_fused ? b->d_absmax.p : nullptr, b->ctx->num_sms, s));
   }
   b->t.kernel_launches++;
-  for (int k = 0; k < K; ++k) grow_tree(b, k, k);
+  for (int k = 0; k < K; ++k) run_tree(b, k);
   if (b->p.profile) {
     CUDA_CHECK(cudaEventRecord(b->round_stop, s));
     CUDA_CHECK(cudaEventSynchronize(b->round_stop));
@@ -1276,8 +1445,9 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
   }
   if (b->p2p.enabled) {
     uint32_t perr = 0;
-    CUDA_CHECK(cudaMemcpy(&perr, b->p2p.err.p, sizeof(perr), cudaMemcpyDeviceToHost));
-    if (perr) fail("peer-memory histogram exchange timed out waiting for another rank (flag slot %u)", perr - 1);
+    CUDA_CHECK(cudaMemcpy(&perr, b->p2p.pp.err, sizeof(perr), cudaMemcpyDeviceToHost));
+    if (perr) fail("peer-memory exchange: %s while waiting for another rank (flag slot %u)",
+                   b->comm && b->comm->aborted.load() ? "communicator aborted" : "timed out", perr - 1);
   }
   for (int k = 0; k < K; ++k) materialize_tree(b, k);
   b->t.rounds++;
@@ -1299,10 +1469,17 @@ float* eval_margin(Booster* b, Matrix* m) {
   if (b->train && m == b->train) { ensure_train_margin(b); return b->margin.p; }
   if (!m->has_raw) fail("evaluation / prediction matrix has no raw data on the device");
   if (m->F != b->n_features) fail("feature count mismatch: matrix has %d, model has %d", m->F, b->n_features);
-  EvalCache*& c = b->eval_cache[m];
+  {   // drop the cached margins of matrices that were freed since the last call
+    std::lock_guard<std::mutex> lk(g_matrix_mu);
+    for (auto it = b->eval_cache.begin(); it != b->eval_cache.end();) {
+      if (!g_live_matrices.count(it->first)) { delete it->second; it = b->eval_cache.erase(it); } else ++it;
+    }
+  }
+  if (!m->uid) fail("evaluation matrix is not a registered matrix handle");
+  EvalCache*& c = b->eval_cache[m->uid];
   const int K = b->p.num_class;
-  if (!c || c->n != m->n) {
-    delete c; c = new EvalCache(); c->n = m->n;
+  if (!c || c->n != m->n || c->margin_version != m->margin_version) {
+    delete c; c = new EvalCache(); c->n = m->n; c->margin_version = m->margin_version;
     c->margin.ensure((size_t)std::max<int64_t>(m->n * K, 1));
     init_margin(b, c->margin.p, m);
     c->n_trees_applied = 0;
@@ -1350,6 +1527,11 @@ int B2_CommCreate(const uint8_t uid[128], int rank, int world, int device, B2Han
     ncclUniqueId id; memcpy(id.internal, uid, 128);
     int r = nccl()->CommInitRank(&h->c.comm, world, id, rank);
     if (r != 0) { delete h; fail("ncclCommInitRank failed: %s", nccl()->GetErrorString(r)); }
+    // abort word of the peer-memory waits, written through its own stream while a kernel may be spinning
+    if (cudaMalloc((void**)&h->c.d_abort, sizeof(uint32_t)) != cudaSuccess || cudaMemset(h->c.d_abort, 0, sizeof(uint32_t)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->c.abort_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError(); h->c.d_abort = nullptr; h->c.abort_stream = nullptr;
+    }
   }
   *out = (B2Handle)h;
   API_END
@@ -1378,13 +1560,23 @@ int B2_CommAllReduce(B2Handle comm, double* inout, int32_t n, int32_t op) {
 int B2_CommAbort(B2Handle comm) {
   API_BEGIN
   CommH* h = from_handle<CommH>(comm, kComm, "communicator");
-  if (h->c.comm && !h->c.aborted.exchange(true)) nccl()->CommAbort(h->c.comm);
+  if (h->c.comm && !h->c.aborted.exchange(true)) {
+    if (h->c.d_abort && h->c.abort_stream) {   // release kernels that spin on a peer flag (p2p.cuh) before NCCL is torn down
+      static const uint32_t one = 1;
+      cudaSetDevice(h->c.device);
+      cudaMemcpyAsync(h->c.d_abort, &one, sizeof(one), cudaMemcpyHostToDevice, h->c.abort_stream);
+      cudaStreamSynchronize(h->c.abort_stream);
+    }
+    nccl()->CommAbort(h->c.comm);
+  }
   API_END
 }
 int B2_CommFree(B2Handle comm) {
   API_BEGIN
   CommH* h = from_handle<CommH>(comm, kComm, "communicator");
   if (h->c.comm && !h->c.aborted.load()) nccl()->CommDestroy(h->c.comm);
+  if (h->c.abort_stream) cudaStreamDestroy(h->c.abort_stream);
+  if (h->c.d_abort) cudaFree(h->c.d_abort);
   delete h;
   API_END
 }
@@ -1400,6 +1592,7 @@ int B2_MatrixCreateFromDense(const float* data, int64_t n_rows, int32_t n_cols, 
     upload_pipelined(ctx, m->raw.p, data, (size_t)n_rows * n_cols * sizeof(float));
   } catch (...) { delete m; throw; }
   m->has_raw = true;
+  { std::lock_guard<std::mutex> lk(g_matrix_mu); m->uid = g_next_matrix_uid++; g_live_matrices.insert(m->uid); }
   *out = (B2Handle)m;
   API_END
 }
@@ -1411,7 +1604,7 @@ int B2_MatrixSetFloatInfo(B2Handle mh, const char* field, const float* values, i
   DevBuf<float>* dst = nullptr; int64_t* cnt = nullptr;
   if (f == "label") { dst = &m->label; cnt = &m->n_label; if (len != m->n) fail("label length %lld != rows %lld", (long long)len, (long long)m->n); }
   else if (f == "weight") { dst = &m->weight; cnt = &m->n_weight; if (len != m->n && len != 0) fail("weight length %lld != rows %lld", (long long)len, (long long)m->n); }
-  else if (f == "base_margin") { dst = &m->base_margin; cnt = &m->n_base_margin; if (len != 0 && (m->n == 0 || len % m->n != 0)) fail("base_margin length %lld is not a multiple of rows %lld", (long long)len, (long long)m->n); }
+  else if (f == "base_margin") { dst = &m->base_margin; cnt = &m->n_base_margin; m->margin_version++; if (len != 0 && (m->n == 0 || len % m->n != 0)) fail("base_margin length %lld is not a multiple of rows %lld", (long long)len, (long long)m->n); }
   else if (f == "feature_weights") {
     // DMatrix.set_info(feature_weights=...) (main.py:439-442): weights of the column sampler, Q16 fixed point
     if (len != 0 && len != m->F) fail("feature_weights length %lld != features %d", (long long)len, m->F);
@@ -1513,6 +1706,7 @@ int B2_MatrixFree(B2Handle mh) {
   API_BEGIN
   Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
   cudaSetDevice(m->ctx->device);
+  { std::lock_guard<std::mutex> lk(g_matrix_mu); g_live_matrices.erase(m->uid); }
   delete m;
   API_END
 }

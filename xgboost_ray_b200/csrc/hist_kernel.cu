@@ -48,7 +48,7 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
   const int group0 = (blockIdx.x % n_cta_groups) * kGPC;
   const int stream = blockIdx.x / n_cta_groups;
   const int n_streams = gridDim.x / n_cta_groups;
-  if (stream >= total_chunks) return;
+  if (total_chunks <= 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   // lane -> (row of the warp step, group of the CTA, 16-byte half of the group slice).  rot is distinct for the
   // 16 (row, group) pairs of a warp, so at every step the 32 lanes hit 32 different banks (bank = slot).
@@ -63,7 +63,16 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
 
   int cur = -1;          // work index whose partial sums are in shared memory
   int rows_in_window = 0;
-  for (int chunk = stream; chunk < total_chunks; chunk += n_streams) {
+  // A stream takes a CONTIGUOUS range of the chunk list, so consecutive chunks of a CTA mostly belong to the same
+  // node and the 2 x 16K-cell node flush happens once per node per CTA instead of once per chunk (with the strided
+  // assignment of round 1 every chunk of a deep level was a node change: levels 6-7 cost 1.5x the root per row).
+  // debug_mode bit 2 (B2_HIST_DEBUG_MODE=4) restores the strided assignment for A/B timing.
+  const bool strided = (debug_mode & 4) != 0;
+  debug_mode &= 3;
+  const int c_begin = strided ? stream : (int)(((long long)stream * total_chunks) / n_streams);
+  const int c_end = strided ? total_chunks : (int)(((long long)(stream + 1) * total_chunks) / n_streams);
+  const int c_step = strided ? n_streams : 1;
+  for (int chunk = c_begin; chunk < c_end; chunk += c_step) {
     // locate the node of this chunk (uniform across the CTA): last w with chunk_begin <= chunk
     int lo = 0, hi = n_work - 1;
     while (lo < hi) {

@@ -42,26 +42,69 @@ __device__ __forceinline__ float b2_sigmoid(float x) {
   return __fdiv_rn(1.0f, denom);
 }
 
-// gh layout: class-major [K][n] float2 so that each class tree reads a contiguous slice
+// gh layout: class-major [K][n] float2 so that each class tree reads a contiguous slice.
+// absmax (nullable, [K][2] uint32 float bit patterns, zeroed by the caller): max |g|, max |h| per class, gathered in
+// the same pass (the fixed-point scale of each class tree needs it; a separate pass re-read 8 bytes per row).
+constexpr int kFusedMaxK = 16;   // classes whose running maxima fit in registers; more classes use absmax_kernel
+
+__device__ __forceinline__ void absmax_publish(float mg, float mh, uint32_t* __restrict__ out) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, o));
+    mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], __float_as_uint(mg)); atomicMax(&out[1], __float_as_uint(mh)); }
+}
+
 __global__ void gradient_kernel(int objective, int K, const float* __restrict__ margin, const float* __restrict__ label,
-                                const float* __restrict__ weight, int64_t n, float scale_pos_weight, float2* __restrict__ gh) {
+                                const float* __restrict__ weight, int64_t n, float scale_pos_weight, float2* __restrict__ gh,
+                                uint32_t* __restrict__ absmax) {
+  if (objective != 2) {
+    float mg = 0.0f, mh = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      float w = weight ? weight[i] : 1.0f;
+      if (objective == 1 && label[i] == 1.0f) w = __fmul_rn(w, scale_pos_weight);   // RegLossObj: positive rows
+      float2 v;
+      if (objective == 0) {
+        v = make_float2(__fmul_rn(__fadd_rn(margin[i], -label[i]), w), w);
+      } else {
+        const float p = b2_sigmoid(margin[i]);
+        float hh = __fmul_rn(p, __fadd_rn(1.0f, -p));
+        if (hh < 1e-16f) hh = 1e-16f;
+        v = make_float2(__fmul_rn(__fadd_rn(p, -label[i]), w), __fmul_rn(hh, w));
+      }
+      gh[i] = v;
+      mg = fmaxf(mg, fabsf(v.x)); mh = fmaxf(mh, fabsf(v.y));
+    }
+    if (absmax) absmax_publish(mg, mh, absmax);
+    return;
+  }
+  const bool fused = absmax != nullptr && K <= kFusedMaxK;
+  float mg[kFusedMaxK], mh[kFusedMaxK];
+#pragma unroll
+  for (int k = 0; k < kFusedMaxK; ++k) { mg[k] = 0.0f; mh[k] = 0.0f; }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float w = weight ? weight[i] : 1.0f;
-    if (objective == 1 && label[i] == 1.0f) w = __fmul_rn(w, scale_pos_weight);   // RegLossObj: positive rows
-    if (objective == 0) {
-      gh[i] = make_float2(__fmul_rn(__fadd_rn(margin[i], -label[i]), w), w);
-    } else if (objective == 1) {
-      const float p = b2_sigmoid(margin[i]);
-      float hh = __fmul_rn(p, __fadd_rn(1.0f, -p));
-      if (hh < 1e-16f) hh = 1e-16f;
-      gh[i] = make_float2(__fmul_rn(__fadd_rn(p, -label[i]), w), __fmul_rn(hh, w));
+    const float w = weight ? weight[i] : 1.0f;
+    const float* m = margin + i * K;
+    float mx = m[0];
+    for (int k = 1; k < K; ++k) if (m[k] > mx) mx = m[k];
+    float s = 0.0f;
+    for (int k = 0; k < K; ++k) s = __fadd_rn(s, b2_expf(__fadd_rn(m[k], -mx)));
+    const int y = (int)label[i];
+    if (fused) {
+#pragma unroll
+      for (int k = 0; k < kFusedMaxK; ++k) {
+        if (k < K) {
+          const float p = __fdiv_rn(b2_expf(__fadd_rn(m[k], -mx)), s);
+          float hh = __fmul_rn(__fmul_rn(2.0f, p), __fadd_rn(1.0f, -p));
+          if (hh < 1e-16f) hh = 1e-16f;
+          const float g = (k == y) ? __fadd_rn(p, -1.0f) : p;
+          const float2 v = make_float2(__fmul_rn(g, w), __fmul_rn(hh, w));
+          gh[(int64_t)k * n + i] = v;
+          mg[k] = fmaxf(mg[k], fabsf(v.x)); mh[k] = fmaxf(mh[k], fabsf(v.y));
+        }
+      }
     } else {
-      const float* m = margin + i * K;
-      float mx = m[0];
-      for (int k = 1; k < K; ++k) if (m[k] > mx) mx = m[k];
-      float s = 0.0f;
-      for (int k = 0; k < K; ++k) s = __fadd_rn(s, b2_expf(__fadd_rn(m[k], -mx)));
-      const int y = (int)label[i];
       for (int k = 0; k < K; ++k) {
         const float p = __fdiv_rn(b2_expf(__fadd_rn(m[k], -mx)), s);
         float hh = __fmul_rn(__fmul_rn(2.0f, p), __fadd_rn(1.0f, -p));
@@ -70,6 +113,11 @@ __global__ void gradient_kernel(int objective, int K, const float* __restrict__ 
         gh[(int64_t)k * n + i] = make_float2(__fmul_rn(g, w), __fmul_rn(hh, w));
       }
     }
+  }
+  if (fused) {
+#pragma unroll
+    for (int k = 0; k < kFusedMaxK; ++k)
+      if (k < K) absmax_publish(mg[k], mh[k], absmax + 2 * k);
   }
 }
 
@@ -240,10 +288,11 @@ static inline int grid_for(int64_t n, int num_sms) {
 }
 
 extern "C" {
+int b2_gradient_fused_max_classes() { return b2::kFusedMaxK; }
 int b2_launch_gradient(int objective, int K, const float* margin, const float* label, const float* weight, int64_t n,
-                       float scale_pos_weight, float2* gh, int num_sms, cudaStream_t s) {
+                       float scale_pos_weight, float2* gh, uint32_t* absmax, int num_sms, cudaStream_t s) {
   if (n <= 0) return 0;
-  b2::gradient_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, K, margin, label, weight, n, scale_pos_weight, gh);
+  b2::gradient_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(objective, K, margin, label, weight, n, scale_pos_weight, gh, absmax);
   return (int)cudaGetLastError();
 }
 int b2_launch_subsample(float2* gh, int64_t n, uint32_t seed, uint32_t tree, uint32_t rank, double subsample, int num_sms,

@@ -1,113 +1,135 @@
-// p2p_exchange.cu -- histogram exchange over NVLink peer memory (EXPERIMENTAL, opt-in: B2_EXCHANGE_P2P=1).
+// p2p_exchange.cu -- histogram exchange fused with the sibling subtraction over NVLink peer memory.
 //
-// Replaces, for one tree level, the pair  ncclReduceScatter(int64 histograms) ... ncclAllGather(candidates)  that
-// stands in for the reference's Rabit allreduce (xgboost_ray/main.py:745-752 -> xgboost collective; SURVEY.md 8a
-// row a11, 8e).  Every rank maps the build buffer, the candidate table and a small flag array of every peer
-// (cudaIpcOpenMemHandle, engine.cu) and then
-//   1. p2p_signal(slot HIST)     after its histogram kernel: "my partial histograms of this level are complete";
-//   2. p2p_reduce_kernel         waits for all ranks' HIST flags and sums the W partial copies of the slice it owns
-//                                 straight out of the peers' memory (exact int64, any order) into its level buffer;
-//   3. p2p_signal(slot READ)     "I have finished reading your build buffers" (a rank waits for this before it
-//                                 zeroes its build buffer for the next level);
-//   4. p2p_push_cands_kernel     after the split scan: stores its candidates into every peer's candidate table,
-//      p2p_signal(slot CAND), p2p_wait(slot CAND) in front of the decide kernel.
-// Flags are monotonically increasing epochs written with st.release.sys and polled with ld.acquire.sys; a bounded
-// spin (about ten seconds) raises an error word instead of hanging the GPU when a peer has died.
-//
-// Status: compiles, NOT yet validated on hardware (the round-1 GPU budget was spent); the default exchange is NCCL.
-#include "common.cuh"
+// Replaces, for one tree level, what the reference gets from Rabit's allreduce inside xgb.train()
+// (xgboost_ray/main.py:745-752) and what the NCCL path of this engine does with
+// ncclReduceScatter + hist_subtract_kernel: ONE kernel
+//   1. publishes "my partial histograms of this level are complete" to every rank (epoch flag, p2p.cuh),
+//   2. waits for the same flag of every rank,
+//   3. sums the W partial copies of the feature-slot slice this rank owns straight out of the peers' memory
+//      (exact int64, so the order of ranks does not matter), stores the built child's slice into the level buffer and
+//   4. derives the sibling's slice  parent - built  in the same pass (the parent level is local).
+// The split candidates travel the other way: decide_kernel (control_kernel.cu) stores this rank's candidates into
+// every peer's table before it decides.  No NCCL call is left inside a tree.
+#include "p2p.cuh"
 
 namespace b2 {
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ ulonglong2 ld_volatile_v2(const long long* p) {
-  ulonglong2 v;
-  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-  return v;
+// grid = (x, n_pairs upper bound); pair p: triples[3p] = parent slot (previous level buffer), [3p+1] = built slot,
+// [3p+2] = sibling slot (this level buffer).  triples == nullptr: the root (one node, nothing to subtract).
+__global__ void __launch_bounds__(256)
+p2p_reduce_subtract_kernel(B2P2P pp, const long long* __restrict__ parent_level, long long* __restrict__ level,
+                           const int32_t* __restrict__ triples, const B2LevelCtl* __restrict__ ctl, int node_cap,
+                           int64_t slice_elems) {
+  const uint32_t epoch = p2p_next_epoch(pp, kSlotHist);
+  const unsigned n_ctas = gridDim.x * gridDim.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0) p2p_signal(pp, kSlotHist, epoch);
+  const int n_pairs = triples ? ctl->n_pairs : 1;
+  const int p = blockIdx.y;
+  if (p < n_pairs) {
+    p2p_wait(pp, kSlotHist, epoch);
+    const int par_slot = triples ? triples[3 * p] : 0, built_slot = triples ? triples[3 * p + 1] : 0;
+    const int sib_slot = triples ? triples[3 * p + 2] : 0;
+    const size_t src = ((size_t)pp.rank * node_cap + built_slot) * (size_t)slice_elems;
+    long long* built = level + (size_t)built_slot * slice_elems;
+    long long* sib = level + (size_t)sib_slot * slice_elems;
+    const long long* par = parent_level + (size_t)par_slot * slice_elems;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < slice_elems; i += (int64_t)gridDim.x * blockDim.x * 2) {
+      unsigned long long a = 0, b = 0;
+      for (int w = 0; w < pp.world; ++w) {
+        const ulonglong2 v = ld_volatile_v2(pp.build[w] + src + i);
+        a += v.x; b += v.y;
+      }
+      built[i] = (long long)a; built[i + 1] = (long long)b;
+      if (triples) { sib[i] = par[i] - (long long)a; sib[i + 1] = par[i + 1] - (long long)b; }
+    }
+  }
+  p2p_finish_grid(pp, kSlotHist, epoch, n_ctas);
 }
 
-// thread w < world: wait until rank w has published `epoch` in `slot` of MY flag array
-__device__ __forceinline__ void wait_flags(const B2P2P& pp, int slot, uint32_t epoch, uint32_t* err) {
+// per-tree fixed-point scale: every rank stores its max|g|, max|h| bit patterns into every rank's misc table, then
+// takes the maximum over the ranks (replaces ncclAllReduce(max) + quant_exponent_kernel)
+__global__ void p2p_quant_exponent_kernel(B2P2P pp, const uint32_t* __restrict__ absmax, int32_t* __restrict__ qexp) {
+  const uint32_t epoch = p2p_next_epoch(pp, kSlotAbsmax);
   if ((int)threadIdx.x < pp.world) {
-    const uint32_t* f = pp.flags[pp.rank] + slot * pp.world + threadIdx.x;
-    long long spins = 0;
-    while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
-      __nanosleep(200);
-      if (++spins > 50000000LL) { atomicExch(err, 1u + (uint32_t)slot); break; }   // ~10 s: a peer is gone
-    }
+    const long long v = (long long)(((unsigned long long)absmax[1] << 32) | (unsigned long long)absmax[0]);
+    st_volatile_u64(pp.misc[threadIdx.x] + (size_t)pp.rank * pp.misc_stride, v);
   }
   __syncthreads();
-}
-
-__global__ void p2p_signal_kernel(B2P2P pp, int slot, uint32_t epoch) {
-  if ((int)threadIdx.x < pp.world) {
-    __threadfence_system();
-    st_release_sys(pp.flags[threadIdx.x] + slot * pp.world + pp.rank, epoch);
-  }
-}
-__global__ void p2p_wait_kernel(B2P2P pp, int slot, uint32_t epoch, uint32_t* err) { wait_flags(pp, slot, epoch, err); }
-
-// level_buf[i] = sum over ranks w of build_w[rank * shard_stride + i], i < n_elems (n_elems even: slices are 16-byte multiples)
-__global__ void __launch_bounds__(256)
-p2p_reduce_kernel(B2P2P pp, uint32_t epoch, long long* __restrict__ level_buf, size_t n_elems, size_t shard_stride,
-                  uint32_t* err) {
-  wait_flags(pp, kSlotHist, epoch, err);
-  const size_t base = (size_t)pp.rank * shard_stride;
-  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n_elems; i += (size_t)gridDim.x * blockDim.x * 2) {
-    unsigned long long a = 0, b = 0;
+  p2p_signal(pp, kSlotAbsmax, epoch);
+  p2p_wait(pp, kSlotAbsmax, epoch);
+  if (threadIdx.x == 0) {
+    uint32_t mg = 0, mh = 0;
     for (int w = 0; w < pp.world; ++w) {
-      const ulonglong2 v = ld_volatile_v2(pp.build[w] + base + i);
-      a += v.x; b += v.y;
+      const unsigned long long v = ld_volatile_u64(pp.misc[pp.rank] + (size_t)w * pp.misc_stride);
+      const uint32_t g = (uint32_t)(v & 0xffffffffu), h = (uint32_t)(v >> 32);
+      mg = g > mg ? g : mg; mh = h > mh ? h : mh;
     }
-    level_buf[i] = (long long)a; level_buf[i + 1] = (long long)b;
+    qexp[0] = mg == 0 ? 0 : (int)((mg >> 23) & 0xffu) - 126;
+    qexp[1] = mh == 0 ? 0 : (int)((mh >> 23) & 0xffu) - 126;
   }
+  __syncthreads();
+  p2p_finish_single(pp, kSlotAbsmax, epoch);
 }
 
-// my candidates [n] -> region `rank` of every rank's table (own table included)
-__global__ void p2p_push_cands_kernel(B2P2P pp, const B2SplitCand* __restrict__ local, int n, int cand_cap) {
-  constexpr int kWords = sizeof(B2SplitCand) / 8;
-  static_assert(sizeof(B2SplitCand) % 8 == 0, "candidates are copied as 64-bit words");
-  const size_t total = (size_t)pp.world * n * kWords;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int w = (int)(t / ((size_t)n * kWords));
-    const size_t r = t - (size_t)w * n * kWords;
-    reinterpret_cast<unsigned long long*>(pp.cands[w] + (size_t)pp.rank * cand_cap)[r] =
-        reinterpret_cast<const unsigned long long*>(local)[r];
+// leaf sums: every rank stores its [n_leaves][2] int64 sums into every rank's misc table (offset 2), then replaces its
+// local sums with the total over the ranks (replaces ncclAllReduce(sum) in front of leaf_values_kernel)
+__global__ void __launch_bounds__(1024)
+p2p_leaf_sums_kernel(B2P2P pp, const int32_t* __restrict__ n_leaves, long long* __restrict__ sums) {
+  const uint32_t epoch = p2p_next_epoch(pp, kSlotLeaf);
+  const int n = 2 * *n_leaves;
+  for (int w = 0; w < pp.world; ++w)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) st_volatile_u64(pp.misc[w] + (size_t)pp.rank * pp.misc_stride + 2 + i, sums[i]);
+  __syncthreads();
+  p2p_signal(pp, kSlotLeaf, epoch);
+  p2p_wait(pp, kSlotLeaf, epoch);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned long long t = 0;
+    for (int w = 0; w < pp.world; ++w) {
+      t += ld_volatile_u64(pp.misc[pp.rank] + (size_t)w * pp.misc_stride + 2 + i);
+    }
+    sums[i] = (long long)t;
   }
+  __syncthreads();
+  p2p_finish_single(pp, kSlotLeaf, epoch);
+}
+
+// teardown barrier: nobody frees a mapped buffer while a peer may still be reading it
+__global__ void p2p_close_kernel(B2P2P pp) {
+  const uint32_t epoch = p2p_next_epoch(pp, kSlotClose);
+  p2p_signal(pp, kSlotClose, epoch);
+  p2p_wait(pp, kSlotClose, epoch);
+  p2p_finish_single(pp, kSlotClose, epoch);
 }
 
 }  // namespace b2
 
 extern "C" {
-int b2_p2p_struct_bytes() { return (int)sizeof(B2P2P); }
 int b2_p2p_flag_words(int world) { return kP2PSlots * world; }
-int b2_launch_p2p_signal(const void* pp, int slot, uint32_t epoch, cudaStream_t s) {
-  b2::p2p_signal_kernel<<<1, 32, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), slot, epoch);
+int b2_launch_p2p_reduce_subtract(const void* pp, const long long* parent_level, long long* level, const int32_t* triples,
+                                  const B2LevelCtl* ctl, int max_pairs, int node_cap, int64_t slice_elems, int num_sms,
+                                  cudaStream_t s) {
+  if (max_pairs <= 0 || slice_elems <= 0) return 0;
+  // enough CTAs to keep the NVLink reads of all peers in flight, few enough that the wait/finish overhead stays small
+  int bx = (int)((slice_elems / 2 + 255) / 256);
+  int cap = (4 * num_sms + max_pairs - 1) / max_pairs;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, max_pairs);
+  b2::p2p_reduce_subtract_kernel<<<grid, 256, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), parent_level, level, triples, ctl,
+                                                     node_cap, slice_elems);
   return (int)cudaGetLastError();
 }
-int b2_launch_p2p_wait(const void* pp, int slot, uint32_t epoch, uint32_t* err, cudaStream_t s) {
-  b2::p2p_wait_kernel<<<1, 32, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), slot, epoch, err);
+int b2_launch_p2p_quant_exponent(const void* pp, const uint32_t* absmax, int32_t* qexp, cudaStream_t s) {
+  b2::p2p_quant_exponent_kernel<<<1, 32, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), absmax, qexp);
   return (int)cudaGetLastError();
 }
-int b2_launch_p2p_reduce(const void* pp, uint32_t epoch, long long* level_buf, size_t n_elems, size_t shard_stride, uint32_t* err,
-                         int num_sms, cudaStream_t s) {
-  if (n_elems == 0) return 0;
-  size_t want = (n_elems / 2 + 255) / 256;
-  int grid = (int)(want < (size_t)num_sms * 4 ? want : (size_t)num_sms * 4);
-  if (grid < 1) grid = 1;
-  b2::p2p_reduce_kernel<<<grid, 256, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), epoch, level_buf, n_elems, shard_stride, err);
+int b2_launch_p2p_leaf_sums(const void* pp, const int32_t* n_leaves, long long* sums, cudaStream_t s) {
+  b2::p2p_leaf_sums_kernel<<<1, 1024, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), n_leaves, sums);
   return (int)cudaGetLastError();
 }
-int b2_launch_p2p_push_cands(const void* pp, const B2SplitCand* local, int n, int cand_cap, int num_sms, cudaStream_t s) {
-  if (n <= 0) return 0;
-  b2::p2p_push_cands_kernel<<<num_sms, 256, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), local, n, cand_cap);
+int b2_launch_p2p_close(const void* pp, cudaStream_t s) {
+  b2::p2p_close_kernel<<<1, 32, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp));
   return (int)cudaGetLastError();
 }
 }

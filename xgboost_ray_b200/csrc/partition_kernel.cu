@@ -63,7 +63,7 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
     for (int it = 0; it < kIters; ++it) {
       const int r = it * kPartThreads + threadIdx.x;
       const bool valid = r < nrows;
-      rid[it] = valid ? __ldg(ridx_in + w.seg_begin + row0 + r) : 0;
+      rid[it] = valid ? (ridx_in ? __ldg(ridx_in + w.seg_begin + row0 + r) : w.seg_begin + row0 + r) : 0;   // root: identity
       int b = valid ? (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid[it]) : 0;
       bool l;
       if (kCat) {
@@ -115,7 +115,8 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
 __global__ void __launch_bounds__(256)
 leaf_sums_kernel(const float2* __restrict__ gh, const int32_t* __restrict__ ridx0, const int32_t* __restrict__ ridx1,
                  const SegWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl, const int32_t* __restrict__ qexp,
-                 int leaf_bits, long long* __restrict__ sums /* [n_leaves][2] */) {
+                 int leaf_bits, long long* __restrict__ sums /* [n_leaves][2] */,
+                 uint16_t* __restrict__ pos /* nullable: row -> leaf index, read by margin_update_kernel */) {
   const int n_work = ctl->hist_n_work, total_chunks = ctl->hist_total_chunks;
   __shared__ long long sg[8], sh[8];
   const double kg = ldexp(1.0, leaf_bits - qexp[0]), kh = ldexp(1.0, leaf_bits - qexp[1]);
@@ -126,12 +127,13 @@ leaf_sums_kernel(const float2* __restrict__ gh, const int32_t* __restrict__ ridx
       if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
     }
     const SegWork w = work[lo];
-    const int32_t* ridx = w.buf ? ridx1 : ridx0;
+    const int32_t* ridx = w.pad0 ? nullptr : (w.buf ? ridx1 : ridx0);   // pad0: the leaf is the root (rows = identity)
     const int row0 = (chunk - w.chunk_begin) * kPartChunk;
     const int nrows = min(kPartChunk, w.seg_count - row0);
     long long ag = 0, ah = 0;
     for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
       const int row = ridx ? __ldg(ridx + w.seg_begin + row0 + r) : (w.seg_begin + row0 + r);
+      if (pos) pos[row] = (uint16_t)w.id;
       const float2 v = __ldg(gh + row);
       ag += __double2ll_rn(__dmul_rn((double)v.x, kg));
       ah += __double2ll_rn(__dmul_rn((double)v.y, kh));
@@ -163,7 +165,7 @@ pred_update_kernel(float* __restrict__ margin, int K, int k, const int32_t* __re
       if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
     }
     const SegWork w = work[lo];
-    const int32_t* ridx = w.buf ? ridx1 : ridx0;
+    const int32_t* ridx = w.pad0 ? nullptr : (w.buf ? ridx1 : ridx0);
     const int row0 = (chunk - w.chunk_begin) * kPartChunk;
     const int nrows = min(kPartChunk, w.seg_count - row0);
     const float v = __ldg(leaf_value + w.id);
@@ -172,6 +174,70 @@ pred_update_kernel(float* __restrict__ margin, int K, int k, const int32_t* __re
       margin[row * K + k] += v;
     }
   }
+}
+
+// ---- last split level (d = max_depth - 1): the children are leaves, so their rows need no ordered index list any
+// more.  Instead of partition -> finalize -> leaf_sums -> pred_update (three scattered passes over all rows) one pass
+// decides left/right, adds the row's fp32 gradient pair to the 40-bit fixed-point sums of the child LEAF and records
+// the leaf index of the row; the margin is then updated by a streaming kernel (margin_update_kernel).
+// Leaf index of child `side` of split j: leaf_base + 2 j + side -- exactly the index decide_kernel gives the node at
+// the next level (leaves are numbered in node order; leaf_base = leaves that existed before this level's children).
+template <bool kCat>
+__global__ void __launch_bounds__(kPartThreads)
+final_assign_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const int32_t* __restrict__ ridx_in,
+                    const B2SplitWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl, const float2* __restrict__ gh,
+                    const int32_t* __restrict__ qexp, int leaf_bits, long long* __restrict__ sums,
+                    uint16_t* __restrict__ pos) {
+  const int n_work = ctl->n_split, total_chunks = ctl->part_chunks, leaf_base = ctl->leaf_base_next;
+  __shared__ long long s_acc[kPartThreads / 32][4];
+  const double kg = ldexp(1.0, leaf_bits - qexp[0]), kh = ldexp(1.0, leaf_bits - qexp[1]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+    int lo = 0, hi = n_work - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const B2SplitWork w = work[lo];
+    const int row0 = (chunk - w.chunk_begin) * kPartChunk;
+    const int nrows = min(kPartChunk, w.seg_count - row0);
+    const bool is_cat = kCat && w.is_cat != 0;
+    const int leaf_l = leaf_base + 2 * lo;
+    long long lg = 0, lh = 0, rg = 0, rh = 0;
+#pragma unroll 4
+    for (int r = threadIdx.x; r < nrows; r += kPartThreads) {
+      const int rid = ridx_in ? __ldg(ridx_in + w.seg_begin + row0 + r) : w.seg_begin + row0 + r;
+      const int b = (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid);
+      bool go_left = b <= w.split_bin;
+      if (kCat && is_cat) go_left = ((__ldg(&work[lo].cat_bits[b >> 5]) >> (b & 31)) & 1u) == 0u;   // category in the set -> right
+      const bool l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : go_left;
+      const float2 v = __ldg(gh + rid);
+      const long long qg = __double2ll_rn(__dmul_rn((double)v.x, kg)), qh = __double2ll_rn(__dmul_rn((double)v.y, kh));
+      if (l) { lg += qg; lh += qh; } else { rg += qg; rh += qh; }
+      pos[rid] = (uint16_t)(leaf_l + (l ? 0 : 1));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lg += __shfl_xor_sync(0xffffffffu, lg, o); lh += __shfl_xor_sync(0xffffffffu, lh, o);
+      rg += __shfl_xor_sync(0xffffffffu, rg, o); rh += __shfl_xor_sync(0xffffffffu, rh, o);
+    }
+    if (lane == 0) { s_acc[warp][0] = lg; s_acc[warp][1] = lh; s_acc[warp][2] = rg; s_acc[warp][3] = rh; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      long long t = 0;
+      for (int i = 0; i < kPartThreads / 32; ++i) t += s_acc[i][threadIdx.x];
+      atomicAdd((unsigned long long*)&sums[2 * leaf_l + threadIdx.x], (unsigned long long)t);   // [leaf_l][g,h], [leaf_l+1][g,h]
+    }
+    __syncthreads();
+  }
+}
+
+// margin[row*K + k] += leaf_value[pos[row]] -- streaming, rows in natural order
+__global__ void __launch_bounds__(256)
+margin_update_kernel(float* __restrict__ margin, int K, int k, const uint16_t* __restrict__ pos,
+                     const float* __restrict__ leaf_value, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    margin[i * K + k] += __ldg(leaf_value + pos[i]);
 }
 
 __global__ void iota_kernel(int32_t* out, int64_t n) {
@@ -199,10 +265,30 @@ int b2_launch_partition(const uint8_t* bins_col, int64_t col_stride, const int32
   return (int)cudaGetLastError();
 }
 int b2_launch_leaf_sums(const float2* gh, const int32_t* ridx0, const int32_t* ridx1, const void* work, const B2LevelCtl* ctl,
-                        int max_chunks, const int32_t* qexp, int leaf_bits, long long* sums, int num_sms, cudaStream_t stream) {
+                        int max_chunks, const int32_t* qexp, int leaf_bits, long long* sums, uint16_t* pos, int num_sms,
+                        cudaStream_t stream) {
   if (max_chunks <= 0) return 0;
   int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
-  b2::leaf_sums_kernel<<<grid, 256, 0, stream>>>(gh, ridx0, ridx1, (const b2::SegWork*)work, ctl, qexp, leaf_bits, sums);
+  b2::leaf_sums_kernel<<<grid, 256, 0, stream>>>(gh, ridx0, ridx1, (const b2::SegWork*)work, ctl, qexp, leaf_bits, sums, pos);
+  return (int)cudaGetLastError();
+}
+int b2_launch_final_assign(const uint8_t* bins_col, int64_t col_stride, const int32_t* ridx_in, const B2SplitWork* work,
+                           const B2LevelCtl* ctl, int max_chunks, const float2* gh, const int32_t* qexp, int leaf_bits,
+                           long long* sums, uint16_t* pos, int any_categorical, int num_sms, cudaStream_t stream) {
+  if (max_chunks <= 0) return 0;
+  int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
+  if (any_categorical)
+    b2::final_assign_kernel<true><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, work, ctl, gh, qexp, leaf_bits, sums, pos);
+  else
+    b2::final_assign_kernel<false><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, work, ctl, gh, qexp, leaf_bits, sums, pos);
+  return (int)cudaGetLastError();
+}
+int b2_launch_margin_update(float* margin, int K, int k, const uint16_t* pos, const float* leaf_value, int64_t n, int num_sms,
+                            cudaStream_t stream) {
+  if (n <= 0) return 0;
+  int64_t want = (n + 255) / 256;
+  int grid = (int)(want < (int64_t)num_sms * 16 ? want : (int64_t)num_sms * 16);
+  b2::margin_update_kernel<<<grid, 256, 0, stream>>>(margin, K, k, pos, leaf_value, n);
   return (int)cudaGetLastError();
 }
 int b2_launch_pred_update(float* margin, int K, int k, const int32_t* ridx0, const int32_t* ridx1, const void* work,

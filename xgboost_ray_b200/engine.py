@@ -944,13 +944,19 @@ def train(params, dtrain, num_boost_round=10, evals=(), obj=None, feval=None, ma
     if xgb_model is not None:
         if isinstance(xgb_model, Booster):
             src = xgb_model
-            bst._trees = src.get_trees()
-            bst.n_features = src.n_features
-            bst.feature_names = src.feature_names
+            src.get_trees()
         else:
-            tmp = Booster(params)
-            tmp.load_model(xgb_model)
-            bst._trees, bst.n_features, bst.feature_names = tmp._trees, tmp.n_features, tmp.feature_names
+            src = Booster(params)
+            src.load_model(xgb_model)
+        bst._trees = list(src._trees)
+        bst.n_features, bst.feature_names, bst.feature_types = src.n_features, src.feature_names, src.feature_types
+        bst._attrs = dict(src._attrs)
+        # The trees of the source model were fitted around ITS intercept: a continuation (checkpoint restart,
+        # main.py:1211-1220) must keep it, also when the user gave no base_score and it was estimated from the labels.
+        if bst.params.get("base_score") is None and bst._trees:
+            if src.params.get("base_score") is None:
+                raise XGBoostError("cannot continue training: the model passed as xgb_model carries no base_score")
+            bst.params["base_score"] = float(src.params["base_score"])
     bst._attach(dtrain)
     evals = list(evals or [])
     for dm, _ in evals:
