@@ -49,6 +49,11 @@ int B2_CommFree(B2Handle comm);
  * :439-442, get_label().size :727). */
 int B2_MatrixCreateFromDense(const float* data, int64_t n_rows, int32_t n_cols, float missing, int device,
                              B2Handle* out);
+/* A shard that arrives as several row blocks (the reference's RayDataIter hands xgb.DeviceQuantileDMatrix one block
+ * per Ray object / file, xgboost_ray/matrix.py:127-196, main.py:387-418): allocate the device matrix once, then
+ * upload each block at its row offset -- no host-side concatenation (matrix.py:65-67). */
+int B2_MatrixCreate(int64_t n_rows, int32_t n_cols, float missing, int device, B2Handle* out);
+int B2_MatrixSetRows(B2Handle m, int64_t row_begin, const float* data, int64_t n_rows);
 /* field: "label" | "weight" | "base_margin" (len n_rows, or n_rows*num_class for base_margin) */
 int B2_MatrixSetFloatInfo(B2Handle m, const char* field, const float* values, int64_t len);
 /* feature types: is_cat[f] != 0 marks feature f categorical (xgb.DMatrix(feature_types=[...'c'...],
@@ -63,6 +68,11 @@ int B2_MatrixNumCol(B2Handle m, int32_t* out);
  * matrix.  ref != 0 reuses the cuts of an already quantised matrix.  keep_raw == 0 frees the
  * device copy of the float data afterwards (it is needed again only for Predict on this matrix). */
 int B2_MatrixQuantize(B2Handle m, B2Handle comm, int32_t max_bin, B2Handle ref, int32_t keep_raw);
+/* Quantise with GIVEN cut points (no sketch, no communication): a restart after an actor failure continues with the
+ * cuts of the first attempt even when the world size changed, so old and new trees split on the same bins
+ * (xgboost_ray/elastic.py:19-178, main.py:1644-1713; SURVEY.md 5 "freeze cuts from attempt 0"). */
+int B2_MatrixQuantizeWithCuts(B2Handle m, const int32_t* ptrs /*[F+1]*/, const float* vals, const float* mins /*[F]*/,
+                              const uint8_t* has_missing /*[F]*/, int32_t max_bin, int32_t keep_raw);
 /* re-upload the float data of a matrix whose device copy was freed (same shape) */
 int B2_MatrixEnsureRaw(B2Handle m, const float* data);
 int B2_MatrixCutsSize(B2Handle m, int32_t* total_cuts);

@@ -1,4 +1,6 @@
-"""TEST-ONLY stand-in for xgboost_ray_b200.engine, selected with XGBOOST_RAY_B200_ENGINE=tests.cpu_engine.
+"""TEST-ONLY stand-in for xgboost_ray_b200.engine.  The CPU suite installs it with a monkeypatch of the import seam in
+the driver process and with the `UseCpuEngine` distributed callback (below) in every spawned actor process; the product
+package has no switch for it.
 
 It lets the -m "not gpu" suite drive the host layer (actors, sharding, communicator bootstrap,
 callbacks, checkpoints, restart, predict recombination) on a CPU-only box.  Arithmetic is done by
@@ -42,6 +44,26 @@ class callback:
 _state = {"rank": 0, "world": 1, "inited": False}
 
 
+def install():
+    """Route xgboost_ray_b200.xgb.xgboost (the import seam of xgboost_ray/xgb.py) to this module in THIS process."""
+    import sys
+    import xgboost_ray_b200.xgb as seam
+    seam.xgboost = sys.modules[__name__]
+
+
+try:
+    from xgboost_ray_b200.callback import DistributedCallback as _DistributedCallback
+except Exception:  # pragma: no cover
+    _DistributedCallback = object
+
+
+class UseCpuEngine(_DistributedCallback):
+    """Distributed callback whose on_init hook (first thing an actor process runs) installs the stand-in there."""
+
+    def on_init(self, actor, *args, **kwargs):
+        install()
+
+
 def device_count():
     return 0
 
@@ -66,6 +88,9 @@ class CommunicatorContext:
             port = int(self.args["b2_uid"].decode().split(":")[1])
             dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
             _state["inited"] = True
+        return self
+
+    def activate(self):
         return self
 
     def abort(self):
@@ -104,6 +129,8 @@ def _allgather(obj):
 class DMatrix:
     def __init__(self, data, label=None, weight=None, base_margin=None, missing=None, feature_names=None,
                  feature_types=None, **kw):
+        if isinstance(data, (list, tuple)):     # several row blocks of one shard
+            data = np.concatenate([np.asarray(b) for b in data], axis=0)
         self.data = np.ascontiguousarray(np.asarray(data), np.float32)
         self.label = None if label is None else np.asarray(label, np.float32).reshape(-1)
         self.weight = None if weight is None else np.asarray(weight, np.float32).reshape(-1)

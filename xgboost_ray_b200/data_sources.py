@@ -25,9 +25,11 @@ class RayFileType(Enum):
 class LoadedFrame:
     """Column-named float32 table: `values` [n, c] C-contiguous and `columns` names."""
 
-    def __init__(self, values: np.ndarray, columns: List[str]):
+    def __init__(self, values: np.ndarray, columns: List[str], feature_types: Optional[List[str]] = None):
         self.values = np.ascontiguousarray(values, dtype=np.float32)
         self.columns = [str(c) for c in columns]
+        # per column 'c' (pandas `category` dtype, stored as its codes) or 'q'; None = all numeric
+        self.feature_types = list(feature_types) if feature_types is not None and "c" in feature_types else None
 
     def __len__(self):
         return self.values.shape[0]
@@ -37,7 +39,8 @@ class LoadedFrame:
 
     def drop(self, names):
         keep = [i for i, c in enumerate(self.columns) if c not in set(map(str, names))]
-        return LoadedFrame(self.values[:, keep], [self.columns[i] for i in keep])
+        types = [self.feature_types[i] for i in keep] if self.feature_types else None
+        return LoadedFrame(self.values[:, keep], [self.columns[i] for i in keep], types)
 
 
 def _from_pandas(df, ignore=None, indices=None):
@@ -45,8 +48,22 @@ def _from_pandas(df, ignore=None, indices=None):
         df = df[[c for c in df.columns if c not in set(ignore)]]
     if indices is not None:
         df = df.iloc[indices]
-    return LoadedFrame(df.to_numpy(dtype=np.float32, na_value=np.nan) if hasattr(df, "to_numpy") else np.asarray(df),
-                       list(df.columns))
+    if not hasattr(df, "to_numpy"):
+        return LoadedFrame(np.asarray(df), list(df.columns))
+    is_cat = [str(dt) == "category" for dt in df.dtypes]
+    if not any(is_cat):
+        return LoadedFrame(df.to_numpy(dtype=np.float32, na_value=np.nan), list(df.columns))
+    # xgboost's pandas adapter (xgb.DMatrix(df, enable_categorical=True), reached through main.py:437): a `category`
+    # column is its integer codes, code -1 (NaN) is a missing value; the column is typed 'c'
+    out = np.empty((len(df), len(df.columns)), np.float32)
+    for j, (c, cat) in enumerate(zip(df.columns, is_cat)):
+        if cat:
+            codes = df[c].cat.codes.to_numpy().astype(np.float32)
+            codes[codes < 0] = np.nan
+            out[:, j] = codes
+        else:
+            out[:, j] = df[c].to_numpy(dtype=np.float32, na_value=np.nan)
+    return LoadedFrame(out, list(df.columns), ["c" if cat else "q" for cat in is_cat])
 
 
 class DataSource:

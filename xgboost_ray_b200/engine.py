@@ -47,12 +47,15 @@ ABI = {
     "B2_CommAbort": (C.c_int, [_H]),
     "B2_CommFree": (C.c_int, [_H]),
     "B2_MatrixCreateFromDense": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
+    "B2_MatrixCreate": (C.c_int, [C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
+    "B2_MatrixSetRows": (C.c_int, [_H, C.c_int64, _FP, C.c_int64]),
     "B2_MatrixSetFloatInfo": (C.c_int, [_H, C.c_char_p, _FP, C.c_int64]),
     "B2_MatrixSetFeatureTypes": (C.c_int, [_H, _BP, C.c_int32]),
     "B2_MatrixGetFeatureTypes": (C.c_int, [_H, _BP]),
     "B2_MatrixNumRow": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "B2_MatrixNumCol": (C.c_int, [_H, C.POINTER(C.c_int32)]),
     "B2_MatrixQuantize": (C.c_int, [_H, _H, C.c_int32, _H, C.c_int32]),
+    "B2_MatrixQuantizeWithCuts": (C.c_int, [_H, _IP, _FP, _FP, _BP, C.c_int32, C.c_int32]),
     "B2_MatrixEnsureRaw": (C.c_int, [_H, _FP]),
     "B2_MatrixCutsSize": (C.c_int, [_H, _IP]),
     "B2_MatrixGetCuts": (C.c_int, [_H, _IP, _FP, _FP, _BP]),
@@ -165,7 +168,14 @@ class CommunicatorContext:
             _check(lib().B2_CommCreate(buf, rank, world, int(self.args.get("b2_device", _default_device())),
                                        C.byref(h)))
             self.handle = h.value
+        self.rank, self.world = rank, world
         _coll.handle, _coll.rank, _coll.world = self.handle, rank, world
+        return self
+
+    def activate(self):
+        """Make an already entered communicator the current one of THIS thread (an actor keeps a healthy communicator
+        across train() calls; every call trains on a fresh thread and the collective state is thread-local)."""
+        _coll.handle, _coll.rank, _coll.world = self.handle, self.rank, self.world
         return self
 
     def abort(self):
@@ -229,12 +239,24 @@ class DMatrix:
                 data = np.stack(cols, axis=1) if cols else np.zeros((len(data), 0), np.float32)
             else:
                 data = data.values
-        data = np.asarray(data)
-        if data.ndim == 1:
-            data = data.reshape(-1, 1)
-        if data.ndim != 2:
-            raise XGBoostError("DMatrix data must be 2-dimensional")
-        self._host = _f32c(data)
+        blocks = None
+        if hasattr(data, "next") and hasattr(data, "reset"):       # xgboost.DataIter protocol (matrix.py:127-196)
+            blocks, label, weight, base_margin = _drain_data_iter(data, label, weight, base_margin)
+        elif isinstance(data, (list, tuple)) and data and all(hasattr(b, "shape") for b in data):
+            blocks = [np.asarray(b.values if hasattr(b, "values") and not isinstance(b, np.ndarray) else b) for b in data]
+        if blocks is not None:
+            blocks = [b.reshape(-1, 1) if b.ndim == 1 else b for b in blocks]
+            if len({b.shape[1] for b in blocks}) != 1:
+                raise XGBoostError("all row blocks of a DMatrix must have the same number of columns")
+            data = _BlockList([_f32c(b) for b in blocks])
+        else:
+            data = np.asarray(data)
+            if data.ndim == 1:
+                data = data.reshape(-1, 1)
+            if data.ndim != 2:
+                raise XGBoostError("DMatrix data must be 2-dimensional")
+            data = _f32c(data)
+        self._host = data
         self.missing = float("nan") if missing is None else float(missing)
         self.device = _default_device() if device is None else int(device)
         self.feature_names = list(feature_names) if feature_names is not None else None
@@ -249,8 +271,15 @@ class DMatrix:
         self._base_margin = None
         h = _H(0)
         n, f = self._host.shape
-        _check(lib().B2_MatrixCreateFromDense(_fp(self._host), n, f, self.missing, self.device, C.byref(h)))
-        self.handle = h.value
+        if isinstance(self._host, _BlockList):
+            # several row blocks (multi-file shard / DataIter): one device allocation, each block uploaded at its row
+            # offset -- the host never concatenates them
+            _check(lib().B2_MatrixCreate(n, f, self.missing, self.device, C.byref(h)))
+            self.handle = h.value
+            self._upload_blocks()
+        else:
+            _check(lib().B2_MatrixCreateFromDense(_fp(self._host), n, f, self.missing, self.device, C.byref(h)))
+            self.handle = h.value
         if self.feature_types is not None:
             if len(self.feature_types) != f:
                 raise XGBoostError("feature_types has %d entries for %d features" % (len(self.feature_types), f))
@@ -299,20 +328,37 @@ class DMatrix:
         return self._host.shape[1]
 
     # -- engine side
-    def _ensure_quantized(self, max_bin, keep_raw=False):
+    def _upload_blocks(self):
+        at = 0
+        for b in self._host.blocks:
+            _check(lib().B2_MatrixSetRows(self.handle, at, _fp(b), b.shape[0]))
+            at += b.shape[0]
+
+    def _ensure_quantized(self, max_bin, keep_raw=False, cuts=None):
+        """GPU sketch + binning.  `cuts` = (ptrs, vals, mins, has_missing) freezes the cut points instead of sketching
+        (restart of an interrupted training with the cuts of its first attempt)."""
         if self._quantized:
             return
-        ref_h = 0
-        if self.ref is not None:
-            self.ref._ensure_quantized(max_bin, keep_raw=True)
-            ref_h = self.ref.handle
         mb = int(self.max_bin or max_bin or 256)
-        _check(lib().B2_MatrixQuantize(self.handle, _coll.handle, mb, ref_h, 1 if keep_raw else 0))
+        if cuts is not None:
+            ptrs, vals, mins, hm = (np.ascontiguousarray(cuts[0], np.int32), _f32c(cuts[1]), _f32c(cuts[2]),
+                                    np.ascontiguousarray(cuts[3], np.uint8))
+            if ptrs.size != self.num_col() + 1:
+                raise XGBoostError("frozen cuts are for %d features, the matrix has %d" % (ptrs.size - 1, self.num_col()))
+            _check(lib().B2_MatrixQuantizeWithCuts(self.handle, _ip(ptrs), _fp(vals), _fp(mins), _bp(hm), mb, 1 if keep_raw else 0))
+        else:
+            ref_h = 0
+            if self.ref is not None:
+                self.ref._ensure_quantized(max_bin, keep_raw=True)
+                ref_h = self.ref.handle
+            _check(lib().B2_MatrixQuantize(self.handle, _coll.handle, mb, ref_h, 1 if keep_raw else 0))
         self._quantized = True
         self._has_raw = bool(keep_raw)
 
     def _ensure_raw(self):
         if not self._has_raw:
+            if isinstance(self._host, _BlockList):   # rare (predicting on a block-built training matrix): one host copy
+                self._host = np.concatenate(self._host.blocks, axis=0)
             _check(lib().B2_MatrixEnsureRaw(self.handle, _fp(self._host)))
             self._has_raw = True
 
@@ -339,6 +385,34 @@ class DMatrix:
                 self.handle = 0
         except Exception:
             pass
+
+
+class _BlockList:
+    """Row blocks of one shard, presented with the little of the ndarray surface DMatrix needs."""
+
+    def __init__(self, blocks):
+        self.blocks = blocks
+        self.shape = (sum(b.shape[0] for b in blocks), blocks[0].shape[1])
+
+
+def _drain_data_iter(it, label, weight, base_margin):
+    """Pull every batch out of an xgboost.DataIter-style object: `it.next(input_data)` calls `input_data(data=...,
+    label=..., weight=..., base_margin=...)` once per batch and returns 0 at the end (matrix.py:166-196)."""
+    got = {"data": [], "label": [], "weight": [], "base_margin": []}
+
+    def input_data(data=None, label=None, weight=None, base_margin=None, **kw):
+        got["data"].append(np.asarray(data.values if hasattr(data, "values") and not isinstance(data, np.ndarray) else data))
+        for k, v in (("label", label), ("weight", weight), ("base_margin", base_margin)):
+            if v is not None:
+                got[k].append(np.asarray(v.values if hasattr(v, "values") and not isinstance(v, np.ndarray) else v).reshape(-1))
+
+    it.reset()
+    while it.next(input_data):
+        pass
+    if not got["data"]:
+        raise XGBoostError("the data iterator produced no batch")
+    cat = lambda k, given: given if given is not None else (np.concatenate(got[k]) if got[k] else None)  # noqa: E731
+    return got["data"], cat("label", label), cat("weight", weight), cat("base_margin", base_margin)
 
 
 class QuantileDMatrix(DMatrix):
@@ -427,6 +501,8 @@ class Booster:
         self.handle = 0
         self._train = None
         self._trees = []          # list of dict of numpy arrays (host copy for pickling / dumps)
+        self._cuts = None         # (ptrs, vals, mins, has_missing) of the matrix this model was trained on; travels with
+        #                           pickles (checkpoints) so that a restarted training quantises with the SAME cuts
         self._attrs = {}
         self.feature_names = None
         self.feature_types = None
@@ -456,7 +532,8 @@ class Booster:
         """Create the device booster bound to `dtrain` (quantising it if needed)."""
         old_trees = self.get_trees() if (self.handle or self._trees) else []
         self._free()
-        dtrain._ensure_quantized(int(self.params.get("max_bin", 256)))
+        dtrain._ensure_quantized(int(self.params.get("max_bin", 256)), cuts=self._cuts if old_trees else None)
+        self._cuts = dtrain.get_cuts()
         h = _H(0)
         _check(lib().B2_BoosterCreate(self._param_text(), dtrain.handle, _coll.handle, C.byref(h)))
         self.handle = h.value
@@ -775,7 +852,8 @@ class Booster:
                 sum_hess=np.asarray(t["sum_hessian"], np.float64)))
 
     def __getstate__(self):
-        return {"raw": bytes(self.save_raw()), "best_iteration": self.best_iteration, "best_score": self.best_score}
+        return {"raw": bytes(self.save_raw()), "best_iteration": self.best_iteration, "best_score": self.best_score,
+                "cuts": self._cuts}
 
     def __setstate__(self, state):
         self.params = {}
@@ -786,7 +864,9 @@ class Booster:
         self.feature_names = None
         self.feature_types = None
         self.n_features = None
+        self._cuts = None
         self.load_model(state["raw"])
+        self._cuts = state.get("cuts")
         self.best_iteration = state.get("best_iteration")
         self.best_score = state.get("best_score")
 
@@ -951,6 +1031,9 @@ def train(params, dtrain, num_boost_round=10, evals=(), obj=None, feval=None, ma
         bst._trees = list(src._trees)
         bst.n_features, bst.feature_names, bst.feature_types = src.n_features, src.feature_names, src.feature_types
         bst._attrs = dict(src._attrs)
+        # a restart after an actor failure (main.py sets _freeze_cuts on the unpickled checkpoint) continues with the
+        # cuts of the first attempt; a user-level continuation re-sketches the matrix it is given, like xgboost
+        bst._cuts = src._cuts if getattr(src, "_freeze_cuts", False) else None
         # The trees of the source model were fitted around ITS intercept: a continuation (checkpoint restart,
         # main.py:1211-1220) must keep it, also when the user gave no base_score and it was estimated from the labels.
         if bst.params.get("base_score") is None and bst._trees:

@@ -11,7 +11,12 @@ One shard maps to one GPU actor.  A shard is a dict of float32 numpy blocks (dat
 base_margin, ...), which is what the device upload consumes; the Ray object store of the reference
 is replaced by plain process-local references handed to the actor processes.
 """
+import atexit
+import copy
+import os
+import threading
 import uuid
+from concurrent.futures import ThreadPoolExecutor
 from enum import Enum
 from typing import Dict, Iterable, List, Optional, Sequence
 
@@ -56,6 +61,79 @@ def combine_data(sharding: RayShardingMode, data: Iterable) -> np.ndarray:
     for r, d in enumerate(data):
         out[r::len(data)] = d
     return out
+
+
+# ---- shard hand-off through /dev/shm (the role of ray.put / the plasma store, matrix.py:471-484): the driver writes
+# every shard ONCE, row-sliced straight out of the source array by several threads, into a memory-mapped .npy file; the
+# actor process maps the file read-only and uploads from it.  Nothing is pickled through a pipe.
+_SHM_FILES = set()
+_SHM_LOCK = threading.Lock()
+
+
+def _shm_dir() -> Optional[str]:
+    d = os.environ.get("B2_SHM_DIR", "/dev/shm")
+    return d if d and os.path.isdir(d) and os.access(d, os.W_OK) else None
+
+
+def _cleanup_shm():
+    with _SHM_LOCK:
+        files = list(_SHM_FILES)
+        _SHM_FILES.clear()
+    for f in files:
+        try:
+            os.unlink(f)
+        except OSError:
+            pass
+
+
+atexit.register(_cleanup_shm)
+_COPY_POOL = None
+
+
+def _copy_pool():
+    global _COPY_POOL
+    if _COPY_POOL is None:
+        _COPY_POOL = ThreadPoolExecutor(max_workers=max(1, min(32, (os.cpu_count() or 1))))
+    return _COPY_POOL
+
+
+def _parallel_copy(dst: np.ndarray, src: np.ndarray):
+    """dst[:] = src with the rows split over threads (numpy releases the GIL inside the copy loops)."""
+    n = len(dst)
+    if n == 0:
+        return
+    if dst.nbytes < (8 << 20):
+        np.copyto(dst, src, casting="unsafe")
+        return
+    pool = _copy_pool()
+    parts = pool._max_workers * 2
+    step = (n + parts - 1) // parts
+    list(pool.map(lambda i: np.copyto(dst[i:i + step], src[i:i + step], casting="unsafe"), range(0, n, step)))
+
+
+def _shared_copy(src: Optional[np.ndarray], tag: str):
+    """Copy `src` (any strided view) into a float32 .npy file under /dev/shm; returns (array view, ('shm', path)).
+    Without a usable /dev/shm the copy stays in process memory and travels by pickle."""
+    if src is None:
+        return None, None
+    d = _shm_dir()
+    if d is not None:
+        try:
+            st = os.statvfs(d)
+            if st.f_bavail * st.f_frsize < src.size * 4 + (64 << 20):
+                d = None
+        except OSError:
+            d = None
+    if d is None:
+        a = np.empty(src.shape, np.float32)
+        _parallel_copy(a, src)
+        return a, a
+    path = os.path.join(d, "b2x_%d_%s_%s.npy" % (os.getpid(), tag, uuid.uuid4().hex[:12]))
+    a = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=tuple(src.shape))
+    with _SHM_LOCK:
+        _SHM_FILES.add(path)
+    _parallel_copy(a, src)
+    return a, ("shm", path)
 
 
 def _column_or_array(frame: LoadedFrame, spec, exclude: set):
@@ -107,9 +185,11 @@ class RayDMatrix:
         if self.distributed:
             self.sharding = RayShardingMode.FIXED if sharding == RayShardingMode.FIXED else sharding
         self.refs: Dict[int, Dict[str, Optional[np.ndarray]]] = {}
+        self._shared: Dict[int, Dict] = {}      # rank -> {field: ('shm', path) | ndarray | None}: what an actor is sent
         self.n = None
         self.loaded = False
         self._columns = None
+        self._inferred_types = None             # feature types of pandas `category` columns ('c' / 'q')
         if num_actors is not None and not lazy:
             self.load_data(num_actors)
 
@@ -136,6 +216,12 @@ class RayDMatrix:
         lu = _column_or_array(frame, self.label_upper_bound, exclude)
         fw = None if self.feature_weights is None else np.asarray(self.feature_weights, np.float32)
         x = frame.drop(exclude) if exclude else frame
+        if x.feature_types is not None:
+            if not self.enable_categorical:
+                raise ValueError("The data has `category` columns. Pass `enable_categorical=True` to the RayDMatrix "
+                                 "(they are trained on as categorical features) or convert them to numbers first.")
+            if self.feature_types is None:
+                self._inferred_types = list(x.feature_types)
         return x, y, w, fw, b, ll, lu
 
     def load_data(self, num_actors: Optional[int] = None, rank: Optional[int] = None):
@@ -159,16 +245,23 @@ class RayDMatrix:
             ranks = [rank] if rank is not None else list(range(W))
             n_files = self.data_source.get_n(self.data)
             total = 0
+            cat = lambda parts: None if parts[0] is None else np.concatenate(parts)  # noqa: E731
             for r in ranks:
                 idx = list(range(n_files))[_get_sharding_indices(
                     RayShardingMode.INTERLEAVED if self.sharding != RayShardingMode.BATCH else RayShardingMode.BATCH,
                     r, W, n_files)]
-                frame = self.data_source.load_data(self.data, ignore=self.ignore, indices=idx, **self.kwargs)
-                x, y, w, fw, b, ll, lu = self._split(frame)
-                self._columns = x.columns
-                self.refs[r] = {"data": x.values, "label": y, "weight": w, "feature_weights": fw, "base_margin": b,
-                                "label_lower_bound": ll, "label_upper_bound": lu, "qid": None}
-                total += len(x)
+                # one row block per file (matrix.py:127-196: the shards of an actor stay separate and go to the device
+                # matrix one by one); only the small side columns are concatenated
+                parts = [self._split(self.data_source.load_data(self.data, ignore=self.ignore, indices=[i], **self.kwargs))
+                         for i in idx]
+                self._columns = parts[0][0].columns
+                blocks = [p[0].values for p in parts]
+                self.refs[r] = {"data": blocks if len(blocks) > 1 else blocks[0], "label": cat([p[1] for p in parts]),
+                                "weight": cat([p[2] for p in parts]), "feature_weights": parts[0][3],
+                                "base_margin": cat([p[4] for p in parts]), "label_lower_bound": cat([p[5] for p in parts]),
+                                "label_upper_bound": cat([p[6] for p in parts]), "qid": None}
+                self._shared[r] = dict(self.refs[r])
+                total += sum(len(b) for b in blocks)
             self.n = total if rank is None else self.n
             self.sharding = RayShardingMode.FIXED
         else:
@@ -185,10 +278,11 @@ class RayDMatrix:
             self._columns = x.columns
             for r in range(W):
                 sl = _get_sharding_indices(self.sharding, r, W, n)
-                sel = lambda a: None if a is None else np.ascontiguousarray(a[sl])  # noqa: E731
-                self.refs[r] = {"data": sel(x.values), "label": sel(y), "weight": sel(w), "feature_weights": fw,
-                                "base_margin": sel(b), "label_lower_bound": sel(ll), "label_upper_bound": sel(lu),
-                                "qid": None}
+                ref, shared = {"feature_weights": fw, "qid": None}, {"feature_weights": fw, "qid": None}
+                for name, a in (("data", x.values), ("label", y), ("weight", w), ("base_margin", b),
+                                ("label_lower_bound", ll), ("label_upper_bound", lu)):
+                    ref[name], shared[name] = _shared_copy(None if a is None else a[sl], "%x_%d_%s" % (self._uid & 0xffffffff, r, name))
+                self.refs[r], self._shared[r] = ref, shared
             self.n = n
         self.loaded = True
 
@@ -198,9 +292,36 @@ class RayDMatrix:
             self.load_data(num_actors=num_actors, rank=rank)
         return dict(self.refs[rank])
 
+    def get_shared(self, rank: int, num_actors: Optional[int] = None) -> Dict:
+        """What the actor of `rank` is sent: /dev/shm descriptors of its shard (arrays when /dev/shm is unusable)."""
+        self.get_data(rank, num_actors)
+        return dict(self._shared[rank])
+
+    def without_data(self) -> "RayDMatrix":
+        """Copy that carries the data SPEC only (file names, column names): what an actor needs to read its own files
+        (distributed loading, matrix.py:614-693)."""
+        m = copy.copy(self)
+        m.refs, m._shared, m.loaded = {}, {}, False
+        return m
+
     def unload_data(self):
-        self.refs = {}
+        for sh in self._shared.values():
+            for v in sh.values():
+                if isinstance(v, tuple) and len(v) == 2 and v[0] == "shm":
+                    with _SHM_LOCK:
+                        _SHM_FILES.discard(v[1])
+                    try:
+                        os.unlink(v[1])
+                    except OSError:
+                        pass
+        self.refs, self._shared = {}, {}
         self.loaded = False
+
+    def __del__(self):
+        try:
+            self.unload_data()
+        except Exception:
+            pass
 
     def update_matrix_properties(self, matrix):
         """numpy sources reset names to f0..fN (data_sources/numpy.py:21-23); frames keep theirs."""
