@@ -48,7 +48,7 @@ def test_train_predict_one_actor_matches_oracle(oracle, sharding):
     assert extra["total_n"] == len(y) and extra["training_time_s"] > 0
     assert len(res["train"]["logloss"]) == 6
     assert abs(res["train"]["logloss"][-1] - ob.metric("logloss", ob.margin, y)) < 1e-6
-    assert abs(res["train"]["error"][-1] - ob.metric("error", ob.margin, y)) < 1e-9
+    assert abs(res["train"]["error"][-1] - ob.metric("error", ob.margin, y)) < 1e-6   # the eval line carries 6 decimals
     p = predict(bst, RayDMatrix(x, sharding=mode), ray_params=RayParams(num_actors=1))
     assert p.shape == (len(y),)
     assert np.max(np.abs(p - ob.predict(x))) <= 1e-5
