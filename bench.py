@@ -279,6 +279,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-public-e2e", action="store_true", help="skip the end-to-end run through train(RayDMatrix, RayParams)")
     ap.add_argument("--profile", type=int, default=1, help="2 = per-phase CUDA-event timers (adds event records)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -405,10 +406,50 @@ def main():
             cpu = {"value": n_cpu / dt, "unit": "rounds/s", "cores": int(O.lib().or_num_threads()), "kind": "port",
                    "sample": "%d full-size rounds (%dx%d, depth %d) of the oracle port, float64 histograms, %.1fs" % (
                        n_cpu, args.rows, args.cols, args.depth, dt)}
+    # ================= e2e through the PUBLIC API (the call a user of the reference makes):
+    #   train(params, RayDMatrix(X, y), num_boost_round=K, ray_params=RayParams(num_actors=N))
+    # issued by rank 0 alone with the WHOLE matrix in host memory; it shards the rows, hands the shards to N actor
+    # processes (one per GPU), they upload, sketch, bin, train K rounds (per-round metric read back) and return the model.
+    # One untimed warm-up call on a small matrix starts the actor processes, their CUDA contexts and the communicator,
+    # the counterpart of the W warm-up steps of the device-resident arm (Ray keeps warm workers the same way).
+    e2e_public = None
+    if not args.no_e2e and not args.no_public_e2e:
+        del dm
+        torch.cuda.empty_cache()
+        cpu_group = dist.new_group(backend="gloo") if world > 1 else None
+        if rank == 0:
+            try:
+                from xgboost_ray_b200 import RayDMatrix, RayParams, main as M, train as ray_train
+                Xf, yf = (X, y) if world == 1 else synth_shard(args.rows, args.cols, 0, 1, workload=args.workload)
+                pub_params = {k: v for k, v in params.items() if k != "profile"}
+                nw = min(200_000, args.rows)
+                ray_train(pub_params, RayDMatrix(Xf[:nw], yf[:nw], **dm_kw), num_boost_round=3, verbose_eval=False,
+                          ray_params=RayParams(num_actors=world))
+                t0 = time.perf_counter()
+                dmat = RayDMatrix(Xf, yf, **dm_kw)
+                res, extra = {}, {}
+                bpub = ray_train(pub_params, dmat, num_boost_round=args.steps, evals=[(dmat, "train")], evals_result=res,
+                                 additional_results=extra, verbose_eval=False, ray_params=RayParams(num_actors=world))
+                pub_wall = time.perf_counter() - t0
+                e2e_public = {"value": args.steps / pub_wall, "unit": "rounds/s",
+                              "h2d_bytes_per_step": int((Xf.nbytes + yf.nbytes) / args.steps), "d2h_bytes_per_step": 8,
+                              "seconds_total": pub_wall, "seconds_in_train_call": extra.get("total_time_s"),
+                              "seconds_training_attempt": extra.get("training_time_s"),
+                              "api": "xgboost_ray_b200.train(params, RayDMatrix(X, y), num_boost_round=K, evals=[(dtrain, 'train')], "
+                                     "ray_params=RayParams(num_actors=%d)) -- whole host matrix in, Booster out; warm actor pool" % world,
+                              "trees": bpub.num_trees(), "final_train_metric": {k: v[-1] for k, v in res["train"].items()}}
+                M.shutdown_actors()
+            except Exception as exc:  # noqa: BLE001 -- the bench line must still be printed
+                e2e_public = {"error": repr(exc)[:500]}
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if e2e_public is not None and "value" in e2e_public:
+        # the headline end-to-end number is the public API; the engine-level number (what one actor does) stays beside it
+        e2e_engine, e2e = e2e, dict(e2e_public, engine_level=e2e)
     peak, peak_kind = measured_peak()
     # ncu --set full capture of one boosting round (C3): dram bytes per launch and the algorithmic bytes of the SAME launches
     traffic, traffic_alg = hist_traffic_per_launch() if args.workload == "C3" else (None, None)

@@ -16,7 +16,7 @@ def _dump(bst):
     return bst.get_dump(dump_format="json", with_stats=True)
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("sharding", ["INTERLEAVED", "BATCH"])
 def test_two_gpu_model_identical_to_one_gpu_and_oracle(oracle, sharding):
     if _ngpu() < 2:
@@ -47,7 +47,7 @@ def test_two_gpu_model_identical_to_one_gpu_and_oracle(oracle, sharding):
     assert np.max(np.abs(p2 - ob.predict(x))) <= 1e-5               # recombined in original row order
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 def test_two_gpu_toy_matrix(oracle):
     """test_end_to_end.py:162-211 on real GPUs: halves over-fit alone, two actors are exact."""
     if _ngpu() < 2:
@@ -61,7 +61,7 @@ def test_two_gpu_toy_matrix(oracle):
     assert bst.num_trees() == 8
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 def test_config_c1_breast_cancer_two_actors(oracle):
     """BASELINE config C1: breast_cancer, binary:logistic, tree_method=hist, RayParams(num_actors=2) -- here on
     two GPU actors; the model must equal the oracle's and the committed golden fixture's split sequence."""
@@ -89,7 +89,7 @@ def test_config_c1_breast_cancer_two_actors(oracle):
     assert res["train"]["logloss"][-1] < res["train"]["logloss"][0]
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 def test_two_gpu_categorical_identical_to_one_gpu_and_oracle(oracle):
     """Categorical splits (config C5's feature kind): the category-set candidates travel through the candidate
     allgather; 1 GPU, 2 GPUs and the oracle agree."""
@@ -122,7 +122,7 @@ def test_two_gpu_categorical_identical_to_one_gpu_and_oracle(oracle):
     assert np.max(np.abs(p2 - ob.predict(x))) <= 1e-5
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 def test_two_gpu_weighted_rows_identical_to_one_gpu_and_oracle(oracle):
     """Sample weights: weighted quantile sketch (integer rank sums, merged over the ranks) + weighted gradients."""
     if _ngpu() < 2:
@@ -145,7 +145,7 @@ def test_two_gpu_weighted_rows_identical_to_one_gpu_and_oracle(oracle):
         assert np.array_equal(t["split_cond"].view(np.uint32), o.split_cond.view(np.uint32))   # same (weighted) cuts
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 def test_two_gpu_custom_objective_and_metric():
     """test_xgboost_api.py:77-152 on two GPU actors: custom objective through B2_BoosterBoostOneIter, custom metric
     averaged over the actors (B2_CommAllReduce, xgboost's _allreduce_metric)."""
@@ -166,7 +166,7 @@ def test_two_gpu_custom_objective_and_metric():
     assert np.allclose(res1["dtrain"]["PyRMSLE"], res2["dtrain"]["PyRMSLE"], atol=0.1)
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 def test_two_gpu_exchange_paths_identical(oracle, exchange, monkeypatch):
     """The NVLink peer-memory exchange (default) and the NCCL reduce-scatter / allgather path give the same model as
@@ -199,7 +199,7 @@ def test_two_gpu_exchange_paths_identical(oracle, exchange, monkeypatch):
     M.shutdown_actors()
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(300)
 def test_two_gpu_actor_killed_restart_and_elastic_continuation(oracle, tmp_path):
     """test_fault_tolerance.py:401-444 with two GPU actors: rank 1 is killed at round 7 while rank 0 waits for it in the
     histogram exchange -> the stop event aborts the communicator, the dead actor is restarted, training continues from

@@ -35,7 +35,10 @@ def make_data(n, f, seed, kind="uniform", nan_frac=0.0):
 
 
 # ------------------------------------------------------------------ histogram kernel (a10)
-@pytest.mark.parametrize("n,f", [(1, 1), (17, 3), (1000, 28), (5000, 100), (3000, 50), (2000, 200), (4097, 33)])
+# F = 32 a + r with 0 < r <= 16 puts the r leftover features into a NARROW last group (one lane per row, pow2ceil(r) steps,
+# 32 / w shared-memory replicas): widths 1, 2, 4, 8, 16 alone and behind full groups are all covered here
+@pytest.mark.parametrize("n,f", [(1, 1), (17, 3), (1000, 28), (5000, 100), (3000, 50), (2000, 200), (4097, 33),
+                                 (3001, 2), (2500, 34), (3000, 12), (777, 16), (2000, 48), (1500, 7), (6000, 104)])
 def test_hist_kernel_bit_exact(eng, oracle, n, f):
     rng = np.random.RandomState(n + f)
     bins = rng.randint(0, 256, size=(n, f)).astype(np.uint8)
@@ -95,7 +98,8 @@ def test_hist_kernel_variants_bit_exact(oracle):
         "        ref = O.hist_int(bins, qg, qh, ridx); got, _ = E.hist_build_raw(bins, qg, qh, ridx=ridx, window_rows=4096, chunk_rows=2048)\n"
         "        assert np.array_equal(ref, got), (f, ridx is None)\n"
         "print('variant ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for env in ({"B2_HIST_TMA": "1"}, {"B2_HIST_VARIANT": "0"}, {"B2_HIST_VARIANT": "1"}, {"B2_HIST_VARIANT": "2"}):
+    for env in ({"B2_HIST_TMA": "1"}, {"B2_HIST_VARIANT": "0"}, {"B2_HIST_VARIANT": "1"}, {"B2_HIST_VARIANT": "2"},
+                {"B2_HIST_VARIANT": "3"}, {"B2_HIST_NARROW": "0"}, {"B2_HIST_VARIANT": "2", "B2_HIST_NARROW": "0"}):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
 
@@ -575,3 +579,41 @@ def test_custom_objective_known_answer_single_process(eng):
     assert list(np.round(bst.predict(eng.DMatrix(x)))) == list(y)
     assert len(res["dtrain"]["PyRMSLE"]) == 10 and res["dtrain"]["PyRMSLE"][-1] < res["dtrain"]["PyRMSLE"][0]
     assert eng.collective.allreduce([1.0, 2.0]).tolist() == [1.0, 2.0]      # no communicator: identity
+
+
+def _auc_ref(p, y, w=None):
+    """xgboost BinaryROCAUC: descending predictions, ties form one step, trapezoids."""
+    p = np.asarray(p, np.float64); y = np.asarray(y, np.float64)
+    w = np.ones_like(y) if w is None else np.asarray(w, np.float64)
+    order = np.argsort(-p, kind="stable")
+    p, y, w = p[order], y[order], w[order]
+    tp = np.cumsum(y * w); fp = np.cumsum((1 - y) * w)
+    ends = np.nonzero(np.append(p[1:] != p[:-1], True))[0]
+    tp_e, fp_e = np.concatenate([[0.0], tp[ends]]), np.concatenate([[0.0], fp[ends]])
+    area = np.sum((fp_e[1:] - fp_e[:-1]) * (tp_e[1:] + tp_e[:-1]) * 0.5)
+    return area / (fp[-1] * tp[-1])
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_auc_metric(eng, weighted):
+    """`auc` (the metric of the reference's ranking / sklearn tests): equals the trapezoid AUC of the
+    transformed predictions, with ties and sample weights; early stopping maximises it."""
+    rng = np.random.RandomState(4)
+    n, f = 30000, 8
+    X = np.round(rng.uniform(0, 10, size=(n, f)), 1).astype(np.float32)        # coarse values: many tied predictions
+    y = (X[:, 0] + X[:, 1] + rng.normal(scale=3.0, size=n) > 10).astype(np.float32)
+    w = rng.gamma(2.0, 1.0, size=n).astype(np.float32) if weighted else None
+    params = {"objective": "binary:logistic", "max_depth": 3, "eta": 0.3, "base_score": 0.5, "eval_metric": ["logloss", "auc"]}
+    dm = eng.DMatrix(X, label=y, weight=w)
+    Xv, yv = X[: n // 3] + np.float32(0.05), y[: n // 3]
+    dv = eng.DMatrix(Xv, label=yv, weight=None if w is None else w[: n // 3])
+    res = {}
+    bst = eng.train(params, dm, num_boost_round=5, evals=[(dm, "train"), (dv, "valid")], evals_result=res, verbose_eval=False)
+    assert abs(res["train"]["auc"][-1] - _auc_ref(bst.predict(eng.DMatrix(X)), y, w)) < 2e-6
+    assert abs(res["valid"]["auc"][-1] - _auc_ref(bst.predict(eng.DMatrix(Xv)), yv, None if w is None else w[: n // 3])) < 2e-6
+    assert res["train"]["auc"][-1] > res["train"]["auc"][0] > 0.5
+    one = eng.DMatrix(X[:100], label=np.ones(100, np.float32))
+    assert abs(float(bst.eval(one).split("auc:")[-1]) - 0.5) < 1e-9            # a single class: 0.5
+    bst2 = eng.train(dict(params, eval_metric="auc"), dm, num_boost_round=50, evals=[(dv, "valid")], early_stopping_rounds=3,
+                     verbose_eval=False)
+    assert bst2.best_iteration is not None and bst2.best_score >= 0.5

@@ -72,7 +72,7 @@ def test_multiclass_toy_matrix_through_public_api():
     assert p.shape == (32, 4) and list(np.argmax(p, axis=1)) == list(y)
 
 
-@pytest.mark.timeout(900)
+@pytest.mark.timeout(420)
 def test_actor_killed_restart_from_checkpoint_equals_uninterrupted(oracle, tmp_path):
     """test_fault_tolerance.py:401-444 on the GPU: kill -9 the actor at round 7, the driver restarts it and training
     continues from checkpoint 5; the trees equal those of an uninterrupted run and of the oracle.  No base_score is
@@ -105,11 +105,10 @@ def test_stop_event_interrupts_actor_training():
     from xgboost_ray_b200 import RayDMatrix, RayParams
     from xgboost_ray_b200 import main as M
     x, y = _data(seed=5, n=50000, f=20)
-    ctx = mp.get_context("spawn")
-    queue, stop_event = ctx.Queue(), ctx.Event()
+    stop_event = M._StopFlag(mp.get_context("spawn"))
     rp = M._validate_ray_params(RayParams(num_actors=1))
     _, rp.gpus_per_actor = M._autodetect_resources(rp)
-    actors = M._create_actors(rp, queue, stop_event)
+    actors = M._create_actors(rp, stop_event)
     try:
         d = RayDMatrix(x, y)
         d.load_data(1)

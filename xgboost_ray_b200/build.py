@@ -25,6 +25,7 @@ SOURCES = {
     "control_kernel.cu": ["--fmad=false"],
     "objective_kernel.cu": ["--fmad=false"],   # bit-exact gradients vs the oracle
     "sketch.cu": ["--fmad=false"],
+    "auc_kernel.cu": ["--fmad=false"],
     "p2p_exchange.cu": [],                     # NVLink peer-memory histogram exchange
     "engine.cu": [],
 }

@@ -30,7 +30,7 @@
 // ---------------------------------------------------------------- kernel launchers (other TUs)
 extern "C" {
 int b2_launch_hist(const uint8_t*, int, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
-                   const B2LevelCtl*, int, int, int, cudaStream_t);
+                   const B2LevelCtl*, int, int, int, int, cudaStream_t);
 int b2_make_bins_tensor_map(void*, const uint8_t*, int64_t, int, int);
 int b2_launch_hist_tma(const void*, const void*, const int2*, const int32_t*, const B2HistWork*, int, int, int, int, int, long long*,
                        const B2LevelCtl*, int, int, int64_t, int, cudaStream_t);
@@ -83,6 +83,8 @@ int b2_launch_metric(int, int, int, const float*, const float*, const float*, in
 int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, const int32_t*, const uint32_t*, int, int, int,
                       float*, int, cudaStream_t);
 int b2_launch_fill(float*, int64_t, float, int, cudaStream_t);
+size_t b2_auc_temp_bytes(int64_t);
+int b2_auc_binary(const float*, const float*, const float*, int64_t, void*, size_t, double*, int, cudaStream_t);
 int b2_launch_transform(int, int, float*, int64_t, int, cudaStream_t);
 int b2_extract_batch();
 int b2_launch_extract_keys(const float*, int64_t, int, int, int, float, uint32_t*, int64_t, int, cudaStream_t);
@@ -150,20 +152,84 @@ Ctx* get_ctx(int device) {
   return c;
 }
 
+// Device memory goes through a small caching pool: matrices and boosters allocate and free the same few large blocks
+// over and over (every DMatrix, every sketch), cudaFree synchronises the device, and once a peer's buffers are mapped
+// for the NVLink exchange every cudaMalloc also has to be mapped into the peers (measured: the second quantisation of
+// a bench run took 0.28 s with peer mappings against 0.06 s without).  Freed blocks are kept per device and handed out
+// again when their size fits (<= 25 % + 1 MiB slack); the cache is bounded by B2_POOL_MAX_GB (default 48) and emptied
+// when an allocation fails.
+struct DevPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached = 0;
+};
+DevPool g_dev_pool[64];
+size_t pool_cap_bytes() {
+  static size_t cap = 0;
+  if (!cap) { const char* e = getenv("B2_POOL_MAX_GB"); double gb = e ? atof(e) : 48.0; cap = (size_t)(gb < 0 ? 0 : gb * 1e9) + 1; }
+  return cap;
+}
+void pool_trim(DevPool& pool, size_t keep) {   // caller holds pool.mu
+  while (pool.cached > keep && !pool.free_blocks.empty()) {
+    auto it = std::prev(pool.free_blocks.end());   // largest first
+    cudaFree(it->second);
+    pool.cached -= it->first;
+    pool.free_blocks.erase(it);
+  }
+}
+void* pool_alloc(size_t bytes, size_t* got, int* dev_out) {
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  *dev_out = dev;
+  bytes = (bytes + 511) & ~(size_t)511;
+  DevPool& pool = g_dev_pool[dev];
+  {
+    std::lock_guard<std::mutex> lk(pool.mu);
+    auto it = pool.free_blocks.lower_bound(bytes);
+    if (it != pool.free_blocks.end() && it->first <= bytes + bytes / 4 + ((size_t)1 << 20)) {
+      void* p = it->second; *got = it->first;
+      pool.cached -= it->first;
+      pool.free_blocks.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {   // out of memory: give the cached blocks back and try once more
+    cudaGetLastError();
+    { std::lock_guard<std::mutex> lk(pool.mu); pool_trim(pool, 0); }
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); fail("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); }
+  *got = bytes;
+  return p;
+}
+void pool_free(void* p, size_t bytes, int dev) {
+  if (!p) return;
+  if (dev < 0 || dev >= 64) dev = 0;
+  DevPool& pool = g_dev_pool[dev];
+  std::lock_guard<std::mutex> lk(pool.mu);
+  if (bytes > pool_cap_bytes()) { cudaFree(p); return; }
+  pool.free_blocks.emplace(bytes, p);
+  pool.cached += bytes;
+  if (pool.cached > pool_cap_bytes()) pool_trim(pool, pool_cap_bytes() / 2);
+}
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  size_t cap = 0;
+  size_t cap = 0;          // elements the caller may use
+  size_t block_bytes = 0;  // size of the pooled block behind p
+  int dev = 0;
   void ensure(size_t n) {
     if (n <= cap) return;
-    if (p) cudaFree(p);
-    p = nullptr;
-    size_t want = n;
-    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
-    if (e != cudaSuccess) { cap = 0; fail("cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e)); }
-    cap = want;
+    release();
+    size_t got = 0;
+    p = (T*)pool_alloc(n * sizeof(T), &got, &dev);
+    block_bytes = got;
+    cap = n;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) pool_free(p, block_bytes, dev); p = nullptr; cap = 0; block_bytes = 0; }
   ~DevBuf() { release(); }
 };
 
@@ -329,6 +395,7 @@ struct Matrix : HandleBase {
   int64_t col_stride = 0;
   bool quantized = false;
   int n_groups = 0, row_stride = 0, max_bin = 0;
+  int narrow_w = 0;                   // > 0: the last group is narrow (<= 16 features, width rounded up to a power of two)
   std::vector<int32_t> group_first, group_size, feat_byte;
   std::vector<int32_t> cut_ptrs;
   std::vector<float> cut_vals, min_vals;
@@ -346,18 +413,29 @@ struct Matrix : HandleBase {
   DevBuf<uint32_t> d_fwq;
 };
 
+// Feature -> (group, slot) layout of the bin matrix.  F = 32 a + r: when 0 < r <= 16 the first `a` groups are full and
+// the r leftover features form a NARROW last group, which the histogram kernel processes one lane per row in
+// pow2ceil(r) steps instead of two lanes in 16 (hist_kernel.cu, v3) -- F = 100 then costs 6.25 shared-atomic wavefronts
+// per row instead of 8.  Otherwise the features are spread evenly over ceil(F / 32) groups.  B2_HIST_NARROW=0 keeps the
+// even layout of round 1.
 void setup_groups(Matrix* m) {
   const int F = m->F;
+  static int narrow_on = -1;
+  if (narrow_on < 0) { const char* e = getenv("B2_HIST_NARROW"); narrow_on = (e && atoi(e) == 0) ? 0 : 1; }
   m->n_groups = (F + B2_GROUP_SLOTS - 1) / B2_GROUP_SLOTS;
   if (m->n_groups < 1) m->n_groups = 1;
   m->row_stride = m->n_groups * B2_GROUP_SLOTS;
   m->group_first.assign(m->n_groups, 0);
   m->group_size.assign(m->n_groups, 0);
   m->feat_byte.assign(F, 0);
+  m->narrow_w = 0;
+  const int r = F % B2_GROUP_SLOTS;
+  const bool narrow = narrow_on && r > 0 && r <= 16;
+  if (narrow) { m->narrow_w = 1; while (m->narrow_w < r) m->narrow_w <<= 1; }
   const int base = F / m->n_groups, rem = F % m->n_groups;
   int f = 0;
   for (int g = 0; g < m->n_groups; ++g) {
-    const int sz = base + (g < rem ? 1 : 0);
+    const int sz = narrow ? (g + 1 < m->n_groups ? B2_GROUP_SLOTS : r) : base + (g < rem ? 1 : 0);
     m->group_first[g] = f; m->group_size[g] = sz;
     for (int s = 0; s < sz; ++s) m->feat_byte[f + s] = g * B2_GROUP_SLOTS + s;
     f += sz;
@@ -1079,7 +1157,7 @@ void grow_tree(Booster* b, int k, int slot, TreeStats& st) {
                                         build_target(b, b->hist[0].p), nullptr, sh, 1, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, nullptr, b->d_hist_work.p, 1, chunks, chunk_rows, window, G,
-                                    build_target(b, b->hist[0].p), nullptr, sh, 1, ctx->num_sms, s));
+                                    build_target(b, b->hist[0].p), nullptr, sh, 1, m->narrow_w, ctx->num_sms, s));
       record_hist_launch(b, st, e0, e1, false);
       st.hist_launches++; st.kernel_launches++;
     }
@@ -1168,7 +1246,7 @@ void grow_tree(Booster* b, int k, int slot, TreeStats& st) {
                                         max_nodes_level, n, ctx->num_sms, s));
       else
         LAUNCH_CHECK(b2_launch_hist(m->bins.p, m->row_stride, b->q.p, b->ridx[nxt].p, b->d_hist_work.p, 0, 0, 0, window, G, tgt,
-                                    ctl + nxt, sh, max_nodes_level, ctx->num_sms, s));
+                                    ctl + nxt, sh, max_nodes_level, m->narrow_w, ctx->num_sms, s));
       record_hist_launch(b, st, e0, e1, false);
       st.hist_launches++; st.kernel_launches++;
       mark_phase(b, 1);
@@ -1461,7 +1539,8 @@ int metric_id(const char* name) {
   if (s == "mlogloss") return 3;
   if (s == "merror") return 4;
   if (s == "mae") return 5;
-  fail("unsupported eval metric '%s' (supported: rmse, mae, logloss, error, mlogloss, merror)", s.c_str());
+  if (s == "auc") return 6;
+  fail("unsupported eval metric '%s' (supported: rmse, mae, logloss, error, auc, mlogloss, merror)", s.c_str());
 }
 
 // margin of matrix m under the current model (cached per matrix, only new trees are applied)
@@ -1798,6 +1877,24 @@ int B2_BoosterEvalSet(B2Handle bh, B2Handle mh, const char* metric, double* out)
   CUDA_CHECK(cudaMemsetAsync(b->d_metric.p, 0, 2 * sizeof(double), s));
   if ((mid == 3 || mid == 4) != (b->p.objective == kObjSoftprob))
     fail("metric '%s' does not fit objective '%s'", metric, b->p.objective_name.c_str());
+  if (mid == 6) {
+    // binary ROC AUC on the transformed prediction (auc_kernel.cu): local (area, fp*tp) pairs summed over the workers
+    if (b->p.objective == kObjSoftprob) fail("metric 'auc' is implemented for binary labels (binary:logistic / regression scores) only");
+    DevBuf<float> pred; DevBuf<uint8_t> tmp;
+    const size_t rows = (size_t)std::max<int64_t>(m->n, 1);
+    pred.ensure(rows);
+    if (m->n > 0) CUDA_CHECK(cudaMemcpyAsync(pred.p, margin, (size_t)m->n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    LAUNCH_CHECK(b2_launch_transform(b->p.objective, 1, pred.p, m->n, b->ctx->num_sms, s));
+    const size_t tb = b2_auc_temp_bytes(m->n);
+    tmp.ensure(tb);
+    LAUNCH_CHECK(b2_auc_binary(pred.p, m->label.p, m->n_weight ? m->weight.p : nullptr, m->n, tmp.p, tb, b->d_metric.p, b->ctx->num_sms, s));
+    allreduce(b->comm, b->d_metric.p, 2, kNcclFloat64, kNcclSum, s);
+    double h[2];
+    CUDA_CHECK(cudaMemcpyAsync(h, b->d_metric.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    *out = h[1] > 0 ? h[0] / h[1] : 0.5;   // only one class present: xgboost reports 0.5
+    return 0;
+  }
   LAUNCH_CHECK(b2_launch_metric(b->p.objective, mid, b->p.num_class, margin, m->label.p, m->n_weight ? m->weight.p : nullptr, m->n, b->d_metric.p,
                                 b->ctx->num_sms, s));
   allreduce(b->comm, b->d_metric.p, 2, kNcclFloat64, kNcclSum, s);
@@ -1994,7 +2091,7 @@ int B2_HistBuildRaw(const uint8_t* bins, int64_t n_rows, int32_t n_cols, const i
                                       d_hist.p, nullptr, 0, 1, n_rows, ctx->num_sms, s));
     else
       LAUNCH_CHECK(b2_launch_hist(d_bins.p, m.row_stride, d_gp.p, ridx ? d_ridx.p : nullptr, d_work.p, 1, chunks, chunk_rows,
-                                  window_rows, m.n_groups, d_hist.p, nullptr, 0, 1, ctx->num_sms, s));
+                                  window_rows, m.n_groups, d_hist.p, nullptr, 0, 1, m.narrow_w, ctx->num_sms, s));
   }
   CUDA_CHECK(cudaEventRecord(e1, s));
   std::vector<long long> h(node_elems);

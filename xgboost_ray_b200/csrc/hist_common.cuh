@@ -95,8 +95,10 @@ struct HistTarget {
   int node_cap;               // node slots per shard in this launch's buffer
   int n_groups;
 };
-__device__ __forceinline__ size_t target_index(const HistTarget& t, int node_slot, int group, int e) {
-  const int bin = e >> 6, plane = (e >> 5) & 1, slot = e & 31;
+// slot_mask = 31 for a full group; w - 1 for a narrow group of width w (its shared-memory histogram holds 32 / w
+// replicas of the w slots side by side, all of which fold onto the same global cell here)
+__device__ __forceinline__ size_t target_index(const HistTarget& t, int node_slot, int group, int e, int slot_mask = 31) {
+  const int bin = e >> 6, plane = (e >> 5) & 1, slot = e & 31 & slot_mask;
   const int shards = 1 << t.log2_shards, sp = B2_GROUP_SLOTS >> t.log2_shards;
   const int r = slot & (shards - 1), sl = slot >> t.log2_shards;
   const size_t slice_elems = (size_t)t.n_groups * 2 * B2_BINS * sp;
@@ -106,24 +108,24 @@ __device__ __forceinline__ size_t target_index(const HistTarget& t, int node_slo
 // lazy window flush: only cells whose magnitude reached 2^30 are moved to the global histogram.  Called
 // (between barriers) at least every `window_rows` = 2^(30 - qbits) rows, during which a cell can grow by
 // less than 2^30, so no int32 cell can overflow; for well spread bins nothing is flushed at all.
-__device__ __forceinline__ void flush_large_cells(int32_t* s_hist, const HistTarget& t, int node_slot, int group) {
+__device__ __forceinline__ void flush_large_cells(int32_t* s_hist, const HistTarget& t, int node_slot, int group, int slot_mask = 31) {
   for (int e = threadIdx.x * 4; e < B2_GROUP_ELEMS; e += blockDim.x * 4) {
     const int4 v = *reinterpret_cast<const int4*>(s_hist + e);
     const int vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (vv[k] >= (1 << 30) || vv[k] <= -(1 << 30)) {
-        atomicAdd(t.base + target_index(t, node_slot, group, e + k), (unsigned long long)(long long)vv[k]);
+        atomicAdd(t.base + target_index(t, node_slot, group, e + k, slot_mask), (unsigned long long)(long long)vv[k]);
         s_hist[e + k] = 0;
       }
     }
   }
 }
 // node flush: shared int32 partial sums -> global int64 histogram (RED.64), cells are left zeroed
-__device__ __forceinline__ void flush_planes(int32_t* s_hist, const HistTarget& t, int node_slot, int group) {
+__device__ __forceinline__ void flush_planes(int32_t* s_hist, const HistTarget& t, int node_slot, int group, int slot_mask = 31) {
   for (int e = threadIdx.x; e < B2_GROUP_ELEMS; e += blockDim.x) {
     const long long v = s_hist[e];
-    if (v != 0) { atomicAdd(t.base + target_index(t, node_slot, group, e), (unsigned long long)v); s_hist[e] = 0; }
+    if (v != 0) { atomicAdd(t.base + target_index(t, node_slot, group, e, slot_mask), (unsigned long long)v); s_hist[e] = 0; }
   }
 }
 

@@ -23,7 +23,7 @@
 #include "hist_common.cuh"
 
 #ifndef B2_HIST_DEFAULT_VARIANT
-#define B2_HIST_DEFAULT_VARIANT 2
+#define B2_HIST_DEFAULT_VARIANT 3
 #endif
 
 namespace b2 {
@@ -145,6 +145,203 @@ hist_build_kernel(const uint8_t* __restrict__ bins, int row_stride, const int2* 
   }
 }
 
+// ================================================================ v3: group pairs with a narrow last group
+// F = 32 a + r features are laid out as `a` full groups plus, when 0 < r <= 16, one NARROW group of w = pow2ceil(r)
+// slots (engine.cu setup_groups).  A full group costs 2 shared-atomic wavefronts per row (32 slots x 2 planes / 32
+// lanes); the r leftover features used to cost as much as a full group of 32 (F = 100 spent 22 % of its atomics on
+// padding slots).  A narrow group keeps 32 / w replicas of its w slots side by side in its 64 KiB plane pair:
+// lane l adds to replica l / w and walks the slots rotated by l % w, so one lane handles one ROW and the 32 lanes of
+// a warp still hit 32 different banks -- w steps for 32 rows, i.e. w / 16 wavefronts per row.
+// A CTA type = one pair of groups; types get CTAs in proportion to their cost (B2HistPlan), every type walks the
+// whole chunk list with its own number of streams.
+
+template <int W>
+struct NarrowBytes {   // the W bin bytes of one row, rotated so that step j reads byte j
+  uint32_t w[W >= 4 ? W / 4 : 1];
+};
+template <int W>
+__device__ __forceinline__ NarrowBytes<W> load_narrow(const uint8_t* __restrict__ p, int rot) {
+  NarrowBytes<W> r;
+  if constexpr (W == 16) {
+    uint4 v = rotate_bytes(ldg_nc_v4(p), rot);
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  } else if constexpr (W == 8) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    uint32_t a = v.x, b = v.y;
+    if (rot & 4) { uint32_t t = a; a = b; b = t; }
+    const int bs = (rot & 3) * 8;
+    r.w[0] = __funnelshift_r(a, b, bs); r.w[1] = __funnelshift_r(b, a, bs);
+  } else if constexpr (W == 4) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+    r.w[0] = __funnelshift_r(v, v, (rot & 3) * 8);
+  } else if constexpr (W == 2) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint16_t*>(p));
+    r.w[0] = (rot & 1) ? ((v >> 8) | ((v & 0xffu) << 8)) : v;
+  } else {
+    r.w[0] = __ldg(p);
+  }
+  return r;
+}
+
+// one narrow group, rows [0, nrows) of a chunk: lane = row, W steps
+template <bool kGather, int W>
+__device__ __forceinline__ void narrow_pass(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                                            const int32_t* __restrict__ ridx, int64_t pos0, int nrows, int byte_off,
+                                            uint32_t smem_g, int lane, int warp, int n_warps) {
+  const int rot = lane & (W - 1), rep = lane / W;
+  const uint32_t base = smem_g + (uint32_t)(rep * W) * 4u;
+  // two-stage register pipeline over the warp's rows (warp-uniform trip count)
+  int r = warp * 32 + lane;
+  int64_t rid = r < nrows ? (kGather ? (int64_t)__ldg(ridx + pos0 + r) : pos0 + r) : -1;
+  NarrowBytes<W> cur; int2 gp = make_int2(0, 0);
+#pragma unroll
+  for (int k = 0; k < (W >= 4 ? W / 4 : 1); ++k) cur.w[k] = 0;
+  if (rid >= 0) { cur = load_narrow<W>(bins + rid * row_stride + byte_off, rot); gp = __ldg(gpair + rid); }
+  for (int r0 = warp * 32; r0 < nrows; r0 += n_warps * 32) {
+    const int rn = r0 + n_warps * 32 + lane;
+    const int64_t rid_n = rn < nrows ? (kGather ? (int64_t)__ldg(ridx + pos0 + rn) : pos0 + rn) : -1;
+    NarrowBytes<W> nxt; int2 gpn = make_int2(0, 0);
+#pragma unroll
+    for (int k = 0; k < (W >= 4 ? W / 4 : 1); ++k) nxt.w[k] = 0;
+    if (rid_n >= 0) { nxt = load_narrow<W>(bins + rid_n * row_stride + byte_off, rot); gpn = __ldg(gpair + rid_n); }
+    if (rid >= 0) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const uint32_t bin256 = __byte_perm(cur.w[j >> 2], 0u, 0x4404u | ((uint32_t)(j & 3) << 4));
+        const uint32_t a = base + bin256 + (((uint32_t)(j + rot)) & (uint32_t)(W - 1)) * 4u;
+        red_shared_add(a, gp.x);
+        red_shared_add(a + B2_GROUP_SLOTS * 4, gp.y);
+      }
+    }
+    rid = rid_n; cur = nxt; gp = gpn;
+  }
+}
+
+// full groups of a CTA, rows [0, nrows) of a chunk: kGPC = 2 -> four lanes cover the 64 contiguous bytes of the pair,
+// kGPC = 1 -> two lanes cover the 32 bytes of the single group (the register pipeline of hist_build_kernel)
+template <bool kGather, int kGPC>
+__device__ __forceinline__ void full_pass(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                                          const int32_t* __restrict__ ridx, int64_t pos0, int nrows, int group0,
+                                          uint32_t smem_base, int lane, int warp, int n_warps) {
+  constexpr int kLanesPerRow = 2 * kGPC;
+  constexpr int kRowsPerWarp = 32 / kLanesPerRow;
+  const int sub = lane / kLanesPerRow, gsel = (lane % kLanesPerRow) >> 1, half = lane & 1;
+  const int rot = sub * kGPC + gsel;
+  const int lane_byte_off = (group0 + gsel) * 32 + half * 16;
+  const uint32_t smem_g = smem_base + gsel * (B2_GROUP_ELEMS * 4);
+  const int iter_rows = n_warps * kRowsPerWarp;
+  const int rbase = warp * kRowsPerWarp;
+  const int r0 = rbase + sub;
+  int64_t id0 = fetch_rid<kGather>(ridx, pos0, r0, nrows);
+  int64_t id1 = fetch_rid<kGather>(ridx, pos0, r0 + iter_rows, nrows);
+  int64_t id2 = fetch_rid<kGather>(ridx, pos0, r0 + 2 * iter_rows, nrows);
+  RowData s0 = load_row_id(bins, gpair, id0, row_stride, lane_byte_off);
+  id0 = fetch_rid<kGather>(ridx, pos0, r0 + 3 * iter_rows, nrows);
+  RowData s1 = load_row_id(bins, gpair, id1, row_stride, lane_byte_off);
+  id1 = fetch_rid<kGather>(ridx, pos0, r0 + 4 * iter_rows, nrows);
+  RowData s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
+  id2 = fetch_rid<kGather>(ridx, pos0, r0 + 5 * iter_rows, nrows);
+  for (int r = rbase; r < nrows; r += 3 * iter_rows) {   // warp-uniform trip count
+    accumulate_row(s0, smem_g, rot, half);
+    s0 = load_row_id(bins, gpair, id0, row_stride, lane_byte_off);
+    id0 = fetch_rid<kGather>(ridx, pos0, r + sub + 6 * iter_rows, nrows);
+    if (r + iter_rows < nrows) accumulate_row(s1, smem_g, rot, half);
+    s1 = load_row_id(bins, gpair, id1, row_stride, lane_byte_off);
+    id1 = fetch_rid<kGather>(ridx, pos0, r + sub + 7 * iter_rows, nrows);
+    if (r + 2 * iter_rows < nrows) accumulate_row(s2, smem_g, rot, half);
+    s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
+    id2 = fetch_rid<kGather>(ridx, pos0, r + sub + 8 * iter_rows, nrows);
+  }
+}
+
+template <bool kGather>
+__device__ __forceinline__ void narrow_dispatch(int w, const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                                                const int32_t* __restrict__ ridx, int64_t pos0, int nrows, int byte_off,
+                                                uint32_t smem_g, int lane, int warp, int n_warps) {
+  switch (w) {
+    case 16: narrow_pass<kGather, 16>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_g, lane, warp, n_warps); break;
+    case 8: narrow_pass<kGather, 8>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_g, lane, warp, n_warps); break;
+    case 4: narrow_pass<kGather, 4>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_g, lane, warp, n_warps); break;
+    case 2: narrow_pass<kGather, 2>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_g, lane, warp, n_warps); break;
+    default: narrow_pass<kGather, 1>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_g, lane, warp, n_warps); break;
+  }
+}
+
+template <bool kGather>
+__global__ void __launch_bounds__(1024, 1)
+hist_build_kernel_v3(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                     const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
+                     int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
+                     const B2LevelCtl* __restrict__ ctl, int log2_shards, int node_cap, B2HistPlan plan) {
+  HistTarget target; target.base = (unsigned long long*)hist; target.log2_shards = log2_shards; target.node_cap = node_cap;
+  target.n_groups = n_groups;
+  if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
+  extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][2][32]
+  int type = 0, cta0 = 0, cta1 = plan.cta_begin[1];
+#pragma unroll
+  for (int t = 1; t < B2_HIST_MAX_TYPES; ++t)   // constant indices: the plan stays in the parameter bank
+    if (t < plan.n_types && (int)blockIdx.x >= plan.cta_begin[t]) { type = t; cta0 = plan.cta_begin[t]; cta1 = plan.cta_begin[t + 1]; }
+  const int stream = (int)blockIdx.x - cta0;
+  const int n_streams = cta1 - cta0;
+  if (total_chunks <= 0 || n_streams <= 0) return;
+  const int g0 = 2 * type, g1 = g0 + 1;
+  const bool has1 = g1 < n_groups;
+  const bool narrow0 = plan.narrow_w > 0 && g0 == n_groups - 1;            // the pair is the narrow group alone
+  const bool narrow1 = has1 && plan.narrow_w > 0 && g1 == n_groups - 1;    // full group + narrow group
+  const int mask0 = narrow0 ? plan.narrow_w - 1 : 31, mask1 = narrow1 ? plan.narrow_w - 1 : 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(s_hist);
+
+  for (int e = threadIdx.x; e < 2 * B2_GROUP_ELEMS; e += blockDim.x) s_hist[e] = 0;
+  __syncthreads();
+
+  int cur = -1;          // work index whose partial sums are in shared memory
+  int rows_in_window = 0;
+  const int c_begin = (int)(((long long)stream * total_chunks) / n_streams);
+  const int c_end = (int)(((long long)(stream + 1) * total_chunks) / n_streams);
+  for (int chunk = c_begin; chunk < c_end; ++chunk) {
+    int lo = 0, hi = n_work - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const int w = lo;
+    const int seg_begin = __ldg(&work[w].seg_begin), seg_count = __ldg(&work[w].seg_count);
+    const int row0 = (chunk - __ldg(&work[w].chunk_begin)) * chunk_rows;
+    const int nrows = min(chunk_rows, seg_count - row0);
+    if (cur >= 0 && w != cur) {
+      __syncthreads();
+      flush_planes(s_hist, target, __ldg(&work[cur].hist_index), g0, mask0);
+      if (has1) flush_planes(s_hist + B2_GROUP_ELEMS, target, __ldg(&work[cur].hist_index), g1, mask1);
+      __syncthreads();
+      rows_in_window = 0;
+    } else if (cur >= 0 && rows_in_window + nrows > window_rows) {
+      __syncthreads();
+      flush_large_cells(s_hist, target, __ldg(&work[cur].hist_index), g0, mask0);
+      if (has1) flush_large_cells(s_hist + B2_GROUP_ELEMS, target, __ldg(&work[cur].hist_index), g1, mask1);
+      __syncthreads();
+      rows_in_window = 0;
+    }
+    cur = w;
+    rows_in_window += nrows;
+    const int64_t pos0 = (int64_t)seg_begin + row0;
+    if (has1 && !narrow1) {
+      full_pass<kGather, 2>(bins, row_stride, gpair, ridx, pos0, nrows, g0, smem0, lane, warp, n_warps);
+    } else {
+      if (!narrow0) full_pass<kGather, 1>(bins, row_stride, gpair, ridx, pos0, nrows, g0, smem0, lane, warp, n_warps);
+      if (narrow0 || narrow1)
+        narrow_dispatch<kGather>(plan.narrow_w, bins, row_stride, gpair, ridx, pos0, nrows, (narrow0 ? g0 : g1) * 32,
+                                 smem0 + (narrow0 ? 0u : (uint32_t)(B2_GROUP_ELEMS * 4)), lane, warp, n_warps);
+    }
+  }
+  if (cur >= 0) {
+    __syncthreads();
+    flush_planes(s_hist, target, __ldg(&work[cur].hist_index), g0, mask0);
+    if (has1) flush_planes(s_hist + B2_GROUP_ELEMS, target, __ldg(&work[cur].hist_index), g1, mask1);
+  }
+}
+
 // ---------------------------------------------------------------- sibling = parent - built
 __global__ void hist_subtract_kernel(const long long* __restrict__ parent_level, long long* __restrict__ level,
                                      const int32_t* __restrict__ triples, int n_pairs, int64_t node_elems,
@@ -167,20 +364,65 @@ extern "C" {
 // Launch on `stream`.  grid = n_groups * n_streams persistent CTAs; returns the cudaError.
 int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const int32_t* ridx,
                    const B2HistWork* work, int n_work, int total_chunks, int chunk_rows, int window_rows,
-                   int n_groups, long long* hist, const B2LevelCtl* ctl, int log2_shards, int node_cap, int num_sms,
-                   cudaStream_t stream) {
+                   int n_groups, long long* hist, const B2LevelCtl* ctl, int log2_shards, int node_cap, int narrow_w,
+                   int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   static int debug_mode = -1, variant = -1;
   if (debug_mode < 0) { const char* e = getenv("B2_HIST_DEBUG_MODE"); debug_mode = e ? atoi(e) : 0; }
   // variants (B2_HIST_VARIANT): 0 = 256 threads x 3 CTAs/SM, one group per CTA
   //                             1 = 512 threads x 2 CTAs/SM, one group per CTA
-  //                             2 = 1024 threads x 1 CTA/SM, two groups per CTA (default; A/B in profiles/r01_summary.md)
+  //                             2 = 1024 threads x 1 CTA/SM, two groups per CTA (round-1 default; A/B in profiles/r01_summary.md)
+  //                             3 = group pairs with a narrow last group, CTAs per pair by cost (default)
   if (variant < 0) {
     const char* e = getenv("B2_HIST_VARIANT");
     variant = e ? atoi(e) : B2_HIST_DEFAULT_VARIANT;
     const char* t = getenv("B2_HIST_THREADS");   // older spelling of variant 0
     if (!e && t && atoi(t) == 256) variant = 0;
-    if (variant < 0 || variant > 2) variant = B2_HIST_DEFAULT_VARIANT;
+    if (variant < 0 || variant > 3) variant = B2_HIST_DEFAULT_VARIANT;
+  }
+  if (variant == 3) {
+    // ---- group pairs with a narrow last group: CTAs per type in proportion to the atomic wavefronts per row
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaFuncSetAttribute(b2::hist_build_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
+      cudaFuncSetAttribute(b2::hist_build_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
+      attr3 = true;
+    }
+    if (!ctl && (total_chunks <= 0 || n_work <= 0)) return 0;
+    if (!ctl && chunk_rows > window_rows) return (int)cudaErrorInvalidValue;
+    B2HistPlan plan;
+    plan.n_types = (n_groups + 1) / 2; plan.narrow_w = narrow_w;
+    if (plan.n_types > B2_HIST_MAX_TYPES) return (int)cudaErrorInvalidValue;
+    int cost[B2_HIST_MAX_TYPES], total_cost = 0;
+    for (int t = 0; t < plan.n_types; ++t) {
+      cost[t] = 0;
+      for (int g = 2 * t; g < 2 * t + 2 && g < n_groups; ++g) cost[t] += (narrow_w > 0 && g == n_groups - 1) ? narrow_w : 32;
+      total_cost += cost[t];
+    }
+    int n_ctas = num_sms, assigned = 0, biggest = 0;
+    if (n_ctas < plan.n_types) n_ctas = plan.n_types;
+    int streams[B2_HIST_MAX_TYPES];
+    for (int t = 0; t < plan.n_types; ++t) {
+      streams[t] = (int)(((long long)n_ctas * cost[t] + total_cost / 2) / total_cost);
+      if (streams[t] < 1) streams[t] = 1;
+      if (!ctl && streams[t] > total_chunks) streams[t] = total_chunks;
+      assigned += streams[t];
+      if (cost[t] > cost[biggest]) biggest = t;
+    }
+    if (ctl || assigned > n_ctas) {   // make the persistent grid exactly one CTA per SM
+      streams[biggest] += n_ctas - assigned;
+      if (streams[biggest] < 1) streams[biggest] = 1;
+    }
+    plan.cta_begin[0] = 0;
+    for (int t = 0; t < plan.n_types; ++t) plan.cta_begin[t + 1] = plan.cta_begin[t] + streams[t];
+    for (int t = plan.n_types + 1; t <= B2_HIST_MAX_TYPES; ++t) plan.cta_begin[t] = plan.cta_begin[plan.n_types];
+    dim3 grid3(plan.cta_begin[plan.n_types]), block3(1024);
+    const int smem3 = 2 * B2_GROUP_ELEMS * (int)sizeof(int32_t);
+    if (ridx) b2::hist_build_kernel_v3<true><<<grid3, block3, smem3, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
+                                                                                chunk_rows, window_rows, n_groups, hist, ctl, log2_shards, node_cap, plan);
+    else b2::hist_build_kernel_v3<false><<<grid3, block3, smem3, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
+                                                                           chunk_rows, window_rows, n_groups, hist, ctl, log2_shards, node_cap, plan);
+    return (int)cudaGetLastError();
   }
   const int gpc = variant == 2 ? 2 : 1;
   const int smem = gpc * B2_GROUP_ELEMS * (int)sizeof(int32_t);  // 64 KiB per group

@@ -747,58 +747,80 @@ class Booster:
             params = {params: value}
         self.params.update(_params_dict(params))
 
-    # -- (de)serialisation: XGBoost JSON model schema + "split_bins" extension
+    # -- (de)serialisation: XGBoost's JSON model format (doc/model.schema of dmlc/xgboost 2.x).  Everything
+    # a stock xgboost needs is where it expects it (objective parameter block, learner_model_param, gbtree_model_param,
+    # string-valued parameters, strict JSON numbers); what only this engine uses (split bins, its own parameter set)
+    # is carried under `attributes` with a "b2." prefix, which xgboost preserves and ignores.
+    @staticmethod
+    def _tree_json(i, t, n_features):
+        n = len(t["left"])
+        leaf = t["split_feature"] < 0
+        st = np.asarray(t.get("split_type", np.zeros(n, np.uint8)))
+        cats, cat_nodes, cat_segs, cat_sizes = [], [], [], []
+        for nid in np.nonzero((st != 0) & ~leaf)[0]:
+            c = _cat_list(t["cat_bits"][nid])
+            cat_nodes.append(int(nid)); cat_segs.append(len(cats)); cat_sizes.append(len(c)); cats.extend(c)
+        # split_conditions: leaf value for a leaf, threshold for a numeric split; a categorical split keeps its categories
+        # in the arrays above and xgboost does not read the number (RegTree::ExpandCategorical stores NaN, which is not
+        # JSON): 0 is written instead
+        cond = np.where(leaf, t["value"], np.where(st != 0, np.float32(0.0), t["split_cond"])).astype(np.float32)
+        cond = np.where(np.isfinite(cond), cond, np.float32(0.0))
+        return {
+            "base_weights": [float(x) for x in t["base_weight"]],
+            "categories": cats, "categories_nodes": cat_nodes, "categories_segments": cat_segs,
+            "categories_sizes": cat_sizes,
+            "default_left": [int(x) for x in t["default_left"]],
+            "id": i,
+            "left_children": [int(x) for x in t["left"]],
+            "loss_changes": [float(x) for x in t["loss_chg"]],
+            "parents": [int(x) if x >= 0 else 2147483647 for x in t["parent"]],
+            "right_children": [int(x) for x in t["right"]],
+            "split_conditions": [float(x) for x in cond],
+            "split_indices": [int(x) if x >= 0 else 0 for x in t["split_feature"]],
+            "split_type": [int(x) for x in st],
+            "sum_hessian": [float(x) for x in t["sum_hess"]],
+            "tree_param": {"num_deleted": "0", "num_feature": str(n_features), "num_nodes": str(n),
+                           "size_leaf_vector": "1"},
+        }
+
     def _model_dict(self):
         K = self.num_class
-        trees = []
-        for i, t in enumerate(self.get_trees()):
-            n = len(t["left"])
-            leaf = t["split_feature"] < 0
-            st = t.get("split_type", np.zeros(n, np.uint8))
-            cats, cat_nodes, cat_segs, cat_sizes = [], [], [], []
-            for nid in np.nonzero(np.asarray(st) & ~leaf)[0]:
-                c = _cat_list(t["cat_bits"][nid])
-                cat_nodes.append(int(nid)); cat_segs.append(len(cats)); cat_sizes.append(len(c)); cats.extend(c)
-            trees.append({
-                "base_weights": [float(x) for x in t["base_weight"]],
-                "categories": cats, "categories_nodes": cat_nodes, "categories_segments": cat_segs,
-                "categories_sizes": cat_sizes,
-                "default_left": [int(x) for x in t["default_left"]],
-                "id": i,
-                "left_children": [int(x) for x in t["left"]],
-                "loss_changes": [float(x) for x in t["loss_chg"]],
-                "parents": [int(x) if x >= 0 else 2147483647 for x in t["parent"]],
-                "right_children": [int(x) for x in t["right"]],
-                "split_conditions": [float(v) if lf else float(c) for lf, v, c in zip(leaf, t["value"], t["split_cond"])],
-                "split_indices": [int(x) if x >= 0 else 0 for x in t["split_feature"]],
-                "split_type": [int(x) for x in st],
-                "sum_hessian": [float(x) for x in t["sum_hess"]],
-                "split_bins": [int(x) for x in t["split_bin"]],
-                "tree_param": {"num_deleted": "0", "num_feature": str(self.n_features), "num_nodes": str(n),
-                               "size_leaf_vector": "1"},
-            })
+        src = self.get_trees()
+        cache = self.__dict__.setdefault("_tree_json_cache", [])     # finished trees never change: convert each once
+        if len(cache) > len(src):
+            del cache[:]
+        for i in range(len(cache), len(src)):
+            cache.append((self._tree_json(i, src[i], self.n_features), [int(x) for x in src[i]["split_bin"]]))
+        trees = [c[0] for c in cache]
         obj = self.params.get("objective", "reg:squarederror")
+        if obj.startswith("multi:"):
+            obj_block = {"name": obj, "softmax_multiclass_param": {"num_class": str(K)}}
+        else:
+            obj_block = {"name": obj, "reg_loss_param": {"scale_pos_weight": _num_str(self.params.get("scale_pos_weight", 1))}}
+        attrs = {k: str(v) for k, v in self._attrs.items() if not k.startswith("b2.")}
+        attrs["b2.params"] = json.dumps({k: self.params[k] for k in sorted(self.params) if _json_ok(self.params[k]) and
+                                         k not in ("objective", "num_class", "base_score", "scale_pos_weight")})   # those have their own fields
+        attrs["b2.split_bins"] = json.dumps([c[1] for c in cache], separators=(",", ":"))
         return {
             "learner": {
-                "attributes": dict(self._attrs),
-                "feature_names": list(self.feature_names or []),
-                "feature_types": list(self.feature_types or []),
-                "gradient_booster": {"name": "gbtree", "model": {
+                "attributes": attrs,
+                "feature_names": [str(x) for x in (self.feature_names or [])],
+                "feature_types": [_xgb_feature_type(x) for x in (self.feature_types or [])],
+                "gradient_booster": {"model": {
                     "gbtree_model_param": {"num_parallel_tree": "1", "num_trees": str(len(trees))},
                     "iteration_indptr": list(range(0, len(trees) + 1, K)) if K else [],
                     "tree_info": [i % K for i in range(len(trees))],
-                    "trees": trees}},
-                "learner_model_param": {"base_score": repr(float(self.params.get("base_score", 0.5))),
+                    "trees": trees}, "name": "gbtree"},
+                "learner_model_param": {"base_score": _num_str(self.params.get("base_score", 0.5) if self.params.get("base_score") is not None else 0.5),
                                         "boost_from_average": "1", "num_class": str(K if K > 1 else 0),
                                         "num_feature": str(self.n_features), "num_target": "1"},
-                "objective": {"name": obj},
-                "b2_params": {k: self.params[k] for k in self.params if _json_ok(self.params[k])},
+                "objective": obj_block,
             },
-            "version": [2, 0, 0],
+            "version": [2, 0, 3],
         }
 
     def save_raw(self, raw_format="json"):
-        return bytearray(json.dumps(self._model_dict()).encode())
+        return bytearray(json.dumps(self._model_dict(), allow_nan=False).encode())
 
     def save_model(self, fname):
         with open(fname, "wb") as f:
@@ -813,20 +835,27 @@ class Booster:
         d = json.loads(raw.decode())
         L = d["learner"]
         self._free()
-        params = dict(L.get("b2_params", {}))
+        self.__dict__.pop("_tree_json_cache", None)
+        attrs = dict(L.get("attributes", {}))
+        params = dict(json.loads(attrs.pop("b2.params"))) if "b2.params" in attrs else dict(L.get("b2_params", {}))
+        split_bins = json.loads(attrs.pop("b2.split_bins")) if "b2.split_bins" in attrs else None
         params["objective"] = L["objective"]["name"]
         nc = int(L["learner_model_param"].get("num_class", "0"))
+        nc = max(nc, int(L["objective"].get("softmax_multiclass_param", {}).get("num_class", "0")))
         if nc > 1:
             params["num_class"] = nc
-        params.setdefault("base_score", float(L["learner_model_param"]["base_score"]))
+        spw = L["objective"].get("reg_loss_param", {}).get("scale_pos_weight")
+        if spw is not None and float(spw) != 1.0:
+            params["scale_pos_weight"] = float(spw)
+        params["base_score"] = float(L["learner_model_param"]["base_score"])
         params.update({k: v for k, v in self.params.items() if k not in params})
         self.params = params
         self.n_features = int(L["learner_model_param"]["num_feature"])
         self.feature_names = L.get("feature_names") or None
-        self.feature_types = L.get("feature_types") or None
-        self._attrs = dict(L.get("attributes", {}))
+        self.feature_types = [_b2_feature_type(x) for x in L.get("feature_types") or []] or None
+        self._attrs = attrs
         self._trees = []
-        for t in L["gradient_booster"]["model"]["trees"]:
+        for ti, t in enumerate(L["gradient_booster"]["model"]["trees"]):
             left = np.asarray(t["left_children"], np.int32)
             leaf = left < 0
             sc = np.asarray(t["split_conditions"], np.float32)
@@ -839,12 +868,21 @@ class Booster:
                     if not 0 <= int(c) < 256:
                         raise XGBoostError("model has category %r outside [0, 255]" % (c,))
                     bits[nid, int(c) >> 5] |= np.uint32(1 << (int(c) & 31))
+            sb = t.get("split_bins") if split_bins is None else split_bins[ti]
+            cat_split = (st != 0) & ~leaf
+            # a categorical node: one-hot splits keep their category as the condition, set splits have none (NaN)
+            ncat = np.array([bin(int(w)).count("1") for w in bits.reshape(len(left), -1).astype(np.uint64).sum(axis=1)]) if False else None
+            cond = np.where(leaf, 0, sc).astype(np.float32)
+            for nid in np.nonzero(cat_split)[0]:
+                cl = _cat_list(bits[nid])
+                b_ = int(sb[nid]) if sb is not None else (cl[0] if len(cl) == 1 else -1)
+                cond[nid] = np.float32(b_) if b_ >= 0 else np.float32("nan")
             self._trees.append(dict(
                 split_type=st, cat_bits=bits,
                 left=left, right=np.asarray(t["right_children"], np.int32), parent=parent,
                 split_feature=np.where(leaf, -1, np.asarray(t["split_indices"], np.int32)).astype(np.int32),
-                split_bin=np.asarray(t.get("split_bins", [-1] * len(left)), np.int32),
-                split_cond=np.where(leaf, 0, sc).astype(np.float32),
+                split_bin=np.asarray(sb if sb is not None else [-1] * len(left), np.int32),
+                split_cond=cond,
                 default_left=np.asarray(t["default_left"], np.uint8),
                 value=np.where(leaf, sc, np.asarray(t["base_weights"], np.float32)).astype(np.float32),
                 base_weight=np.asarray(t["base_weights"], np.float32),
@@ -879,7 +917,7 @@ class Booster:
         return json.dumps({"learner": {"gradient_booster": {"name": "gbtree"},
                                        "objective": {"name": self.params.get("objective", "reg:squarederror")},
                                        "b2_params": {k: v for k, v in self.params.items() if _json_ok(v)}},
-                           "version": [2, 0, 0]})
+                           "version": [2, 0, 3]})
 
     # -- dumps (A.11)
     def get_dump(self, fmap="", with_stats=False, dump_format="text"):
@@ -927,6 +965,21 @@ class Booster:
     def cancel(self):
         if self.handle:
             lib().B2_BoosterCancel(self.handle)
+
+
+def _num_str(v):
+    """Parameter values are strings in xgboost's JSON; floats with the 9 significant digits of a binary32."""
+    f = float(v)
+    return str(int(f)) if f == int(f) and abs(f) < 1e15 else "%.9g" % f
+
+
+def _xgb_feature_type(t):
+    """'q' / 'c' of the DMatrix interface -> the names xgboost stores in a model file."""
+    return {"q": "float", "c": "c", "i": "int"}.get(str(t), str(t))
+
+
+def _b2_feature_type(t):
+    return {"float": "q", "int": "q", "i": "q", "c": "c", "q": "q"}.get(str(t), str(t))
 
 
 def _json_ok(v):
