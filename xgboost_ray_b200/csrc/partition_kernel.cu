@@ -85,13 +85,24 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       if (lane == 0) s_warp_left[warp][it] = __popc(bal[it]);
     }
     __syncthreads();
-    // exclusive prefix over (it, warp) in row order: index = it*8 + warp
-    if (threadIdx.x == 0) {
-      int acc = 0;
-      for (int it = 0; it < kIters; ++it)
-        for (int wp = 0; wp < kPartThreads / 32; ++wp) { s_pref[wp][it] = acc; acc += s_warp_left[wp][it]; }
-      s_base_left = atomicAdd(&counters[2 * lo], acc);
-      s_base_right = atomicAdd(&counters[2 * lo + 1], nrows - acc);
+    // exclusive prefix over (it, warp) in row order: index = it*8 + warp.  One warp scans the 64 counts with shuffles
+    // (a single thread walking them serially kept the other 255 threads of the CTA waiting for ~2000 cycles per chunk)
+    if (warp == 0) {
+      constexpr int kCounts = kIters * (kPartThreads / 32);           // 64
+      static_assert(kCounts == 64, "two counts per lane");
+      const int i0 = 2 * lane, i1 = 2 * lane + 1;                       // index = it * 8 + wp
+      const int c0 = s_warp_left[i0 & 7][i0 >> 3], c1 = s_warp_left[i1 & 7][i1 >> 3];
+      int incl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const int excl = incl - (c0 + c1);
+      s_pref[i0 & 7][i0 >> 3] = excl;
+      s_pref[i1 & 7][i1 >> 3] = excl + c0;
+      if (lane == 31) {
+        const int acc = incl;
+        s_base_left = atomicAdd(&counters[2 * lo], acc);
+        s_base_right = atomicAdd(&counters[2 * lo + 1], nrows - acc);
+      }
     }
     __syncthreads();
     const int base_l = s_base_left, base_r = s_base_right;
