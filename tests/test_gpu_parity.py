@@ -617,3 +617,44 @@ def test_auc_metric(eng, weighted):
     bst2 = eng.train(dict(params, eval_metric="auc"), dm, num_boost_round=50, evals=[(dv, "valid")], early_stopping_rounds=3,
                      verbose_eval=False)
     assert bst2.best_iteration is not None and bst2.best_score >= 0.5
+
+
+def test_num_parallel_tree_known_answers(eng, tmp_path):
+    """num_parallel_tree (random forests; xgboost_ray/tests/test_sklearn.py:277-286 `num_parallel_tree` dump length):
+    n trees per class and round from the SAME gradients, leaf values scaled by eta / n.  Without sampling the n trees of a
+    round are identical and their sum is the single tree of an ordinary round -- bit for bit (n is a power of two)."""
+    rng = np.random.RandomState(8)
+    n, f = 20000, 10
+    X = rng.uniform(0, 10, size=(n, f)).astype(np.float32)
+    y = (X[:, 0] * 2 + np.sin(X[:, 1]) * 3 + rng.normal(scale=0.3, size=n)).astype(np.float32)
+    base = {"objective": "reg:squarederror", "max_depth": 4, "eta": 0.5, "base_score": 0.5}
+    b1 = eng.train(base, eng.DMatrix(X, label=y), num_boost_round=3, verbose_eval=False)
+    b4 = eng.train(dict(base, num_parallel_tree=4), eng.DMatrix(X, label=y), num_boost_round=3, verbose_eval=False)
+    assert b4.num_trees() == 12 and b4.num_boosted_rounds() == 3 and len(b4.get_dump()) == 12
+    t1, t4 = b1.get_trees(), b4.get_trees()
+    for r in range(3):
+        for j in range(4):
+            assert np.array_equal(t4[4 * r + j]["split_feature"], t1[r]["split_feature"])
+            assert np.array_equal(t4[4 * r + j]["split_bin"], t1[r]["split_bin"])
+            leaf = t1[r]["split_feature"] < 0
+            assert np.array_equal(t4[4 * r + j]["value"][leaf] * np.float32(4.0), t1[r]["value"][leaf])
+    assert np.array_equal(b4.predict(eng.DMatrix(X)), b1.predict(eng.DMatrix(X)))
+    assert np.array_equal(b4.predict(eng.DMatrix(X), iteration_range=(0, 2)), b1.predict(eng.DMatrix(X), iteration_range=(0, 2)))
+    f_ = str(tmp_path / "rf.json")
+    b4.save_model(f_)
+    b4l = eng.Booster(model_file=f_)
+    assert b4l.num_parallel_tree == 4 and b4l.num_boosted_rounds() == 3
+    assert np.array_equal(b4l.predict(eng.DMatrix(X)), b4.predict(eng.DMatrix(X)))
+    # 3 classes x 2 parallel trees: trees of a class sit next to each other (tree_info 0 0 1 1 2 2)
+    yc = (X[:, 0] // 3.4).astype(np.float32)
+    m1 = eng.train({"objective": "multi:softprob", "num_class": 3, "max_depth": 3, "eta": 0.5}, eng.DMatrix(X, label=yc), 2, verbose_eval=False)
+    m2 = eng.train({"objective": "multi:softprob", "num_class": 3, "max_depth": 3, "eta": 0.5, "num_parallel_tree": 2},
+                   eng.DMatrix(X, label=yc), 2, verbose_eval=False)
+    assert m2.num_trees() == 12 and np.allclose(m2.predict(eng.DMatrix(X)), m1.predict(eng.DMatrix(X)), atol=1e-6)
+    # a forest proper: one round, row and column sampling -> different trees, averaged leaves, sane fit
+    rf = eng.train(dict(base, eta=1.0, num_parallel_tree=16, subsample=0.8, colsample_bynode=0.8, seed=3, max_depth=6),
+                   eng.DMatrix(X, label=y), num_boost_round=1, verbose_eval=False)
+    ts = rf.get_trees()
+    assert len(ts) == 16 and any(not np.array_equal(ts[0]["split_feature"], t["split_feature"]) or
+                                 not np.array_equal(ts[0]["split_bin"], t["split_bin"]) for t in ts[1:])
+    assert np.mean((rf.predict(eng.DMatrix(X)) - y) ** 2) < 0.25 * np.var(y)

@@ -144,3 +144,23 @@ def test_eval_matrix_freed_and_reallocated_is_not_served_from_a_stale_cache():
         seen.append(got)
         del dm
     assert len(set(round(v, 6) for v in seen)) > 1
+
+
+@pytest.mark.timeout(420)
+def test_sklearn_random_forest_estimators_on_the_gpu():
+    """xgboost_ray/sklearn.py:602-637, 880-914 (RayXGBRFRegressor / RayXGBRFClassifier): one round of n_estimators
+    parallel trees through the public fit / predict surface."""
+    from sklearn.datasets import load_digits
+    from xgboost_ray_b200 import RayParams
+    from xgboost_ray_b200.sklearn import RayXGBRFClassifier, RayXGBRFRegressor
+    rng = np.random.RandomState(0)
+    X = rng.uniform(0, 10, size=(4000, 6)).astype(np.float32)
+    y = (X[:, 0] * 2 + X[:, 1] + rng.normal(scale=0.2, size=4000)).astype(np.float32)
+    rf = RayXGBRFRegressor(n_estimators=16, max_depth=6, random_state=5).fit(X, y, ray_params=RayParams(num_actors=1))
+    assert len(rf.get_booster().get_dump()) == 16 and rf.get_booster().num_boosted_rounds() == 1
+    assert np.mean((rf.predict(X, ray_params=RayParams(num_actors=1)) - y) ** 2) < 0.2 * np.var(y)
+    d = load_digits(n_class=2)
+    clf = RayXGBRFClassifier(n_estimators=8, max_depth=4, random_state=1).fit(d.data.astype(np.float32)[::2], d.target[::2],
+                                                                            ray_params=RayParams(num_actors=1))
+    pred = clf.predict(d.data.astype(np.float32)[1::2], ray_params=RayParams(num_actors=1))
+    assert np.mean(pred != d.target[1::2]) < 0.1

@@ -193,9 +193,14 @@ def test_sklearn_parameters_and_attributes(tmp_path):
     imp = reg.feature_importances_
     assert imp.shape == (6,) and abs(imp.sum() - 1.0) < 1e-5 and imp.argmax() == 2
     assert "validation_0" in reg.evals_result() and len(reg.evals_result()["validation_0"]["rmse"]) == 8
-    for cls in (RayXGBRFRegressor, RayXGBRFClassifier, RayXGBRanker):
-        with pytest.raises(NotImplementedError):
-            cls()
+    with pytest.raises(NotImplementedError):
+        RayXGBRanker()
+    rf = RayXGBRFRegressor(n_estimators=7, max_depth=3)
+    p = rf.get_xgb_params()
+    assert p["num_parallel_tree"] == 7 and p["learning_rate"] == 1.0 and p["subsample"] == 0.8 and p["colsample_bynode"] == 0.8
+    assert rf.get_num_boosting_rounds() == 1 and rf.get_params()["reg_lambda"] == 1e-5
+    from sklearn.base import clone
+    assert clone(RayXGBRFClassifier(n_estimators=3, subsample=0.5)).get_params()["subsample"] == 0.5
 
 
 @pytest.mark.timeout(600)

@@ -80,7 +80,7 @@ int b2_launch_absmax(const float2*, int64_t, uint32_t*, int, cudaStream_t);
 int b2_launch_quant_exponent(const uint32_t*, int32_t*, cudaStream_t);
 int b2_launch_quantize(const float2*, int64_t, const int32_t*, int, int2*, int, cudaStream_t);
 int b2_launch_metric(int, int, int, const float*, const float*, const float*, int64_t, double*, int, cudaStream_t);
-int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, const int32_t*, const uint32_t*, int, int, int,
+int b2_launch_predict(const float*, int64_t, int, float, const B2TreeNodeDev*, const int32_t*, const uint32_t*, int, int, int, int,
                       float*, int, cudaStream_t);
 int b2_launch_fill(float*, int64_t, float, int, cudaStream_t);
 size_t b2_auc_temp_bytes(int64_t);
@@ -618,6 +618,7 @@ struct Params {
   int objective = kObjSquaredError;
   std::string objective_name = "reg:squarederror";
   int num_class = 1;
+  int num_parallel_tree = 1;   // trees grown per class and round from the SAME gradients (random forests); leaf values are scaled by eta / n
   int max_depth = 6;
   float eta = 0.3f, gamma = 0.0f, min_child_weight = 1.0f, lambda = 1.0f, alpha = 0.0f, base_score = 0.5f;
   int qbits = 18;
@@ -678,6 +679,7 @@ struct Booster : HandleBase {
   bool margin_ready = false;
   DevBuf<float> margin;          // [n][K]
   DevBuf<float2> gh;             // [K][n]
+  DevBuf<float2> gh_round;       // copy of the round's gradients (num_parallel_tree > 1 with row sampling)
   DevBuf<int2> q;                // [n]
   DevBuf<int32_t> ridx[2];
   DevBuf<long long> hist[2];
@@ -796,6 +798,7 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
       else if (v == "multi:softprob" || v == "multi:softmax") p->objective = kObjSoftprob;
       else fail("unsupported objective '%s' (supported: reg:squarederror, binary:logistic, multi:softprob, multi:softmax)", v.c_str());
     } else if (k == "num_class") p->num_class = i();
+    else if (k == "num_parallel_tree") p->num_parallel_tree = i();
     else if (k == "max_depth") p->max_depth = i();
     else if (k == "eta" || k == "learning_rate") p->eta = f();
     else if (k == "gamma" || k == "min_split_loss") p->gamma = f();
@@ -823,6 +826,7 @@ void parse_params(const char* text, Params* p, int* max_bin_out) {
   if (p->objective != kObjSoftprob) p->num_class = 1;
   if (p->objective == kObjSoftprob && p->num_class < 2) fail("multi:softprob needs num_class >= 2");
   if (p->max_depth < 1 || p->max_depth > 14) fail("max_depth must be in [1, 14], got %d", p->max_depth);
+  if (p->num_parallel_tree < 1 || p->num_parallel_tree > 4096) fail("num_parallel_tree must be in [1, 4096], got %d", p->num_parallel_tree);
   if (p->qbits < 8 || p->qbits > 24) fail("hist_qbits must be in [8, 24], got %d", p->qbits);
   for (float v : {p->subsample, p->colsample_bytree, p->colsample_bylevel, p->colsample_bynode})
     if (!(v > 0.0f && v <= 1.0f)) fail("subsample / colsample_* must be in (0, 1], got %g", (double)v);
@@ -1080,7 +1084,7 @@ void grow_tree(Booster* b, int k, int slot, TreeStats& st) {
   static const bool leaf_fused = env_flag("B2_LEAF_FUSED", true);
   mark_phase(b, -1);
   // ---- fixed-point quantisation (global scale via max over the ranks)
-  const uint32_t tree_index = (uint32_t)b->trees.size() + (uint32_t)k;   // the k-th class tree of this round
+  const uint32_t tree_index = (uint32_t)b->trees.size() + (uint32_t)slot;   // position of this tree in the model (sampling seed)
   uint32_t* d_absmax = b->d_absmax.p + 2 * k;
   if (p.subsample < 1.0f) {
     LAUNCH_CHECK(b2_launch_subsample(b->gh.p + (size_t)k * n, n, (uint32_t)p.seed, tree_index, b->comm ? (uint32_t)b->comm->rank : 0u,
@@ -1127,7 +1131,7 @@ void grow_tree(Booster* b, int k, int slot, TreeStats& st) {
   dp.inv_scale_g = dp.inv_scale_h = 1.0;
   dp.max_cat_to_onehot = p.max_cat_to_onehot; dp.max_cat_threshold = p.max_cat_threshold;
   dp.max_delta_step = (double)p.max_delta_step;
-  B2CtlParams cp; cp.mcw = dp.min_child_weight; cp.lambda = dp.lambda; cp.alpha = dp.alpha; cp.max_delta_step = dp.max_delta_step; cp.gamma = p.gamma; cp.eta = p.eta;
+  B2CtlParams cp; cp.mcw = dp.min_child_weight; cp.lambda = dp.lambda; cp.alpha = dp.alpha; cp.max_delta_step = dp.max_delta_step; cp.gamma = p.gamma; cp.eta = p.eta / (float)p.num_parallel_tree;
   const B2TreeDev tree = tree_dev(b);
   int32_t* d_n_leaves = tree.n_nodes + 1;
   long long* d_level_rows = b->t_i64.p + 2 * L.max_nodes;
@@ -1304,15 +1308,15 @@ void prepare_tree_buffers(Booster* b, int slot) {
 // One class tree: replay its CUDA graph when the launch sequence is the same for every tree (no row / column sampling,
 // fused |g|,|h| maxima, no per-phase profiling), otherwise enqueue the kernels one by one.  The first tree of a class
 // slot always runs with direct launches (it allocates), the second is captured, the following ones replay.
-void run_tree(Booster* b, int k) {
+void run_tree(Booster* b, int k, int slot) {
   cudaStream_t s = b->ctx->stream; const Params& p = b->p;
-  prepare_tree_buffers(b, k);
+  prepare_tree_buffers(b, slot);
   static const bool want_graph = env_flag("B2_GRAPH", true);
   const bool eligible = want_graph && !b->graph_failed && b->absmax_fused && p.subsample >= 1.0f && !p.use_cols() &&
-                        p.profile < 2 && !use_tma_hist();
+                        p.profile < 2 && !use_tma_hist() && p.num_parallel_tree == 1;
   auto direct = [&]() {
     TreeStats st;
-    grow_tree(b, k, k, st);
+    grow_tree(b, k, slot, st);
     apply_tree_stats(b, st.hist_launches, st.kernel_launches, st.allreduce_bytes, st.hist_ev);
     b->direct_trees[k]++;
   };
@@ -1324,7 +1328,7 @@ void run_tree(Booster* b, int k) {
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
-      try { grow_tree(b, k, k, st); }
+      try { grow_tree(b, k, slot, st); }
       catch (const B2Error& e) { cudaStreamEndCapture(s, &graph); if (graph) cudaGraphDestroy(graph); cudaGetLastError(); throw; }
       ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && graph != nullptr;
     }
@@ -1480,7 +1484,7 @@ void ensure_train_margin(Booster* b) {
     if (!m->has_raw) fail("continuing training from existing trees needs the raw data of the train matrix (B2_MatrixEnsureRaw)");
     sync_device_trees(b);
     LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, 0, (int)b->trees.size(),
-                                   b->p.num_class, b->margin.p, b->ctx->num_sms, b->ctx->stream));
+                                   b->p.num_class, b->p.num_parallel_tree, b->margin.p, b->ctx->num_sms, b->ctx->stream));
   }
   b->margin_ready = true;
 }
@@ -1511,7 +1515,20 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
                                     b->p.scale_pos_weight, b->gh.p, b->absmax_fused ? b->d_absmax.p : nullptr, b->ctx->num_sms, s));
   }
   b->t.kernel_launches++;
-  for (int k = 0; k < K; ++k) run_tree(b, k);
+  const int npt = b->p.num_parallel_tree;
+  // row sampling zeroes the dropped rows' gradient pairs in place: the parallel trees of a round each sample from the
+  // round's ORIGINAL gradients, so those are kept aside and restored in front of every further tree
+  const bool restore_gh = npt > 1 && b->p.subsample < 1.0f;
+  if (restore_gh) {
+    b->gh_round.ensure((size_t)std::max<int64_t>(n * K, 1));
+    CUDA_CHECK(cudaMemcpyAsync(b->gh_round.p, b->gh.p, (size_t)n * K * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+  }
+  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < npt; ++j) {
+      if (restore_gh && j > 0)
+        CUDA_CHECK(cudaMemcpyAsync(b->gh.p + (size_t)k * n, b->gh_round.p + (size_t)k * n, (size_t)n * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+      run_tree(b, k, k * npt + j);
+    }
   if (b->p.profile) {
     CUDA_CHECK(cudaEventRecord(b->round_stop, s));
     CUDA_CHECK(cudaEventSynchronize(b->round_stop));
@@ -1527,7 +1544,7 @@ void boost_round(Booster* b, const float* custom_g, const float* custom_h, int64
     if (perr) fail("peer-memory exchange: %s while waiting for another rank (flag slot %u)",
                    b->comm && b->comm->aborted.load() ? "communicator aborted" : "timed out", perr - 1);
   }
-  for (int k = 0; k < K; ++k) materialize_tree(b, k);
+  for (int slot = 0; slot < K * npt; ++slot) materialize_tree(b, slot);
   b->t.rounds++;
 }
 
@@ -1566,7 +1583,7 @@ float* eval_margin(Booster* b, Matrix* m) {
   const int nt = (int)b->trees.size();
   if (c->n_trees_applied < nt) {
     sync_device_trees(b);
-    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, c->n_trees_applied, nt, K,
+    LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, c->n_trees_applied, nt, K, b->p.num_parallel_tree,
                                    c->margin.p, b->ctx->num_sms, b->ctx->stream));
     c->n_trees_applied = nt;
   }
@@ -1921,7 +1938,7 @@ int B2_BoosterPredict(B2Handle bh, B2Handle mh, int32_t output_margin, int32_t t
   DevBuf<float> tmp; tmp.ensure((size_t)std::max<int64_t>(out_len, 1));
   init_margin(b, tmp.p, m);
   sync_device_trees(b);
-  LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, tree_begin, tree_end, K, tmp.p,
+  LAUNCH_CHECK(b2_launch_predict(m->raw.p, m->n, m->F, m->missing, b->d_nodes.p, b->d_tree_offset.p, b->d_cat_table.p, tree_begin, tree_end, K, b->p.num_parallel_tree, tmp.p,
                                  b->ctx->num_sms, s));
   if (!output_margin) LAUNCH_CHECK(b2_launch_transform(b->p.objective, K, tmp.p, m->n, b->ctx->num_sms, s));
   if (out_len > 0) CUDA_CHECK(cudaMemcpyAsync(out, tmp.p, out_len * sizeof(float), cudaMemcpyDeviceToHost, s));

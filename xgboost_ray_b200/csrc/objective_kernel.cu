@@ -245,12 +245,13 @@ __global__ void metric_kernel(int objective, int metric, int K, const float* __r
 }
 
 // A.9 traversal on raw floats: x < cond -> left, missing -> default.  nodes of all trees are
-// concatenated; tree_offset[t] is the first node of tree t; tree t adds to class t % K.
+// concatenated; tree_offset[t] is the first node of tree t; tree t adds to class (t / npt) % K (xgboost lays the
+// num_parallel_tree trees of a class out next to each other, GBTree::BoostNewTrees).
 // Categorical node (cat_slot >= 0; common/categorical.h Decision): category in the node's set -> right;
 // not in the set, negative or beyond the set -> left.
 __global__ void predict_kernel(const float* __restrict__ X, int64_t n, int F, float missing, int missing_is_nan,
                                const B2TreeNodeDev* __restrict__ nodes, const int32_t* __restrict__ tree_offset,
-                               const uint32_t* __restrict__ cat_table, int tree_begin, int tree_end, int K,
+                               const uint32_t* __restrict__ cat_table, int tree_begin, int tree_end, int K, int npt,
                                float* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float* x = X + i * F;
@@ -269,7 +270,7 @@ __global__ void predict_kernel(const float* __restrict__ X, int64_t n, int F, fl
         } else nid = v < nd.cond ? nd.left : nd.right;
         nd = tn[nid];
       }
-      out[i * K + (t % K)] += nd.value;
+      out[i * K + ((t / npt) % K)] += nd.value;
     }
   }
 }
@@ -347,11 +348,11 @@ int b2_launch_metric(int objective, int metric, int K, const float* margin, cons
   return (int)cudaGetLastError();
 }
 int b2_launch_predict(const float* X, int64_t n, int F, float missing, const B2TreeNodeDev* nodes,
-                      const int32_t* tree_offset, const uint32_t* cat_table, int tree_begin, int tree_end, int K, float* out,
-                      int num_sms, cudaStream_t s) {
+                      const int32_t* tree_offset, const uint32_t* cat_table, int tree_begin, int tree_end, int K, int npt,
+                      float* out, int num_sms, cudaStream_t s) {
   if (n <= 0 || tree_end <= tree_begin) return 0;
   b2::predict_kernel<<<grid_for(n, num_sms), 256, 0, s>>>(X, n, F, missing, missing != missing ? 1 : 0, nodes, tree_offset,
-                                                         cat_table, tree_begin, tree_end, K, out);
+                                                         cat_table, tree_begin, tree_end, K, npt < 1 ? 1 : npt, out);
   return (int)cudaGetLastError();
 }
 int b2_launch_fill(float* out, int64_t n, float v, int num_sms, cudaStream_t s) {

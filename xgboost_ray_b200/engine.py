@@ -458,12 +458,12 @@ _ENGINE_KEYS = ("objective", "num_class", "max_depth", "eta", "learning_rate", "
                 "min_child_weight", "lambda", "reg_lambda", "alpha", "reg_alpha", "base_score", "hist_qbits",
                 "hist_chunk_rows", "profile", "max_cat_to_onehot", "max_cat_threshold", "scale_pos_weight",
                 "max_delta_step", "subsample", "colsample_bytree", "colsample_bylevel", "colsample_bynode", "seed",
-                "random_state")
+                "random_state", "num_parallel_tree")
 
 # xgboost parameters that change the trained model and that this engine does not implement: a value different
 # from the neutral one is an error, never silently ignored (a drop-in must not train a different model quietly)
 _UNSUPPORTED_NEUTRAL = {
-    "sampling_method": ("uniform",), "max_leaves": (0,), "grow_policy": ("depthwise",), "num_parallel_tree": (1,),
+    "sampling_method": ("uniform",), "max_leaves": (0,), "grow_policy": ("depthwise",),
     "monotone_constraints": (None, "", "()", (), []), "interaction_constraints": (None, "", "[]", (), []),
     "multi_strategy": ("one_output_per_tree",), "refresh_leaf": (1, True), "process_type": ("default",),
     "updater": (None, "grow_quantile_histmaker", "grow_gpu_hist"),
@@ -603,8 +603,12 @@ class Booster:
         obj = self.params.get("objective", "reg:squarederror")
         return int(self.params.get("num_class", 1)) if obj.startswith("multi:") else 1
 
+    @property
+    def num_parallel_tree(self):
+        return max(1, int(self.params.get("num_parallel_tree", 1) or 1))
+
     def num_boosted_rounds(self):
-        return self.num_trees() // max(1, self.num_class)
+        return self.num_trees() // max(1, self.num_class * self.num_parallel_tree)
 
     def num_features(self):
         return self.n_features
@@ -713,7 +717,7 @@ class Booster:
         else:
             data._ensure_raw()
             tb, te = iteration_range if iteration_range else (0, 0)
-            tb_t, te_trees = tb * K, te * K
+            tb_t, te_trees = tb * K * self.num_parallel_tree, te * K * self.num_parallel_tree
             if ntree_limit:
                 tb_t, te_trees = 0, ntree_limit
             _check(lib().B2_BoosterPredict(self.handle, data.handle, 1 if output_margin else 0, tb_t, te_trees,
@@ -799,7 +803,7 @@ class Booster:
             obj_block = {"name": obj, "reg_loss_param": {"scale_pos_weight": _num_str(self.params.get("scale_pos_weight", 1))}}
         attrs = {k: str(v) for k, v in self._attrs.items() if not k.startswith("b2.")}
         attrs["b2.params"] = json.dumps({k: self.params[k] for k in sorted(self.params) if _json_ok(self.params[k]) and
-                                         k not in ("objective", "num_class", "base_score", "scale_pos_weight")})   # those have their own fields
+                                         k not in ("objective", "num_class", "base_score", "scale_pos_weight", "num_parallel_tree")})   # those have their own fields
         attrs["b2.split_bins"] = json.dumps([c[1] for c in cache], separators=(",", ":"))
         return {
             "learner": {
@@ -807,9 +811,9 @@ class Booster:
                 "feature_names": [str(x) for x in (self.feature_names or [])],
                 "feature_types": [_xgb_feature_type(x) for x in (self.feature_types or [])],
                 "gradient_booster": {"model": {
-                    "gbtree_model_param": {"num_parallel_tree": "1", "num_trees": str(len(trees))},
-                    "iteration_indptr": list(range(0, len(trees) + 1, K)) if K else [],
-                    "tree_info": [i % K for i in range(len(trees))],
+                    "gbtree_model_param": {"num_parallel_tree": str(self.num_parallel_tree), "num_trees": str(len(trees))},
+                    "iteration_indptr": list(range(0, len(trees) + 1, K * self.num_parallel_tree)),
+                    "tree_info": [(i // self.num_parallel_tree) % K for i in range(len(trees))],
                     "trees": trees}, "name": "gbtree"},
                 "learner_model_param": {"base_score": _num_str(self.params.get("base_score", 0.5) if self.params.get("base_score") is not None else 0.5),
                                         "boost_from_average": "1", "num_class": str(K if K > 1 else 0),
@@ -848,6 +852,9 @@ class Booster:
         if spw is not None and float(spw) != 1.0:
             params["scale_pos_weight"] = float(spw)
         params["base_score"] = float(L["learner_model_param"]["base_score"])
+        npt = int(L["gradient_booster"]["model"].get("gbtree_model_param", {}).get("num_parallel_tree", "1"))
+        if npt > 1:
+            params["num_parallel_tree"] = npt
         params.update({k: v for k, v in self.params.items() if k not in params})
         self.params = params
         self.n_features = int(L["learner_model_param"]["num_feature"])

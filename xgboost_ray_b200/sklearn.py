@@ -78,6 +78,9 @@ class RayXGBMixin(BaseEstimator):
             p["seed"] = int(self.random_state)
         return p
 
+    def get_num_boosting_rounds(self):
+        return self.n_estimators
+
     def _ray_params(self, ray_params):
         if ray_params is None:
             return RayParams(num_actors=self.n_jobs if self.n_jobs and self.n_jobs > 0 else 1)
@@ -105,7 +108,7 @@ class RayXGBMixin(BaseEstimator):
                           for i, (ex, ey) in enumerate(eval_set or ()))
         self.evals_result_ = {}
         self.additional_results_ = {}
-        self._Booster = train(params, train_dmatrix, self.n_estimators, evals=evals, evals_result=self.evals_result_,
+        self._Booster = train(params, train_dmatrix, self.get_num_boosting_rounds(), evals=evals, evals_result=self.evals_result_,
                               additional_results=self.additional_results_, ray_params=self._ray_params(ray_params), **kw)
         self.n_features_in_ = self._Booster.n_features
         self.best_iteration = getattr(self._Booster, "best_iteration", None)
@@ -195,13 +198,44 @@ class _Unsupported:
         raise NotImplementedError(self._why)
 
 
-class RayXGBRFRegressor(_Unsupported):
-    """xgboost_ray/sklearn.py:563-640: random-forest mode needs num_parallel_tree > 1, which this engine does not grow."""
-    _why = "random forest estimators need num_parallel_tree > 1, which the B200 hist engine does not implement"
+_RF_DEFAULTS = {"learning_rate": 1.0, "subsample": 0.8, "colsample_bynode": 0.8, "reg_lambda": 1e-5}
 
 
-class RayXGBRFClassifier(_Unsupported):
-    _why = RayXGBRFRegressor._why
+def _rf_init(base):
+    """__init__ with the explicit parameter list of `base` (scikit-learn reads it for get_params / clone) and the
+    defaults of xgboost's XGBRF* estimators (xgboost_ray/sklearn.py:611-628)."""
+    import inspect
+    sig = inspect.signature(base.__init__)
+    new_sig = sig.replace(parameters=[p.replace(default=_RF_DEFAULTS.get(n, p.default)) for n, p in sig.parameters.items()])
+
+    def __init__(self, *args, **kwargs):
+        bound = new_sig.bind(self, *args, **kwargs)
+        bound.apply_defaults()
+        base.__init__(*bound.args, **bound.kwargs)
+
+    __init__.__signature__ = new_sig
+    return __init__
+
+
+class _RandomForestMixin:
+    """xgboost_ray/sklearn.py:602-637, 880-914: ONE boosting round that grows n_estimators trees in parallel
+    (num_parallel_tree) on row / column samples of the same gradients, leaf values averaged."""
+
+    def get_xgb_params(self):
+        params = super().get_xgb_params()
+        params["num_parallel_tree"] = self.n_estimators
+        return params
+
+    def get_num_boosting_rounds(self):
+        return 1
+
+
+class RayXGBRFRegressor(_RandomForestMixin, RayXGBRegressor):
+    __init__ = _rf_init(RayXGBRegressor)
+
+
+class RayXGBRFClassifier(_RandomForestMixin, RayXGBClassifier):
+    __init__ = _rf_init(RayXGBClassifier)
 
 
 class RayXGBRanker(_Unsupported):
