@@ -91,11 +91,61 @@ def synth_block(block, rows, cols, seed=1234, workload="C3"):
     return X, y
 
 
+def synth_block_gpu(block, rows, cols, seed=1234, workload="C4", device="cuda"):
+    """The large configurations (C4 100M x 50, C5 50M x 200) generate their blocks with torch's Philox generator on the
+    GPU (numpy needs minutes of host time for 10^10 values); same distributions as synth_block, returned as host arrays.
+    The stream depends on (seed, block) only, so every rank count sees the same global matrix."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 100003 + block)
+    a = torch.from_numpy(np.random.default_rng(seed).normal(size=10).astype(np.float32)).to(device)
+    if workload == "C5":
+        n_cat = cols // 4
+        n_num = cols - n_cat
+        X = torch.empty((rows, cols), dtype=torch.float32, device=device)
+        X[:, :n_num] = torch.rand((rows, n_num), generator=g, device=device) * 10.0
+        cards = [(4, 16, 64, 256)[j % 4] for j in range(n_cat)]
+        for j, c in enumerate(cards):
+            X[:, n_num + j] = torch.randint(0, c, (rows,), generator=g, device=device).float()
+        wrng = np.random.default_rng(seed + 5)
+        k_num, k_cat = min(20, n_num), min(8, n_cat)
+        W = torch.from_numpy(wrng.normal(size=(k_num, 10)).astype(np.float32)).to(device)
+        score = (X[:, :k_num] - 5.0) @ W
+        for j in range(k_cat):
+            eff = torch.from_numpy(wrng.normal(scale=4.0, size=(cards[j], 10)).astype(np.float32)).to(device)
+            score += eff[X[:, n_num + j].long()]
+        score += torch.randn(score.shape, generator=g, device=device)
+        return X.cpu().numpy(), score.argmax(dim=1).float().cpu().numpy()
+    if workload == "C3":
+        X = torch.rand((rows, cols), generator=g, device=device) * 10.0
+        k = min(10, cols)
+        y = X[:, :k] @ a[:k]
+        if cols > 10:
+            y = y + torch.sin(X[:, 10])
+        y = y + torch.randn(rows, generator=g, device=device) * 0.1
+        return X.cpu().numpy(), y.cpu().numpy()
+    if workload == "C2":
+        X = torch.randn((rows, cols), generator=g, device=device)
+        heavy = cols - (3 * cols) // 4
+        X[:, cols - heavy:] = torch.exp(X[:, cols - heavy:])
+        Z = X
+    else:
+        X = torch.rand((rows, cols), generator=g, device=device) * 10.0
+        Z = (X[:, :8] - 5.0) * 0.4
+    k = min(8, cols)
+    sc = Z[:, :k] @ a[:k] + 0.5 * Z[:, 0] * Z[:, 1]
+    y = (torch.rand(rows, generator=g, device=device) < torch.sigmoid(sc)).float()
+    return X.cpu().numpy(), y.cpu().numpy()
+
+
+GPU_GEN = {"on": False}     # set by main() for the configurations with more than 2e9 values (or --gen gpu)
+
+
 def synth_shard(n_rows, cols, rank, world, block_rows=1_000_000, workload="C3"):
     """Rows rank, rank+world, ... of the global matrix (INTERLEAVED sharding, matrix.py:1100)."""
     n_local = len(range(rank, n_rows, world))
     cache = os.environ.get("B2_BENCH_CACHE")   # optional .npy cache of the generated shard (A/B runs inside one gpurun call)
-    cpath = os.path.join(cache, "%s_%d_%d_%d_%d.npz" % (workload, n_rows, cols, rank, world)) if cache else None
+    cpath = os.path.join(cache, "%s%s_%d_%d_%d_%d.npz" % (workload, "g" if GPU_GEN["on"] else "", n_rows, cols, rank, world)) if cache else None
     if cpath and os.path.exists(cpath):
         z = np.load(cpath)
         return z["X"], z["y"]
@@ -104,7 +154,7 @@ def synth_shard(n_rows, cols, rank, world, block_rows=1_000_000, workload="C3"):
     at = 0
     for b, start in enumerate(range(0, n_rows, block_rows)):
         rows = min(block_rows, n_rows - start)
-        X, y = synth_block(b, rows, cols, workload=workload)
+        X, y = (synth_block_gpu if GPU_GEN["on"] else synth_block)(b, rows, cols, workload=workload)
         first = (rank - start) % world
         m = len(range(first, rows, world))
         Xs[at:at + m] = X[first::world]
@@ -279,6 +329,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--gen", default="auto", choices=["auto", "cpu", "gpu"],
+                    help="synthetic data generator: numpy on the host, or torch Philox on the GPU (default for > 2e9 values)")
     ap.add_argument("--no-public-e2e", action="store_true", help="skip the end-to-end run through train(RayDMatrix, RayParams)")
     ap.add_argument("--profile", type=int, default=1, help="2 = per-phase CUDA-event timers (adds event records)")
     args = ap.parse_args()
@@ -291,6 +343,7 @@ def main():
     args.objective = wl["objective"]
     args.num_class = wl.get("num_class")
     args.feature_types = feature_types(args.workload, args.cols)
+    GPU_GEN["on"] = args.gen == "gpu" or (args.gen == "auto" and args.rows * args.cols > 2_000_000_000)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -434,7 +487,7 @@ def main():
                 e2e_public = {"value": args.steps / pub_wall, "unit": "rounds/s",
                               "h2d_bytes_per_step": int((Xf.nbytes + yf.nbytes) / args.steps), "d2h_bytes_per_step": 8,
                               "seconds_total": pub_wall, "seconds_in_train_call": extra.get("total_time_s"),
-                              "seconds_training_attempt": extra.get("training_time_s"),
+                              "seconds_training_attempt": extra.get("training_time_s"), "timing": extra.get("timing"),
                               "api": "xgboost_ray_b200.train(params, RayDMatrix(X, y), num_boost_round=K, evals=[(dtrain, 'train')], "
                                      "ray_params=RayParams(num_actors=%d)) -- whole host matrix in, Booster out; warm actor pool" % world,
                               "trees": bpub.num_trees(), "final_train_metric": {k: v[-1] for k, v in res["train"].items()}}

@@ -26,6 +26,9 @@ typedef uint64_t B2Handle;
 
 const char* B2_GetLastError(void);
 int B2_GetVersion(void);
+/* process-wide engine options (the environment variables of the same name in upper case with a B2_ prefix are their
+ * defaults): "hist_narrow" = "0" | "1" -- feature-group layout of matrices quantised from now on. */
+int B2_SetOption(const char* key, const char* value);
 int B2_DeviceCount(int* out);
 
 /* ---- communicator: replaces the Rabit bridge.
@@ -54,6 +57,14 @@ int B2_MatrixCreateFromDense(const float* data, int64_t n_rows, int32_t n_cols, 
  * upload each block at its row offset -- no host-side concatenation (matrix.py:65-67). */
 int B2_MatrixCreate(int64_t n_rows, int32_t n_cols, float missing, int device, B2Handle* out);
 int B2_MatrixSetRows(B2Handle m, int64_t row_begin, const float* data, int64_t n_rows);
+/* The shard lives in ANOTHER process (the driver that holds the user's matrix): rows of n_cols floats, remote_row_stride
+ * bytes apart starting at remote_addr in process `pid`, are read with process_vm_readv straight into the pinned upload
+ * buffers -- the hand-off the reference does through the Ray object store (ray.put per shard, xgboost_ray/matrix.py:
+ * 471-484, fetched in main.py:654-670) without ever materialising the shard on the host a second time.  Needs ptrace
+ * permission on `pid` (same user; the driver allows its actors with prctl(PR_SET_PTRACER)); fails with a message
+ * otherwise and the caller falls back to the shared-memory file hand-off. */
+int B2_MatrixCreateFromProcess(int64_t pid, uint64_t remote_addr, int64_t remote_row_stride_bytes, int64_t n_rows,
+                               int32_t n_cols, float missing, int device, B2Handle* out);
 /* field: "label" | "weight" | "base_margin" (len n_rows, or n_rows*num_class for base_margin) */
 int B2_MatrixSetFloatInfo(B2Handle m, const char* field, const float* values, int64_t len);
 /* feature types: is_cat[f] != 0 marks feature f categorical (xgb.DMatrix(feature_types=[...'c'...],

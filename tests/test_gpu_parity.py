@@ -35,17 +35,18 @@ def make_data(n, f, seed, kind="uniform", nan_frac=0.0):
 
 
 # ------------------------------------------------------------------ histogram kernel (a10)
-# F = 32 a + r with 0 < r <= 16 puts the r leftover features into a NARROW last group (one lane per row, pow2ceil(r) steps,
-# 32 / w shared-memory replicas): widths 1, 2, 4, 8, 16 alone and behind full groups are all covered here
+# with B2_HIST_NARROW=1 F = 32 a + r, 0 < r <= 16 puts the r leftover features into a NARROW last group (one lane per row,
+# pow2ceil(r) steps, 32 / w shared-memory replicas): widths 1, 2, 4, 8, 16 alone and behind full groups are all covered
+@pytest.mark.parametrize("narrow", [0, 1])
 @pytest.mark.parametrize("n,f", [(1, 1), (17, 3), (1000, 28), (5000, 100), (3000, 50), (2000, 200), (4097, 33),
                                  (3001, 2), (2500, 34), (3000, 12), (777, 16), (2000, 48), (1500, 7), (6000, 104)])
-def test_hist_kernel_bit_exact(eng, oracle, n, f):
+def test_hist_kernel_bit_exact(eng, oracle, n, f, narrow):
     rng = np.random.RandomState(n + f)
     bins = rng.randint(0, 256, size=(n, f)).astype(np.uint8)
     qg = rng.randint(-(1 << 18), 1 << 18, size=n).astype(np.int32)
     qh = rng.randint(0, 1 << 18, size=n).astype(np.int32)
     ref = oracle.hist_int(bins, qg, qh)
-    got, _ = eng.hist_build_raw(bins, qg, qh, window_rows=4096, chunk_rows=512)
+    got, _ = eng.hist_build_raw(bins, qg, qh, window_rows=4096, chunk_rows=512, narrow=narrow)
     assert np.array_equal(ref, got)
 
 
@@ -99,7 +100,7 @@ def test_hist_kernel_variants_bit_exact(oracle):
         "        assert np.array_equal(ref, got), (f, ridx is None)\n"
         "print('variant ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for env in ({"B2_HIST_TMA": "1"}, {"B2_HIST_VARIANT": "0"}, {"B2_HIST_VARIANT": "1"}, {"B2_HIST_VARIANT": "2"},
-                {"B2_HIST_VARIANT": "3"}, {"B2_HIST_NARROW": "0"}, {"B2_HIST_VARIANT": "2", "B2_HIST_NARROW": "0"}):
+                {"B2_HIST_VARIANT": "3"}, {"B2_HIST_NARROW": "1"}, {"B2_HIST_VARIANT": "2", "B2_HIST_NARROW": "1"}):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
 

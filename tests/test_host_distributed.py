@@ -246,6 +246,9 @@ def test_actor_pool_shared_memory_and_actor_side_file_loading(tmp_path):
     b1 = train(params, d, num_boost_round=3, additional_results=e1, ray_params=RayParams(num_actors=2), callbacks=[PidRecorder()])
     shm = [v[1] for sh in d._shared.values() for v in sh.values() if isinstance(v, tuple) and v[0] == "shm"]
     assert shm and all(os.path.exists(p) for p in shm)
+    # the feature matrix itself is not copied at all: the actors read their rows out of this process
+    assert e1["timing"]["shard_transport"] == "remote" and all(sh["data"][0] == "remote" for sh in d._shared.values())
+    assert e1["timing"]["actor0"]["upload_s"] >= 0
     b2 = train(params, RayDMatrix(x, y), num_boost_round=3, additional_results=e2, ray_params=RayParams(num_actors=2),
                callbacks=[PidRecorder()])
     pids = lambda e: sorted(item[1] for per_rank in e["callback_returns"] for item in per_rank)  # noqa: E731
@@ -270,7 +273,17 @@ def test_actor_pool_shared_memory_and_actor_side_file_loading(tmp_path):
     assert e3["total_n"] == 600 and not df_all.refs                   # the driver never loaded the rows
     assert b3.get_dump() == b1.get_dump()                             # same rows, same model (row order does not matter)
     M.shutdown_actors()
-    assert not glob.glob("/dev/shm/b2x_%d_*" % os.getpid()) or True
+    # forced file hand-off (what the driver falls back to when the kernel refuses process_vm_readv): same model
+    os.environ["B2_SHARD_TRANSPORT"] = "shm"
+    try:
+        e4 = {}
+        d4 = RayDMatrix(x, y)
+        b4 = train(params, d4, num_boost_round=3, additional_results=e4, ray_params=RayParams(num_actors=2))
+        assert e4["timing"]["shard_transport"] == "shm" and all(sh["data"][0] == "shm" for sh in d4._shared.values())
+        assert b4.get_dump() == b1.get_dump()
+    finally:
+        del os.environ["B2_SHARD_TRANSPORT"]
+        M.shutdown_actors()
 
 
 @pytest.mark.timeout(300)

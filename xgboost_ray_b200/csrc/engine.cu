@@ -8,6 +8,9 @@
 //   smaller-child hist -> allreduce -> sibling subtraction -> ... -> leaf sums -> margin update.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <errno.h>
+#include <sys/types.h>
+#include <sys/uio.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -259,8 +262,57 @@ struct PinnedPool {
 };
 std::map<int, PinnedPool*> g_pools;
 
+// Where the rows of an upload come from: this process (src) or ANOTHER process' memory (pid / remote_addr), row by row
+// `row_stride` bytes apart -- the driver's matrix read with process_vm_readv straight into the pinned staging slices, so
+// a shard never exists as a second host copy (matrix.py:471-484 puts every shard into the object store instead).
+struct UploadSource {
+  const void* src = nullptr;      // local, contiguous
+  long long pid = 0;              // != 0: remote
+  uint64_t remote_addr = 0;       // address of row 0 in process `pid`
+  size_t row_bytes = 0, row_stride = 0;
+};
+// copy `len` bytes starting at byte offset `off` of the (virtually contiguous) source into dst; returns false on error
+bool fetch_slice(const UploadSource& u, void* dst, size_t off, size_t len, std::string* err) {
+  if (u.pid == 0) { memcpy(dst, (const char*)u.src + off, len); return true; }
+  if (u.row_stride == u.row_bytes) {   // contiguous rows: one (or a few) big reads
+    size_t done = 0;
+    while (done < len) {
+      struct iovec l = {(char*)dst + done, len - done}, r = {(void*)(uintptr_t)(u.remote_addr + off + done), len - done};
+      const ssize_t got = process_vm_readv((pid_t)u.pid, &l, 1, &r, 1, 0);
+      if (got <= 0) { if (err) *err = std::string("process_vm_readv: ") + strerror(errno); return false; }
+      done += (size_t)got;
+    }
+    return true;
+  }
+  // strided rows (INTERLEAVED sharding): one remote iovec per (part of a) row, at most 512 per call
+  constexpr int kMaxIov = 512;
+  struct iovec riov[kMaxIov];
+  size_t done = 0;
+  while (done < len) {
+    int n = 0; size_t batch = 0;
+    while (n < kMaxIov && done + batch < len) {
+      const size_t pos = off + done + batch, row = pos / u.row_bytes, in_row = pos % u.row_bytes;
+      const size_t take = std::min(u.row_bytes - in_row, len - done - batch);
+      riov[n].iov_base = (void*)(uintptr_t)(u.remote_addr + row * u.row_stride + in_row);
+      riov[n].iov_len = take;
+      batch += take; ++n;
+    }
+    struct iovec l = {(char*)dst + done, batch};
+    const ssize_t got = process_vm_readv((pid_t)u.pid, &l, 1, riov, (unsigned long)n, 0);
+    if (got != (ssize_t)batch) { if (err) *err = std::string("process_vm_readv: ") + (got < 0 ? strerror(errno) : "short read"); return false; }
+    done += batch;
+  }
+  return true;
+}
+
+void upload_pipelined(Ctx* ctx, void* dst, const UploadSource& u, size_t bytes);
 void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
-  if (bytes < ((size_t)64 << 20)) {
+  UploadSource u; u.src = src;
+  upload_pipelined(ctx, dst, u, bytes);
+}
+void upload_pipelined(Ctx* ctx, void* dst, const UploadSource& u, size_t bytes) {
+  const void* src = u.src;
+  if (u.pid == 0 && bytes < ((size_t)64 << 20)) {
     if (bytes) CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return;
@@ -285,6 +337,7 @@ void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
   const int W = n_workers;
   pool->init(W);
   std::atomic<int> failed{0};
+  std::mutex err_mu; std::string fetch_err;
   auto worker = [&](int w) {
     if (cudaSetDevice(ctx->device) != cudaSuccess) { failed = 1; return; }
     int use = 0;
@@ -292,7 +345,8 @@ void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
       const int k = use % PinnedPool::kSlots;
       const size_t off = i * PinnedPool::kSlice, len = std::min(PinnedPool::kSlice, bytes - off);
       if (use >= PinnedPool::kSlots && cudaEventSynchronize(pool->done[w][k]) != cudaSuccess) { failed = 1; return; }
-      memcpy(pool->buf[w][k], (const char*)src + off, len);
+      std::string e;
+      if (!fetch_slice(u, pool->buf[w][k], off, len, &e)) { std::lock_guard<std::mutex> lk(err_mu); fetch_err = e; failed = 2; return; }
       if (cudaMemcpyAsync((char*)dst + off, pool->buf[w][k], len, cudaMemcpyHostToDevice, pool->stream[w]) != cudaSuccess ||
           cudaEventRecord(pool->done[w][k], pool->stream[w]) != cudaSuccess) { failed = 1; return; }
     }
@@ -301,6 +355,7 @@ void upload_pipelined(Ctx* ctx, void* dst, const void* src, size_t bytes) {
   std::vector<std::thread> th;
   for (int w = 0; w < W; ++w) th.emplace_back(worker, w);
   for (auto& t : th) t.join();
+  if (failed.load() == 2) fail("reading the shard out of the driver process failed: %s", fetch_err.c_str());
   if (failed.load()) fail("pipelined host->device upload failed: %s", cudaGetErrorString(cudaGetLastError()));
 }
 
@@ -413,15 +468,19 @@ struct Matrix : HandleBase {
   DevBuf<uint32_t> d_fwq;
 };
 
-// Feature -> (group, slot) layout of the bin matrix.  F = 32 a + r: when 0 < r <= 16 the first `a` groups are full and
-// the r leftover features form a NARROW last group, which the histogram kernel processes one lane per row in
-// pow2ceil(r) steps instead of two lanes in 16 (hist_kernel.cu, v3) -- F = 100 then costs 6.25 shared-atomic wavefronts
-// per row instead of 8.  Otherwise the features are spread evenly over ceil(F / 32) groups.  B2_HIST_NARROW=0 keeps the
-// even layout of round 1.
+// Feature -> (group, slot) layout of the bin matrix.  Default: the features are spread EVENLY over ceil(F / 32) groups, so
+// that every CTA type of the histogram kernel (one pair of groups) costs the same and the types walk the chunk list in
+// lock step -- the CTAs that read the two 64-byte halves of a row do it at the same time and the row is fetched from
+// DRAM once.  B2_HIST_NARROW=1 selects the layout "a full groups + one NARROW group of the r = F mod 32 <= 16 leftover
+// features" (one lane per row, pow2ceil(r) steps; hist_kernel.cu v3).  It removes the padding-slot atomics (F = 100:
+// 6.25 instead of 8 wavefronts per row) but the CTA types then cost 4 : 2.25 and drift apart; measured on C3 (profiles/
+// r02_summary.md): DRAM traffic 2.8x, kernel 0.328 ms per launch against 0.219 ms for the even layout.  Kept as an
+// opt-in, parity-tested variant and as the record of that experiment.
+int g_hist_narrow = -1;   // -1: read B2_HIST_NARROW on first use; B2_SetOption("hist_narrow", ...) overrides it
 void setup_groups(Matrix* m) {
   const int F = m->F;
-  static int narrow_on = -1;
-  if (narrow_on < 0) { const char* e = getenv("B2_HIST_NARROW"); narrow_on = (e && atoi(e) == 0) ? 0 : 1; }
+  if (g_hist_narrow < 0) { const char* e = getenv("B2_HIST_NARROW"); g_hist_narrow = (e && atoi(e) != 0) ? 1 : 0; }
+  const int narrow_on = g_hist_narrow;
   m->n_groups = (F + B2_GROUP_SLOTS - 1) / B2_GROUP_SLOTS;
   if (m->n_groups < 1) m->n_groups = 1;
   m->row_stride = m->n_groups * B2_GROUP_SLOTS;
@@ -1596,6 +1655,13 @@ float* eval_margin(Booster* b, Matrix* m) {
 extern "C" {
 
 const char* B2_GetLastError(void) { return g_last_error.c_str(); }
+int B2_SetOption(const char* key, const char* value) {
+  API_BEGIN
+  std::string k(key ? key : ""), v(value ? value : "");
+  if (k == "hist_narrow") g_hist_narrow = atoi(v.c_str()) != 0 ? 1 : 0;   // layout of matrices quantised from now on
+  else fail("unknown option '%s'", k.c_str());
+  API_END
+}
 int B2_GetVersion(void) { return 100; }
 int B2_DeviceCount(int* out) {
   API_BEGIN
@@ -1699,6 +1765,24 @@ int B2_MatrixCreate(int64_t n_rows, int32_t n_cols, float missing, int device, B
   Ctx* ctx = get_ctx(device);
   Matrix* m = new Matrix(); m->kind = kMatrix; m->ctx = ctx; m->n = n_rows; m->F = n_cols; m->missing = missing;
   try { m->raw.ensure((size_t)std::max<int64_t>(n_rows * n_cols, 1)); } catch (...) { delete m; throw; }
+  m->has_raw = true;
+  { std::lock_guard<std::mutex> lk(g_matrix_mu); m->uid = g_next_matrix_uid++; g_live_matrices.insert(m->uid); }
+  *out = (B2Handle)m;
+  API_END
+}
+int B2_MatrixCreateFromProcess(int64_t pid, uint64_t remote_addr, int64_t remote_row_stride_bytes, int64_t n_rows, int32_t n_cols,
+                               float missing, int device, B2Handle* out) {
+  API_BEGIN
+  if (n_rows < 0 || n_cols <= 0) fail("invalid matrix shape %lld x %d", (long long)n_rows, n_cols);
+  if (n_rows >= (1LL << 31)) fail("at most 2^31-1 rows per GPU shard (row ids are int32), got %lld", (long long)n_rows);
+  if (pid <= 0 || remote_row_stride_bytes < (int64_t)n_cols * 4) fail("invalid remote source (pid %lld, row stride %lld)", (long long)pid, (long long)remote_row_stride_bytes);
+  Ctx* ctx = get_ctx(device);
+  Matrix* m = new Matrix(); m->kind = kMatrix; m->ctx = ctx; m->n = n_rows; m->F = n_cols; m->missing = missing;
+  try {
+    m->raw.ensure((size_t)std::max<int64_t>(n_rows * n_cols, 1));
+    UploadSource u; u.pid = pid; u.remote_addr = remote_addr; u.row_bytes = (size_t)n_cols * 4; u.row_stride = (size_t)remote_row_stride_bytes;
+    upload_pipelined(ctx, m->raw.p, u, (size_t)n_rows * n_cols * sizeof(float));
+  } catch (...) { delete m; throw; }
   m->has_raw = true;
   { std::lock_guard<std::mutex> lk(g_matrix_mu); m->uid = g_next_matrix_uid++; g_live_matrices.insert(m->uid); }
   *out = (B2Handle)m;

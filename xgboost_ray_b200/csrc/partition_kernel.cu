@@ -99,9 +99,14 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       s_pref[i0 & 7][i0 >> 3] = excl;
       s_pref[i1 & 7][i1 >> 3] = excl + c0;
       if (lane == 31) {
+        // ONE 64-bit atomic per chunk claims both output ranges: low word = left rows so far (what finalize_level reads
+        // as the left child's size), high word = rows so far; rights so far = rows - lefts.  At the shallow levels all
+        // chunks hit the same one or two counters and the same-address atomics serialise (level 0: 9.8K of them).
         const int acc = incl;
-        s_base_left = atomicAdd(&counters[2 * lo], acc);
-        s_base_right = atomicAdd(&counters[2 * lo + 1], nrows - acc);
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2 * lo),
+                                                 ((unsigned long long)(unsigned)nrows << 32) | (unsigned long long)(unsigned)acc);
+        s_base_left = (int)(unsigned)(old & 0xffffffffull);
+        s_base_right = (int)(unsigned)(old >> 32) - s_base_left;
       }
     }
     __syncthreads();

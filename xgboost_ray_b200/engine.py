@@ -39,6 +39,7 @@ _H = C.c_uint64
 ABI = {
     "B2_GetLastError": (C.c_char_p, []),
     "B2_GetVersion": (C.c_int, []),
+    "B2_SetOption": (C.c_int, [C.c_char_p, C.c_char_p]),
     "B2_DeviceCount": (C.c_int, [C.POINTER(C.c_int)]),
     "B2_GetUniqueId": (C.c_int, [_BP]),
     "B2_CommCreate": (C.c_int, [_BP, C.c_int, C.c_int, C.c_int, C.POINTER(_H)]),
@@ -48,6 +49,8 @@ ABI = {
     "B2_CommFree": (C.c_int, [_H]),
     "B2_MatrixCreateFromDense": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
     "B2_MatrixCreate": (C.c_int, [C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
+    "B2_MatrixCreateFromProcess": (C.c_int, [C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int,
+                                             C.POINTER(_H)]),
     "B2_MatrixSetRows": (C.c_int, [_H, C.c_int64, _FP, C.c_int64]),
     "B2_MatrixSetFloatInfo": (C.c_int, [_H, C.c_char_p, _FP, C.c_int64]),
     "B2_MatrixSetFeatureTypes": (C.c_int, [_H, _BP, C.c_int32]),
@@ -240,11 +243,16 @@ class DMatrix:
             else:
                 data = data.values
         blocks = None
-        if hasattr(data, "next") and hasattr(data, "reset"):       # xgboost.DataIter protocol (matrix.py:127-196)
+        remote = data if (hasattr(data, "pid") and hasattr(data, "row_stride") and hasattr(data, "addr")) else None
+        if remote is not None:                                     # rows of another process (matrix.RemoteBlock)
+            data = remote
+        elif hasattr(data, "next") and hasattr(data, "reset"):       # xgboost.DataIter protocol (matrix.py:127-196)
             blocks, label, weight, base_margin = _drain_data_iter(data, label, weight, base_margin)
         elif isinstance(data, (list, tuple)) and data and all(hasattr(b, "shape") for b in data):
             blocks = [np.asarray(b.values if hasattr(b, "values") and not isinstance(b, np.ndarray) else b) for b in data]
-        if blocks is not None:
+        if remote is not None:
+            pass
+        elif blocks is not None:
             blocks = [b.reshape(-1, 1) if b.ndim == 1 else b for b in blocks]
             if len({b.shape[1] for b in blocks}) != 1:
                 raise XGBoostError("all row blocks of a DMatrix must have the same number of columns")
@@ -271,7 +279,12 @@ class DMatrix:
         self._base_margin = None
         h = _H(0)
         n, f = self._host.shape
-        if isinstance(self._host, _BlockList):
+        if remote is not None:
+            # the shard lives in the driver process: read it straight into the pinned upload buffers
+            _check(lib().B2_MatrixCreateFromProcess(remote.pid, remote.addr, remote.row_stride, n, f, self.missing, self.device,
+                                                    C.byref(h)))
+            self.handle = h.value
+        elif isinstance(self._host, _BlockList):
             # several row blocks (multi-file shard / DataIter): one device allocation, each block uploaded at its row
             # offset -- the host never concatenates them
             _check(lib().B2_MatrixCreate(n, f, self.missing, self.device, C.byref(h)))
@@ -359,6 +372,8 @@ class DMatrix:
         if not self._has_raw:
             if isinstance(self._host, _BlockList):   # rare (predicting on a block-built training matrix): one host copy
                 self._host = np.concatenate(self._host.blocks, axis=0)
+            elif not isinstance(self._host, np.ndarray):   # rows of another process: fetch them once
+                self._host = _f32c(np.asarray(self._host))
             _check(lib().B2_MatrixEnsureRaw(self.handle, _fp(self._host)))
             self._has_raw = True
 
@@ -1149,8 +1164,20 @@ def train(params, dtrain, num_boost_round=10, evals=(), obj=None, feval=None, ma
     return bst
 
 
-def hist_build_raw(bins, qg, qh, ridx=None, window_rows=8192, chunk_rows=2048, device=None):
-    """Kernel-level entry (tests / roofline probe): returns (hist [F,256,2] int64, kernel_ms)."""
+def set_option(key, value):
+    """Process-wide engine option (B2_SetOption)."""
+    _check(lib().B2_SetOption(str(key).encode(), str(value).encode()))
+
+
+def hist_build_raw(bins, qg, qh, ridx=None, window_rows=8192, chunk_rows=2048, device=None, narrow=None):
+    """Kernel-level entry (tests / roofline probe): returns (hist [F,256,2] int64, kernel_ms).  narrow = 0 / 1 selects
+    the feature-group layout for this call (None: the process default)."""
+    if narrow is not None:
+        try:
+            set_option("hist_narrow", int(narrow))
+            return hist_build_raw(bins, qg, qh, ridx, window_rows, chunk_rows, device)
+        finally:
+            set_option("hist_narrow", 1 if os.environ.get("B2_HIST_NARROW", "0") not in ("", "0") else 0)
     bins = np.ascontiguousarray(bins, np.uint8)
     n, f = bins.shape
     qg = np.ascontiguousarray(qg, np.int32)

@@ -136,6 +136,75 @@ def _shared_copy(src: Optional[np.ndarray], tag: str):
     return a, ("shm", path)
 
 
+# ---- zero-copy hand-off: the actor reads its rows straight out of the DRIVER's memory (process_vm_readv) into the pinned
+# upload buffers of the engine (B2_MatrixCreateFromProcess).  The shard is then never copied on the host at all; the
+# /dev/shm files above remain the fallback when the kernel refuses the read (ptrace restrictions).
+_PTRACE_ALLOWED = [False]
+
+
+def allow_actors_to_read_this_process():
+    """prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY): lets the actor processes (children) read this process' memory where the
+    Yama LSM restricts ptrace to descendants.  A no-op error (EINVAL) where Yama is not in use."""
+    if _PTRACE_ALLOWED[0]:
+        return
+    _PTRACE_ALLOWED[0] = True
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        libc.prctl(0x59616D61, ctypes.c_ulong(0xFFFFFFFFFFFFFFFF), 0, 0, 0)
+    except Exception:
+        pass
+
+
+class RemoteBlock:
+    """n_rows x n_cols float32 rows living in process `pid` at `addr`, `row_stride` bytes apart."""
+
+    def __init__(self, pid, addr, row_stride, n_rows, n_cols):
+        self.pid, self.addr, self.row_stride = int(pid), int(addr), int(row_stride)
+        self.shape = (int(n_rows), int(n_cols))
+        self.ndim = 2
+        self.dtype = np.dtype(np.float32)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __array__(self, dtype=None, copy=None):
+        """Materialise on the host (the CPU stand-in engine and rare re-uploads use this; the GPU path does not)."""
+        import ctypes
+
+        class _IoVec(ctypes.Structure):
+            _fields_ = [("base", ctypes.c_void_p), ("len", ctypes.c_size_t)]
+
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        n, f = self.shape
+        out = np.empty((n, f), np.float32)
+        row_bytes = f * 4
+        if n == 0:
+            return out
+        if self.row_stride == row_bytes:
+            done, total = 0, n * row_bytes
+            while done < total:
+                lo = _IoVec(out.ctypes.data + done, total - done)
+                ro = _IoVec(self.addr + done, total - done)
+                got = libc.process_vm_readv(self.pid, ctypes.byref(lo), 1, ctypes.byref(ro), 1, 0)
+                if got <= 0:
+                    raise OSError(ctypes.get_errno(), "process_vm_readv failed: %s" % os.strerror(ctypes.get_errno()))
+                done += got
+        else:
+            step = 512
+            riov = (_IoVec * step)()
+            for r0 in range(0, n, step):
+                k = min(step, n - r0)
+                for i in range(k):
+                    riov[i].base = self.addr + (r0 + i) * self.row_stride
+                    riov[i].len = row_bytes
+                lo = _IoVec(out.ctypes.data + r0 * row_bytes, k * row_bytes)
+                got = libc.process_vm_readv(self.pid, ctypes.byref(lo), 1, riov, k, 0)
+                if got != k * row_bytes:
+                    raise OSError(ctypes.get_errno(), "process_vm_readv failed: %s" % os.strerror(ctypes.get_errno()))
+        return out if dtype is None else out.astype(dtype, copy=False)
+
+
 def _column_or_array(frame: LoadedFrame, spec, exclude: set):
     """`spec` is None, a column name of the loaded frame, or an array-like of row values."""
     if spec is None:
@@ -224,9 +293,13 @@ class RayDMatrix:
                 self._inferred_types = list(x.feature_types)
         return x, y, w, fw, b, ll, lu
 
-    def load_data(self, num_actors: Optional[int] = None, rank: Optional[int] = None):
+    def load_data(self, num_actors: Optional[int] = None, rank: Optional[int] = None, transport: Optional[str] = None):
         """Central loading (matrix.py:431-487): read once, shard per rank.  Distributed (file lists,
-        matrix.py:614-693): rank r reads files r, r+W, ... itself."""
+        matrix.py:614-693): rank r reads files r, r+W, ... itself.  transport = "remote": the feature matrix is NOT
+        copied per shard -- every shard is a description of its rows inside this process that the actor reads directly
+        (RemoteBlock); "shm" (default): shards are written to /dev/shm files."""
+        if transport is not None:
+            self._transport = transport
         if num_actors is not None:
             if self.num_actors is not None and num_actors != self.num_actors:
                 raise ValueError(f"The `RayDMatrix` was initialized or `load_data()`has been called with a different "
@@ -276,11 +349,21 @@ class RayDMatrix:
                 if v is not None and len(v) != n:
                     raise ValueError(f"`{name}` has {len(v)} rows but the data has {n}")
             self._columns = x.columns
+            remote = getattr(self, "_transport", "shm") == "remote" and x.values.flags.c_contiguous and n > 0
+            if remote:
+                allow_actors_to_read_this_process()
+                self._keep_alive = x.values            # the actors read these bytes until their upload is done
             for r in range(W):
                 sl = _get_sharding_indices(self.sharding, r, W, n)
                 ref, shared = {"feature_weights": fw, "qid": None}, {"feature_weights": fw, "qid": None}
                 for name, a in (("data", x.values), ("label", y), ("weight", w), ("base_margin", b),
                                 ("label_lower_bound", ll), ("label_upper_bound", lu)):
+                    if name == "data" and remote:
+                        view = a[sl]                  # no copy: a strided / contiguous view of the caller's matrix
+                        ref[name] = view
+                        shared[name] = ("remote", os.getpid(), int(view.ctypes.data) if len(view) else 0,
+                                        int(view.strides[0]) if len(view) else a.shape[1] * 4, len(view), a.shape[1])
+                        continue
                     ref[name], shared[name] = _shared_copy(None if a is None else a[sl], "%x_%d_%s" % (self._uid & 0xffffffff, r, name))
                 self.refs[r], self._shared[r] = ref, shared
             self.n = n
@@ -315,6 +398,7 @@ class RayDMatrix:
                     except OSError:
                         pass
         self.refs, self._shared = {}, {}
+        self._keep_alive = None
         self.loaded = False
 
     def __del__(self):
