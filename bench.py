@@ -392,6 +392,8 @@ def main():
         if rank == 0:
             sampler.start()      # NVML init takes longer than a short timed region; samples are reset below
         dm = E.DMatrix(X, label=y, **dm_kw)
+        if world > 1:
+            E.collective.allreduce([0.0])    # NCCL connects its peers lazily on the first collective: keep that out of quantise_seconds
         t0 = time.time()
         dm._ensure_quantized(256)
         t_quant = time.time() - t0

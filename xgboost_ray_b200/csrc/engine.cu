@@ -284,23 +284,33 @@ bool fetch_slice(const UploadSource& u, void* dst, size_t off, size_t len, std::
     }
     return true;
   }
-  // strided rows (INTERLEAVED sharding): one remote iovec per (part of a) row, at most 512 per call
-  constexpr int kMaxIov = 512;
-  struct iovec riov[kMaxIov];
+  // strided rows (INTERLEAVED sharding: every W-th row of the driver's matrix).  One remote iovec per row costs the
+  // kernel a page pin per 400-byte row (measured: 3 s for a 2 GB shard, 23 s with two actors contending); instead the
+  // CONTIGUOUS span that covers a batch of rows is read with one iovec into a scratch buffer and the wanted rows are
+  // picked out of it locally -- W times the bytes over the memory bus, two orders of magnitude fewer page pins.
+  constexpr size_t kSpan = (size_t)4 << 20;
+  static thread_local std::vector<char> scratch;
+  if (scratch.size() < kSpan + u.row_stride) scratch.resize(kSpan + u.row_stride);
+  const size_t rows_per_batch = std::max<size_t>(1, kSpan / u.row_stride);
   size_t done = 0;
   while (done < len) {
-    int n = 0; size_t batch = 0;
-    while (n < kMaxIov && done + batch < len) {
-      const size_t pos = off + done + batch, row = pos / u.row_bytes, in_row = pos % u.row_bytes;
-      const size_t take = std::min(u.row_bytes - in_row, len - done - batch);
-      riov[n].iov_base = (void*)(uintptr_t)(u.remote_addr + row * u.row_stride + in_row);
-      riov[n].iov_len = take;
-      batch += take; ++n;
+    const size_t pos = off + done, row0 = pos / u.row_bytes;
+    const size_t last_byte = std::min(off + len, (row0 + rows_per_batch) * u.row_bytes) - 1;
+    const size_t row1 = last_byte / u.row_bytes;                      // last row touched by this batch
+    const size_t span = (row1 - row0) * u.row_stride + u.row_bytes;
+    size_t got_total = 0;
+    while (got_total < span) {
+      struct iovec l = {scratch.data() + got_total, span - got_total};
+      struct iovec r = {(void*)(uintptr_t)(u.remote_addr + row0 * u.row_stride + got_total), span - got_total};
+      const ssize_t got = process_vm_readv((pid_t)u.pid, &l, 1, &r, 1, 0);
+      if (got <= 0) { if (err) *err = std::string("process_vm_readv: ") + strerror(errno); return false; }
+      got_total += (size_t)got;
     }
-    struct iovec l = {(char*)dst + done, batch};
-    const ssize_t got = process_vm_readv((pid_t)u.pid, &l, 1, riov, (unsigned long)n, 0);
-    if (got != (ssize_t)batch) { if (err) *err = std::string("process_vm_readv: ") + (got < 0 ? strerror(errno) : "short read"); return false; }
-    done += batch;
+    for (size_t row = row0; row <= row1; ++row) {
+      const size_t b0 = std::max(pos, row * u.row_bytes), b1 = std::min(off + len, (row + 1) * u.row_bytes);   // byte range of this row inside the slice
+      memcpy((char*)dst + (b0 - off), scratch.data() + (row - row0) * u.row_stride + (b0 - row * u.row_bytes), b1 - b0);
+    }
+    done = std::min(off + len, (row1 + 1) * u.row_bytes) - off;
   }
   return true;
 }
@@ -742,8 +752,13 @@ struct Booster : HandleBase {
   DevBuf<int2> q;                // [n]
   DevBuf<int32_t> ridx[2];
   DevBuf<long long> hist[2];
-  DevBuf<long long> hist_build;     // reduce-scatter send buffer [shards][node_cap][slice] (only when shards > 1)
-  DevBuf<B2SplitCand> d_cands_all;  // allgathered candidates [shards][nodes][cpn]
+  // Everything a peer maps lives in ONE allocation (one cudaIpc handle per peer instead of four): the build buffer, the
+  // candidate table, the misc table and the flag words are views into it
+  template <typename T> struct View { T* p = nullptr; };
+  DevBuf<uint8_t> xarena;
+  size_t xoff_cands = 0, xoff_misc = 0, xoff_flags = 0, x_misc_stride = 0;
+  View<long long> hist_build;       // reduce-scatter send buffer [shards][node_cap][slice] (only when shards > 1)
+  View<B2SplitCand> d_cands_all;    // candidates of all ranks [shards][nodes][cpn]
   int shards = 1, log2_shards = 0, sp = 32, cpn = 1;   // cpn = candidates per node (numeric CTAs + categorical CTAs)
   int cpn_num = 1;
   DevBuf<uint32_t> t_cat;                  // [max_nodes][8] category sets of the tree being grown
@@ -752,8 +767,9 @@ struct Booster : HandleBase {
   struct P2PState {
     bool enabled = false, tried = false;
     B2P2P pp;
-    DevBuf<uint32_t> flags, words;        // words: [kP2PSlots] epoch, [kP2PSlots] done, err, local abort stand-in
-    DevBuf<long long> misc;               // [world][misc_stride]
+    DevBuf<uint32_t> words;               // [kP2PSlots] epoch, [kP2PSlots] done, err, local abort stand-in (never mapped by peers)
+    uint32_t* flags = nullptr;            // views into Booster::xarena
+    long long* misc = nullptr;            // [world][misc_stride]
     std::vector<void*> opened;
     int cand_cap = 0;
   } p2p;
@@ -972,24 +988,19 @@ void p2p_setup(Booster* b) {
   if (env && (strcmp(env, "nccl") == 0 || strcmp(env, "NCCL") == 0)) return;
   Comm* c = b->comm; cudaStream_t s = b->ctx->stream; const int W = c->world;
   if (W > B2_P2P_MAX_WORLD) return;
-  const size_t lcap = (size_t)1 << b->p.max_depth;
-  const size_t misc_stride = 2 + 2 * lcap;                       // even: 16-byte aligned regions
+  const size_t misc_stride = b->x_misc_stride;
   const size_t n_flags = (size_t)b2_p2p_flag_words(W), n_words = 2 * (size_t)kP2PSlots + 2;
-  st.flags.ensure(n_flags); st.words.ensure(n_words); st.misc.ensure((size_t)W * misc_stride);
-  CUDA_CHECK(cudaMemsetAsync(st.flags.p, 0, n_flags * sizeof(uint32_t), s));
+  st.words.ensure(n_words);
+  CUDA_CHECK(cudaMemsetAsync(st.flags, 0, n_flags * sizeof(uint32_t), s));
   CUDA_CHECK(cudaMemsetAsync(st.words.p, 0, n_words * sizeof(uint32_t), s));
-  CUDA_CHECK(cudaMemsetAsync(st.misc.p, 0, (size_t)W * misc_stride * sizeof(long long), s));
-  struct Handles { cudaIpcMemHandle_t build, cands, misc, flags; };
-  Handles mine; int ok = 1;
-  if (cudaIpcGetMemHandle(&mine.build, b->hist_build.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.cands, b->d_cands_all.p) != cudaSuccess ||
-      cudaIpcGetMemHandle(&mine.misc, st.misc.p) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, st.flags.p) != cudaSuccess) {
-    ok = 0; cudaGetLastError(); memset(&mine, 0, sizeof(mine));
-  }
-  DevBuf<uint8_t> d_mine, d_all; d_mine.ensure(sizeof(Handles)); d_all.ensure(sizeof(Handles) * (size_t)W);
-  CUDA_CHECK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(Handles), cudaMemcpyHostToDevice, s));
-  NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(Handles), kNcclUint8, c->comm, s));   // also orders the memsets before any peer store
-  std::vector<Handles> all((size_t)W);
-  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Handles) * (size_t)W, cudaMemcpyDeviceToHost, s));
+  CUDA_CHECK(cudaMemsetAsync(st.misc, 0, (size_t)W * misc_stride * sizeof(long long), s));
+  cudaIpcMemHandle_t mine; int ok = 1;
+  if (cudaIpcGetMemHandle(&mine, b->xarena.p) != cudaSuccess) { ok = 0; cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+  DevBuf<uint8_t> d_mine, d_all; d_mine.ensure(sizeof(mine)); d_all.ensure(sizeof(mine) * (size_t)W);
+  CUDA_CHECK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+  NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(mine), kNcclUint8, c->comm, s));   // also orders the memsets before any peer store
+  std::vector<cudaIpcMemHandle_t> all((size_t)W);
+  CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(mine) * (size_t)W, cudaMemcpyDeviceToHost, s));
   CUDA_CHECK(cudaStreamSynchronize(s));
   memset(&st.pp, 0, sizeof(st.pp));
   st.pp.world = W; st.pp.rank = c->rank; st.pp.cand_cap = st.cand_cap; st.pp.misc_stride = (int32_t)misc_stride;
@@ -997,14 +1008,15 @@ void p2p_setup(Booster* b) {
   st.pp.abort_flag = c->d_abort ? c->d_abort : st.words.p + 2 * kP2PSlots + 1;
   st.pp.spin_limit = (long long)p2p_timeout_seconds() * 1000000LL;
   for (int w = 0; w < W && ok; ++w) {
-    if (w == c->rank) { st.pp.build[w] = b->hist_build.p; st.pp.cands[w] = b->d_cands_all.p; st.pp.misc[w] = st.misc.p; st.pp.flags[w] = st.flags.p; continue; }
-    void *pb = nullptr, *pc = nullptr, *pm = nullptr, *pf = nullptr;
-    if (cudaIpcOpenMemHandle(&pb, all[w].build, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&pc, all[w].cands, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&pm, all[w].misc, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-        cudaIpcOpenMemHandle(&pf, all[w].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
-    for (void* q : {pb, pc, pm, pf}) if (q) st.opened.push_back(q);
-    st.pp.build[w] = (long long*)pb; st.pp.cands[w] = (B2SplitCand*)pc; st.pp.misc[w] = (long long*)pm; st.pp.flags[w] = (uint32_t*)pf;
+    uint8_t* base = b->xarena.p;
+    if (w != c->rank) {
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      st.opened.push_back(q);
+      base = (uint8_t*)q;
+    }
+    st.pp.build[w] = (long long*)base; st.pp.cands[w] = (B2SplitCand*)(base + b->xoff_cands);
+    st.pp.misc[w] = (long long*)(base + b->xoff_misc); st.pp.flags[w] = (uint32_t*)(base + b->xoff_flags);
   }
   // agree: max over ranks of "failed"
   DevBuf<int32_t> d_ok; d_ok.ensure(1);
@@ -1052,7 +1064,20 @@ void ensure_ctl_tables(Booster* b) {
   b->cpn_num = (G * b->sp + 31) / 32;
   b->cpn = b->cpn_num + (b->train->any_cat() ? b2_cat_ctas() : 0);
   b->hist[0].ensure(half * b->slice_elems); b->hist[1].ensure(half * b->slice_elems);
-  if (b->shards > 1) { b->hist_build.ensure(half * b->node_elems); b->d_cands_all.ensure(half * b->cpn * b->shards); }
+  if (b->shards > 1) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t build_bytes = up(half * b->node_elems * sizeof(long long));
+    const size_t cands_bytes = up(half * b->cpn * b->shards * sizeof(B2SplitCand));
+    b->x_misc_stride = 2 + 2 * lcap;                                   // even: 16-byte aligned regions
+    const size_t misc_bytes = up((size_t)b->shards * b->x_misc_stride * sizeof(long long));
+    const size_t flag_bytes = up((size_t)b2_p2p_flag_words(b->shards) * sizeof(uint32_t));
+    b->xoff_cands = build_bytes; b->xoff_misc = b->xoff_cands + cands_bytes; b->xoff_flags = b->xoff_misc + misc_bytes;
+    b->xarena.ensure(b->xoff_flags + flag_bytes);
+    b->hist_build.p = (long long*)b->xarena.p;
+    b->d_cands_all.p = (B2SplitCand*)(b->xarena.p + b->xoff_cands);
+    b->p2p.misc = (long long*)(b->xarena.p + b->xoff_misc);
+    b->p2p.flags = (uint32_t*)(b->xarena.p + b->xoff_flags);
+  }
   b->d_cands.ensure(half * b->cpn);
   CUDA_CHECK(cudaMemsetAsync(b->t_i64.p, 0, L.i64_count * 8, b->ctx->stream));
   b->p2p.cand_cap = (int)(half * b->cpn);
