@@ -17,7 +17,8 @@
 namespace b2 {
 
 constexpr int kCtlThreads = 1024;
-constexpr int kPartChunkRows = 2048;  // must match partition_kernel.cu
+constexpr int kPartChunkRows = 2048;   // leaf-segment work items; must match partition_kernel.cu kPartChunk
+constexpr int kSplitChunkRows = 8192;  // split-node work items; must match partition_kernel.cu kSplitChunk
 
 __device__ __forceinline__ double c_calc_gain(double G, double H, const B2CtlParams& p) {
   return b2_calc_gain(G, H, p.mcw, p.lambda, p.alpha, p.max_delta_step);
@@ -107,7 +108,7 @@ decide_kernel(B2LevelCtl* __restrict__ ctl_cur, B2LevelCtl* __restrict__ ctl_nxt
     }
     const int rank = scan_split.step(expand ? 1 : 0);
     const int lrank = scan_leaf.step((in && !expand) ? 1 : 0);
-    const int chunks = expand ? (sg.count + kPartChunkRows - 1) / kPartChunkRows : 0;
+    const int chunks = expand ? (sg.count + kSplitChunkRows - 1) / kSplitChunkRows : 0;
     const int chunk_begin = scan_chunks.step(chunks);
     if (in && !expand) {
       B2LeafDev lf; lf.nid = sg.nid; lf.buf = sg.buf; lf.begin = sg.begin; lf.count = sg.count;

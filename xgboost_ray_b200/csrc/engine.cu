@@ -60,6 +60,7 @@ int b2_launch_eval_cat_splits(const long long*, int, const B2EvalNode*, int, con
 int b2_launch_cat_stats(const float*, int64_t, int, float, const int32_t*, int, int32_t*, int, cudaStream_t);
 int b2_launch_root_totals(const long long*, int, B2EvalNode*, const int32_t*, int, B2TrainParamDev, int, cudaStream_t);
 int b2_part_chunk_rows();
+int b2_split_chunk_rows();
 int b2_launch_partition(const uint8_t*, int64_t, const int32_t*, int32_t*, const B2SplitWork*, const B2LevelCtl*, int, int32_t*,
                         int, int, cudaStream_t);
 int b2_launch_leaf_sums(const float2*, const int32_t*, const int32_t*, const void*, const B2LevelCtl*, int, const int32_t*, int,
@@ -815,10 +816,11 @@ struct Booster : HandleBase {
       if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
       for (auto& pr : kv.second.hist_ev) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     }
-    if (p2p.enabled && ctx) {   // nobody frees a mapped buffer while a peer may still read it (bounded wait)
-      b2_launch_p2p_close(&p2p.pp, ctx->stream);
-      cudaStreamSynchronize(ctx->stream);
-    }
+    // No barrier with the peers here: a peer touches this rank's arena only inside the exchange kernels of a round, and
+    // every one of those accesses happens-before a flag that this rank waited for before ITS round completed -- once the
+    // last round is synchronised the arena is quiescent.  (A barrier in the destructor made a rank whose peer keeps its
+    // Booster alive -- the rank that returns the model -- spin until the peer-wait timeout: 23 s per train() call.)
+    if (ctx) cudaStreamSynchronize(ctx->stream);
     for (void* q : p2p.opened) cudaIpcCloseMemHandle(q);
     for (auto e : ev_pool) cudaEventDestroy(e);
     if (round_start) cudaEventDestroy(round_start);
@@ -1222,10 +1224,10 @@ void grow_tree(Booster* b, int k, int slot, TreeStats& st) {
   B2LevelCtl* ctl = b->d_ctl.p;
   const int window = window_rows_for(p.qbits);
   const int n_streams = std::max(1, ctx->num_sms * 3 / G);
-  const int pchunk = b2_part_chunk_rows();
-  const int max_part_chunks_total = (int)((n + pchunk - 1) / pchunk);
+  const int pchunk = b2_split_chunk_rows(), lchunk = b2_part_chunk_rows();
+  const int max_part_chunks_total = (int)((n + pchunk - 1) / pchunk);   // + nodes of the level: upper bound of the split work items
   const size_t lcap = (size_t)1 << D;
-  const int max_leaf_chunks = max_part_chunks_total + (int)lcap;
+  const int max_leaf_chunks = (int)((n + lchunk - 1) / lchunk) + (int)lcap;
 
   LAUNCH_CHECK(b2_launch_tree_init(tree, ctl, b->d_seg[0].p, b->d_ev[0].p, d_n_leaves, (int)n, b->d_hist_work.p, s));
   CUDA_CHECK(cudaMemsetAsync(b->d_leaf_sums.p, 0, 2 * lcap * sizeof(long long), s));

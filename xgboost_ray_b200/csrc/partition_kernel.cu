@@ -23,17 +23,28 @@ typedef B2SegWork SegWork;
 // kMode 0: numeric only.  1: category set in shared memory (the validated categorical path).  2 (experimental,
 // B2_PART_CAT_MODE=2): category set in eight uniform registers selected with a 3-level select tree, no shared-memory
 // load in the row loop.
-template <int kMode>
+constexpr int kSplitChunk = 8192;                       // rows per work item of the split-node kernels (partition, final assign)
+constexpr int kSplitPasses = kSplitChunk / kPartChunk;  // a work item is processed as 4 register passes of 2048 rows
+
+// One work item = 8192 consecutive rows of one split node.  The rows go through registers in 4 passes of 2048 (8 per
+// thread: 8 row-id loads and 8 bin-byte loads in flight); row id + left flag are parked in shared memory, ONE 64-bit
+// atomic claims the output ranges of the whole item, then the rows are written out.  Round 1 claimed per 2048 rows:
+// at the shallow levels the counters of all nodes sit in one cache line, the atomics of ~4900 chunks serialise in one
+// L2 slice (~14 ns each) and every level cost 50-70 us however little data it moved (ncu: long-scoreboard stalls,
+// DRAM at 10 % of peak, profiles/r02/).
+template <int kMode, bool kRoot>
 __global__ void __launch_bounds__(kPartThreads)
 partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const int32_t* __restrict__ ridx_in,
                  int32_t* __restrict__ ridx_out, const B2SplitWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl,
-                 int32_t* __restrict__ counters /* [2*n_work]: left, right */) {
+                 int32_t* __restrict__ counters /* [2*n_work]: low word lefts, high word rows claimed */) {
   const int n_work = ctl->n_split, total_chunks = ctl->part_chunks;
-  __shared__ int s_warp_left[kPartThreads / 32][kPartChunk / kPartThreads];
+  constexpr int kIters = kPartChunk / kPartThreads;                  // 8 rows per thread and pass
+  constexpr int kWarps = kPartThreads / 32;
+  constexpr int kCounts = kSplitPasses * kIters * kWarps;            // 256 per-warp left counts of a work item
+  __shared__ uint32_t s_rid[kSplitChunk];                            // bit 31 = row goes left
+  __shared__ int s_cnt[kCounts];                                     // index = (pass * kIters + it) * kWarps + warp (row order)
   __shared__ int s_base_left, s_base_right;
-  __shared__ int s_pref[kPartThreads / 32][kPartChunk / kPartThreads];
-  __shared__ uint32_t s_cat[8];   // category set of the chunk's split (all zero for a numeric split)
-  constexpr int kIters = kPartChunk / kPartThreads;
+  __shared__ uint32_t s_cat[8];   // category set of the item's split (all zero for a numeric split)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
     int lo = 0, hi = n_work - 1;
@@ -42,11 +53,8 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
     }
     const B2SplitWork w = work[lo];
-    const int row0 = (chunk - w.chunk_begin) * kPartChunk;
-    const int nrows = min(kPartChunk, w.seg_count - row0);
-    // the category set goes through shared memory so that the row loop below stays branch-free straight-line code
-    // (a divergent global load in its body kept the compiler from batching the 8 row-id / bin-byte loads: the
-    // kernel ran 1.7x slower, profiles/r01_summary.md)
+    const int row0 = (chunk - w.chunk_begin) * kSplitChunk;
+    const int nrows = min(kSplitChunk, w.seg_count - row0);
     constexpr bool kCat = kMode != 0;
     if (kMode == 1) {
       if (threadIdx.x < 8) s_cat[threadIdx.x] = w.is_cat ? __ldg(&work[lo].cat_bits[threadIdx.x]) : 0u;
@@ -58,68 +66,93 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       c0 = lo4.x; c1 = lo4.y; c2 = lo4.z; c3 = lo4.w; c4 = hi4.x; c5 = hi4.y; c6 = hi4.z; c7 = hi4.w;
     }
     const bool is_cat = kCat && w.is_cat != 0, has_missing = w.has_missing != 0, default_left = w.default_left != 0;
-    int rid[kIters]; bool left[kIters]; unsigned bal[kIters];
-#pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int r = it * kPartThreads + threadIdx.x;
-      const bool valid = r < nrows;
-      rid[it] = valid ? (ridx_in ? __ldg(ridx_in + w.seg_begin + row0 + r) : w.seg_begin + row0 + r) : 0;   // root: identity
-      int b = valid ? (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid[it]) : 0;
-      bool l;
-      if (kCat) {
-        uint32_t word;
-        if (kMode == 1) word = s_cat[b >> 5];
-        else {
-          const uint32_t w01 = (b & 32) ? c1 : c0, w23 = (b & 32) ? c3 : c2, w45 = (b & 32) ? c5 : c4, w67 = (b & 32) ? c7 : c6;
-          const uint32_t w03 = (b & 64) ? w23 : w01, w47 = (b & 64) ? w67 : w45;
-          word = (b & 128) ? w47 : w03;
-        }
-        const bool in_set = ((word >> (b & 31)) & 1u) != 0u;                     // category in the set -> right
-        const bool go_left = is_cat ? !in_set : (b <= w.split_bin);
-        l = (has_missing && b == B2_MISSING_BIN) ? default_left : go_left;
-      } else {
-        l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : (b <= w.split_bin);
+#pragma unroll 1
+    for (int pass = 0; pass < kSplitPasses; ++pass) {
+      const int pbase = pass * kPartChunk;
+      if (pbase >= nrows) {   // nothing left in this item (uniform): its counts are zero
+        if (threadIdx.x < kIters * kWarps) s_cnt[pass * kIters * kWarps + threadIdx.x] = 0;
+        continue;
       }
-      left[it] = valid && l;
-      bal[it] = __ballot_sync(0xffffffffu, left[it]);
-      if (lane == 0) s_warp_left[warp][it] = __popc(bal[it]);
+      // two straight-line batches -- 8 row-id loads, then 8 bin-byte loads -- so that all of them are in flight together
+      // (any branch between them, e.g. a test for the root's identity list, makes ptxas issue them as 8 dependent pairs)
+      int rid[kIters]; bool left[kIters]; int bin[kIters];
+      const int32_t* rsrc = kRoot ? nullptr : ridx_in + w.seg_begin + row0 + pbase + threadIdx.x;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int r = pbase + it * kPartThreads + threadIdx.x;
+        rid[it] = kRoot ? (r < nrows ? w.seg_begin + row0 + r : 0) : (r < nrows ? __ldg(rsrc + it * kPartThreads) : 0);
+      }
+      const uint8_t* col = bins_col + (int64_t)w.feature * col_stride;
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) bin[it] = (int)__ldg(col + rid[it]);   // row 0 for lanes past the end: harmless
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const int r = pbase + it * kPartThreads + threadIdx.x;
+        const bool valid = r < nrows;
+        const int b = bin[it];
+        bool l;
+        if (kCat) {
+          uint32_t word;
+          if (kMode == 1) word = s_cat[b >> 5];
+          else {
+            const uint32_t w01 = (b & 32) ? c1 : c0, w23 = (b & 32) ? c3 : c2, w45 = (b & 32) ? c5 : c4, w67 = (b & 32) ? c7 : c6;
+            const uint32_t w03 = (b & 64) ? w23 : w01, w47 = (b & 64) ? w67 : w45;
+            word = (b & 128) ? w47 : w03;
+          }
+          const bool in_set = ((word >> (b & 31)) & 1u) != 0u;                     // category in the set -> right
+          const bool go_left = is_cat ? !in_set : (b <= w.split_bin);
+          l = (has_missing && b == B2_MISSING_BIN) ? default_left : go_left;
+        } else {
+          l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : (b <= w.split_bin);
+        }
+        left[it] = valid && l;
+      }
+#pragma unroll
+      for (int it = 0; it < kIters; ++it) {
+        const unsigned bal = __ballot_sync(0xffffffffu, left[it]);
+        if (lane == 0) s_cnt[(pass * kIters + it) * kWarps + warp] = __popc(bal);
+        s_rid[pbase + it * kPartThreads + threadIdx.x] = (uint32_t)rid[it] | (left[it] ? 0x80000000u : 0u);
+      }
     }
     __syncthreads();
-    // exclusive prefix over (it, warp) in row order: index = it*8 + warp.  One warp scans the 64 counts with shuffles
-    // (a single thread walking them serially kept the other 255 threads of the CTA waiting for ~2000 cycles per chunk)
+    // exclusive prefix of the 256 counts in row order (warp 0: 8 consecutive counts per lane), then one atomic
     if (warp == 0) {
-      constexpr int kCounts = kIters * (kPartThreads / 32);           // 64
-      static_assert(kCounts == 64, "two counts per lane");
-      const int i0 = 2 * lane, i1 = 2 * lane + 1;                       // index = it * 8 + wp
-      const int c0 = s_warp_left[i0 & 7][i0 >> 3], c1 = s_warp_left[i1 & 7][i1 >> 3];
-      int incl = c0 + c1;
+      int c[kCounts / 32], sum = 0;
+#pragma unroll
+      for (int k = 0; k < kCounts / 32; ++k) { c[k] = s_cnt[lane * (kCounts / 32) + k]; sum += c[k]; }
+      int incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      const int excl = incl - (c0 + c1);
-      s_pref[i0 & 7][i0 >> 3] = excl;
-      s_pref[i1 & 7][i1 >> 3] = excl + c0;
+      int run = incl - sum;
+#pragma unroll
+      for (int k = 0; k < kCounts / 32; ++k) { s_cnt[lane * (kCounts / 32) + k] = run; run += c[k]; }
       if (lane == 31) {
-        // ONE 64-bit atomic per chunk claims both output ranges: low word = left rows so far (what finalize_level reads
-        // as the left child's size), high word = rows so far; rights so far = rows - lefts.  At the shallow levels all
-        // chunks hit the same one or two counters and the same-address atomics serialise (level 0: 9.8K of them).
-        const int acc = incl;
+        // low word = left rows so far (what finalize_level reads as the left child's size), high word = rows so far
         const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2 * lo),
-                                                 ((unsigned long long)(unsigned)nrows << 32) | (unsigned long long)(unsigned)acc);
+                                                 ((unsigned long long)(unsigned)nrows << 32) | (unsigned long long)(unsigned)incl);
         s_base_left = (int)(unsigned)(old & 0xffffffffull);
         s_base_right = (int)(unsigned)(old >> 32) - s_base_left;
       }
     }
     __syncthreads();
     const int base_l = s_base_left, base_r = s_base_right;
+#pragma unroll 1
+    for (int pass = 0; pass < kSplitPasses; ++pass) {
+      const int pbase = pass * kPartChunk;
+      if (pbase >= nrows) break;
 #pragma unroll
-    for (int it = 0; it < kIters; ++it) {
-      const int r = it * kPartThreads + threadIdx.x;
-      if (r < nrows) {
-        const int lrank = s_pref[warp][it] + __popc(bal[it] & ((1u << lane) - 1u));
-        if (left[it]) ridx_out[w.seg_begin + base_l + lrank] = rid[it];
-        else {
-          const int rrank = r - lrank;  // rights before this row inside the chunk
-          ridx_out[w.seg_begin + w.seg_count - 1 - (base_r + rrank)] = rid[it];
+      for (int it = 0; it < kIters; ++it) {
+        const int r = pbase + it * kPartThreads + threadIdx.x;
+        const uint32_t v = s_rid[r];
+        const bool l = (v & 0x80000000u) != 0u;
+        const unsigned bal = __ballot_sync(0xffffffffu, l);
+        if (r < nrows) {
+          const int lrank = s_cnt[(pass * kIters + it) * kWarps + warp] + __popc(bal & ((1u << lane) - 1u));
+          if (l) ridx_out[w.seg_begin + base_l + lrank] = (int32_t)(v & 0x7fffffffu);
+          else {
+            const int rrank = r - lrank;  // rights before this row inside the item
+            ridx_out[w.seg_begin + w.seg_count - 1 - (base_r + rrank)] = (int32_t)v;
+          }
         }
       }
     }
@@ -198,7 +231,7 @@ pred_update_kernel(float* __restrict__ margin, int K, int k, const int32_t* __re
 // the leaf index of the row; the margin is then updated by a streaming kernel (margin_update_kernel).
 // Leaf index of child `side` of split j: leaf_base + 2 j + side -- exactly the index decide_kernel gives the node at
 // the next level (leaves are numbered in node order; leaf_base = leaves that existed before this level's children).
-template <bool kCat>
+template <bool kCat, bool kRoot>
 __global__ void __launch_bounds__(kPartThreads)
 final_assign_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const int32_t* __restrict__ ridx_in,
                     const B2SplitWork* __restrict__ work, const B2LevelCtl* __restrict__ ctl, const float2* __restrict__ gh,
@@ -215,22 +248,34 @@ final_assign_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, co
       if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
     }
     const B2SplitWork w = work[lo];
-    const int row0 = (chunk - w.chunk_begin) * kPartChunk;
-    const int nrows = min(kPartChunk, w.seg_count - row0);
+    const int row0 = (chunk - w.chunk_begin) * kSplitChunk;
+    const int nrows = min(kSplitChunk, w.seg_count - row0);
     const bool is_cat = kCat && w.is_cat != 0;
     const int leaf_l = leaf_base + 2 * lo;
     long long lg = 0, lh = 0, rg = 0, rh = 0;
-#pragma unroll 4
-    for (int r = threadIdx.x; r < nrows; r += kPartThreads) {
-      const int rid = ridx_in ? __ldg(ridx_in + w.seg_begin + row0 + r) : w.seg_begin + row0 + r;
-      const int b = (int)__ldg(bins_col + (int64_t)w.feature * col_stride + rid);
-      bool go_left = b <= w.split_bin;
-      if (kCat && is_cat) go_left = ((__ldg(&work[lo].cat_bits[b >> 5]) >> (b & 31)) & 1u) == 0u;   // category in the set -> right
-      const bool l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : go_left;
-      const float2 v = __ldg(gh + rid);
-      const long long qg = __double2ll_rn(__dmul_rn((double)v.x, kg)), qh = __double2ll_rn(__dmul_rn((double)v.y, kh));
-      if (l) { lg += qg; lh += qh; } else { rg += qg; rh += qh; }
-      pos[rid] = (uint16_t)(leaf_l + (l ? 0 : 1));
+    // batches of 4 rows per thread: 4 row-id loads, then 4 bin bytes + 4 gradient pairs, all in flight together
+    constexpr int kBatch = 4;
+    const uint8_t* col = bins_col + (int64_t)w.feature * col_stride;
+    for (int r0 = threadIdx.x; r0 < nrows; r0 += kBatch * kPartThreads) {
+      int rid[kBatch]; int bin[kBatch]; float2 v[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int r = r0 + k * kPartThreads;
+        rid[k] = r < nrows ? (kRoot ? w.seg_begin + row0 + r : __ldg(ridx_in + w.seg_begin + row0 + r)) : -1;
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) { bin[k] = (int)__ldg(col + (rid[k] < 0 ? 0 : rid[k])); v[k] = __ldg(gh + (rid[k] < 0 ? 0 : rid[k])); }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        if (rid[k] < 0) continue;
+        const int b = bin[k];
+        bool go_left = b <= w.split_bin;
+        if (kCat && is_cat) go_left = ((__ldg(&work[lo].cat_bits[b >> 5]) >> (b & 31)) & 1u) == 0u;   // category in the set -> right
+        const bool l = (w.has_missing && b == B2_MISSING_BIN) ? (w.default_left != 0) : go_left;
+        const long long qg = __double2ll_rn(__dmul_rn((double)v[k].x, kg)), qh = __double2ll_rn(__dmul_rn((double)v[k].y, kh));
+        if (l) { lg += qg; lh += qh; } else { rg += qg; rh += qh; }
+        pos[rid[k]] = (uint16_t)(leaf_l + (l ? 0 : 1));
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -263,21 +308,25 @@ __global__ void iota_kernel(int32_t* out, int64_t n) {
 }  // namespace b2
 
 extern "C" {
-int b2_part_chunk_rows() { return b2::kPartChunk; }
+int b2_part_chunk_rows() { return b2::kPartChunk; }     // leaf-segment work items (leaf_sums / pred_update)
+int b2_split_chunk_rows() { return b2::kSplitChunk; }   // split-node work items (partition / final_assign)
 
 int b2_launch_partition(const uint8_t* bins_col, int64_t col_stride, const int32_t* ridx_in, int32_t* ridx_out,
                         const B2SplitWork* work, const B2LevelCtl* ctl, int max_chunks, int32_t* counters, int any_categorical,
                         int num_sms, cudaStream_t stream) {
   if (max_chunks <= 0) return 0;
-  int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
+  int grid = max_chunks < num_sms * 6 ? max_chunks : num_sms * 6;   // 6 CTAs per SM are resident (33 KB of shared memory, 48 registers)
   static int cat_mode = -1;
   if (cat_mode < 0) { const char* e = getenv("B2_PART_CAT_MODE"); cat_mode = (e && atoi(e) == 2) ? 2 : 1; }
-  if (any_categorical && cat_mode == 2)
-    b2::partition_kernel<2><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
-  else if (any_categorical)
-    b2::partition_kernel<1><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
-  else
-    b2::partition_kernel<0><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);
+#define B2_PART_LAUNCH(MODE)                                                                                                  \
+  do {                                                                                                                        \
+    if (ridx_in) b2::partition_kernel<MODE, false><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters); \
+    else b2::partition_kernel<MODE, true><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);         \
+  } while (0)
+  if (any_categorical && cat_mode == 2) B2_PART_LAUNCH(2);
+  else if (any_categorical) B2_PART_LAUNCH(1);
+  else B2_PART_LAUNCH(0);
+#undef B2_PART_LAUNCH
   return (int)cudaGetLastError();
 }
 int b2_launch_leaf_sums(const float2* gh, const int32_t* ridx0, const int32_t* ridx1, const void* work, const B2LevelCtl* ctl,
@@ -293,10 +342,10 @@ int b2_launch_final_assign(const uint8_t* bins_col, int64_t col_stride, const in
                            long long* sums, uint16_t* pos, int any_categorical, int num_sms, cudaStream_t stream) {
   if (max_chunks <= 0) return 0;
   int grid = max_chunks < num_sms * 8 ? max_chunks : num_sms * 8;
-  if (any_categorical)
-    b2::final_assign_kernel<true><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, work, ctl, gh, qexp, leaf_bits, sums, pos);
-  else
-    b2::final_assign_kernel<false><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, work, ctl, gh, qexp, leaf_bits, sums, pos);
+#define B2_FA_LAUNCH(CAT, ROOT) b2::final_assign_kernel<CAT, ROOT><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, work, ctl, gh, qexp, leaf_bits, sums, pos)
+  if (any_categorical) { if (ridx_in) B2_FA_LAUNCH(true, false); else B2_FA_LAUNCH(true, true); }
+  else { if (ridx_in) B2_FA_LAUNCH(false, false); else B2_FA_LAUNCH(false, true); }
+#undef B2_FA_LAUNCH
   return (int)cudaGetLastError();
 }
 int b2_launch_margin_update(float* margin, int K, int k, const uint16_t* pos, const float* leaf_value, int64_t n, int num_sms,
