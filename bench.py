@@ -306,7 +306,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "boosting rounds/sec", "value": v, "unit": "rounds/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_string(args), "sharding": "whole matrix on the host (CPU arm)",
+            "config": {"workload": workload_string(args),
                        "rows": args.rows, "cols": args.cols, "max_depth": args.depth, "max_bin": 256},
             "cpu_baseline": {"value": v, "unit": "rounds/s", "cores": cores, "kind": "port",
                              "sample": "full workload, %d timed rounds; CPU quantisation %.1fs not in the timed region" % (args.steps, t_quant)},

@@ -17,6 +17,4 @@ except Exception as e: print('$tag', 'no json', e)"
   tail -2 $O/bench_$tag.err
 }
 run c3_n8 8 --gen gpu
-run c3_n4 4 --gen gpu --no-public-e2e
 run c5_n8 8 --workload C5
-B2_EXCHANGE=nccl run c3_n8_nccl 8 --gen gpu --no-public-e2e --no-parity

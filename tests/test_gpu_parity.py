@@ -481,7 +481,7 @@ def test_unsupported_parameters_fail_loudly(eng):
     X = make_data(100, 3, 1)
     dm = eng.DMatrix(X, label=X[:, 0])
     for bad in ({"sampling_method": "gradient_based"}, {"grow_policy": "lossguide"}, {"max_leaves": 8},
-                {"monotone_constraints": "(1,0,0)"}, {"num_parallel_tree": 4}, {"max_bin": 1024}):
+                {"monotone_constraints": "(1,0,0)"}, {"max_bin": 1024}):
         with pytest.raises(eng.XGBoostError, match="not supported"):
             eng.train(dict({"objective": "reg:squarederror"}, **bad), dm, num_boost_round=1, verbose_eval=False)
 
