@@ -105,6 +105,23 @@ __device__ __forceinline__ size_t target_index(const HistTarget& t, int node_slo
   return ((size_t)r * t.node_cap + node_slot) * slice_elems + ((size_t)(group * 2 + plane) * B2_BINS + bin) * sp + sl;
 }
 
+// Same 16 steps when the group's shared-memory histogram starts on a 64 KiB boundary: the cell address
+//   group_base | bin << 8 | (half * 64 + slot * 4)
+// has the bin in byte 1 and everything else in bytes 0, 2, 3, so ONE prmt merges the bin byte of the row with the
+// per-step base (a loop-invariant register) -- 3 instructions per update pair instead of 4 (no add).
+__device__ __forceinline__ void accumulate_row_aligned(const RowData& d, uint32_t smem_g /* multiple of 65536 */, int rot, int half) {
+  uint4 b = rotate_bytes(d.bins, rot);
+  const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+  const uint32_t base = smem_g + half * 64;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t bj = base + (((uint32_t)(j + rot) & 15u) << 2);            // loop invariant: byte 1 is zero
+    const uint32_t a = __byte_perm(w[j >> 2], bj, 0x7604u | ((uint32_t)(j & 3) << 4));
+    red_shared_add(a, d.gp.x);
+    red_shared_add(a + B2_GROUP_SLOTS * 4, d.gp.y);
+  }
+}
+
 // lazy window flush: only cells whose magnitude reached 2^30 are moved to the global histogram.  Called
 // (between barriers) at least every `window_rows` = 2^(30 - qbits) rows, during which a cell can grow by
 // less than 2^30, so no int32 cell can overflow; for well spread bins nothing is flushed at all.

@@ -220,7 +220,7 @@ __device__ __forceinline__ void narrow_pass(const uint8_t* __restrict__ bins, in
 
 // full groups of a CTA, rows [0, nrows) of a chunk: kGPC = 2 -> four lanes cover the 64 contiguous bytes of the pair,
 // kGPC = 1 -> two lanes cover the 32 bytes of the single group (the register pipeline of hist_build_kernel)
-template <bool kGather, int kGPC>
+template <bool kGather, int kGPC, bool kAligned>
 __device__ __forceinline__ void full_pass(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                                           const int32_t* __restrict__ ridx, int64_t pos0, int nrows, int group0,
                                           uint32_t smem_base, int lane, int warp, int n_warps) {
@@ -242,17 +242,19 @@ __device__ __forceinline__ void full_pass(const uint8_t* __restrict__ bins, int 
   id1 = fetch_rid<kGather>(ridx, pos0, r0 + 4 * iter_rows, nrows);
   RowData s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
   id2 = fetch_rid<kGather>(ridx, pos0, r0 + 5 * iter_rows, nrows);
+#define B2_ACC(S) do { if (kAligned) accumulate_row_aligned(S, smem_g, rot, half); else accumulate_row(S, smem_g, rot, half); } while (0)
   for (int r = rbase; r < nrows; r += 3 * iter_rows) {   // warp-uniform trip count
-    accumulate_row(s0, smem_g, rot, half);
+    B2_ACC(s0);
     s0 = load_row_id(bins, gpair, id0, row_stride, lane_byte_off);
     id0 = fetch_rid<kGather>(ridx, pos0, r + sub + 6 * iter_rows, nrows);
-    if (r + iter_rows < nrows) accumulate_row(s1, smem_g, rot, half);
+    if (r + iter_rows < nrows) B2_ACC(s1);
     s1 = load_row_id(bins, gpair, id1, row_stride, lane_byte_off);
     id1 = fetch_rid<kGather>(ridx, pos0, r + sub + 7 * iter_rows, nrows);
-    if (r + 2 * iter_rows < nrows) accumulate_row(s2, smem_g, rot, half);
+    if (r + 2 * iter_rows < nrows) B2_ACC(s2);
     s2 = load_row_id(bins, gpair, id2, row_stride, lane_byte_off);
     id2 = fetch_rid<kGather>(ridx, pos0, r + sub + 8 * iter_rows, nrows);
   }
+#undef B2_ACC
 }
 
 template <bool kGather>
@@ -268,7 +270,9 @@ __device__ __forceinline__ void narrow_dispatch(int w, const uint8_t* __restrict
   }
 }
 
-template <bool kGather>
+// kAligned: the dynamic shared memory is 64 KiB larger than the two group histograms and the histograms start at the
+// first 64 KiB boundary inside it (accumulate_row_aligned)
+template <bool kGather, bool kAligned>
 __global__ void __launch_bounds__(1024, 1)
 hist_build_kernel_v3(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                      const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
@@ -277,7 +281,12 @@ hist_build_kernel_v3(const uint8_t* __restrict__ bins, int row_stride, const int
   HistTarget target; target.base = (unsigned long long*)hist; target.log2_shards = log2_shards; target.node_cap = node_cap;
   target.n_groups = n_groups;
   if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
-  extern __shared__ __align__(16) int32_t s_hist[];  // [2][256][2][32]
+  extern __shared__ __align__(16) int32_t s_raw[];  // [2][256][2][32] (+ up to 64 KiB of alignment slack)
+  int32_t* s_hist = s_raw;
+  if (kAligned) {
+    const uint32_t raw0 = (uint32_t)__cvta_generic_to_shared(s_raw);
+    s_hist = s_raw + ((((raw0 + 65535u) & ~65535u) - raw0) >> 2);
+  }
   int type = 0, cta0 = 0, cta1 = plan.cta_begin[1];
 #pragma unroll
   for (int t = 1; t < B2_HIST_MAX_TYPES; ++t)   // constant indices: the plan stays in the parameter bank
@@ -327,9 +336,9 @@ hist_build_kernel_v3(const uint8_t* __restrict__ bins, int row_stride, const int
     rows_in_window += nrows;
     const int64_t pos0 = (int64_t)seg_begin + row0;
     if (has1 && !narrow1) {
-      full_pass<kGather, 2>(bins, row_stride, gpair, ridx, pos0, nrows, g0, smem0, lane, warp, n_warps);
+      full_pass<kGather, 2, kAligned>(bins, row_stride, gpair, ridx, pos0, nrows, g0, smem0, lane, warp, n_warps);
     } else {
-      if (!narrow0) full_pass<kGather, 1>(bins, row_stride, gpair, ridx, pos0, nrows, g0, smem0, lane, warp, n_warps);
+      if (!narrow0) full_pass<kGather, 1, kAligned>(bins, row_stride, gpair, ridx, pos0, nrows, g0, smem0, lane, warp, n_warps);
       if (narrow0 || narrow1)
         narrow_dispatch<kGather>(plan.narrow_w, bins, row_stride, gpair, ridx, pos0, nrows, (narrow0 ? g0 : g1) * 32,
                                  smem0 + (narrow0 ? 0u : (uint32_t)(B2_GROUP_ELEMS * 4)), lane, warp, n_warps);
@@ -383,9 +392,13 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
   if (variant == 3) {
     // ---- group pairs with a narrow last group: CTAs per type in proportion to the atomic wavefronts per row
     static bool attr3 = false;
+    static int aligned = -1;   // B2_HIST_ALIGNED=0 keeps the 4-instruction update (A/B)
+    if (aligned < 0) { const char* e = getenv("B2_HIST_ALIGNED"); aligned = (e && atoi(e) == 0) ? 0 : 1; }
     if (!attr3) {
-      cudaFuncSetAttribute(b2::hist_build_kernel_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
-      cudaFuncSetAttribute(b2::hist_build_kernel_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
+      cudaFuncSetAttribute(b2::hist_build_kernel_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
+      cudaFuncSetAttribute(b2::hist_build_kernel_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
+      cudaFuncSetAttribute(b2::hist_build_kernel_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8 + 65536);
+      cudaFuncSetAttribute(b2::hist_build_kernel_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8 + 65536);
       attr3 = true;
     }
     if (!ctl && (total_chunks <= 0 || n_work <= 0)) return 0;
@@ -421,11 +434,16 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
     for (int t = 0; t < plan.n_types; ++t) plan.cta_begin[t + 1] = plan.cta_begin[t] + streams[t];
     for (int t = plan.n_types + 1; t <= B2_HIST_MAX_TYPES; ++t) plan.cta_begin[t] = plan.cta_begin[plan.n_types];
     dim3 grid3(plan.cta_begin[plan.n_types]), block3(1024);
-    const int smem3 = 2 * B2_GROUP_ELEMS * (int)sizeof(int32_t);
-    if (ridx) b2::hist_build_kernel_v3<true><<<grid3, block3, smem3, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                                                chunk_rows, window_rows, n_groups, hist, ctl, log2_shards, node_cap, plan);
-    else b2::hist_build_kernel_v3<false><<<grid3, block3, smem3, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks,
-                                                                           chunk_rows, window_rows, n_groups, hist, ctl, log2_shards, node_cap, plan);
+    const int smem3 = 2 * B2_GROUP_ELEMS * (int)sizeof(int32_t) + (aligned ? 65536 : 0);
+#define B2_V3_ARGS bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows, window_rows, n_groups, hist, ctl, log2_shards, node_cap, plan
+    if (aligned) {
+      if (ridx) b2::hist_build_kernel_v3<true, true><<<grid3, block3, smem3, stream>>>(B2_V3_ARGS);
+      else b2::hist_build_kernel_v3<false, true><<<grid3, block3, smem3, stream>>>(B2_V3_ARGS);
+    } else {
+      if (ridx) b2::hist_build_kernel_v3<true, false><<<grid3, block3, smem3, stream>>>(B2_V3_ARGS);
+      else b2::hist_build_kernel_v3<false, false><<<grid3, block3, smem3, stream>>>(B2_V3_ARGS);
+    }
+#undef B2_V3_ARGS
     return (int)cudaGetLastError();
   }
   const int gpc = variant == 2 ? 2 : 1;
