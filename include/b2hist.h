@@ -65,6 +65,14 @@ int B2_MatrixSetRows(B2Handle m, int64_t row_begin, const float* data, int64_t n
  * otherwise and the caller falls back to the shared-memory file hand-off. */
 int B2_MatrixCreateFromProcess(int64_t pid, uint64_t remote_addr, int64_t remote_row_stride_bytes, int64_t n_rows,
                                int32_t n_cols, float missing, int device, B2Handle* out);
+/* INTERLEAVED sharding (RayShardingMode.INTERLEAVED, xgboost_ray/matrix.py:71-87 / _get_sharding_indices :989-1003: rank r
+ * owns rows r, r+W, r+2W, ...) of a matrix that lives in process `pid`, n_total_rows x n_cols floats, C-contiguous at
+ * remote_addr.  A strided shard costs every rank a read of the WHOLE matrix span on the host (W-fold amplification), so
+ * this COLLECTIVE call (every rank of `comm`, shard_rank == its rank) has rank w read one contiguous 1/W block, stages it
+ * in HBM, and a gather kernel pulls the rows each rank owns out of the peers' staged blocks over NVLink (cudaIpc-mapped
+ * peer memory).  Result: the same device matrix B2_MatrixCreateFromProcess builds from the strided shard. */
+int B2_MatrixCreateFromProcessInterleaved(int64_t pid, uint64_t remote_addr, int64_t n_total_rows, int32_t n_cols,
+                                          int32_t shard_rank, B2Handle comm, float missing, int device, B2Handle* out);
 /* field: "label" | "weight" | "base_margin" (len n_rows, or n_rows*num_class for base_margin) */
 int B2_MatrixSetFloatInfo(B2Handle m, const char* field, const float* values, int64_t len);
 /* feature types: is_cat[f] != 0 marks feature f categorical (xgb.DMatrix(feature_types=[...'c'...],

@@ -244,3 +244,35 @@ def test_two_gpu_actor_killed_restart_and_elastic_continuation(oracle, tmp_path)
         leaf = o.split_feature < 0
         assert np.max(np.abs(t["value"][leaf] - o.value[leaf])) <= 1e-5
     M.shutdown_actors()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("ingest", ["nvlink", "host"])
+def test_two_gpu_interleaved_shards_redistributed_over_nvlink(ingest, monkeypatch):
+    """INTERLEAVED shards of a driver-resident matrix: every rank reads one contiguous half and the rows are exchanged
+    on the device (B2_MatrixCreateFromProcessInterleaved); the strided host read (B2_INTERLEAVED_INGEST=0) gives the same
+    device matrix, hence byte-identical trees -- also with a row count that is not a multiple of the world size, an eval
+    matrix of a different size, and on the pooled second call."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import xgboost_ray_b200.main as M
+    from xgboost_ray_b200 import RayDMatrix, RayParams, train
+    M.shutdown_actors()
+    monkeypatch.setenv("B2_INTERLEAVED_INGEST", "1" if ingest == "nvlink" else "0")
+    rng = np.random.RandomState(33)
+    n, f = 70001, 23
+    x = rng.normal(size=(n, f)).astype(np.float32)
+    x[rng.uniform(size=x.shape) < 0.02] = np.nan
+    y = (np.nan_to_num(x[:, 2]) - np.nan_to_num(x[:, 7]) ** 2 + rng.normal(scale=0.3, size=n)).astype(np.float32)
+    xe, ye = x[:9999], y[:9999]
+    params = {"objective": "reg:squarederror", "max_depth": 7, "eta": 0.2, "base_score": 0.0, "eval_metric": "rmse"}
+    r1, r2, add = {}, {}, {}
+    b1 = train(params, RayDMatrix(x, y), num_boost_round=5, evals=[(RayDMatrix(xe, ye), "e")], evals_result=r1,
+               ray_params=RayParams(num_actors=1))
+    b2 = train(params, RayDMatrix(x, y), num_boost_round=5, evals=[(RayDMatrix(xe, ye), "e")], evals_result=r2,
+               additional_results=add, ray_params=RayParams(num_actors=2))
+    b3 = train(params, RayDMatrix(x, y), num_boost_round=5, ray_params=RayParams(num_actors=2))
+    assert add["timing"]["actor0"]["ingest"] == ("nvlink-redistributed" if ingest == "nvlink" else "host")
+    assert _dump(b1) == _dump(b2) == _dump(b3)
+    assert np.allclose(r1["e"]["rmse"], r2["e"]["rmse"], rtol=0, atol=1e-9)
+    M.shutdown_actors()

@@ -100,8 +100,8 @@ def test_hist_kernel_variants_bit_exact(oracle):
         "        assert np.array_equal(ref, got), (f, ridx is None)\n"
         "print('variant ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for env in ({"B2_HIST_TMA": "1"}, {"B2_HIST_VARIANT": "0"}, {"B2_HIST_VARIANT": "1"}, {"B2_HIST_VARIANT": "2"},
-                {"B2_HIST_VARIANT": "3"}, {"B2_HIST_ALIGNED": "0"}, {"B2_HIST_NARROW": "1"},
-                {"B2_HIST_NARROW": "1", "B2_HIST_ALIGNED": "0"}, {"B2_HIST_VARIANT": "2", "B2_HIST_NARROW": "1"}):
+                {"B2_HIST_VARIANT": "3"}, {"B2_HIST_ALIGNED": "1"}, {"B2_HIST_NARROW": "1"},
+                {"B2_HIST_NARROW": "1", "B2_HIST_ALIGNED": "1"}, {"B2_HIST_VARIANT": "2", "B2_HIST_NARROW": "1"}):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])
 

@@ -48,6 +48,7 @@ int b2_launch_p2p_reduce_subtract(const void*, const long long*, long long*, con
 int b2_launch_p2p_quant_exponent(const void*, const uint32_t*, int32_t*, cudaStream_t);
 int b2_launch_p2p_leaf_sums(const void*, const int32_t*, long long*, cudaStream_t);
 int b2_launch_p2p_close(const void*, cudaStream_t);
+int b2_launch_gather_interleaved_rows(const void*, float*, int, cudaStream_t);
 int b2_launch_final_assign(const uint8_t*, int64_t, const int32_t*, const B2SplitWork*, const B2LevelCtl*, int, const float2*,
                            const int32_t*, int, long long*, uint16_t*, int, int, cudaStream_t);
 int b2_launch_margin_update(float*, int, int, const uint16_t*, const float*, int64_t, int, cudaStream_t);
@@ -1810,6 +1811,87 @@ int B2_MatrixCreateFromProcess(int64_t pid, uint64_t remote_addr, int64_t remote
     UploadSource u; u.pid = pid; u.remote_addr = remote_addr; u.row_bytes = (size_t)n_cols * 4; u.row_stride = (size_t)remote_row_stride_bytes;
     upload_pipelined(ctx, m->raw.p, u, (size_t)n_rows * n_cols * sizeof(float));
   } catch (...) { delete m; throw; }
+  m->has_raw = true;
+  { std::lock_guard<std::mutex> lk(g_matrix_mu); m->uid = g_next_matrix_uid++; g_live_matrices.insert(m->uid); }
+  *out = (B2Handle)m;
+  API_END
+}
+// host mirror of b2::B2RowBlocks (p2p_exchange.cu)
+struct RowBlocksHost {
+  const float* base[B2_P2P_MAX_WORLD];
+  long long start[B2_P2P_MAX_WORLD + 1];
+  int world, rank, n_cols;
+  long long n_mine;
+};
+int B2_MatrixCreateFromProcessInterleaved(int64_t pid, uint64_t remote_addr, int64_t n_total_rows, int32_t n_cols, int32_t shard_rank,
+                                          B2Handle commh, float missing, int device, B2Handle* out) {
+  API_BEGIN
+  if (n_total_rows < 0 || n_cols <= 0 || pid <= 0) fail("invalid remote matrix (%lld x %d, pid %lld)", (long long)n_total_rows, n_cols, (long long)pid);
+  Comm* c = commh ? &from_handle<CommH>(commh, kComm, "communicator")->c : nullptr;
+  if (!c || c->world < 2 || c->world > B2_P2P_MAX_WORLD) fail("interleaved remote ingest needs a communicator of 2..%d ranks", B2_P2P_MAX_WORLD);
+  const int W = c->world, rank = c->rank;
+  Ctx* ctx = get_ctx(device); cudaStream_t s = ctx->stream;
+  // contiguous block of this rank (BATCH split of the global rows) and the rows it finally owns (INTERLEAVED)
+  RowBlocksHost rb; memset(&rb, 0, sizeof(rb));
+  const int64_t per = n_total_rows / W, extra = n_total_rows % W;
+  for (int w = 0; w <= W; ++w) rb.start[w] = (long long)(w * per + std::min<int64_t>(w, extra));
+  const int64_t b0 = rb.start[rank], bn = rb.start[rank + 1] - b0;
+  const int64_t n_mine = rank < n_total_rows ? (n_total_rows - rank + W - 1) / W : 0;
+  if (n_mine >= (1LL << 31)) fail("at most 2^31-1 rows per GPU shard (row ids are int32), got %lld", (long long)n_mine);
+  rb.world = W; rb.rank = rank; rb.n_cols = n_cols; rb.n_mine = (long long)n_mine;
+  {   // collective call: every rank must hold the shard of its own rank, or all of them fail together
+    DevBuf<int32_t> d_ok; d_ok.ensure(1);
+    int32_t bad = shard_rank == rank ? 0 : 1;
+    CUDA_CHECK(cudaMemcpyAsync(d_ok.p, &bad, sizeof(bad), cudaMemcpyHostToDevice, s));
+    allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
+    CUDA_CHECK(cudaMemcpyAsync(&bad, d_ok.p, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (bad) fail("interleaved remote ingest: shard %d handed to rank %d (or a mismatch on another rank)", shard_rank, rank);
+  }
+  Matrix* m = new Matrix(); m->kind = kMatrix; m->ctx = ctx; m->n = n_mine; m->F = n_cols; m->missing = missing;
+  std::vector<void*> opened;
+  try {
+    DevBuf<float> stage; stage.ensure((size_t)std::max<int64_t>(bn * n_cols, 1));
+    UploadSource u; u.pid = pid; u.remote_addr = remote_addr + (uint64_t)b0 * (uint64_t)n_cols * 4u; u.row_bytes = (size_t)n_cols * 4; u.row_stride = u.row_bytes;
+    upload_pipelined(ctx, stage.p, u, (size_t)bn * n_cols * sizeof(float));
+    m->raw.ensure((size_t)std::max<int64_t>(n_mine * n_cols, 1));
+    // exchange the IPC handles of the staged blocks; one failed mapping anywhere makes every rank fail together
+    cudaIpcMemHandle_t mine; int ok = 1;
+    if (cudaIpcGetMemHandle(&mine, stage.p) != cudaSuccess) { ok = 0; cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+    DevBuf<uint8_t> d_mine, d_all; d_mine.ensure(sizeof(mine)); d_all.ensure(sizeof(mine) * (size_t)W);
+    CUDA_CHECK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+    NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(mine), kNcclUint8, c->comm, s));   // also: every rank's block is uploaded
+    std::vector<cudaIpcMemHandle_t> all((size_t)W);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(mine) * (size_t)W, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int w = 0; w < W && ok; ++w) {
+      if (w == rank) { rb.base[w] = stage.p; continue; }
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      opened.push_back(q); rb.base[w] = (const float*)q;
+    }
+    DevBuf<int32_t> d_ok; d_ok.ensure(1);
+    int32_t neg = ok ? 0 : 1;
+    CUDA_CHECK(cudaMemcpyAsync(d_ok.p, &neg, sizeof(neg), cudaMemcpyHostToDevice, s));
+    allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
+    CUDA_CHECK(cudaMemcpyAsync(&neg, d_ok.p, sizeof(neg), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    if (neg) {
+      // no peer mapping on some rank (no NVLink / IPC): every rank reads its own strided shard from the driver instead
+      for (void* q : opened) cudaIpcCloseMemHandle(q);
+      opened.clear();
+      UploadSource us; us.pid = pid; us.remote_addr = remote_addr + (uint64_t)rank * (uint64_t)n_cols * 4u;
+      us.row_bytes = (size_t)n_cols * 4; us.row_stride = us.row_bytes * (size_t)W;
+      upload_pipelined(ctx, m->raw.p, us, (size_t)n_mine * n_cols * sizeof(float));
+    } else {
+      LAUNCH_CHECK(b2_launch_gather_interleaved_rows(&rb, m->raw.p, ctx->num_sms, s));
+      // nobody releases its block while a peer may still be pulling rows out of it
+      allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
+      CUDA_CHECK(cudaStreamSynchronize(s));
+      for (void* q : opened) cudaIpcCloseMemHandle(q);
+      opened.clear();
+    }
+  } catch (...) { for (void* q : opened) cudaIpcCloseMemHandle(q); delete m; throw; }
   m->has_raw = true;
   { std::lock_guard<std::mutex> lk(g_matrix_mu); m->uid = g_next_matrix_uid++; g_live_matrices.insert(m->uid); }
   *out = (B2Handle)m;

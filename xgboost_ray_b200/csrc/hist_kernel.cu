@@ -392,8 +392,8 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
   if (variant == 3) {
     // ---- group pairs with a narrow last group: CTAs per type in proportion to the atomic wavefronts per row
     static bool attr3 = false;
-    static int aligned = -1;   // B2_HIST_ALIGNED=0 keeps the 4-instruction update (A/B)
-    if (aligned < 0) { const char* e = getenv("B2_HIST_ALIGNED"); aligned = (e && atoi(e) == 0) ? 0 : 1; }
+    static int aligned = -1;   // B2_HIST_ALIGNED=1: 64 KiB-aligned histograms, one PRMT forms the cell address (measured slower, profiles/r02/b7_*)
+    if (aligned < 0) { const char* e = getenv("B2_HIST_ALIGNED"); aligned = (e && atoi(e) != 0) ? 1 : 0; }
     if (!attr3) {
       cudaFuncSetAttribute(b2::hist_build_kernel_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);
       cudaFuncSetAttribute(b2::hist_build_kernel_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_GROUP_ELEMS * 8);

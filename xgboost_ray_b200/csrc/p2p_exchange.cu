@@ -93,6 +93,31 @@ p2p_leaf_sums_kernel(B2P2P pp, const int32_t* __restrict__ n_leaves, long long* 
   p2p_finish_single(pp, kSlotLeaf, epoch);
 }
 
+// INTERLEAVED sharding without host-side amplification: every rank uploads ONE contiguous block of the driver's matrix
+// (rows [start_w, start_w + count_w) on rank w, BATCH-style split) and then pulls the rows it owns -- global rows
+// rank, rank + W, rank + 2W, ... -- out of the peers' blocks over NVLink.  One warp per row, coalesced float4 / float
+// copies.  blocks[w] = device pointer of rank w's block (own pointer for w == rank).
+struct B2RowBlocks {
+  const float* base[B2_P2P_MAX_WORLD];
+  long long start[B2_P2P_MAX_WORLD + 1];   // first global row of every block; start[W] = n_total
+  int world, rank, n_cols;
+  long long n_mine;
+};
+__global__ void __launch_bounds__(256)
+gather_interleaved_rows_kernel(B2RowBlocks rb, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long j = warp; j < rb.n_mine; j += n_warps) {
+    const long long i = rb.rank + j * rb.world;                 // global row
+    int w = 0;
+#pragma unroll
+    for (int k = 1; k < B2_P2P_MAX_WORLD; ++k) if (k < rb.world && i >= rb.start[k]) w = k;
+    const float* src = rb.base[w] + (i - rb.start[w]) * rb.n_cols;
+    float* dst = out + j * rb.n_cols;
+    for (int c = lane; c < rb.n_cols; c += 32) dst[c] = src[c];
+  }
+}
+
 // teardown barrier: nobody frees a mapped buffer while a peer may still be reading it
 __global__ void p2p_close_kernel(B2P2P pp) {
   const uint32_t epoch = p2p_next_epoch(pp, kSlotClose);
@@ -128,6 +153,15 @@ int b2_launch_p2p_leaf_sums(const void* pp, const int32_t* n_leaves, long long* 
   b2::p2p_leaf_sums_kernel<<<1, 1024, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp), n_leaves, sums);
   return (int)cudaGetLastError();
 }
+int b2_launch_gather_interleaved_rows(const void* blocks, float* out, int num_sms, cudaStream_t s) {
+  const b2::B2RowBlocks& rb = *reinterpret_cast<const b2::B2RowBlocks*>(blocks);
+  if (rb.n_mine <= 0) return 0;
+  long long want = (rb.n_mine * 32 + 255) / 256;
+  int grid = (int)(want < (long long)num_sms * 16 ? want : (long long)num_sms * 16);
+  b2::gather_interleaved_rows_kernel<<<grid, 256, 0, s>>>(rb, out);
+  return (int)cudaGetLastError();
+}
+int b2_row_blocks_bytes() { return (int)sizeof(b2::B2RowBlocks); }
 int b2_launch_p2p_close(const void* pp, cudaStream_t s) {
   b2::p2p_close_kernel<<<1, 32, 0, s>>>(*reinterpret_cast<const B2P2P*>(pp));
   return (int)cudaGetLastError();

@@ -49,6 +49,8 @@ ABI = {
     "B2_CommFree": (C.c_int, [_H]),
     "B2_MatrixCreateFromDense": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
     "B2_MatrixCreate": (C.c_int, [C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
+    "B2_MatrixCreateFromProcessInterleaved": (C.c_int, [C.c_int64, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                                        C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
     "B2_MatrixCreateFromProcess": (C.c_int, [C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int,
                                              C.POINTER(_H)]),
     "B2_MatrixSetRows": (C.c_int, [_H, C.c_int64, _FP, C.c_int64]),
@@ -279,7 +281,17 @@ class DMatrix:
         self._base_margin = None
         h = _H(0)
         n, f = self._host.shape
-        if remote is not None:
+        self.ingest = "host"
+        inter = getattr(remote, "interleave", None) if remote is not None else None
+        if (inter is not None and _coll.handle and _coll.world == inter[3] and n * f > 0
+                and os.environ.get("B2_INTERLEAVED_INGEST", "1") != "0"):
+            # INTERLEAVED shard and every rank of the communicator builds its shard of the same matrix right now: each
+            # rank reads one contiguous block from the driver, the rows are redistributed over NVLink
+            _check(lib().B2_MatrixCreateFromProcessInterleaved(remote.pid, inter[0], inter[1], f, inter[2], _coll.handle,
+                                                               self.missing, self.device, C.byref(h)))
+            self.handle = h.value
+            self.ingest = "nvlink-redistributed"
+        elif remote is not None:
             # the shard lives in the driver process: read it straight into the pinned upload buffers
             _check(lib().B2_MatrixCreateFromProcess(remote.pid, remote.addr, remote.row_stride, n, f, self.missing, self.device,
                                                     C.byref(h)))

@@ -159,8 +159,11 @@ def allow_actors_to_read_this_process():
 class RemoteBlock:
     """n_rows x n_cols float32 rows living in process `pid` at `addr`, `row_stride` bytes apart."""
 
-    def __init__(self, pid, addr, row_stride, n_rows, n_cols):
+    def __init__(self, pid, addr, row_stride, n_rows, n_cols, interleave=None):
         self.pid, self.addr, self.row_stride = int(pid), int(addr), int(row_stride)
+        # (address of the full C-contiguous matrix, its row count, shard rank, number of shards) when these rows are the
+        # INTERLEAVED shard `rank` of that matrix: lets W ranks read 1/W each and redistribute on the device
+        self.interleave = tuple(int(v) for v in interleave) if interleave else None
         self.shape = (int(n_rows), int(n_cols))
         self.ndim = 2
         self.dtype = np.dtype(np.float32)
@@ -361,8 +364,11 @@ class RayDMatrix:
                     if name == "data" and remote:
                         view = a[sl]                  # no copy: a strided / contiguous view of the caller's matrix
                         ref[name] = view
+                        inter = None
+                        if self.sharding == RayShardingMode.INTERLEAVED and W > 1 and n >= W:
+                            inter = (int(a.ctypes.data), n, r, W)
                         shared[name] = ("remote", os.getpid(), int(view.ctypes.data) if len(view) else 0,
-                                        int(view.strides[0]) if len(view) else a.shape[1] * 4, len(view), a.shape[1])
+                                        int(view.strides[0]) if len(view) else a.shape[1] * 4, len(view), a.shape[1], inter)
                         continue
                     ref[name], shared[name] = _shared_copy(None if a is None else a[sl], "%x_%d_%s" % (self._uid & 0xffffffff, r, name))
                 self.refs[r], self._shared[r] = ref, shared
