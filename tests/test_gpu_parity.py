@@ -93,14 +93,14 @@ def test_hist_kernel_variants_bit_exact(oracle):
         "rng = np.random.RandomState(3); n = 70001\n"
         "qg = rng.randint(-(1 << 18), 1 << 18, size=n).astype(np.int32); qh = rng.randint(0, 1 << 18, size=n).astype(np.int32)\n"
         "sel = np.sort(rng.choice(n, 33333, replace=False)).astype(np.int32)\n"
-        "for f in (100, 70, 17):\n"   # 4, 3 (odd: a half-empty CTA in the two-group variant) and 1 feature groups
+        "for f in (100, 70, 17, 96, 105, 112):\n"   # 4, 3 (odd: a half-empty CTA in the two-group variant) and 1 feature groups; 96..112: the all-groups-per-CTA kernel
         "    bins = rng.randint(0, 256, size=(n, f)).astype(np.uint8)\n"
         "    for ridx in (None, sel):\n"
         "        ref = O.hist_int(bins, qg, qh, ridx); got, _ = E.hist_build_raw(bins, qg, qh, ridx=ridx, window_rows=4096, chunk_rows=2048)\n"
         "        assert np.array_equal(ref, got), (f, ridx is None)\n"
         "print('variant ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for env in ({"B2_HIST_TMA": "1"}, {"B2_HIST_VARIANT": "0"}, {"B2_HIST_VARIANT": "1"}, {"B2_HIST_VARIANT": "2"},
-                {"B2_HIST_VARIANT": "3"}, {"B2_HIST_ALIGNED": "1"}, {"B2_HIST_NARROW": "1"},
+                {"B2_HIST_VARIANT": "3"}, {"B2_HIST_VARIANT": "4"}, {"B2_HIST_ALIGNED": "1"}, {"B2_HIST_NARROW": "1"},
                 {"B2_HIST_NARROW": "1", "B2_HIST_ALIGNED": "1"}, {"B2_HIST_VARIANT": "2", "B2_HIST_NARROW": "1"}):
         r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "variant ok" in r.stdout, (env, r.stdout[-500:], r.stderr[-1500:])

@@ -47,6 +47,7 @@ int b2_launch_p2p_reduce_subtract(const void*, const long long*, long long*, con
                                   cudaStream_t);
 int b2_launch_p2p_quant_exponent(const void*, const uint32_t*, int32_t*, cudaStream_t);
 int b2_launch_p2p_leaf_sums(const void*, const int32_t*, long long*, cudaStream_t);
+int b2_hist_variant();
 int b2_launch_p2p_close(const void*, cudaStream_t);
 int b2_launch_gather_interleaved_rows(const void*, float*, int, cudaStream_t);
 int b2_launch_final_assign(const uint8_t*, int64_t, const int32_t*, const B2SplitWork*, const B2LevelCtl*, int, const float2*,
@@ -501,7 +502,9 @@ void setup_groups(Matrix* m) {
   m->feat_byte.assign(F, 0);
   m->narrow_w = 0;
   const int r = F % B2_GROUP_SLOTS;
-  const bool narrow = narrow_on && r > 0 && r <= 16;
+  // kernel v4 (all groups of a row in one CTA) wants three full groups + a narrow leftover group
+  const bool v4_layout = b2_hist_variant() == 4 && F > 96 && F <= 112;
+  const bool narrow = (narrow_on || v4_layout) && r > 0 && r <= 16;
   if (narrow) { m->narrow_w = 1; while (m->narrow_w < r) m->narrow_w <<= 1; }
   const int base = F / m->n_groups, rem = F % m->n_groups;
   int f = 0;

@@ -351,6 +351,164 @@ hist_build_kernel_v3(const uint8_t* __restrict__ bins, int row_stride, const int
   }
 }
 
+// ---------------------------------------------------------------- v4: every CTA builds ALL feature groups of its rows
+// ncu of v3 (profiles/r02/b7_hist_traffic.json): the kernel runs at ~0.96 shared-atomic wavefronts per clock per SM, the
+// limit of that pipe, while DRAM sits at 28 % -- the only way down is fewer wavefronts per row.  F = 100 in the even
+// layout pays for 128 slots.  v4 serves 96 < F <= 112 (and F = 96): three full groups (192 KiB of int32 cells) plus the
+// <= 16 leftover features as a narrow group in a 32 KiB [256 bins][2 planes][16 slots] block = 224 KiB, ONE CTA type, so
+// a row is read once by one CTA (no lock-step problem between types, see B2_HIST_NARROW in v3) and costs
+// 3 x 2 + w / 8 wavefronts instead of 8.  Lane pair p = lane >> 1 owns a row (16 rows per warp step), lane & 1 selects
+// the 16-byte half of each group; the three register stages of the pipeline are the three groups of the row.
+
+// one narrow group in the 16-slot layout, rows [0, nrows) of a chunk: lane = row, W steps; lanes l and l + 16 share banks
+template <bool kGather, int W>
+__device__ __forceinline__ void narrow_pass16(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                                              const int32_t* __restrict__ ridx, int64_t pos0, int nrows, int byte_off,
+                                              uint32_t smem_n, int lane, int warp, int n_warps) {
+  const int rot = lane & (W - 1), rep = (lane / W) & (16 / W - 1);
+  const uint32_t base = smem_n + (uint32_t)(rep * W) * 4u;
+  int r = warp * 32 + lane;
+  int64_t rid = r < nrows ? (kGather ? (int64_t)__ldg(ridx + pos0 + r) : pos0 + r) : -1;
+  NarrowBytes<W> cur; int2 gp = make_int2(0, 0);
+#pragma unroll
+  for (int k = 0; k < (W >= 4 ? W / 4 : 1); ++k) cur.w[k] = 0;
+  if (rid >= 0) { cur = load_narrow<W>(bins + rid * row_stride + byte_off, rot); gp = __ldg(gpair + rid); }
+  for (int r0 = warp * 32; r0 < nrows; r0 += n_warps * 32) {
+    const int rn = r0 + n_warps * 32 + lane;
+    const int64_t rid_n = rn < nrows ? (kGather ? (int64_t)__ldg(ridx + pos0 + rn) : pos0 + rn) : -1;
+    NarrowBytes<W> nxt; int2 gpn = make_int2(0, 0);
+#pragma unroll
+    for (int k = 0; k < (W >= 4 ? W / 4 : 1); ++k) nxt.w[k] = 0;
+    if (rid_n >= 0) { nxt = load_narrow<W>(bins + rid_n * row_stride + byte_off, rot); gpn = __ldg(gpair + rid_n); }
+    if (rid >= 0) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const uint32_t bin128 = __byte_perm(cur.w[j >> 2], 0u, 0x4404u | ((uint32_t)(j & 3) << 4)) >> 1;
+        const uint32_t a = base + bin128 + (((uint32_t)(j + rot)) & (uint32_t)(W - 1)) * 4u;
+        red_shared_add(a, gp.x);
+        red_shared_add(a + 64u, gp.y);
+      }
+    }
+    rid = rid_n; cur = nxt; gp = gpn;
+  }
+}
+template <bool kGather>
+__device__ __forceinline__ void narrow_dispatch16(int w, const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                                                  const int32_t* __restrict__ ridx, int64_t pos0, int nrows, int byte_off,
+                                                  uint32_t smem_n, int lane, int warp, int n_warps) {
+  switch (w) {
+    case 16: narrow_pass16<kGather, 16>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_n, lane, warp, n_warps); break;
+    case 8: narrow_pass16<kGather, 8>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_n, lane, warp, n_warps); break;
+    case 4: narrow_pass16<kGather, 4>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_n, lane, warp, n_warps); break;
+    case 2: narrow_pass16<kGather, 2>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_n, lane, warp, n_warps); break;
+    default: narrow_pass16<kGather, 1>(bins, row_stride, gpair, ridx, pos0, nrows, byte_off, smem_n, lane, warp, n_warps); break;
+  }
+}
+// 16-slot narrow block -> global histogram; large_only = the lazy window flush
+__device__ __forceinline__ void flush_narrow16(int32_t* s_n, const HistTarget& t, int node_slot, int group, int narrow_w, bool large_only) {
+  for (int i = threadIdx.x; i < B2_BINS * 2 * 16; i += blockDim.x) {
+    const int v = s_n[i];
+    if (v == 0 || (large_only && v < (1 << 30) && v > -(1 << 30))) continue;
+    const int bin = i >> 5, plane = (i >> 4) & 1, slot = i & 15 & (narrow_w - 1);
+    atomicAdd(t.base + target_index(t, node_slot, group, bin * 64 + plane * 32 + slot), (unsigned long long)(long long)v);
+    s_n[i] = 0;
+  }
+}
+
+__device__ __forceinline__ uint4 load_bins16(const uint8_t* __restrict__ bins, int rid, int row_stride, int off) {
+  return rid >= 0 ? ldg_nc_v4(bins + (int64_t)rid * row_stride + off) : make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void accumulate_bins(uint4 v, int2 gp, uint32_t smem_g, int rot, int half) {
+  RowData d; d.bins = v; d.gp = gp;
+  accumulate_row(d, smem_g, rot, half);
+}
+// the three full groups of rows [0, nrows): stage k of the register pipeline = group k of the lane pair's row
+// (row ids fit int32: a shard holds fewer than 2^31 rows)
+template <bool kGather>
+__device__ __forceinline__ void full_pass_g3(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                                             const int32_t* __restrict__ ridx, int64_t pos0, int nrows, uint32_t smem_base,
+                                             int lane, int warp, int n_warps) {
+  const int sub = lane >> 1, half = lane & 1, rot = sub;
+  const int off = half * 16;
+  const int iter_rows = n_warps * 16;
+  const int rbase = warp * 16;
+  int id_n = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub, nrows);
+  uint4 s0 = load_bins16(bins, id_n, row_stride, off);
+  uint4 s1 = load_bins16(bins, id_n, row_stride, off + 32);
+  uint4 s2 = load_bins16(bins, id_n, row_stride, off + 64);
+  int2 gp = id_n >= 0 ? __ldg(gpair + id_n) : make_int2(0, 0);
+  id_n = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub + iter_rows, nrows);
+  int id_nn = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub + 2 * iter_rows, nrows);
+  for (int r = rbase; r < nrows; r += iter_rows) {   // warp-uniform trip count
+    accumulate_bins(s0, gp, smem_base, rot, half);
+    s0 = load_bins16(bins, id_n, row_stride, off);
+    const int2 gp_n = id_n >= 0 ? __ldg(gpair + id_n) : make_int2(0, 0);
+    accumulate_bins(s1, gp, smem_base + B2_GROUP_ELEMS * 4, rot, half);
+    s1 = load_bins16(bins, id_n, row_stride, off + 32);
+    accumulate_bins(s2, gp, smem_base + 2 * B2_GROUP_ELEMS * 4, rot, half);
+    s2 = load_bins16(bins, id_n, row_stride, off + 64);
+    gp = gp_n; id_n = id_nn;
+    id_nn = (int)fetch_rid<kGather>(ridx, pos0, r + sub + 3 * iter_rows, nrows);
+  }
+}
+
+template <bool kGather>
+__global__ void __launch_bounds__(1024, 1)
+hist_build_kernel_v4(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                     const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
+                     int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
+                     const B2LevelCtl* __restrict__ ctl, int log2_shards, int node_cap, int narrow_w) {
+  HistTarget target; target.base = (unsigned long long*)hist; target.log2_shards = log2_shards; target.node_cap = node_cap;
+  target.n_groups = n_groups;
+  if (ctl) { n_work = ctl->hist_n_work; total_chunks = ctl->hist_total_chunks; chunk_rows = ctl->hist_chunk_rows; }
+  extern __shared__ __align__(16) int32_t s_hist[];  // [3][256][2][32] then the narrow block [256][2][16]
+  int32_t* s_narrow = s_hist + 3 * B2_GROUP_ELEMS;
+  if (total_chunks <= 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(s_hist);
+  const uint32_t smem_n = smem0 + 3u * B2_GROUP_ELEMS * 4u;
+  for (int e = threadIdx.x; e < 3 * B2_GROUP_ELEMS + B2_BINS * 32; e += blockDim.x) s_hist[e] = 0;
+  __syncthreads();
+  int cur = -1, rows_in_window = 0;
+  const int stream = blockIdx.x, n_streams = gridDim.x;
+  const int c_begin = (int)(((long long)stream * total_chunks) / n_streams);
+  const int c_end = (int)(((long long)(stream + 1) * total_chunks) / n_streams);
+  for (int chunk = c_begin; chunk < c_end; ++chunk) {
+    int lo = 0, hi = n_work - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&work[mid].chunk_begin) <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const int w = lo;
+    const int seg_begin = __ldg(&work[w].seg_begin), seg_count = __ldg(&work[w].seg_count);
+    const int row0 = (chunk - __ldg(&work[w].chunk_begin)) * chunk_rows;
+    const int nrows = min(chunk_rows, seg_count - row0);
+    const bool node_change = cur >= 0 && w != cur;
+    if (node_change || (cur >= 0 && rows_in_window + nrows > window_rows)) {
+      const int node = __ldg(&work[cur].hist_index);
+      __syncthreads();
+      for (int g = 0; g < 3; ++g) {
+        if (node_change) flush_planes(s_hist + g * B2_GROUP_ELEMS, target, node, g);
+        else flush_large_cells(s_hist + g * B2_GROUP_ELEMS, target, node, g);
+      }
+      if (narrow_w > 0) flush_narrow16(s_narrow, target, node, 3, narrow_w, !node_change);
+      __syncthreads();
+      rows_in_window = 0;
+    }
+    cur = w;
+    rows_in_window += nrows;
+    const int64_t pos0 = (int64_t)seg_begin + row0;
+    full_pass_g3<kGather>(bins, row_stride, gpair, ridx, pos0, nrows, smem0, lane, warp, n_warps);
+    if (narrow_w > 0) narrow_dispatch16<kGather>(narrow_w, bins, row_stride, gpair, ridx, pos0, nrows, 96, smem_n, lane, warp, n_warps);
+  }
+  if (cur >= 0) {
+    const int node = __ldg(&work[cur].hist_index);
+    __syncthreads();
+    for (int g = 0; g < 3; ++g) flush_planes(s_hist + g * B2_GROUP_ELEMS, target, node, g);
+    if (narrow_w > 0) flush_narrow16(s_narrow, target, node, 3, narrow_w, false);
+  }
+}
+
 // ---------------------------------------------------------------- sibling = parent - built
 __global__ void hist_subtract_kernel(const long long* __restrict__ parent_level, long long* __restrict__ level,
                                      const int32_t* __restrict__ triples, int n_pairs, int64_t node_elems,
@@ -370,25 +528,53 @@ __global__ void hist_subtract_kernel(const long long* __restrict__ parent_level,
 
 extern "C" {
 
+// the configured kernel variant (B2_HIST_VARIANT); engine.cu picks the bin-matrix layout that suits it
+int b2_hist_variant() {
+  const char* e = getenv("B2_HIST_VARIANT");
+  int v = e ? atoi(e) : B2_HIST_DEFAULT_VARIANT;
+  return (v < 0 || v > 4) ? B2_HIST_DEFAULT_VARIANT : v;
+}
+
 // Launch on `stream`.  grid = n_groups * n_streams persistent CTAs; returns the cudaError.
 int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const int32_t* ridx,
                    const B2HistWork* work, int n_work, int total_chunks, int chunk_rows, int window_rows,
                    int n_groups, long long* hist, const B2LevelCtl* ctl, int log2_shards, int node_cap, int narrow_w,
                    int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
-  static int debug_mode = -1, variant = -1;
+  static int debug_mode = -1, variant_cfg = -1;
   if (debug_mode < 0) { const char* e = getenv("B2_HIST_DEBUG_MODE"); debug_mode = e ? atoi(e) : 0; }
   // variants (B2_HIST_VARIANT): 0 = 256 threads x 3 CTAs/SM, one group per CTA
   //                             1 = 512 threads x 2 CTAs/SM, one group per CTA
   //                             2 = 1024 threads x 1 CTA/SM, two groups per CTA (round-1 default; A/B in profiles/r01_summary.md)
   //                             3 = group pairs with a narrow last group, CTAs per pair by cost (default)
-  if (variant < 0) {
+  if (variant_cfg < 0) {
     const char* e = getenv("B2_HIST_VARIANT");
-    variant = e ? atoi(e) : B2_HIST_DEFAULT_VARIANT;
-    const char* t = getenv("B2_HIST_THREADS");   // older spelling of variant 0
-    if (!e && t && atoi(t) == 256) variant = 0;
-    if (variant < 0 || variant > 3) variant = B2_HIST_DEFAULT_VARIANT;
+    variant_cfg = e ? atoi(e) : B2_HIST_DEFAULT_VARIANT;
+    const char* t = getenv("B2_HIST_THREADS");   // older spelling of variant_cfg 0
+    if (!e && t && atoi(t) == 256) variant_cfg = 0;
+    if (variant_cfg < 0 || variant_cfg > 4) variant_cfg = B2_HIST_DEFAULT_VARIANT;
   }
+  int variant = variant_cfg;
+  if (variant == 4 && ((n_groups == 3 && narrow_w == 0) || (n_groups == 4 && narrow_w > 0))) {
+    // ---- all groups of a row in one CTA: three full groups + the narrow leftover (96 <= F <= 112)
+    static bool attr4 = false;
+    const int smem4 = (3 * B2_GROUP_ELEMS + B2_BINS * 32) * (int)sizeof(int32_t);   // 224 KiB
+    if (!attr4) {
+      cudaFuncSetAttribute(b2::hist_build_kernel_v4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
+      cudaFuncSetAttribute(b2::hist_build_kernel_v4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4);
+      attr4 = true;
+    }
+    if (!ctl && (total_chunks <= 0 || n_work <= 0)) return 0;
+    if (!ctl && chunk_rows > window_rows) return (int)cudaErrorInvalidValue;
+    int n_ctas = num_sms;
+    if (!ctl && n_ctas > total_chunks) n_ctas = total_chunks;
+    if (ridx) b2::hist_build_kernel_v4<true><<<n_ctas, 1024, smem4, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows,
+                                                                              window_rows, n_groups, hist, ctl, log2_shards, node_cap, narrow_w);
+    else b2::hist_build_kernel_v4<false><<<n_ctas, 1024, smem4, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows,
+                                                                            window_rows, n_groups, hist, ctl, log2_shards, node_cap, narrow_w);
+    return (int)cudaGetLastError();
+  }
+  if (variant == 4) variant = 3;   // other feature counts: group pairs
   if (variant == 3) {
     // ---- group pairs with a narrow last group: CTAs per type in proportion to the atomic wavefronts per row
     static bool attr3 = false;

@@ -49,8 +49,8 @@ ABI = {
     "B2_CommFree": (C.c_int, [_H]),
     "B2_MatrixCreateFromDense": (C.c_int, [_FP, C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
     "B2_MatrixCreate": (C.c_int, [C.c_int64, C.c_int32, C.c_float, C.c_int, C.POINTER(_H)]),
-    "B2_MatrixCreateFromProcessInterleaved": (C.c_int, [C.c_int64, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
-                                                        C.c_float, C.c_int, C.POINTER(C.c_void_p)]),
+    "B2_MatrixCreateFromProcessInterleaved": (C.c_int, [C.c_int64, C.c_uint64, C.c_int64, C.c_int32, C.c_int32, _H,
+                                                        C.c_float, C.c_int, C.POINTER(_H)]),
     "B2_MatrixCreateFromProcess": (C.c_int, [C.c_int64, C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_float, C.c_int,
                                              C.POINTER(_H)]),
     "B2_MatrixSetRows": (C.c_int, [_H, C.c_int64, _FP, C.c_int64]),
