@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <set>
@@ -1826,6 +1827,15 @@ struct RowBlocksHost {
   int world, rank, n_cols;
   long long n_mine;
 };
+// Staging block of the interleaved ingest: persistent per device (grow-only), exported ONCE; the peers keep their mapping
+// of it across calls (mapping / unmapping a multi-GB allocation costs more than moving the rows).  A block that had to
+// grow is retired and freed only after the call's closing barrier, when every peer has dropped its mapping of it.
+struct IngestStage { float* p = nullptr; size_t bytes = 0; cudaIpcMemHandle_t h; bool exported = false; };
+IngestStage g_ingest_stage[64];
+std::map<std::string, void*> g_peer_stage;      // handle bytes -> mapped pointer (this process)
+std::mutex g_ingest_mu;
+double wall_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int B2_MatrixCreateFromProcessInterleaved(int64_t pid, uint64_t remote_addr, int64_t n_total_rows, int32_t n_cols, int32_t shard_rank,
                                           B2Handle commh, float missing, int device, B2Handle* out) {
   API_BEGIN
@@ -1834,6 +1844,15 @@ int B2_MatrixCreateFromProcessInterleaved(int64_t pid, uint64_t remote_addr, int
   if (!c || c->world < 2 || c->world > B2_P2P_MAX_WORLD) fail("interleaved remote ingest needs a communicator of 2..%d ranks", B2_P2P_MAX_WORLD);
   const int W = c->world, rank = c->rank;
   Ctx* ctx = get_ctx(device); cudaStream_t s = ctx->stream;
+  static const bool timing = getenv("B2_INGEST_TIMING") && atoi(getenv("B2_INGEST_TIMING")) != 0;
+  double t0 = wall_seconds(), t_prev = t0;
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const double t = wall_seconds();
+    fprintf(stderr, "[b2 ingest rank %d] %-28s %.4f s\n", rank, what, t - t_prev);
+    t_prev = t;
+  };
+  std::lock_guard<std::mutex> ingest_lock(g_ingest_mu);
   // contiguous block of this rank (BATCH split of the global rows) and the rows it finally owns (INTERLEAVED)
   RowBlocksHost rb; memset(&rb, 0, sizeof(rb));
   const int64_t per = n_total_rows / W, extra = n_total_rows % W;
@@ -1842,62 +1861,87 @@ int B2_MatrixCreateFromProcessInterleaved(int64_t pid, uint64_t remote_addr, int
   const int64_t n_mine = rank < n_total_rows ? (n_total_rows - rank + W - 1) / W : 0;
   if (n_mine >= (1LL << 31)) fail("at most 2^31-1 rows per GPU shard (row ids are int32), got %lld", (long long)n_mine);
   rb.world = W; rb.rank = rank; rb.n_cols = n_cols; rb.n_mine = (long long)n_mine;
-  {   // collective call: every rank must hold the shard of its own rank, or all of them fail together
-    DevBuf<int32_t> d_ok; d_ok.ensure(1);
-    int32_t bad = shard_rank == rank ? 0 : 1;
-    CUDA_CHECK(cudaMemcpyAsync(d_ok.p, &bad, sizeof(bad), cudaMemcpyHostToDevice, s));
-    allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
-    CUDA_CHECK(cudaMemcpyAsync(&bad, d_ok.p, sizeof(bad), cudaMemcpyDeviceToHost, s));
+  DevBuf<int32_t> d_flag; d_flag.ensure(1);
+  auto any_rank = [&](int32_t mine) {   // max over the ranks of a flag
+    CUDA_CHECK(cudaMemcpyAsync(d_flag.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
+    allreduce(c, d_flag.p, 1, kNcclInt32, kNcclMax, s);
+    CUDA_CHECK(cudaMemcpyAsync(&mine, d_flag.p, sizeof(mine), cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    if (bad) fail("interleaved remote ingest: shard %d handed to rank %d (or a mismatch on another rank)", shard_rank, rank);
-  }
+    return mine;
+  };
+  // collective call: every rank must hold the shard of its own rank, or all of them fail together
+  if (any_rank(shard_rank == rank ? 0 : 1))
+    fail("interleaved remote ingest: shard %d handed to rank %d (or a mismatch on another rank)", shard_rank, rank);
+  lap("agreement");
   Matrix* m = new Matrix(); m->kind = kMatrix; m->ctx = ctx; m->n = n_mine; m->F = n_cols; m->missing = missing;
-  std::vector<void*> opened;
+  void* retired = nullptr;
   try {
-    DevBuf<float> stage; stage.ensure((size_t)std::max<int64_t>(bn * n_cols, 1));
-    UploadSource u; u.pid = pid; u.remote_addr = remote_addr + (uint64_t)b0 * (uint64_t)n_cols * 4u; u.row_bytes = (size_t)n_cols * 4; u.row_stride = u.row_bytes;
-    upload_pipelined(ctx, stage.p, u, (size_t)bn * n_cols * sizeof(float));
-    m->raw.ensure((size_t)std::max<int64_t>(n_mine * n_cols, 1));
-    // exchange the IPC handles of the staged blocks; one failed mapping anywhere makes every rank fail together
-    cudaIpcMemHandle_t mine; int ok = 1;
-    if (cudaIpcGetMemHandle(&mine, stage.p) != cudaSuccess) { ok = 0; cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
-    DevBuf<uint8_t> d_mine, d_all; d_mine.ensure(sizeof(mine)); d_all.ensure(sizeof(mine) * (size_t)W);
-    CUDA_CHECK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, s));
-    NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(mine), kNcclUint8, c->comm, s));   // also: every rank's block is uploaded
-    std::vector<cudaIpcMemHandle_t> all((size_t)W);
-    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(mine) * (size_t)W, cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaStreamSynchronize(s));
-    for (int w = 0; w < W && ok; ++w) {
-      if (w == rank) { rb.base[w] = stage.p; continue; }
+    IngestStage& st = g_ingest_stage[(device >= 0 && device < 64) ? device : 0];
+    const size_t need = (size_t)std::max<int64_t>(bn * n_cols, 1) * sizeof(float);
+    int ok = 1;
+    if (st.bytes < need) {
+      retired = st.p; st.p = nullptr; st.bytes = 0; st.exported = false;
+      const size_t want = (need + need / 16 + ((size_t)1 << 20)) & ~(((size_t)1 << 20) - 1);
       void* q = nullptr;
-      if (cudaIpcOpenMemHandle(&q, all[w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
-      opened.push_back(q); rb.base[w] = (const float*)q;
+      if (cudaMalloc(&q, want) != cudaSuccess) {
+        cudaGetLastError();
+        { std::lock_guard<std::mutex> lk(g_dev_pool[(device >= 0 && device < 64) ? device : 0].mu); pool_trim(g_dev_pool[(device >= 0 && device < 64) ? device : 0], 0); }
+        if (cudaMalloc(&q, want) != cudaSuccess) { cudaGetLastError(); fail("cudaMalloc of the %zu-byte ingest staging block failed", want); }
+      }
+      st.p = (float*)q; st.bytes = want;
     }
-    DevBuf<int32_t> d_ok; d_ok.ensure(1);
-    int32_t neg = ok ? 0 : 1;
-    CUDA_CHECK(cudaMemcpyAsync(d_ok.p, &neg, sizeof(neg), cudaMemcpyHostToDevice, s));
-    allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
-    CUDA_CHECK(cudaMemcpyAsync(&neg, d_ok.p, sizeof(neg), cudaMemcpyDeviceToHost, s));
+    if (!st.exported) {
+      if (cudaIpcGetMemHandle(&st.h, st.p) == cudaSuccess) st.exported = true;
+      else { ok = 0; cudaGetLastError(); memset(&st.h, 0, sizeof(st.h)); }
+    }
+    lap("staging block");
+    UploadSource u; u.pid = pid; u.remote_addr = remote_addr + (uint64_t)b0 * (uint64_t)n_cols * 4u; u.row_bytes = (size_t)n_cols * 4; u.row_stride = u.row_bytes;
+    upload_pipelined(ctx, st.p, u, (size_t)bn * n_cols * sizeof(float));
+    lap("read block from the driver");
+    m->raw.ensure((size_t)std::max<int64_t>(n_mine * n_cols, 1));
+    // exchange the IPC handles of the staging blocks (also: every rank's block is uploaded)
+    DevBuf<uint8_t> d_mine, d_all; d_mine.ensure(sizeof(st.h)); d_all.ensure(sizeof(st.h) * (size_t)W);
+    CUDA_CHECK(cudaMemcpyAsync(d_mine.p, &st.h, sizeof(st.h), cudaMemcpyHostToDevice, s));
+    NCCL_CHECK(nccl()->AllGather(d_mine.p, d_all.p, sizeof(st.h), kNcclUint8, c->comm, s));
+    std::vector<cudaIpcMemHandle_t> all((size_t)W);
+    CUDA_CHECK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(st.h) * (size_t)W, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    if (neg) {
+    lap("handle exchange");
+    // drop mappings of blocks that no peer exports any more (a peer's block grew), then map what is new
+    std::set<std::string> current;
+    for (int w = 0; w < W; ++w) if (w != rank) current.insert(std::string((const char*)&all[w], sizeof(all[w])));
+    for (auto it = g_peer_stage.begin(); it != g_peer_stage.end();) {
+      if (!current.count(it->first)) { cudaIpcCloseMemHandle(it->second); it = g_peer_stage.erase(it); } else ++it;
+    }
+    for (int w = 0; w < W && ok; ++w) {
+      if (w == rank) { rb.base[w] = st.p; continue; }
+      const std::string key((const char*)&all[w], sizeof(all[w]));
+      auto it = g_peer_stage.find(key);
+      if (it == g_peer_stage.end()) {
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[w], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+        it = g_peer_stage.emplace(key, q).first;
+      }
+      rb.base[w] = (const float*)it->second;
+    }
+    lap("peer mappings");
+    if (any_rank(ok ? 0 : 1)) {
       // no peer mapping on some rank (no NVLink / IPC): every rank reads its own strided shard from the driver instead
-      for (void* q : opened) cudaIpcCloseMemHandle(q);
-      opened.clear();
       UploadSource us; us.pid = pid; us.remote_addr = remote_addr + (uint64_t)rank * (uint64_t)n_cols * 4u;
       us.row_bytes = (size_t)n_cols * 4; us.row_stride = us.row_bytes * (size_t)W;
       upload_pipelined(ctx, m->raw.p, us, (size_t)n_mine * n_cols * sizeof(float));
     } else {
       LAUNCH_CHECK(b2_launch_gather_interleaved_rows(&rb, m->raw.p, ctx->num_sms, s));
-      // nobody releases its block while a peer may still be pulling rows out of it
-      allreduce(c, d_ok.p, 1, kNcclInt32, kNcclMax, s);
-      CUDA_CHECK(cudaStreamSynchronize(s));
-      for (void* q : opened) cudaIpcCloseMemHandle(q);
-      opened.clear();
     }
-  } catch (...) { for (void* q : opened) cudaIpcCloseMemHandle(q); delete m; throw; }
+    // nobody overwrites (next call) or frees (a retired block) its staging block while a peer may still pull rows out of it
+    any_rank(0);
+    lap("row gather + closing barrier");
+    if (retired) { cudaFree(retired); retired = nullptr; }
+  } catch (...) { if (retired) cudaFree(retired); delete m; throw; }
   m->has_raw = true;
   { std::lock_guard<std::mutex> lk(g_matrix_mu); m->uid = g_next_matrix_uid++; g_live_matrices.insert(m->uid); }
   *out = (B2Handle)m;
+  if (timing) fprintf(stderr, "[b2 ingest rank %d] total %.4f s (%lld of %lld rows x %d)\n", rank, wall_seconds() - t0, (long long)n_mine, (long long)n_total_rows, n_cols);
   API_END
 }
 int B2_MatrixSetRows(B2Handle mh, int64_t row_begin, const float* data, int64_t n_rows) {
