@@ -415,45 +415,79 @@ __device__ __forceinline__ void flush_narrow16(int32_t* s_n, const HistTarget& t
   }
 }
 
-__device__ __forceinline__ uint4 load_bins16(const uint8_t* __restrict__ bins, int rid, int row_stride, int off) {
-  return rid >= 0 ? ldg_nc_v4(bins + (int64_t)rid * row_stride + off) : make_uint4(0, 0, 0, 0);
-}
 __device__ __forceinline__ void accumulate_bins(uint4 v, int2 gp, uint32_t smem_g, int rot, int half) {
   RowData d; d.bins = v; d.gp = gp;
   accumulate_row(d, smem_g, rot, half);
 }
-// the three full groups of rows [0, nrows): stage k of the register pipeline = group k of the lane pair's row
-// (row ids fit int32: a shard holds fewer than 2^31 rows)
+// everything a lane needs of one row: its 16-byte half of the three full groups, (even lane only) the first four bytes
+// of the narrow group, the gradient pair.  The loads of a row are issued TOGETHER: the four 32-byte sectors of the
+// 128-byte row are then requested at the same time and DRAM serves them as one line (staggering them over the
+// iteration doubled the DRAM traffic: 3.1 GB instead of 1.36 GB per 10M-row launch, profiles/r02/b10_hist_traffic_v4.json).
+struct RowRegs {
+  uint4 g0, g1, g2;
+  uint32_t nb;
+  int2 gp;
+};
+__device__ __forceinline__ RowRegs load_row_regs(const uint8_t* __restrict__ bins, const int2* __restrict__ gpair, int rid,
+                                                 int row_stride, int off, bool narrow_lane) {
+  RowRegs r;
+  r.g0 = r.g1 = r.g2 = make_uint4(0, 0, 0, 0); r.nb = 0; r.gp = make_int2(0, 0);
+  if (rid >= 0) {
+    const uint8_t* p = bins + (int64_t)rid * row_stride;
+    r.g0 = ldg_nc_v4(p + off);
+    r.g1 = ldg_nc_v4(p + off + 32);
+    r.g2 = ldg_nc_v4(p + off + 64);
+    if (narrow_lane) r.nb = __ldg(reinterpret_cast<const uint32_t*>(p + 96));
+    r.gp = __ldg(gpair + rid);
+  }
+  return r;
+}
+// rows [0, nrows) of a chunk, all groups: lane pair = row (16 rows per warp step), one row of look-ahead in registers.
+// narrow_w in {0, 1, 2, 4}: the even lane of the pair also adds the narrow group's features (16 lanes, 4 replicas x 4
+// slots = 16 banks of the [256][2][16] block).
 template <bool kGather>
-__device__ __forceinline__ void full_pass_g3(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
-                                             const int32_t* __restrict__ ridx, int64_t pos0, int nrows, uint32_t smem_base,
-                                             int lane, int warp, int n_warps) {
+__device__ __forceinline__ void row_pass_v4(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
+                                            const int32_t* __restrict__ ridx, int64_t pos0, int nrows, uint32_t smem_base,
+                                            uint32_t smem_n, int narrow_w, int lane, int warp, int n_warps) {
   const int sub = lane >> 1, half = lane & 1, rot = sub;
   const int off = half * 16;
   const int iter_rows = n_warps * 16;
   const int rbase = warp * 16;
-  int id_n = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub, nrows);
-  uint4 s0 = load_bins16(bins, id_n, row_stride, off);
-  uint4 s1 = load_bins16(bins, id_n, row_stride, off + 32);
-  uint4 s2 = load_bins16(bins, id_n, row_stride, off + 64);
-  int2 gp = id_n >= 0 ? __ldg(gpair + id_n) : make_int2(0, 0);
-  id_n = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub + iter_rows, nrows);
+  const bool narrow_lane = narrow_w > 0 && half == 0;
+  const int nmask = narrow_w - 1;
+  const int nrot = sub & nmask;
+  const uint32_t nbase = smem_n + (uint32_t)(narrow_w > 0 ? (((sub / narrow_w) & (16 / narrow_w - 1)) * narrow_w) : 0) * 4u;
+  int id = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub, nrows);
+  RowRegs cur = load_row_regs(bins, gpair, id, row_stride, off, narrow_lane);
+  int id_n = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub + iter_rows, nrows);
   int id_nn = (int)fetch_rid<kGather>(ridx, pos0, rbase + sub + 2 * iter_rows, nrows);
   for (int r = rbase; r < nrows; r += iter_rows) {   // warp-uniform trip count
-    accumulate_bins(s0, gp, smem_base, rot, half);
-    s0 = load_bins16(bins, id_n, row_stride, off);
-    const int2 gp_n = id_n >= 0 ? __ldg(gpair + id_n) : make_int2(0, 0);
-    accumulate_bins(s1, gp, smem_base + B2_GROUP_ELEMS * 4, rot, half);
-    s1 = load_bins16(bins, id_n, row_stride, off + 32);
-    accumulate_bins(s2, gp, smem_base + 2 * B2_GROUP_ELEMS * 4, rot, half);
-    s2 = load_bins16(bins, id_n, row_stride, off + 64);
-    gp = gp_n; id_n = id_nn;
+    const RowRegs nxt = load_row_regs(bins, gpair, id_n, row_stride, off, narrow_lane);
+    id_n = id_nn;
+    if (id_n >= 0) {   // the row after the next one: pull its line (one 64-byte half per lane of the pair) and its gradient pair into L2
+      const uint8_t* pf = bins + (int64_t)id_n * row_stride + half * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      if (half == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(gpair + id_n));
+    }
     id_nn = (int)fetch_rid<kGather>(ridx, pos0, r + sub + 3 * iter_rows, nrows);
+    accumulate_bins(cur.g0, cur.gp, smem_base, rot, half);
+    accumulate_bins(cur.g1, cur.gp, smem_base + B2_GROUP_ELEMS * 4, rot, half);
+    accumulate_bins(cur.g2, cur.gp, smem_base + 2 * B2_GROUP_ELEMS * 4, rot, half);
+    if (narrow_lane) {
+      for (int j = 0; j < narrow_w; ++j) {
+        const int idx = (j + nrot) & nmask;
+        const uint32_t bin = (cur.nb >> (idx * 8)) & 0xffu;
+        const uint32_t a = nbase + bin * 128u + (uint32_t)idx * 4u;
+        red_shared_add(a, cur.gp.x);
+        red_shared_add(a + 64u, cur.gp.y);
+      }
+    }
+    cur = nxt;
   }
 }
 
 template <bool kGather>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(512, 1)
 hist_build_kernel_v4(const uint8_t* __restrict__ bins, int row_stride, const int2* __restrict__ gpair,
                      const int32_t* __restrict__ ridx, const B2HistWork* __restrict__ work, int n_work,
                      int total_chunks, int chunk_rows, int window_rows, int n_groups, long long* __restrict__ hist,
@@ -467,6 +501,7 @@ hist_build_kernel_v4(const uint8_t* __restrict__ bins, int row_stride, const int
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(s_hist);
   const uint32_t smem_n = smem0 + 3u * B2_GROUP_ELEMS * 4u;
+  const int inline_w = narrow_w <= 4 ? narrow_w : 0;     // wider leftovers: their own pass over the chunk
   for (int e = threadIdx.x; e < 3 * B2_GROUP_ELEMS + B2_BINS * 32; e += blockDim.x) s_hist[e] = 0;
   __syncthreads();
   int cur = -1, rows_in_window = 0;
@@ -498,8 +533,8 @@ hist_build_kernel_v4(const uint8_t* __restrict__ bins, int row_stride, const int
     cur = w;
     rows_in_window += nrows;
     const int64_t pos0 = (int64_t)seg_begin + row0;
-    full_pass_g3<kGather>(bins, row_stride, gpair, ridx, pos0, nrows, smem0, lane, warp, n_warps);
-    if (narrow_w > 0) narrow_dispatch16<kGather>(narrow_w, bins, row_stride, gpair, ridx, pos0, nrows, 96, smem_n, lane, warp, n_warps);
+    row_pass_v4<kGather>(bins, row_stride, gpair, ridx, pos0, nrows, smem0, smem_n, inline_w, lane, warp, n_warps);
+    if (narrow_w > 4) narrow_dispatch16<kGather>(narrow_w, bins, row_stride, gpair, ridx, pos0, nrows, 96, smem_n, lane, warp, n_warps);
   }
   if (cur >= 0) {
     const int node = __ldg(&work[cur].hist_index);
@@ -568,9 +603,9 @@ int b2_launch_hist(const uint8_t* bins, int row_stride, const int2* gpair, const
     if (!ctl && chunk_rows > window_rows) return (int)cudaErrorInvalidValue;
     int n_ctas = num_sms;
     if (!ctl && n_ctas > total_chunks) n_ctas = total_chunks;
-    if (ridx) b2::hist_build_kernel_v4<true><<<n_ctas, 1024, smem4, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows,
+    if (ridx) b2::hist_build_kernel_v4<true><<<n_ctas, 512, smem4, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows,
                                                                               window_rows, n_groups, hist, ctl, log2_shards, node_cap, narrow_w);
-    else b2::hist_build_kernel_v4<false><<<n_ctas, 1024, smem4, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows,
+    else b2::hist_build_kernel_v4<false><<<n_ctas, 512, smem4, stream>>>(bins, row_stride, gpair, ridx, work, n_work, total_chunks, chunk_rows,
                                                                             window_rows, n_groups, hist, ctl, log2_shards, node_cap, narrow_w);
     return (int)cudaGetLastError();
   }

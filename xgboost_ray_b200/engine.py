@@ -284,9 +284,11 @@ class DMatrix:
         self.ingest = "host"
         inter = getattr(remote, "interleave", None) if remote is not None else None
         if (inter is not None and _coll.handle and _coll.world == inter[3] and n * f > 0
-                and os.environ.get("B2_INTERLEAVED_INGEST", "1") != "0"):
+                and os.environ.get("B2_INTERLEAVED_INGEST", "0") not in ("", "0")):
             # INTERLEAVED shard and every rank of the communicator builds its shard of the same matrix right now: each
-            # rank reads one contiguous block from the driver, the rows are redistributed over NVLink
+            # rank reads one contiguous block from the driver, the rows are redistributed over NVLink.  Opt-in
+            # (B2_INTERLEAVED_INGEST=1): validated on 2 GPUs, where it shortens the upload (0.108 vs 0.128 s for 10M x 100)
+            # but not yet the whole call; the default stays the strided host read
             _check(lib().B2_MatrixCreateFromProcessInterleaved(remote.pid, inter[0], inter[1], f, inter[2], _coll.handle,
                                                                self.missing, self.device, C.byref(h)))
             self.handle = h.value
