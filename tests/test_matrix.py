@@ -79,3 +79,32 @@ def test_errors():
         RayDMatrix({"not": "supported"})
     a, b = RayDMatrix(x), RayDMatrix(x)
     assert a != b and hash(a) != hash(b) and a == a                                    # identity by uuid
+
+
+def test_remote_shard_descriptors_carry_the_interleave_layout():
+    """transport='remote': a shard is a description of rows inside THIS process.  INTERLEAVED shards also say where the
+    whole matrix lives (address, rows, shard rank, number of shards) so that W GPU actors can each read one contiguous
+    1/W block and exchange rows on the device (B2_MatrixCreateFromProcessInterleaved); BATCH shards are contiguous and
+    carry no such hint.  Reading a descriptor back (same process here) reproduces the shard."""
+    import os
+    from xgboost_ray_b200 import RayDMatrix, RayShardingMode
+    from xgboost_ray_b200.main import _attach_shared
+    rng = np.random.RandomState(0)
+    x = rng.normal(size=(1003, 7)).astype(np.float32)
+    y = rng.normal(size=1003).astype(np.float32)
+    for mode in (RayShardingMode.INTERLEAVED, RayShardingMode.BATCH):
+        d = RayDMatrix(x, y, sharding=mode)
+        d.load_data(3, transport="remote")
+        for r in range(3):
+            desc = d.get_shared(r, 3)["data"]
+            assert desc[0] == "remote" and desc[1] == os.getpid() and len(desc) == 7
+            block = _attach_shared(desc)
+            want = d.get_data(r, 3)["data"]
+            assert block.shape == want.shape and np.array_equal(np.asarray(block), want)
+            if mode == RayShardingMode.INTERLEAVED:
+                addr, n_total, rank, world = block.interleave
+                assert (n_total, rank, world) == (1003, r, 3) and addr == d._keep_alive.ctypes.data
+                assert block.row_stride == 3 * 7 * 4 and np.array_equal(want, x[r::3])
+            else:
+                assert block.interleave is None and block.row_stride == 7 * 4
+        d.unload_data()
