@@ -490,6 +490,7 @@ def main():
                           ray_params=RayParams(num_actors=world))
                 first_call = time.perf_counter() - t0
                 del dwarm
+                time.sleep(1.0)      # the actors tear the previous call's boosters down after replying; not part of the next call
                 t0 = time.perf_counter()
                 dmat = RayDMatrix(Xf, yf, **dm_kw)
                 res, extra = {}, {}
