@@ -249,6 +249,12 @@ def test_actor_pool_shared_memory_and_actor_side_file_loading(tmp_path):
     # the feature matrix itself is not copied at all: the actors read their rows out of this process
     assert e1["timing"]["shard_transport"] == "remote" and all(sh["data"][0] == "remote" for sh in d._shared.values())
     assert e1["timing"]["actor0"]["upload_s"] >= 0
+    # wall-clock stamps of the driver and of both actors (bench.py reports them with the e2e number)
+    stamps = e1["timing"]["actors"]
+    assert len(stamps) == 2 and len(e1["timing"]["t_future_done"]) == 2
+    for st in stamps:
+        assert e1["timing"]["t_dispatch"] <= st["t_enter"] <= st["t_trained"] <= st["t_thread_end"] <= st["t_return"]
+    assert max(e1["timing"]["t_future_done"]) >= max(st["t_return"] for st in stamps)
     b2 = train(params, RayDMatrix(x, y), num_boost_round=3, additional_results=e2, ray_params=RayParams(num_actors=2),
                callbacks=[PidRecorder()])
     pids = lambda e: sorted(item[1] for per_rank in e["callback_returns"] for item in per_rank)  # noqa: E731
