@@ -20,9 +20,7 @@ typedef B2SegWork SegWork;
 // and 8 bin-byte loads the compiler batches (48 registers).  With the category test in the body it software-pipelines
 // only 2-3 deep and the kernel runs 1.7x slower (ncu launch lists in profiles/), so numeric matrices keep their own
 // instantiation.
-// kMode 0: numeric only.  1: category set in shared memory (the validated categorical path).  2 (experimental,
-// B2_PART_CAT_MODE=2): category set in eight uniform registers selected with a 3-level select tree, no shared-memory
-// load in the row loop.
+// kMode 0: numeric only.  1: category set in shared memory.
 constexpr int kSplitChunk = 8192;                       // rows per work item of the split-node kernels (partition, final assign)
 constexpr int kSplitPasses = kSplitChunk / kPartChunk;  // a work item is processed as 4 register passes of 2048 rows
 
@@ -60,11 +58,6 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
       if (threadIdx.x < 8) s_cat[threadIdx.x] = w.is_cat ? __ldg(&work[lo].cat_bits[threadIdx.x]) : 0u;
       __syncthreads();
     }
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0;
-    if (kMode == 2 && w.is_cat) {
-      const uint4 lo4 = __ldg(reinterpret_cast<const uint4*>(work[lo].cat_bits)), hi4 = __ldg(reinterpret_cast<const uint4*>(work[lo].cat_bits) + 1);
-      c0 = lo4.x; c1 = lo4.y; c2 = lo4.z; c3 = lo4.w; c4 = hi4.x; c5 = hi4.y; c6 = hi4.z; c7 = hi4.w;
-    }
     const bool is_cat = kCat && w.is_cat != 0, has_missing = w.has_missing != 0, default_left = w.default_left != 0;
 #pragma unroll 1
     for (int pass = 0; pass < kSplitPasses; ++pass) {
@@ -92,13 +85,7 @@ partition_kernel(const uint8_t* __restrict__ bins_col, int64_t col_stride, const
         const int b = bin[it];
         bool l;
         if (kCat) {
-          uint32_t word;
-          if (kMode == 1) word = s_cat[b >> 5];
-          else {
-            const uint32_t w01 = (b & 32) ? c1 : c0, w23 = (b & 32) ? c3 : c2, w45 = (b & 32) ? c5 : c4, w67 = (b & 32) ? c7 : c6;
-            const uint32_t w03 = (b & 64) ? w23 : w01, w47 = (b & 64) ? w67 : w45;
-            word = (b & 128) ? w47 : w03;
-          }
+          const uint32_t word = s_cat[b >> 5];
           const bool in_set = ((word >> (b & 31)) & 1u) != 0u;                     // category in the set -> right
           const bool go_left = is_cat ? !in_set : (b <= w.split_bin);
           l = (has_missing && b == B2_MISSING_BIN) ? default_left : go_left;
@@ -316,15 +303,12 @@ int b2_launch_partition(const uint8_t* bins_col, int64_t col_stride, const int32
                         int num_sms, cudaStream_t stream) {
   if (max_chunks <= 0) return 0;
   int grid = max_chunks < num_sms * 6 ? max_chunks : num_sms * 6;   // 6 CTAs per SM are resident (33 KB of shared memory, 48 registers)
-  static int cat_mode = -1;
-  if (cat_mode < 0) { const char* e = getenv("B2_PART_CAT_MODE"); cat_mode = (e && atoi(e) == 2) ? 2 : 1; }
 #define B2_PART_LAUNCH(MODE)                                                                                                  \
   do {                                                                                                                        \
     if (ridx_in) b2::partition_kernel<MODE, false><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters); \
     else b2::partition_kernel<MODE, true><<<grid, b2::kPartThreads, 0, stream>>>(bins_col, col_stride, ridx_in, ridx_out, work, ctl, counters);         \
   } while (0)
-  if (any_categorical && cat_mode == 2) B2_PART_LAUNCH(2);
-  else if (any_categorical) B2_PART_LAUNCH(1);
+  if (any_categorical) B2_PART_LAUNCH(1);
   else B2_PART_LAUNCH(0);
 #undef B2_PART_LAUNCH
   return (int)cudaGetLastError();
